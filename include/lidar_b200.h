@@ -1,0 +1,162 @@
+/* lidar_b200 — C ABI of the B200-native point-cloud hot path.
+ *
+ * This is the drop-in boundary for the hot path of FortuneMU2025/LIDAR_AI_Recommendation_Software.
+ * The reference is pure Python and has NO FFI; the interface each entry point replaces is therefore
+ * a Python call site in the reference, cited as file:line next to every declaration.  The host-side
+ * mirror of those Python callables lives in lidar_ai_recommendation_software_b200/ (ctypes over this
+ * header); INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Rules of the ABI
+ *   - plain C: pointers, sizes, scalars.  No torch / C++ types.
+ *   - every pointer named d_* is DEVICE memory on the current CUDA device, h_* is HOST memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
+ *     enqueued asynchronously on it; no entry point synchronises unless it says so.
+ *   - no hidden allocation: scratch comes from the caller (`d_ws`, `ws_bytes`); each family has a
+ *     *_workspace_bytes() query.  Workspaces need 256-byte alignment.
+ *   - return value: 0 = LIDAR_OK, negative = error; lidar_last_error() returns a thread-local,
+ *     human-readable message for the last failing call on this thread.
+ *   - integer outputs are bit-exact against the CPU oracle (oracle/), see DESIGN.md.
+ */
+#ifndef LIDAR_B200_H_
+#define LIDAR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIDAR_ABI_VERSION 1
+
+#define LIDAR_OK 0
+#define LIDAR_ERR_INVALID (-1)   /* bad argument */
+#define LIDAR_ERR_CUDA (-2)      /* a CUDA runtime call failed */
+#define LIDAR_ERR_WORKSPACE (-3) /* caller workspace too small */
+#define LIDAR_ERR_CAPACITY (-4)  /* an output capacity was exceeded */
+
+/* point layouts */
+#define LIDAR_FMT_F32X4 0 /* float4 x,y,z,intensity (16-byte aligned)            */
+#define LIDAR_FMT_F64X3 1 /* packed (n,3) float64 rows — the reference's layout  */
+
+/* histogram accumulation strategy (lidar_hist2d*) */
+#define LIDAR_HIST_AUTO 0
+#define LIDAR_HIST_GLOBAL 1 /* one RED.ADD per point straight into the L2-resident grid          */
+#define LIDAR_HIST_SHARED 2 /* CTA-private shared-memory grid, warp-aggregated, flushed at the end */
+
+const char* lidar_last_error(void);
+int lidar_abi_version(void);
+/* sm_count, compute capability (major*10+minor), opt-in shared memory per block of `device` */
+int lidar_device_props(int device, int* sm_count, int* cc, size_t* smem_optin);
+
+/* ------------------------------------------------------------------------------------------- *
+ * K1  bounding box.   replaces np.min/np.max at utils/data_processing.py:143,207-208 and
+ *     app_simplified.py:80,116-117.
+ *     d_out8 = {min x,y,z,w, max x,y,z,w} as float64 (w = intensity; 0 for F64X3).  n == 0 gives
+ *     +inf / -inf.  Exact (min/max are order independent).
+ * ------------------------------------------------------------------------------------------- */
+size_t lidar_reduce_workspace_bytes(void);
+int lidar_bbox(const void* d_points, int fmt, int64_t n, double* d_out8, void* d_ws, size_t ws_bytes,
+               void* stream);
+
+/* K1b per-axis moments about a caller-supplied centre: d_out6 = {S(p-c) x,y,z, S(p-c)^2 x,y,z} in
+ *     fp64 (fixed reduction tree: deterministic for a given n).  replaces np.mean / np.std at
+ *     utils/data_processing.py:151-152 and app_simplified.py:88-89 (two passes: c = 0, then c = mean). */
+int lidar_moments(const void* d_points, int fmt, int64_t n, const double* h_center3, double* d_out6,
+                  void* d_ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
+ * K6  2-D histogram with numpy.histogramdd semantics: bin k <=> e[k] <= x < e[k+1], last bin
+ *     closed, everything else (and NaN) dropped; edges and compares in fp64.
+ *     replaces np.histogram2d at utils/data_processing.py:316-319 (np.arange edges),
+ *     utils/visualization.py:130-134 and app_simplified.py:205-209 (np.linspace edges).
+ *     d_u/d_v: fp64 columns with element strides su/sv (points[:,0], points[:,1] -> stride 3).
+ *     d_ex (nx+1), d_ey (ny+1): monotonically increasing fp64 edges.
+ *     d_counts: int32 [nx][ny] row-major (index order [x][y], NOT transposed) — the caller zeroes
+ *     it; counts are ADDED so several shards can accumulate into one grid.
+ * ------------------------------------------------------------------------------------------- */
+int lidar_hist2d_f64(const double* d_u, int64_t su, const double* d_v, int64_t sv, int64_t n,
+                     const double* d_ex, int nx, const double* d_ey, int ny, int32_t* d_counts,
+                     int mode, void* stream);
+/* same, x/y taken from a point cloud in layout `fmt` (F32X4 values are widened exactly) */
+int lidar_hist2d_points(const void* d_points, int fmt, int64_t n, const double* d_ex, int nx,
+                        const double* d_ey, int ny, int32_t* d_counts, int mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
+ * a5  ROI crop (NEW op): keep <=> lo <= p <= hi on x,y,z (fp32 compares
+ *     for F32X4, fp64 for F64X3), order preserving.
+ *     d_mask: uint8[n] (may be NULL); d_out: compacted points in the same layout (capacity n);
+ *     d_count: int64 device scalar = number kept.
+ * ------------------------------------------------------------------------------------------- */
+size_t lidar_compact_workspace_bytes(int64_t n);
+int lidar_roi_crop(const void* d_points, int fmt, int64_t n, const double* h_lo3, const double* h_hi3,
+                   uint8_t* d_mask, void* d_out, int64_t* d_count, void* d_ws, size_t ws_bytes,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
+ * K5  voxel downsample (NEW op).
+ *     i_axis = floor((f64(p_axis) - origin_axis) / voxel) ; key = (ix*Dy + iy)*Dz + iz.
+ *     Voxels come out in ascending key order.  All integer outputs are bit-exact and run-to-run
+ *     deterministic; centroids are the fp32 rounding of an exact fixed-point mean.
+ *
+ *     The frame descriptor lives in DEVICE memory so a whole frame (bbox -> keys -> ranks ->
+ *     centroids [+ density grid]) is enqueued without a host round trip.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct lidar_frame_desc {
+    /* inputs written by lidar_frame_prepare (device side, from the bbox) or by the host */
+    double origin[4];     /* voxel origin x,y,z (+pad)                                         */
+    double bbox_min[4];   /* x,y,z,intensity                                                   */
+    double bbox_max[4];
+    double voxel;         /* voxel edge length                                                 */
+    double fix_scale_xyz; /* 2^k: fixed-point scale of (p - voxel_corner)                      */
+    double fix_scale_w;   /* 2^k: fixed-point scale of intensity                               */
+    int32_t dims[4];      /* Dx, Dy, Dz (+pad)                                                 */
+    int64_t key_space;    /* Dx*Dy*Dz                                                          */
+    /* density grid (calculate_grid_density semantics), filled when grid > 0 */
+    double grid;          /* cell size g, 0 = no density grid                                  */
+    double ex0, ex1, exd; /* x edges: e(0), e(1), delta   (numpy arange fill rule)             */
+    double ey0, ey1, eyd;
+    int32_t nx, ny;       /* bins                                                              */
+    /* outputs */
+    int64_t n_points;
+    int64_t n_voxels;
+    int32_t status;       /* 0 ok, LIDAR_ERR_CAPACITY if key_space / grid exceeded capacities  */
+    int32_t pad;
+} lidar_frame_desc;
+
+/* capacities chosen by the caller once per stream of frames */
+typedef struct lidar_frame_caps {
+    int64_t max_points;
+    int64_t max_key_space; /* bits of occupancy bitmap, e.g. 1<<28                             */
+    int32_t max_nx, max_ny;
+} lidar_frame_caps;
+
+size_t lidar_frame_workspace_bytes(const lidar_frame_caps* caps);
+/* one-time (or after an error): zero the persistent parts of the workspace */
+int lidar_frame_workspace_init(void* d_ws, size_t ws_bytes, const lidar_frame_caps* caps, void* stream);
+
+/* whole frame: bbox -> voxelise (+ density histogram when grid_size > 0).
+ *   d_points      float4[n]
+ *   h_origin3     NULL => per-axis min of the cloud (B.1 default)
+ *   h_xy_range4   NULL => (xmin,xmax,ymin,ymax) of the cloud; else the caller's x_range/y_range
+ *                 (calculate_grid_density(positions, x_range, y_range, g),
+ *                  utils/data_processing.py:282-328)
+ *   d_voxel_key   int32[n]   per-point voxel key (B.1 voxel_idx)
+ *   d_inverse     int32[n]   rank of the point's voxel
+ *   d_centroids   float4[cap n]   (x,y,z,mean intensity) per voxel, ascending key
+ *   d_counts      int32[cap n]
+ *   d_unique_keys int32[cap n]
+ *   d_grid        int32[max_nx*max_ny] laid out [nx][ny] with the ACTUAL ny from the descriptor
+ *   d_desc        device lidar_frame_desc (read it back after the stream is synchronised)
+ */
+int lidar_frame_voxel_density(const void* d_points, int64_t n, double voxel_size, double grid_size,
+                              const double* h_origin3, const double* h_xy_range4,
+                              int32_t* d_voxel_key, int32_t* d_inverse, void* d_centroids,
+                              int32_t* d_counts, int32_t* d_unique_keys, int32_t* d_grid,
+                              lidar_frame_desc* d_desc, const lidar_frame_caps* caps, void* d_ws,
+                              size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIDAR_B200_H_ */

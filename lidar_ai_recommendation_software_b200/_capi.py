@@ -1,0 +1,121 @@
+"""ctypes binding of the C-ABI CUDA core (include/lidar_b200.h -> liblidar_b200.so).
+
+There is no CPU fallback: if the shared library is missing or does not load, importing this module
+raises, and every op of the package fails loudly.  PyTorch is used only to own device memory and
+streams; the pointers handed across the ABI are raw `data_ptr()`s.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch  # noqa: F401  (loads libcudart.so.12 and friends before our library is opened)
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "liblidar_b200.so"
+
+LIDAR_OK = 0
+FMT_F32X4 = 0
+FMT_F64X3 = 1
+HIST_AUTO, HIST_GLOBAL, HIST_SHARED = 0, 1, 2
+
+ERR_NAMES = {-1: "LIDAR_ERR_INVALID", -2: "LIDAR_ERR_CUDA", -3: "LIDAR_ERR_WORKSPACE", -4: "LIDAR_ERR_CAPACITY"}
+
+
+class LidarError(RuntimeError):
+    """Raised when a C-ABI call returns a negative status (apps catch `Exception`, app.py:103-104)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+class FrameDesc(C.Structure):
+    """Mirror of `lidar_frame_desc` (include/lidar_b200.h)."""
+
+    _fields_ = [
+        ("origin", C.c_double * 4),
+        ("bbox_min", C.c_double * 4),
+        ("bbox_max", C.c_double * 4),
+        ("voxel", C.c_double),
+        ("fix_scale_xyz", C.c_double),
+        ("fix_scale_w", C.c_double),
+        ("dims", C.c_int32 * 4),
+        ("key_space", C.c_int64),
+        ("grid", C.c_double),
+        ("ex0", C.c_double), ("ex1", C.c_double), ("exd", C.c_double),
+        ("ey0", C.c_double), ("ey1", C.c_double), ("eyd", C.c_double),
+        ("nx", C.c_int32), ("ny", C.c_int32),
+        ("n_points", C.c_int64),
+        ("n_voxels", C.c_int64),
+        ("status", C.c_int32),
+        ("pad", C.c_int32),
+    ]
+
+
+class FrameCaps(C.Structure):
+    """Mirror of `lidar_frame_caps`."""
+
+    _fields_ = [
+        ("max_points", C.c_int64),
+        ("max_key_space", C.c_int64),
+        ("max_nx", C.c_int32),
+        ("max_ny", C.c_int32),
+    ]
+
+
+_vp, _i32, _i64, _sz, _dbl = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
+
+# name -> (restype, argtypes).  tests/test_abi.py checks this table against include/lidar_b200.h.
+PROTOTYPES: dict[str, tuple] = {
+    "lidar_last_error": (C.c_char_p, []),
+    "lidar_abi_version": (_i32, []),
+    "lidar_device_props": (_i32, [_i32, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "lidar_reduce_workspace_bytes": (_sz, []),
+    "lidar_bbox": (_i32, [_vp, _i32, _i64, _vp, _vp, _sz, _vp]),
+    "lidar_moments": (_i32, [_vp, _i32, _i64, C.POINTER(C.c_double), _vp, _vp, _sz, _vp]),
+    "lidar_hist2d_f64": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
+    "lidar_hist2d_points": (_i32, [_vp, _i32, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
+    "lidar_compact_workspace_bytes": (_sz, [_i64]),
+    "lidar_roi_crop": (_i32, [_vp, _i32, _i64, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp, _vp,
+                              _vp, _sz, _vp]),
+    "lidar_frame_workspace_bytes": (_sz, [C.POINTER(FrameCaps)]),
+    "lidar_frame_workspace_init": (_i32, [_vp, _sz, C.POINTER(FrameCaps), _vp]),
+    "lidar_frame_voxel_density": (_i32, [_vp, _i64, _dbl, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(FrameCaps), _vp, _sz,
+                                         _vp]),
+}
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA core has not been built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (or "
+            "`python -m lidar_ai_recommendation_software_b200.build`). There is no CPU fallback.")
+    try:
+        lib = C.CDLL(str(LIB_PATH), mode=getattr(os, "RTLD_NOW", 2))
+    except OSError as e:  # pragma: no cover - environment specific
+        raise ImportError(f"cannot load {LIB_PATH}: {e}. There is no CPU fallback.") from e
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def last_error() -> str:
+    return (lib.lidar_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc != LIDAR_OK:
+        raise LidarError(rc, last_error())
+
+
+def abi_version() -> int:
+    return int(lib.lidar_abi_version())

@@ -1,0 +1,99 @@
+"""In-tree build of the C-ABI CUDA core (liblidar_b200.so) for sm_100a.
+
+nvcc cross-compiles without a GPU, so this runs in the CPU container; the built .so is git-ignored
+but travels to the GPU box with the repo snapshot.  Only sm_100a is targeted — there is no
+multi-architecture fallback by design.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+INCLUDE = PKG_DIR.parent / "include"
+LIB_PATH = PKG_DIR / "liblidar_b200.so"
+OBJ_DIR = PKG_DIR / "csrc" / "_obj"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--fmad=false",            # no silent a*b+c contraction anywhere: integer decisions are bit-exact
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+]
+# kernels whose bulk fp32 math wants FMA opt back in per file
+FMAD_OK = {"sa_mlp.cu"}
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found: the lidar_b200 CUDA core cannot be built")
+
+
+def _sources() -> list[Path]:
+    return sorted(CSRC.glob("*.cu"))
+
+
+def _stamp(src: Path) -> str:
+    h = hashlib.sha256()
+    h.update(src.read_bytes())
+    for hdr in sorted(CSRC.glob("*.cuh")) + sorted(INCLUDE.glob("*.h")):
+        h.update(hdr.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _compile_one(nvcc: str, src: Path, verbose: bool) -> Path:
+    OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    obj = OBJ_DIR / (src.stem + ".o")
+    stamp_file = OBJ_DIR / (src.stem + ".stamp")
+    stamp = _stamp(src)
+    if obj.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
+        return obj
+    flags = list(NVCC_FLAGS)
+    if src.name in FMAD_OK:
+        flags = [f for f in flags if f != "--fmad=false"]
+    cmd = [nvcc, *flags, "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src.name}:\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        sys.stderr.write(res.stderr)
+    stamp_file.write_text(stamp)
+    return obj
+
+
+def build(verbose: bool = False, force: bool = False) -> Path:
+    """Compile every csrc/*.cu for sm_100a and link liblidar_b200.so in-tree."""
+    nvcc = _nvcc()
+    if force and OBJ_DIR.exists():
+        shutil.rmtree(OBJ_DIR)
+    srcs = _sources()
+    if not srcs:
+        raise RuntimeError(f"no CUDA sources under {CSRC}")
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(lambda s: _compile_one(nvcc, s, verbose), srcs))
+    newest = max(o.stat().st_mtime for o in objs)
+    if (not LIB_PATH.exists()) or LIB_PATH.stat().st_mtime < newest or force:
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH),
+               *map(str, objs), "--cudart", "shared",
+               "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    p = build(verbose="-v" in sys.argv, force="-f" in sys.argv)
+    print(p)

@@ -1,0 +1,187 @@
+// K1 — bounding box / moment reductions.
+//
+// Replaces the numpy reductions of the reference's preprocess stage:
+//   np.min / np.max          utils/data_processing.py:143,207-208 ; app_simplified.py:80,116-117
+//   np.mean / np.std axis 0  utils/data_processing.py:151-152     ; app_simplified.py:88-89
+//
+// One persistent launch: grid = k * SM count CTAs, grid-stride float4 / fp64 loads, warp shuffle
+// tree, one partial per CTA, and the last CTA to finish (atomic ticket) folds the partials in a
+// fixed order, so results are deterministic for a fixed launch shape.  HBM-bound: 16 B (F32X4)
+// or 24 B (F64X3) per point, no writes.
+#include "common.cuh"
+
+namespace lidar {
+
+constexpr int kRedThreads = 256;
+constexpr int kRedMaxBlocks = 1024;
+
+struct ReduceWs {
+    double partial[kRedMaxBlocks][16];
+    unsigned int ticket;
+};
+
+template <class Loader>
+__global__ void __launch_bounds__(kRedThreads)
+bbox_kernel(Loader L, int64_t n, double* __restrict__ out8, ReduceWs* __restrict__ ws) {
+    double mn[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+    double mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Pt p = L.load(i);
+        mn[0] = fmin(mn[0], p.x); mx[0] = fmax(mx[0], p.x);
+        mn[1] = fmin(mn[1], p.y); mx[1] = fmax(mx[1], p.y);
+        mn[2] = fmin(mn[2], p.z); mx[2] = fmax(mx[2], p.z);
+        mn[3] = fmin(mn[3], p.w); mx[3] = fmax(mx[3], p.w);
+    }
+    __shared__ double s_mn[kRedThreads / 32][4];
+    __shared__ double s_mx[kRedThreads / 32][4];
+    __shared__ bool s_last;
+    const int warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        mn[c] = warp_min(mn[c]);
+        mx[c] = warp_max(mx[c]);
+    }
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            s_mn[warp][c] = mn[c];
+            s_mx[warp][c] = mx[c];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        const int c = threadIdx.x & 3;
+        const bool is_max = threadIdx.x >= 4;
+        double v = is_max ? -INFINITY : INFINITY;
+        for (int w = 0; w < kRedThreads / 32; ++w) v = is_max ? fmax(v, s_mx[w][c]) : fmin(v, s_mn[w][c]);
+        ws->partial[blockIdx.x][threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(&ws->ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < 8) {
+        const bool is_max = threadIdx.x >= 4;
+        double v = is_max ? -INFINITY : INFINITY;
+        for (unsigned b = 0; b < gridDim.x; ++b) {
+            double q = ((volatile double*)ws->partial[b])[threadIdx.x];
+            v = is_max ? fmax(v, q) : fmin(v, q);
+        }
+        out8[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) ws->ticket = 0u;
+}
+
+// Σ (p - c) and Σ (p - c)^2 per axis, fp64, c = caller-supplied centre (0 for the mean pass).
+// out6 = {Σdx, Σdy, Σdz, Σdx², Σdy², Σdz²}
+template <class Loader>
+__global__ void __launch_bounds__(kRedThreads)
+moments_kernel(Loader L, int64_t n, double cx, double cy, double cz, double* __restrict__ out6,
+               ReduceWs* __restrict__ ws) {
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Pt p = L.load(i);
+        const double dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
+        s[0] += dx; s[1] += dy; s[2] += dz;
+        s[3] += __dmul_rn(dx, dx); s[4] += __dmul_rn(dy, dy); s[5] += __dmul_rn(dz, dz);
+    }
+    __shared__ double s_p[kRedThreads / 32][6];
+    __shared__ bool s_last;
+    const int warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) s[c] = warp_sum(s[c]);
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s_p[warp][c] = s[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = 0;
+        for (int w = 0; w < kRedThreads / 32; ++w) v += s_p[w][threadIdx.x];
+        ws->partial[blockIdx.x][threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(&ws->ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < 6) {
+        double v = 0;
+        for (unsigned b = 0; b < gridDim.x; ++b) v += ((volatile double*)ws->partial[b])[threadIdx.x];
+        out6[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) ws->ticket = 0u;
+}
+
+static int reduce_grid(int64_t n) {
+    int64_t want = (n + kRedThreads * 4 - 1) / (kRedThreads * 4);
+    int64_t cap = (int64_t)sm_count() * 4;
+    if (cap > kRedMaxBlocks) cap = kRedMaxBlocks;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+}  // namespace lidar
+
+using namespace lidar;
+
+extern "C" {
+
+size_t lidar_reduce_workspace_bytes(void) { return ws_align(sizeof(ReduceWs)); }
+
+int lidar_bbox(const void* d_points, int fmt, int64_t n, double* d_out8, void* d_ws, size_t ws_bytes,
+               void* stream) {
+    LIDAR_REQUIRE(n >= 0, LIDAR_ERR_INVALID, "lidar_bbox: n < 0");
+    LIDAR_REQUIRE(d_out8 != nullptr, LIDAR_ERR_INVALID, "lidar_bbox: d_out8 is NULL");
+    LIDAR_REQUIRE(d_ws && ws_bytes >= sizeof(ReduceWs), LIDAR_ERR_WORKSPACE,
+                  "lidar_bbox: workspace too small (%zu < %zu)", ws_bytes, sizeof(ReduceWs));
+    LIDAR_REQUIRE(n == 0 || d_points != nullptr, LIDAR_ERR_INVALID, "lidar_bbox: d_points is NULL");
+    cudaStream_t st = as_stream(stream);
+    ReduceWs* ws = static_cast<ReduceWs*>(d_ws);
+    LIDAR_CUDA_TRY(cudaMemsetAsync(&ws->ticket, 0, sizeof(unsigned), st));
+    const int grid = reduce_grid(n);
+    if (fmt == LIDAR_FMT_F32X4) {
+        bbox_kernel<<<grid, kRedThreads, 0, st>>>(LoadF32x4{static_cast<const float4*>(d_points)}, n, d_out8, ws);
+    } else if (fmt == LIDAR_FMT_F64X3) {
+        bbox_kernel<<<grid, kRedThreads, 0, st>>>(LoadF64x3{static_cast<const double*>(d_points)}, n, d_out8, ws);
+    } else {
+        LIDAR_REQUIRE(false, LIDAR_ERR_INVALID, "lidar_bbox: unknown point format %d", fmt);
+    }
+    LIDAR_CHECK_LAUNCH();
+    return LIDAR_OK;
+}
+
+int lidar_moments(const void* d_points, int fmt, int64_t n, const double* h_center3, double* d_out6,
+                  void* d_ws, size_t ws_bytes, void* stream) {
+    LIDAR_REQUIRE(n >= 0, LIDAR_ERR_INVALID, "lidar_moments: n < 0");
+    LIDAR_REQUIRE(d_out6 != nullptr && h_center3 != nullptr, LIDAR_ERR_INVALID, "lidar_moments: NULL argument");
+    LIDAR_REQUIRE(d_ws && ws_bytes >= sizeof(ReduceWs), LIDAR_ERR_WORKSPACE, "lidar_moments: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    ReduceWs* ws = static_cast<ReduceWs*>(d_ws);
+    LIDAR_CUDA_TRY(cudaMemsetAsync(&ws->ticket, 0, sizeof(unsigned), st));
+    const int grid = reduce_grid(n);
+    if (fmt == LIDAR_FMT_F32X4) {
+        moments_kernel<<<grid, kRedThreads, 0, st>>>(LoadF32x4{static_cast<const float4*>(d_points)}, n,
+                                                     h_center3[0], h_center3[1], h_center3[2], d_out6, ws);
+    } else if (fmt == LIDAR_FMT_F64X3) {
+        moments_kernel<<<grid, kRedThreads, 0, st>>>(LoadF64x3{static_cast<const double*>(d_points)}, n,
+                                                     h_center3[0], h_center3[1], h_center3[2], d_out6, ws);
+    } else {
+        LIDAR_REQUIRE(false, LIDAR_ERR_INVALID, "lidar_moments: unknown point format %d", fmt);
+    }
+    LIDAR_CHECK_LAUNCH();
+    return LIDAR_OK;
+}
+
+}  // extern "C"

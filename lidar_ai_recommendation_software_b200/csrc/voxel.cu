@@ -1,0 +1,513 @@
+// K5 (+K6 fused) — one LiDAR frame: bbox -> voxel downsample (+ ground-plane density histogram).
+//
+// Voxel downsample is a NEW op (absent from the reference; contract = SURVEY.md Appendix B.1); the
+// fused density grid has calculate_grid_density semantics (utils/data_processing.py:282-328):
+// margin 2g, np.arange edges (fill rule e(i) = a + i*fl(fl(a+g)-a), Appendix A.2), histogramdd
+// binning (Appendix A.1), counts indexed [x][y].
+//
+// Design: "occupancy-bitmap ranking" instead of a key sort.
+//   The voxel key space (Dx*Dy*Dz cells) is held as a bitmap (1 bit per cell, 22 MB for a
+//   100 m x 100 m x 2 m frame at 0.05 m — L2 resident on B200).  The rank of a voxel in ascending
+//   key order is the number of occupied cells before it, i.e. a popcount prefix over the bitmap.
+//   That yields exactly the output order of a stable sort-by-key + segmented reduce, without
+//   moving a single point, and every step is order independent:
+//     k_frame_bbox      min/max of x,y,z,intensity; the last CTA derives the frame descriptor
+//                       (origin, dims, key space, fixed-point scales, histogram edges) ON DEVICE
+//     k_frame_mark      per point: voxel key -> d_voxel_key, atomicOr into the bitmap,
+//                       density bin -> RED.ADD into the grid              (reads 16 B, writes 4 B)
+//     k_frame_scan      single-pass chained scan of bitmap popcounts -> prefix per 256-bit group
+//     k_frame_rank      per point: rank = prefix + popc(bits below) -> d_inverse; integer
+//                       accumulation of (p - voxel_corner) in 2^-k fixed point and of counts
+//     k_frame_finalize  per voxel: centroid = corner + sum/count, count, key; restores the
+//                       all-zero invariant of bitmap and accumulators for the next frame
+//   Integer accumulation makes centroids independent of the order in which atomics land:
+//   bit-identical run to run, and equal to the fp64 mean to ~2^-46 m before the fp32 rounding.
+//
+// Nothing in a frame needs the host: capacities are fixed per stream of frames, the descriptor is
+// read back together with the results.
+#include "common.cuh"
+
+namespace lidar {
+
+constexpr int kFrameThreads = 256;
+constexpr int kScanWordsPerThread = 8;                                // 256-bit group per thread
+constexpr int kScanTileWords = kFrameThreads * kScanWordsPerThread;   // 2048 words = 65536 bits
+
+struct FrameWsLayout {
+    size_t off_partial, off_ctrl, off_bitmap, off_group_prefix, off_tile_desc, off_acc, off_cnt, total;
+    int64_t bitmap_words, groups, tiles;
+};
+
+struct FrameCtrl {
+    unsigned int bbox_ticket;
+    unsigned int scan_ticket;
+    unsigned int pad[2];
+};
+
+constexpr int kBboxMaxBlocks = 1024;
+
+static FrameWsLayout frame_layout(const lidar_frame_caps& c) {
+    FrameWsLayout L;
+    L.bitmap_words = (c.max_key_space + 31) / 32;
+    // round up to whole tiles so the scan never needs a ragged tail
+    L.tiles = (L.bitmap_words + kScanTileWords - 1) / kScanTileWords;
+    L.bitmap_words = L.tiles * kScanTileWords;
+    L.groups = L.bitmap_words / kScanWordsPerThread;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t a = ws_align(o); o = a + bytes; return a; };
+    L.off_partial = take(sizeof(double) * 8 * kBboxMaxBlocks);
+    L.off_ctrl = take(sizeof(FrameCtrl));
+    L.off_bitmap = take(sizeof(uint32_t) * L.bitmap_words);
+    L.off_group_prefix = take(sizeof(uint32_t) * L.groups);
+    L.off_tile_desc = take(sizeof(unsigned long long) * L.tiles);
+    L.off_acc = take(sizeof(long long) * 4 * c.max_points);
+    L.off_cnt = take(sizeof(int32_t) * c.max_points);
+    L.total = ws_align(o);
+    return L;
+}
+
+struct FrameParams {
+    const float4* pts;
+    int64_t n;
+    double voxel, grid;
+    double origin[3];
+    double xyr[4];
+    int has_origin, has_range;
+    int64_t max_key_space;
+    int max_nx, max_ny;
+    int fix_bits_budget;  // 62 - ceil(log2(n))
+};
+
+// ---- descriptor derivation (one thread) -------------------------------------------------------
+__device__ void derive_desc(const FrameParams& P, const double* bb, lidar_frame_desc* D) {
+    int status = 0;
+    for (int c = 0; c < 4; ++c) {
+        D->bbox_min[c] = bb[c];
+        D->bbox_max[c] = bb[4 + c];
+    }
+    D->voxel = P.voxel;
+    D->n_points = P.n;
+    D->n_voxels = 0;
+    long long ks = 1;
+    for (int c = 0; c < 3; ++c) {
+        const double o = P.has_origin ? P.origin[c] : bb[c];
+        D->origin[c] = o;
+        if (bb[c] < o) status = LIDAR_ERR_INVALID;  // a point below the origin would index < 0
+        const double span = floor(__ddiv_rn(__dsub_rn(bb[4 + c], o), P.voxel));
+        long long d = (span >= 0.0 && span < 2147483000.0) ? (long long)span + 1 : 0;
+        if (d <= 0) { d = 1; if (P.n > 0) status = status ? status : LIDAR_ERR_CAPACITY; }
+        D->dims[c] = (int)d;
+        // overflow-safe product
+        if (ks > (1ll << 40)) status = status ? status : LIDAR_ERR_CAPACITY;
+        ks *= d;
+    }
+    D->origin[3] = 0.0;
+    D->dims[3] = 0;
+    D->key_space = ks;
+    if (ks > P.max_key_space || ks >= (1ll << 31)) status = status ? status : LIDAR_ERR_CAPACITY;
+    // fixed point: |p - corner| < 2*voxel, n members at most  ->  2*voxel * 2^k * n < 2^62
+    {
+        int e;
+        frexp(P.voxel * 2.0, &e);  // voxel*2 < 2^e
+        D->fix_scale_xyz = ldexp(1.0, P.fix_bits_budget - e);
+        double wmax = fmax(fabs(bb[3]), fabs(bb[7]));
+        if (!(wmax > 0.0) || !isfinite(wmax)) wmax = 1.0;
+        frexp(wmax, &e);
+        D->fix_scale_w = ldexp(1.0, P.fix_bits_budget - e - 1);
+    }
+    // density grid edges, numpy arange rule (data_processing.py:305-313)
+    D->grid = P.grid;
+    D->nx = D->ny = 0;
+    D->ex0 = D->ex1 = D->exd = D->ey0 = D->ey1 = D->eyd = 0.0;
+    if (P.grid > 0.0) {
+        const double g = P.grid;
+        const double margin = __dmul_rn(g, 2.0);
+        double lo[2], hi[2];
+        lo[0] = P.has_range ? P.xyr[0] : bb[0];
+        hi[0] = P.has_range ? P.xyr[1] : bb[4];
+        lo[1] = P.has_range ? P.xyr[2] : bb[1];
+        hi[1] = P.has_range ? P.xyr[3] : bb[5];
+        for (int c = 0; c < 2; ++c) {
+            const double a = __dsub_rn(lo[c], margin);
+            const double stop = __dadd_rn(__dadd_rn(hi[c], margin), g);
+            const double len = ceil(__ddiv_rn(__dsub_rn(stop, a), g));
+            int nedges = (len > 0.0 && len < 1.0e9) ? (int)len : 0;
+            const double e1 = __dadd_rn(a, g);
+            const double delta = __dsub_rn(e1, a);
+            int nb = nedges - 1;
+            if (nb < 1) { nb = 0; if (P.n > 0) status = status ? status : LIDAR_ERR_CAPACITY; }
+            if (c == 0) { D->ex0 = a; D->ex1 = e1; D->exd = delta; D->nx = nb; }
+            else        { D->ey0 = a; D->ey1 = e1; D->eyd = delta; D->ny = nb; }
+        }
+        if (D->nx > P.max_nx || D->ny > P.max_ny) status = status ? status : LIDAR_ERR_CAPACITY;
+    }
+    if (P.n == 0) status = 0;
+    D->status = status;
+    D->pad = 0;
+}
+
+// ---- k_frame_bbox -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFrameThreads)
+k_frame_bbox(FrameParams P, double* __restrict__ partial, FrameCtrl* __restrict__ ctrl,
+             lidar_frame_desc* __restrict__ D, int32_t* __restrict__ grid_out, int grid_cap,
+             unsigned long long* __restrict__ tile_desc, int64_t tiles) {
+    // zero the per-frame scratch that later kernels accumulate into
+    {
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+        const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (int64_t i = t0; i < grid_cap; i += stride) grid_out[i] = 0;
+        for (int64_t i = t0; i < tiles; i += stride) tile_desc[i] = 0ull;
+    }
+    float mn[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    LoadF32x4 L{P.pts};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+        float4 v = L.raw(i);
+        mn[0] = fminf(mn[0], v.x); mx[0] = fmaxf(mx[0], v.x);
+        mn[1] = fminf(mn[1], v.y); mx[1] = fmaxf(mx[1], v.y);
+        mn[2] = fminf(mn[2], v.z); mx[2] = fmaxf(mx[2], v.z);
+        mn[3] = fminf(mn[3], v.w); mx[3] = fmaxf(mx[3], v.w);
+    }
+    __shared__ float s_v[kFrameThreads / 32][8];
+    __shared__ bool s_last;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+            mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        }
+    }
+    const int warp = threadIdx.x >> 5;
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { s_v[warp][c] = mn[c]; s_v[warp][4 + c] = mx[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        const bool is_max = threadIdx.x >= 4;
+        float v = is_max ? -INFINITY : INFINITY;
+        for (int w = 0; w < kFrameThreads / 32; ++w) v = is_max ? fmaxf(v, s_v[w][threadIdx.x]) : fminf(v, s_v[w][threadIdx.x]);
+        partial[(size_t)blockIdx.x * 8 + threadIdx.x] = (double)v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&ctrl->bbox_ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    __shared__ double s_bb[8];
+    if (threadIdx.x < 8) {
+        const bool is_max = threadIdx.x >= 4;
+        double v = is_max ? -INFINITY : INFINITY;
+        for (unsigned b = 0; b < gridDim.x; ++b) {
+            const double q = ((volatile double*)partial)[(size_t)b * 8 + threadIdx.x];
+            v = is_max ? fmax(v, q) : fmin(v, q);
+        }
+        s_bb[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        derive_desc(P, s_bb, D);
+        ctrl->bbox_ticket = 0u;
+        ctrl->scan_ticket = 0u;
+    }
+}
+
+// analytic arange edge (DOUBLE_fill): e(0)=a, e(1)=fl(a+g), e(i)=fl(a + fl(i*delta))
+__device__ __forceinline__ double arange_edge(double a, double e1, double d, int i) {
+    return i == 0 ? a : (i == 1 ? e1 : __dadd_rn(a, __dmul_rn((double)i, d)));
+}
+__device__ __forceinline__ int arange_bin(double x, double a, double e1, double d, int nb) {
+    const double hi = arange_edge(a, e1, d, nb);
+    if (!(x >= a) || !(x <= hi)) return -1;
+    if (x == hi) return nb - 1;
+    int k = (int)floor(__ddiv_rn(__dsub_rn(x, a), d));
+    k = k < 0 ? 0 : (k > nb - 1 ? nb - 1 : k);
+    while (x < arange_edge(a, e1, d, k)) --k;
+    while (x >= arange_edge(a, e1, d, k + 1)) ++k;
+    return k;
+}
+
+// ---- k_frame_mark -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFrameThreads)
+k_frame_mark(const float4* __restrict__ pts, const lidar_frame_desc* __restrict__ Dg,
+             int32_t* __restrict__ voxel_key, uint32_t* __restrict__ bitmap,
+             int32_t* __restrict__ grid_out) {
+    __shared__ lidar_frame_desc D;
+    if (threadIdx.x == 0) D = *Dg;
+    __syncthreads();
+    if (D.status != 0) return;
+    const int64_t n = D.n_points;
+    const double ox = D.origin[0], oy = D.origin[1], oz = D.origin[2], v = D.voxel;
+    const int Dy = D.dims[1], Dz = D.dims[2];
+    const bool do_grid = D.grid > 0.0;
+    const int ny = D.ny;
+    LoadF32x4 L{pts};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float4 q = L.raw(i);
+        const double x = (double)q.x, y = (double)q.y, z = (double)q.z;
+        const int ix = (int)floor(__ddiv_rn(__dsub_rn(x, ox), v));
+        const int iy = (int)floor(__ddiv_rn(__dsub_rn(y, oy), v));
+        const int iz = (int)floor(__ddiv_rn(__dsub_rn(z, oz), v));
+        const int key = (ix * Dy + iy) * Dz + iz;
+        voxel_key[i] = key;
+        atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+        if (do_grid) {
+            const int bx = arange_bin(x, D.ex0, D.ex1, D.exd, D.nx);
+            const int by = arange_bin(y, D.ey0, D.ey1, D.eyd, ny);
+            if (bx >= 0 && by >= 0) atomicAdd(&grid_out[bx * ny + by], 1);
+        }
+    }
+}
+
+// ---- k_frame_scan -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFrameThreads)
+k_frame_scan(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ group_prefix,
+             unsigned long long* __restrict__ tile_desc, FrameCtrl* __restrict__ ctrl,
+             lidar_frame_desc* __restrict__ Dg) {
+    __shared__ int s_tile;
+    __shared__ unsigned s_warp_sum[kFrameThreads / 32];
+    __shared__ unsigned long long s_excl;
+    if (Dg->status != 0) return;
+    const int64_t words = (Dg->key_space + 31) / 32;
+    const int n_tiles = (int)((words + kScanTileWords - 1) / kScanTileWords);
+    const unsigned lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    while (true) {
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ctrl->scan_ticket, 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= n_tiles) break;
+        // the workspace bitmap is padded to whole tiles, so the loads never run off the end
+        const uint4* src = reinterpret_cast<const uint4*>(bitmap + (size_t)tile * kScanTileWords) + threadIdx.x * 2;
+        const uint4 a = src[0], b = src[1];
+        const unsigned cnt = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+        // exclusive scan over the CTA
+        unsigned inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (unsigned)o) inc += t;
+        }
+        if (lane == 31) s_warp_sum[warp] = inc;
+        __syncthreads();
+        unsigned warp_off = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kFrameThreads / 32; ++w) {
+            const unsigned s = s_warp_sum[w];
+            if (w < warp) warp_off += s;
+            total += s;
+        }
+        if (warp == 0) {
+            const unsigned long long ex = scan_lookback_warp(tile_desc, tile, (unsigned long long)total);
+            if (lane == 0) {
+                s_excl = ex;
+                if (tile == n_tiles - 1) Dg->n_voxels = (int64_t)(ex + total);
+            }
+        }
+        __syncthreads();
+        group_prefix[(size_t)tile * kFrameThreads + threadIdx.x] = (unsigned)s_excl + warp_off + (inc - cnt);
+        __syncthreads();
+    }
+}
+
+// ---- k_frame_rank -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFrameThreads)
+k_frame_rank(const float4* __restrict__ pts, const lidar_frame_desc* __restrict__ Dg,
+             const int32_t* __restrict__ voxel_key, const uint32_t* __restrict__ bitmap,
+             const uint32_t* __restrict__ group_prefix, int32_t* __restrict__ inverse,
+             long long* __restrict__ acc, int32_t* __restrict__ cnt, int32_t* __restrict__ unique_keys) {
+    __shared__ lidar_frame_desc D;
+    if (threadIdx.x == 0) D = *Dg;
+    __syncthreads();
+    if (D.status != 0) return;
+    const int64_t n = D.n_points;
+    const double ox = D.origin[0], oy = D.origin[1], oz = D.origin[2], v = D.voxel;
+    const double sxyz = D.fix_scale_xyz, sw = D.fix_scale_w;
+    const int Dy = D.dims[1], Dz = D.dims[2];
+    LoadF32x4 L{pts};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int key = __ldg(voxel_key + i);
+        const float4 q = L.raw(i);
+        const int g = key >> 8;
+        const uint4* gw = reinterpret_cast<const uint4*>(bitmap + (size_t)g * 8);
+        const uint4 a = gw[0], b = gw[1];
+        const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const int wi = (key >> 5) & 7;
+        unsigned r = __ldg(group_prefix + g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (k < wi) r += __popc(w[k]);
+            else if (k == wi) r += __popc(w[k] & ((1u << (key & 31)) - 1u));
+        }
+        inverse[i] = (int)r;
+        // decode the voxel corner and accumulate the offset in fixed point
+        const int iz = key % Dz;
+        const int t = key / Dz;
+        const int iy = t % Dy;
+        const int ix = t / Dy;
+        const double cx = __dadd_rn(ox, __dmul_rn((double)ix, v));
+        const double cy = __dadd_rn(oy, __dmul_rn((double)iy, v));
+        const double cz = __dadd_rn(oz, __dmul_rn((double)iz, v));
+        const long long fx = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.x, cx), sxyz));
+        const long long fy = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.y, cy), sxyz));
+        const long long fz = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.z, cz), sxyz));
+        const long long fw = __double2ll_rn(__dmul_rn((double)q.w, sw));
+        unsigned long long* A = reinterpret_cast<unsigned long long*>(acc + (size_t)r * 4);
+        atomicAdd(A + 0, (unsigned long long)fx);
+        atomicAdd(A + 1, (unsigned long long)fy);
+        atomicAdd(A + 2, (unsigned long long)fz);
+        atomicAdd(A + 3, (unsigned long long)fw);
+        atomicAdd(cnt + r, 1);
+        unique_keys[r] = key;  // every member stores the same value
+    }
+}
+
+// ---- k_frame_finalize -------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFrameThreads)
+k_frame_finalize(const lidar_frame_desc* __restrict__ Dg, long long* __restrict__ acc,
+                 int32_t* __restrict__ cnt, const int32_t* __restrict__ unique_keys,
+                 uint32_t* __restrict__ bitmap, float4* __restrict__ centroids,
+                 int32_t* __restrict__ counts) {
+    __shared__ lidar_frame_desc D;
+    if (threadIdx.x == 0) D = *Dg;
+    __syncthreads();
+    if (D.status != 0) return;
+    const int64_t V = D.n_voxels;
+    const double ox = D.origin[0], oy = D.origin[1], oz = D.origin[2], v = D.voxel;
+    const double isx = 1.0 / D.fix_scale_xyz, isw = 1.0 / D.fix_scale_w;  // powers of two: exact
+    const int Dy = D.dims[1], Dz = D.dims[2];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < V; r += stride) {
+        const int key = unique_keys[r];
+        const int c = cnt[r];
+        longlong2* A = reinterpret_cast<longlong2*>(acc + (size_t)r * 4);
+        const longlong2 s01 = A[0], s23 = A[1];
+        const int iz = key % Dz;
+        const int t = key / Dz;
+        const int iy = t % Dy;
+        const int ix = t / Dy;
+        const double dc = (double)c;
+        const double cx = __dadd_rn(ox, __dmul_rn((double)ix, v));
+        const double cy = __dadd_rn(oy, __dmul_rn((double)iy, v));
+        const double cz = __dadd_rn(oz, __dmul_rn((double)iz, v));
+        float4 o;
+        o.x = (float)__dadd_rn(cx, __ddiv_rn(__dmul_rn((double)s01.x, isx), dc));
+        o.y = (float)__dadd_rn(cy, __ddiv_rn(__dmul_rn((double)s01.y, isx), dc));
+        o.z = (float)__dadd_rn(cz, __ddiv_rn(__dmul_rn((double)s23.x, isx), dc));
+        o.w = (float)__ddiv_rn(__dmul_rn((double)s23.y, isw), dc);
+        centroids[r] = o;
+        counts[r] = c;
+        // restore the all-zero invariant for the next frame
+        A[0] = make_longlong2(0, 0);
+        A[1] = make_longlong2(0, 0);
+        cnt[r] = 0;
+        bitmap[key >> 5] = 0u;  // racing stores of the same value
+    }
+}
+
+static int frame_grid(int64_t n, int per_thread) {
+    int64_t want = (n + (int64_t)kFrameThreads * per_thread - 1) / ((int64_t)kFrameThreads * per_thread);
+    if (want < 1) want = 1;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    return (int)(want < cap ? want : cap);
+}
+
+}  // namespace lidar
+
+using namespace lidar;
+
+extern "C" {
+
+size_t lidar_frame_workspace_bytes(const lidar_frame_caps* caps) {
+    if (!caps || caps->max_points < 0 || caps->max_key_space <= 0) return 0;
+    return frame_layout(*caps).total;
+}
+
+int lidar_frame_workspace_init(void* d_ws, size_t ws_bytes, const lidar_frame_caps* caps, void* stream) {
+    LIDAR_REQUIRE(caps != nullptr, LIDAR_ERR_INVALID, "lidar_frame_workspace_init: caps is NULL");
+    const FrameWsLayout L = frame_layout(*caps);
+    LIDAR_REQUIRE(d_ws && ws_bytes >= L.total, LIDAR_ERR_WORKSPACE,
+                  "lidar_frame_workspace_init: workspace too small (%zu < %zu)", ws_bytes, L.total);
+    LIDAR_CUDA_TRY(cudaMemsetAsync(d_ws, 0, L.total, as_stream(stream)));
+    return LIDAR_OK;
+}
+
+int lidar_frame_voxel_density(const void* d_points, int64_t n, double voxel_size, double grid_size,
+                              const double* h_origin3, const double* h_xy_range4,
+                              int32_t* d_voxel_key, int32_t* d_inverse, void* d_centroids,
+                              int32_t* d_counts, int32_t* d_unique_keys, int32_t* d_grid,
+                              lidar_frame_desc* d_desc, const lidar_frame_caps* caps, void* d_ws,
+                              size_t ws_bytes, void* stream) {
+    LIDAR_REQUIRE(caps != nullptr, LIDAR_ERR_INVALID, "lidar_frame_voxel_density: caps is NULL");
+    LIDAR_REQUIRE(n >= 0 && n <= caps->max_points, LIDAR_ERR_CAPACITY,
+                  "lidar_frame_voxel_density: n=%lld exceeds caps.max_points=%lld", (long long)n,
+                  (long long)caps->max_points);
+    LIDAR_REQUIRE(n < (1ll << 31), LIDAR_ERR_CAPACITY, "lidar_frame_voxel_density: n must be < 2^31");
+    LIDAR_REQUIRE(voxel_size > 0.0 && voxel_size == voxel_size, LIDAR_ERR_INVALID,
+                  "lidar_frame_voxel_density: voxel_size must be > 0");
+    LIDAR_REQUIRE(grid_size >= 0.0, LIDAR_ERR_INVALID, "lidar_frame_voxel_density: grid_size must be >= 0");
+    LIDAR_REQUIRE(caps->max_key_space > 0 && caps->max_key_space < (1ll << 31), LIDAR_ERR_INVALID,
+                  "lidar_frame_voxel_density: caps.max_key_space must be in (0, 2^31)");
+    LIDAR_REQUIRE(d_desc && d_voxel_key && d_inverse && d_centroids && d_counts && d_unique_keys,
+                  LIDAR_ERR_INVALID, "lidar_frame_voxel_density: NULL output");
+    LIDAR_REQUIRE(grid_size == 0.0 || (d_grid && caps->max_nx > 0 && caps->max_ny > 0), LIDAR_ERR_INVALID,
+                  "lidar_frame_voxel_density: density grid requested without d_grid / capacities");
+    LIDAR_REQUIRE(n == 0 || d_points, LIDAR_ERR_INVALID, "lidar_frame_voxel_density: NULL points");
+    const FrameWsLayout L = frame_layout(*caps);
+    LIDAR_REQUIRE(d_ws && ws_bytes >= L.total, LIDAR_ERR_WORKSPACE,
+                  "lidar_frame_voxel_density: workspace too small (%zu < %zu)", ws_bytes, L.total);
+    char* ws = static_cast<char*>(d_ws);
+    double* partial = reinterpret_cast<double*>(ws + L.off_partial);
+    FrameCtrl* ctrl = reinterpret_cast<FrameCtrl*>(ws + L.off_ctrl);
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(ws + L.off_bitmap);
+    uint32_t* group_prefix = reinterpret_cast<uint32_t*>(ws + L.off_group_prefix);
+    unsigned long long* tile_desc = reinterpret_cast<unsigned long long*>(ws + L.off_tile_desc);
+    long long* acc = reinterpret_cast<long long*>(ws + L.off_acc);
+    int32_t* cnt = reinterpret_cast<int32_t*>(ws + L.off_cnt);
+
+    FrameParams P;
+    P.pts = static_cast<const float4*>(d_points);
+    P.n = n;
+    P.voxel = voxel_size;
+    P.grid = grid_size;
+    P.has_origin = h_origin3 != nullptr;
+    P.has_range = h_xy_range4 != nullptr;
+    for (int c = 0; c < 3; ++c) P.origin[c] = h_origin3 ? h_origin3[c] : 0.0;
+    for (int c = 0; c < 4; ++c) P.xyr[c] = h_xy_range4 ? h_xy_range4[c] : 0.0;
+    P.max_key_space = caps->max_key_space;
+    P.max_nx = caps->max_nx;
+    P.max_ny = caps->max_ny;
+    int lg = 0;
+    while ((1ll << lg) < (n > 1 ? n : 1)) ++lg;
+    P.fix_bits_budget = 62 - lg;
+
+    cudaStream_t st = as_stream(stream);
+    const int grid_cap = grid_size > 0.0 ? caps->max_nx * caps->max_ny : 0;
+    int bgrid = frame_grid(n, 4);
+    if (bgrid > kBboxMaxBlocks) bgrid = kBboxMaxBlocks;
+    k_frame_bbox<<<bgrid, kFrameThreads, 0, st>>>(P, partial, ctrl, d_desc, d_grid, grid_cap, tile_desc, L.tiles);
+    LIDAR_CHECK_LAUNCH();
+    if (n == 0) return LIDAR_OK;
+    k_frame_mark<<<frame_grid(n, 2), kFrameThreads, 0, st>>>(P.pts, d_desc, d_voxel_key, bitmap, d_grid);
+    LIDAR_CHECK_LAUNCH();
+    {
+        int sgrid = sm_count() * 4;
+        if ((int64_t)sgrid > L.tiles) sgrid = (int)L.tiles;
+        k_frame_scan<<<sgrid, kFrameThreads, 0, st>>>(bitmap, group_prefix, tile_desc, ctrl, d_desc);
+        LIDAR_CHECK_LAUNCH();
+    }
+    k_frame_rank<<<frame_grid(n, 2), kFrameThreads, 0, st>>>(P.pts, d_desc, d_voxel_key, bitmap, group_prefix,
+                                                              d_inverse, acc, cnt, d_unique_keys);
+    LIDAR_CHECK_LAUNCH();
+    k_frame_finalize<<<frame_grid(n, 2), kFrameThreads, 0, st>>>(d_desc, acc, cnt, d_unique_keys, bitmap,
+                                                                  static_cast<float4*>(d_centroids), d_counts);
+    LIDAR_CHECK_LAUNCH();
+    return LIDAR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,305 @@
+"""Device-level operators: torch CUDA tensors in, torch CUDA tensors out, all compute in the
+hand-written sm_100a kernels behind the C ABI (include/lidar_b200.h).
+
+These are the building blocks of the drop-in surfaces in `utils/`, `models/` and `apps.py`.
+Nothing here falls back to the CPU: without a CUDA device the functions raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import FMT_F32X4, FMT_F64X3, HIST_AUTO, FrameCaps, FrameDesc, check, lib
+
+__all__ = [
+    "require_cuda", "point_format", "bbox", "moments", "hist2d_counts", "hist2d_points_counts", "roi_crop",
+    "FramePipeline", "voxel_downsample", "arange_edges", "linspace_edges",
+]
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("lidar_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream_ptr() -> int:
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else int(t.data_ptr())
+
+
+class _Scratch(threading.local):
+    """Per-thread, per-device scratch buffers (Streamlit runs one script thread per session)."""
+
+    def __init__(self):
+        self.bufs: dict[tuple, torch.Tensor] = {}
+
+    def get(self, name: str, nbytes: int, device: torch.device) -> torch.Tensor:
+        key = (name, device.index)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self.bufs[key] = buf
+        return buf
+
+
+_scratch = _Scratch()
+
+
+def point_format(points: torch.Tensor) -> int:
+    """F32X4 for (n,4) float32, F64X3 for (n,3) float64 — contiguous CUDA tensors only."""
+    if not points.is_cuda or not points.is_contiguous():
+        raise ValueError("points must be a contiguous CUDA tensor")
+    if points.dim() == 2 and points.shape[1] == 4 and points.dtype == torch.float32:
+        return FMT_F32X4
+    if points.dim() == 2 and points.shape[1] == 3 and points.dtype == torch.float64:
+        return FMT_F64X3
+    raise ValueError(f"unsupported point layout {tuple(points.shape)} {points.dtype}: "
+                     "expected (n,4) float32 or (n,3) float64")
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 reductions
+# ------------------------------------------------------------------------------------------------
+def bbox(points: torch.Tensor) -> torch.Tensor:
+    """(8,) float64 device tensor {min x,y,z,w, max x,y,z,w}; np.min/np.max of
+    utils/data_processing.py:143,207-208."""
+    fmt = point_format(points)
+    dev = points.device
+    out = torch.empty(8, dtype=torch.float64, device=dev)
+    nb = lib.lidar_reduce_workspace_bytes()
+    ws = _scratch.get("reduce", nb, dev)
+    check(lib.lidar_bbox(_ptr(points), fmt, points.shape[0], _ptr(out), _ptr(ws), ws.numel(), _stream_ptr()))
+    return out
+
+
+def moments(points: torch.Tensor, center=(0.0, 0.0, 0.0)) -> torch.Tensor:
+    """(6,) float64 {Σ(p-c) per axis, Σ(p-c)² per axis}; np.mean/np.std of data_processing.py:151-152."""
+    fmt = point_format(points)
+    dev = points.device
+    out = torch.empty(6, dtype=torch.float64, device=dev)
+    nb = lib.lidar_reduce_workspace_bytes()
+    ws = _scratch.get("reduce", nb, dev)
+    c3 = (C.c_double * 3)(*[float(v) for v in center])
+    check(lib.lidar_moments(_ptr(points), fmt, points.shape[0], c3, _ptr(out), _ptr(ws), ws.numel(), _stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# edges (host-side parameter derivation — a few scalars, exactly the reference's numpy calls)
+# ------------------------------------------------------------------------------------------------
+def arange_edges(lo: float, hi: float, grid_size: float) -> np.ndarray:
+    """Edges of calculate_grid_density (utils/data_processing.py:305-313): margin 2g, np.arange."""
+    margin = grid_size * 2
+    lo = lo - margin
+    hi = hi + margin
+    return np.arange(lo, hi + grid_size, grid_size)
+
+
+def linspace_edges(lo: float, hi: float, bins: int) -> np.ndarray:
+    """Edges np.histogram2d builds for an integer `bins` and explicit range
+    (utils/visualization.py:130-134): np.linspace(lo, hi, bins + 1)."""
+    return np.linspace(lo, hi, bins + 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# K6 histogram
+# ------------------------------------------------------------------------------------------------
+def _edges_dev(e: np.ndarray | torch.Tensor, dev) -> torch.Tensor:
+    if isinstance(e, torch.Tensor):
+        return e.to(device=dev, dtype=torch.float64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(e, dtype=np.float64)).to(dev)
+
+
+def hist2d_counts(u: torch.Tensor, v: torch.Tensor, x_edges, y_edges, mode: int = HIST_AUTO,
+                  out: torch.Tensor | None = None) -> torch.Tensor:
+    """int32 (nx, ny) counts with np.histogram2d semantics; `u`, `v` are fp64 CUDA views (any stride)."""
+    if u.dtype != torch.float64 or v.dtype != torch.float64 or not u.is_cuda:
+        raise ValueError("hist2d_counts expects float64 CUDA tensors")
+    if u.dim() != 1 or v.dim() != 1 or u.shape[0] != v.shape[0]:
+        raise ValueError("hist2d_counts expects two 1-D tensors of equal length")
+    dev = u.device
+    ex, ey = _edges_dev(x_edges, dev), _edges_dev(y_edges, dev)
+    nx, ny = ex.numel() - 1, ey.numel() - 1
+    if nx < 1 or ny < 1:
+        raise ValueError("need at least two edges per axis")
+    if out is None:
+        out = torch.zeros((nx, ny), dtype=torch.int32, device=dev)
+    n = u.shape[0]
+    su = u.stride(0) if n > 1 else 1
+    sv = v.stride(0) if n > 1 else 1
+    check(lib.lidar_hist2d_f64(_ptr(u), su, _ptr(v), sv, n, _ptr(ex), nx, _ptr(ey), ny, _ptr(out), mode,
+                               _stream_ptr()))
+    return out
+
+
+def hist2d_points_counts(points: torch.Tensor, x_edges, y_edges, mode: int = HIST_AUTO,
+                         out: torch.Tensor | None = None) -> torch.Tensor:
+    """Same as `hist2d_counts` on the x/y of a point cloud in F32X4 or F64X3 layout."""
+    fmt = point_format(points)
+    dev = points.device
+    ex, ey = _edges_dev(x_edges, dev), _edges_dev(y_edges, dev)
+    nx, ny = ex.numel() - 1, ey.numel() - 1
+    if out is None:
+        out = torch.zeros((nx, ny), dtype=torch.int32, device=dev)
+    check(lib.lidar_hist2d_points(_ptr(points), fmt, points.shape[0], _ptr(ex), nx, _ptr(ey), ny, _ptr(out),
+                                  mode, _stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a5 ROI crop
+# ------------------------------------------------------------------------------------------------
+def roi_crop(points: torch.Tensor, lo, hi, return_mask: bool = True):
+    """Axis-aligned box crop, order preserving.
+
+    Returns (cropped points, mask uint8 (n,) or None).  One host sync to learn the kept count.
+    """
+    fmt = point_format(points)
+    dev = points.device
+    n = points.shape[0]
+    out = torch.empty_like(points)
+    mask = torch.empty(n, dtype=torch.uint8, device=dev) if return_mask else None
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    nb = lib.lidar_compact_workspace_bytes(n)
+    ws = _scratch.get("compact", nb, dev)
+    lo3 = (C.c_double * 3)(*[float(x) for x in lo])
+    hi3 = (C.c_double * 3)(*[float(x) for x in hi])
+    check(lib.lidar_roi_crop(_ptr(points), fmt, n, lo3, hi3, _ptr(mask), _ptr(out), _ptr(count), _ptr(ws),
+                             ws.numel(), _stream_ptr()))
+    kept = int(count.item())
+    return out[:kept], mask
+
+
+# ------------------------------------------------------------------------------------------------
+# K5 (+K6) frame pipeline
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class FrameResult:
+    desc: FrameDesc
+    voxel_key: torch.Tensor      # (n,) int32     per-point voxel key (B.1 voxel_idx)
+    inverse: torch.Tensor        # (n,) int32     rank of the point's voxel
+    centroids: torch.Tensor      # (V,4) float32  x,y,z,mean intensity, ascending key
+    counts: torch.Tensor         # (V,) int32
+    unique_keys: torch.Tensor    # (V,) int32
+    grid_counts: torch.Tensor | None   # (nx,ny) int32, calculate_grid_density counts
+    dims: tuple
+    origin: tuple
+
+    @property
+    def n_voxels(self) -> int:
+        return int(self.desc.n_voxels)
+
+    def grid_edges(self):
+        """(x_edges, y_edges) rebuilt from the device-derived arange parameters (bit-identical to
+        np.arange)."""
+        d = self.desc
+
+        def edges(a, e1, dl, nb):
+            i = np.arange(nb + 1, dtype=np.float64)
+            e = a + i * dl
+            e[0] = a
+            if nb >= 1:
+                e[1] = e1
+            return e
+
+        return edges(d.ex0, d.ex1, d.exd, d.nx), edges(d.ey0, d.ey1, d.eyd, d.ny)
+
+
+class FramePipeline:
+    """Voxel downsample (+ density grid) of float4 frames with fixed capacities, no host round trip.
+
+    One instance per stream of frames: it owns the workspace (occupancy bitmap, accumulators) and
+    the output buffers, so `enqueue()` is five kernel launches and nothing else.
+    """
+
+    def __init__(self, max_points: int, voxel_size: float, grid_size: float = 0.0,
+                 max_key_space: int = 1 << 28, max_nx: int = 1024, max_ny: int = 1024,
+                 device: torch.device | None = None):
+        self.device = device or require_cuda()
+        self.voxel_size = float(voxel_size)
+        self.grid_size = float(grid_size)
+        self.caps = FrameCaps(int(max_points), int(max_key_space), int(max_nx), int(max_ny))
+        nb = lib.lidar_frame_workspace_bytes(C.byref(self.caps))
+        if nb == 0:
+            raise ValueError("invalid frame capacities")
+        dev = self.device
+        self.ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        n = int(max_points)
+        self.voxel_key = torch.empty(n, dtype=torch.int32, device=dev)
+        self.inverse = torch.empty(n, dtype=torch.int32, device=dev)
+        self.centroids = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        self.counts = torch.empty(n, dtype=torch.int32, device=dev)
+        self.unique_keys = torch.empty(n, dtype=torch.int32, device=dev)
+        self.grid = (torch.empty(int(max_nx) * int(max_ny), dtype=torch.int32, device=dev)
+                     if grid_size > 0 else None)
+        self.desc_dev = torch.zeros(C.sizeof(FrameDesc), dtype=torch.uint8, device=dev)
+        self.desc_host = torch.zeros(C.sizeof(FrameDesc), dtype=torch.uint8).pin_memory()
+        self._n = 0
+        self.reset()
+
+    def reset(self) -> None:
+        """(Re)establish the all-zero invariant of the persistent workspace."""
+        check(lib.lidar_frame_workspace_init(_ptr(self.ws), self.ws.numel(), C.byref(self.caps), _stream_ptr()))
+
+    def enqueue(self, points: torch.Tensor, origin=None, xy_range=None) -> None:
+        """Enqueue one frame on the current stream (asynchronous)."""
+        if point_format(points) != FMT_F32X4:
+            raise ValueError("FramePipeline takes (n,4) float32 frames")
+        n = points.shape[0]
+        o3 = (C.c_double * 3)(*[float(v) for v in origin]) if origin is not None else None
+        r4 = (C.c_double * 4)(*[float(v) for v in xy_range]) if xy_range is not None else None
+        self._n = n
+        try:
+            check(lib.lidar_frame_voxel_density(
+                _ptr(points), n, self.voxel_size, self.grid_size, o3, r4, _ptr(self.voxel_key),
+                _ptr(self.inverse), _ptr(self.centroids), _ptr(self.counts), _ptr(self.unique_keys),
+                _ptr(self.grid), _ptr(self.desc_dev), C.byref(self.caps), _ptr(self.ws), self.ws.numel(),
+                _stream_ptr()))
+        except Exception:
+            self.reset()
+            raise
+
+    def result(self) -> FrameResult:
+        """Synchronise, read the device-derived descriptor back and slice the outputs."""
+        self.desc_host.copy_(self.desc_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        desc = FrameDesc.from_buffer_copy(self.desc_host.numpy().tobytes())
+        if desc.status != 0:
+            self.reset()
+            raise _capi.LidarError(int(desc.status),
+                                   f"frame exceeded its capacities: key_space={desc.key_space} "
+                                   f"(max {self.caps.max_key_space}), grid {desc.nx}x{desc.ny} "
+                                   f"(max {self.caps.max_nx}x{self.caps.max_ny})")
+        n, v = self._n, int(desc.n_voxels)
+        grid = None
+        if self.grid is not None:
+            grid = self.grid[: desc.nx * desc.ny].view(desc.nx, desc.ny)
+        return FrameResult(desc, self.voxel_key[:n], self.inverse[:n], self.centroids[:v], self.counts[:v],
+                           self.unique_keys[:v], grid, tuple(desc.dims[:3]), tuple(desc.origin[:3]))
+
+
+def voxel_downsample(points: torch.Tensor, voxel_size: float, origin=None, max_key_space: int | None = None):
+    """One-shot voxel downsample of an (n,4) float32 CUDA tensor.
+
+    Returns a `FrameResult` whose tensors are owned by the caller.
+    """
+    n = points.shape[0]
+    if max_key_space is None:
+        bb = bbox(points).cpu().numpy()
+        org = bb[:3] if origin is None else np.asarray(origin, dtype=np.float64)
+        dims = np.floor((bb[4:7] - org) / float(voxel_size)) + 1
+        max_key_space = int(max(1, np.prod(np.maximum(dims, 1))))
+        if max_key_space >= (1 << 31):
+            raise _capi.LidarError(-4, f"voxel key space {max_key_space} needs more than 31 bits")
+    pipe = FramePipeline(max(n, 1), voxel_size, 0.0, max_key_space=max_key_space, device=points.device)
+    pipe.enqueue(points, origin=origin)
+    return pipe.result()
