@@ -156,6 +156,16 @@ int lidar_frame_voxel_density(const void* d_points, int64_t n, double voxel_size
                               lidar_frame_desc* d_desc, const lidar_frame_caps* caps, void* d_ws,
                               size_t ws_bytes, void* stream);
 
+/* Same call, additionally recording six caller-created cudaEvent_t (passed as void*) on `stream`:
+ * before k_frame_bbox, then after each of bbox, mark, scan, rank, finalize — so a benchmark can
+ * attribute device time to each kernel without a profiler. */
+int lidar_frame_voxel_density_timed(const void* d_points, int64_t n, double voxel_size, double grid_size,
+                                    const double* h_origin3, const double* h_xy_range4,
+                                    int32_t* d_voxel_key, int32_t* d_inverse, void* d_centroids,
+                                    int32_t* d_counts, int32_t* d_unique_keys, int32_t* d_grid,
+                                    lidar_frame_desc* d_desc, const lidar_frame_caps* caps, void* d_ws,
+                                    size_t ws_bytes, void* stream, void** h_events6);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,9 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_frame_voxel_density": (_i32, [_vp, _i64, _dbl, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(FrameCaps), _vp, _sz,
                                          _vp]),
+    "lidar_frame_voxel_density_timed": (_i32, [_vp, _i64, _dbl, _dbl, C.POINTER(C.c_double),
+                                               C.POINTER(C.c_double), _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                               C.POINTER(FrameCaps), _vp, _sz, _vp, C.POINTER(C.c_void_p)]),
 }
 
 

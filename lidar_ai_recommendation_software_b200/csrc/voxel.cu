@@ -437,12 +437,12 @@ int lidar_frame_workspace_init(void* d_ws, size_t ws_bytes, const lidar_frame_ca
     return LIDAR_OK;
 }
 
-int lidar_frame_voxel_density(const void* d_points, int64_t n, double voxel_size, double grid_size,
+static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxel_size, double grid_size,
                               const double* h_origin3, const double* h_xy_range4,
                               int32_t* d_voxel_key, int32_t* d_inverse, void* d_centroids,
                               int32_t* d_counts, int32_t* d_unique_keys, int32_t* d_grid,
                               lidar_frame_desc* d_desc, const lidar_frame_caps* caps, void* d_ws,
-                              size_t ws_bytes, void* stream) {
+                              size_t ws_bytes, void* stream, void** events) {
     LIDAR_REQUIRE(caps != nullptr, LIDAR_ERR_INVALID, "lidar_frame_voxel_density: caps is NULL");
     LIDAR_REQUIRE(n >= 0 && n <= caps->max_points, LIDAR_ERR_CAPACITY,
                   "lidar_frame_voxel_density: n=%lld exceeds caps.max_points=%lld", (long long)n,
@@ -487,27 +487,62 @@ int lidar_frame_voxel_density(const void* d_points, int64_t n, double voxel_size
     P.fix_bits_budget = 62 - lg;
 
     cudaStream_t st = as_stream(stream);
+    auto mark = [&](int i) -> cudaError_t {
+        return events ? cudaEventRecord(static_cast<cudaEvent_t>(events[i]), st) : cudaSuccess;
+    };
     const int grid_cap = grid_size > 0.0 ? caps->max_nx * caps->max_ny : 0;
+    LIDAR_CUDA_TRY(mark(0));
     int bgrid = frame_grid(n, 4);
     if (bgrid > kBboxMaxBlocks) bgrid = kBboxMaxBlocks;
     k_frame_bbox<<<bgrid, kFrameThreads, 0, st>>>(P, partial, ctrl, d_desc, d_grid, grid_cap, tile_desc, L.tiles);
     LIDAR_CHECK_LAUNCH();
-    if (n == 0) return LIDAR_OK;
+    LIDAR_CUDA_TRY(mark(1));
+    if (n == 0) {
+        for (int i = 2; i <= 5; ++i) LIDAR_CUDA_TRY(mark(i));
+        return LIDAR_OK;
+    }
     k_frame_mark<<<frame_grid(n, 2), kFrameThreads, 0, st>>>(P.pts, d_desc, d_voxel_key, bitmap, d_grid);
     LIDAR_CHECK_LAUNCH();
+    LIDAR_CUDA_TRY(mark(2));
     {
         int sgrid = sm_count() * 4;
         if ((int64_t)sgrid > L.tiles) sgrid = (int)L.tiles;
         k_frame_scan<<<sgrid, kFrameThreads, 0, st>>>(bitmap, group_prefix, tile_desc, ctrl, d_desc);
         LIDAR_CHECK_LAUNCH();
     }
+    LIDAR_CUDA_TRY(mark(3));
     k_frame_rank<<<frame_grid(n, 2), kFrameThreads, 0, st>>>(P.pts, d_desc, d_voxel_key, bitmap, group_prefix,
                                                               d_inverse, acc, cnt, d_unique_keys);
     LIDAR_CHECK_LAUNCH();
+    LIDAR_CUDA_TRY(mark(4));
     k_frame_finalize<<<frame_grid(n, 2), kFrameThreads, 0, st>>>(d_desc, acc, cnt, d_unique_keys, bitmap,
                                                                   static_cast<float4*>(d_centroids), d_counts);
     LIDAR_CHECK_LAUNCH();
+    LIDAR_CUDA_TRY(mark(5));
     return LIDAR_OK;
+}
+
+int lidar_frame_voxel_density(const void* d_points, int64_t n, double voxel_size, double grid_size,
+                              const double* h_origin3, const double* h_xy_range4,
+                              int32_t* d_voxel_key, int32_t* d_inverse, void* d_centroids,
+                              int32_t* d_counts, int32_t* d_unique_keys, int32_t* d_grid,
+                              lidar_frame_desc* d_desc, const lidar_frame_caps* caps, void* d_ws,
+                              size_t ws_bytes, void* stream) {
+    return frame_voxel_density_impl(d_points, n, voxel_size, grid_size, h_origin3, h_xy_range4, d_voxel_key,
+                                    d_inverse, d_centroids, d_counts, d_unique_keys, d_grid, d_desc, caps,
+                                    d_ws, ws_bytes, stream, nullptr);
+}
+
+int lidar_frame_voxel_density_timed(const void* d_points, int64_t n, double voxel_size, double grid_size,
+                                    const double* h_origin3, const double* h_xy_range4,
+                                    int32_t* d_voxel_key, int32_t* d_inverse, void* d_centroids,
+                                    int32_t* d_counts, int32_t* d_unique_keys, int32_t* d_grid,
+                                    lidar_frame_desc* d_desc, const lidar_frame_caps* caps, void* d_ws,
+                                    size_t ws_bytes, void* stream, void** h_events6) {
+    LIDAR_REQUIRE(h_events6 != nullptr, LIDAR_ERR_INVALID, "lidar_frame_voxel_density_timed: events is NULL");
+    return frame_voxel_density_impl(d_points, n, voxel_size, grid_size, h_origin3, h_xy_range4, d_voxel_key,
+                                    d_inverse, d_centroids, d_counts, d_unique_keys, d_grid, d_desc, caps,
+                                    d_ws, ws_bytes, stream, h_events6);
 }
 
 }  // extern "C"

@@ -18,7 +18,7 @@ from ._capi import FMT_F32X4, FMT_F64X3, HIST_AUTO, FrameCaps, FrameDesc, check,
 
 __all__ = [
     "require_cuda", "point_format", "bbox", "moments", "hist2d_counts", "hist2d_points_counts", "roi_crop",
-    "FramePipeline", "voxel_downsample", "arange_edges", "linspace_edges",
+    "FramePipeline", "HostFramePipeline", "voxel_downsample", "arange_edges", "linspace_edges",
 ]
 
 
@@ -250,20 +250,32 @@ class FramePipeline:
         """(Re)establish the all-zero invariant of the persistent workspace."""
         check(lib.lidar_frame_workspace_init(_ptr(self.ws), self.ws.numel(), C.byref(self.caps), _stream_ptr()))
 
-    def enqueue(self, points: torch.Tensor, origin=None, xy_range=None) -> None:
-        """Enqueue one frame on the current stream (asynchronous)."""
+    def enqueue(self, points: torch.Tensor, origin=None, xy_range=None, events=None) -> None:
+        """Enqueue one frame on the current stream (asynchronous).
+
+        `events`: optional list of six `torch.cuda.Event(enable_timing=True)` recorded around the five
+        kernels (bench.py attributes device time per kernel with them)."""
         if point_format(points) != FMT_F32X4:
             raise ValueError("FramePipeline takes (n,4) float32 frames")
         n = points.shape[0]
         o3 = (C.c_double * 3)(*[float(v) for v in origin]) if origin is not None else None
         r4 = (C.c_double * 4)(*[float(v) for v in xy_range]) if xy_range is not None else None
         self._n = n
-        try:
-            check(lib.lidar_frame_voxel_density(
-                _ptr(points), n, self.voxel_size, self.grid_size, o3, r4, _ptr(self.voxel_key),
+        args = (_ptr(points), n, self.voxel_size, self.grid_size, o3, r4, _ptr(self.voxel_key),
                 _ptr(self.inverse), _ptr(self.centroids), _ptr(self.counts), _ptr(self.unique_keys),
                 _ptr(self.grid), _ptr(self.desc_dev), C.byref(self.caps), _ptr(self.ws), self.ws.numel(),
-                _stream_ptr()))
+                _stream_ptr())
+        try:
+            if events is None:
+                check(lib.lidar_frame_voxel_density(*args))
+            else:
+                if len(events) != 6:
+                    raise ValueError("need six CUDA events")
+                for e in events:
+                    if not e.cuda_event:      # torch creates the cudaEvent_t lazily, on first record
+                        e.record()
+                ev = (C.c_void_p * 6)(*[int(e.cuda_event) for e in events])
+                check(lib.lidar_frame_voxel_density_timed(*args, ev))
         except Exception:
             self.reset()
             raise
@@ -285,6 +297,106 @@ class FramePipeline:
             grid = self.grid[: desc.nx * desc.ny].view(desc.nx, desc.ny)
         return FrameResult(desc, self.voxel_key[:n], self.inverse[:n], self.centroids[:v], self.counts[:v],
                            self.unique_keys[:v], grid, tuple(desc.dims[:3]), tuple(desc.origin[:3]))
+
+
+class HostFramePipeline:
+    """The call a user of the numpy surface makes: HOST float4 frame in, HOST numpy results out.
+
+    Pinned staging buffers, one H2D copy of the frame, the five frame kernels, one D2H copy per
+    output.  Two slots alternate on two streams so the copies of one frame overlap the kernels of
+    the next (`submit` / `collect`); `process` is the synchronous single-frame form.
+    """
+
+    def __init__(self, max_points: int, voxel_size: float, grid_size: float = 0.0, slots: int = 2,
+                 per_point_outputs: bool = True, **caps):
+        self.device = require_cuda()
+        self.per_point_outputs = per_point_outputs
+        self.slots = []
+        n = int(max_points)
+        for _ in range(slots):
+            pipe = FramePipeline(n, voxel_size, grid_size, device=self.device, **caps)
+            st = torch.cuda.Stream(device=self.device)
+            slot = {
+                "pipe": pipe, "stream": st, "n": 0,
+                "h_in": torch.empty((n, 4), dtype=torch.float32).pin_memory(),
+                "d_in": torch.empty((n, 4), dtype=torch.float32, device=self.device),
+                "h_cent": torch.empty((n, 4), dtype=torch.float32).pin_memory(),
+                "h_cnt": torch.empty(n, dtype=torch.int32).pin_memory(),
+                "h_inv": torch.empty(n, dtype=torch.int32).pin_memory() if per_point_outputs else None,
+                "h_key": torch.empty(n, dtype=torch.int32).pin_memory() if per_point_outputs else None,
+                "h_grid": (torch.empty(pipe.grid.numel(), dtype=torch.int32).pin_memory()
+                           if pipe.grid is not None else None),
+            }
+            self.slots.append(slot)
+        self._next = 0
+        self._pending: list[dict] = []
+        torch.cuda.synchronize(self.device)   # workspace zeroing ran on the constructing stream
+
+    def h2d_bytes(self, n: int) -> int:
+        return n * 16
+
+    def d2h_bytes(self, n: int) -> int:
+        s = self.slots[0]
+        b = n * 16 + n * 4 + C.sizeof(FrameDesc)
+        if self.per_point_outputs:
+            b += 2 * n * 4
+        if s["h_grid"] is not None:
+            b += s["h_grid"].numel() * 4
+        return b
+
+    def submit(self, points: np.ndarray | torch.Tensor, origin=None, xy_range=None) -> None:
+        """Stage one host frame and enqueue copy-in, kernels and copy-out on the slot's stream."""
+        slot = self.slots[self._next]
+        self._next = (self._next + 1) % len(self.slots)
+        if slot in self._pending:
+            raise RuntimeError("all slots busy: call collect() first")
+        src = torch.from_numpy(points) if isinstance(points, np.ndarray) else points
+        n = src.shape[0]
+        if src.is_pinned():
+            h_in = src                      # caller already owns pinned memory: no staging copy
+        else:
+            slot["h_in"][:n].copy_(src)
+            h_in = slot["h_in"][:n]
+        slot["n"] = n
+        pipe = slot["pipe"]
+        with torch.cuda.stream(slot["stream"]):
+            slot["d_in"][:n].copy_(h_in, non_blocking=True)
+            pipe.enqueue(slot["d_in"][:n], origin=origin, xy_range=xy_range)
+            pipe.desc_host.copy_(pipe.desc_dev, non_blocking=True)
+            slot["h_cent"][:n].copy_(pipe.centroids[:n], non_blocking=True)
+            slot["h_cnt"][:n].copy_(pipe.counts[:n], non_blocking=True)
+            if self.per_point_outputs:
+                slot["h_inv"][:n].copy_(pipe.inverse[:n], non_blocking=True)
+                slot["h_key"][:n].copy_(pipe.voxel_key[:n], non_blocking=True)
+            if slot["h_grid"] is not None:
+                slot["h_grid"].copy_(pipe.grid, non_blocking=True)
+        self._pending.append(slot)
+
+    def collect(self, copy: bool = True) -> dict:
+        """Wait for the oldest submitted frame and return its results as numpy arrays."""
+        slot = self._pending.pop(0)
+        slot["stream"].synchronize()
+        pipe = slot["pipe"]
+        desc = FrameDesc.from_buffer_copy(pipe.desc_host.numpy().tobytes())
+        if desc.status != 0:
+            pipe.reset()
+            raise _capi.LidarError(int(desc.status), "frame exceeded its capacities")
+        n, v = slot["n"], int(desc.n_voxels)
+        cp = (lambda a: a.copy()) if copy else (lambda a: a)
+        out = {
+            "centroids": cp(slot["h_cent"].numpy()[:v]), "counts": cp(slot["h_cnt"].numpy()[:v]),
+            "n_voxels": v, "dims": tuple(desc.dims[:3]), "origin": tuple(desc.origin[:3]), "desc": desc,
+        }
+        if self.per_point_outputs:
+            out["inverse"] = cp(slot["h_inv"].numpy()[:n])
+            out["voxel_key"] = cp(slot["h_key"].numpy()[:n])
+        if slot["h_grid"] is not None:
+            out["grid_counts"] = cp(slot["h_grid"].numpy()[: desc.nx * desc.ny].reshape(desc.nx, desc.ny))
+        return out
+
+    def process(self, points, origin=None, xy_range=None) -> dict:
+        self.submit(points, origin=origin, xy_range=xy_range)
+        return self.collect()
 
 
 def voxel_downsample(points: torch.Tensor, voxel_size: float, origin=None, max_key_space: int | None = None):
