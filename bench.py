@@ -61,7 +61,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -142,8 +142,8 @@ def run_reference(args, rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--e2e-steps", type=int, default=40)
@@ -185,13 +185,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ------------------------------------------------------------
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for w in range(args.warmup):
         pipe.enqueue(frames[w % POOL])
     res = pipe.result()
     v_over_n = res.n_voxels / n
-    clocks = ClockSampler(local_rank)
     barrier()
-    clocks.start()
+    clocks.rows.clear()   # keep only samples taken during the timed region
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for s in range(args.steps):

@@ -9,18 +9,9 @@
 // of a kept point = exclusive prefix of the tile (chained scan, common.cuh) + #kept before it in
 // the tile, counted in index order from warp ballots.  Reads 16 B/point, writes 16 B per kept
 // point + 1 B mask: HBM-bound.
-#include "common.cuh"
+#include "compact.cuh"
 
 namespace lidar {
-
-constexpr int kCmpThreads = 256;
-constexpr int kCmpRows = 8;  // points per thread
-constexpr int kCmpTile = kCmpThreads * kCmpRows;
-
-struct CompactCtrl {
-    unsigned int ticket;
-    unsigned int pad[3];
-};
 
 struct BoxPredF32 {
     float lo[3], hi[3];
@@ -34,49 +25,6 @@ struct BoxPredF64 {
         return x >= lo[0] && x <= hi[0] && y >= lo[1] && y <= hi[1] && z >= lo[2] && z <= hi[2];
     }
 };
-
-// Shared skeleton: `keep[j]` flags for this thread's kCmpRows points of `tile` -> output slots.
-// Returns in slot[j] the global output index (or -1).  All threads of the CTA must call it.
-__device__ __forceinline__ void compact_slots(const bool (&keep)[kCmpRows], int tile,
-                                              unsigned long long* tile_desc, long long (&slot)[kCmpRows],
-                                              unsigned long long* total_out, bool is_last_tile) {
-    __shared__ unsigned s_cnt[kCmpRows][kCmpThreads / 32];
-    __shared__ unsigned long long s_base;
-    const unsigned lane = lane_id();
-    const int warp = threadIdx.x >> 5;
-    unsigned ballots[kCmpRows];
-#pragma unroll
-    for (int j = 0; j < kCmpRows; ++j) {
-        ballots[j] = __ballot_sync(0xffffffffu, keep[j]);
-        if (lane == 0) s_cnt[j][warp] = __popc(ballots[j]);
-    }
-    __syncthreads();
-    // exclusive prefix over (row-major j, warp) = index order inside the tile
-    unsigned total = 0;
-    unsigned my_off[kCmpRows];
-#pragma unroll
-    for (int j = 0; j < kCmpRows; ++j) {
-#pragma unroll
-        for (int w = 0; w < kCmpThreads / 32; ++w) {
-            if (w == warp) my_off[j] = total;
-            total += s_cnt[j][w];
-        }
-    }
-    if (warp == 0) {
-        const unsigned long long ex = scan_lookback_warp(tile_desc, tile, (unsigned long long)total);
-        if (lane == 0) {
-            s_base = ex;
-            if (is_last_tile && total_out) *total_out = ex + total;
-        }
-    }
-    __syncthreads();
-    const unsigned long long base = s_base;
-#pragma unroll
-    for (int j = 0; j < kCmpRows; ++j) {
-        slot[j] = keep[j] ? (long long)(base + my_off[j] + __popc(ballots[j] & lanemask_lt())) : -1ll;
-    }
-    __syncthreads();  // s_cnt / s_base are reused by the next tile
-}
 
 __global__ void __launch_bounds__(kCmpThreads)
 roi_crop_f32x4_kernel(const float4* __restrict__ pts, int64_t n, BoxPredF32 pred, uint8_t* __restrict__ mask,
@@ -144,20 +92,6 @@ roi_crop_f64x3_kernel(const double* __restrict__ pts, int64_t n, BoxPredF64 pred
                 o[0] = x[j]; o[1] = y[j]; o[2] = z[j];
             }
     }
-}
-
-struct CompactLayout {
-    size_t off_ctrl, off_desc, total;
-    int64_t tiles;
-};
-static CompactLayout compact_layout(int64_t n) {
-    CompactLayout L;
-    L.tiles = (n + kCmpTile - 1) / kCmpTile;
-    if (L.tiles < 1) L.tiles = 1;
-    L.off_ctrl = 0;
-    L.off_desc = ws_align(sizeof(CompactCtrl));
-    L.total = ws_align(L.off_desc + sizeof(unsigned long long) * L.tiles);
-    return L;
 }
 
 }  // namespace lidar

@@ -1,0 +1,441 @@
+// K2-K4 — the per-point stages of the reference's preprocess functions on (n,3) float64 clouds:
+//
+//   lidar_sigma_filter     3-sigma inlier mask + order-preserving compaction + height colours
+//                          utils/data_processing.py:143-157 ; app_simplified.py:80-91
+//   lidar_select_kth       two adjacent order statistics of a strided fp64 column (radix select),
+//                          the inputs of np.percentile(z, 30)   data_processing.py:164 ; app_simplified.py:98
+//   lidar_ground_split     z <= thr split: plane-fit moments over the ground points and compaction of
+//                          the non-ground points (+ their inlier indices)   data_processing.py:165-188
+//   lidar_standardize      (x - mean) / scale, StandardScaler.transform     data_processing.py:190-191
+//   lidar_scatter_labels   full_labels = -1; full_labels[non_ground] = labels   data_processing.py:203-204
+//
+// All of them stream the cloud once (24 B/point in, <= 48 B/point out): HBM-bound.  Every compare
+// that decides a mask bit is done in fp64 on the stored values with the reference's own expression.
+#include "compact.cuh"
+
+namespace lidar {
+
+// ------------------------------------------------------------------------------------------------
+// 3-sigma filter
+// ------------------------------------------------------------------------------------------------
+struct SigmaParams {
+    double mean[3], thr[3], tol[3];
+    double zmin, zden;  // colours: h = (z - zmin) / zden
+};
+
+__global__ void __launch_bounds__(kCmpThreads)
+sigma_filter_kernel(const double* __restrict__ pts, int64_t n, SigmaParams P, uint8_t* __restrict__ mask,
+                    double* __restrict__ out_pts, double* __restrict__ out_col, int64_t* __restrict__ count,
+                    unsigned long long* __restrict__ guard, unsigned long long* tile_desc, CompactCtrl* ctrl,
+                    int n_tiles) {
+    __shared__ int s_tile;
+    unsigned guard_local = 0;
+    while (true) {
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ctrl->ticket, 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= n_tiles) break;
+        const int64_t base = (int64_t)tile * kCmpTile;
+        double x[kCmpRows], y[kCmpRows], z[kCmpRows];
+        bool keep[kCmpRows];
+#pragma unroll
+        for (int j = 0; j < kCmpRows; ++j) {
+            const int64_t i = base + (int64_t)j * kCmpThreads + threadIdx.x;
+            keep[j] = false;
+            if (i < n) {
+                x[j] = __ldg(pts + 3 * i);
+                y[j] = __ldg(pts + 3 * i + 1);
+                z[j] = __ldg(pts + 3 * i + 2);
+                const double ax = fabs(__dsub_rn(x[j], P.mean[0]));
+                const double ay = fabs(__dsub_rn(y[j], P.mean[1]));
+                const double az = fabs(__dsub_rn(z[j], P.mean[2]));
+                keep[j] = ax < P.thr[0] && ay < P.thr[1] && az < P.thr[2];
+                // knife-edge certificate: mean/std come from a parallel fp64 reduction and may differ
+                // from numpy's sequential sum in the last bits; the mask can only differ for points
+                // this close to the threshold
+                if (fabs(ax - P.thr[0]) <= P.tol[0] || fabs(ay - P.thr[1]) <= P.tol[1] ||
+                    fabs(az - P.thr[2]) <= P.tol[2])
+                    ++guard_local;
+                if (mask) mask[i] = keep[j] ? 1 : 0;
+            }
+        }
+        long long slot[kCmpRows];
+        compact_slots(keep, tile, tile_desc, slot, reinterpret_cast<unsigned long long*>(count), tile == n_tiles - 1);
+#pragma unroll
+        for (int j = 0; j < kCmpRows; ++j)
+            if (slot[j] >= 0) {
+                double* o = out_pts + 3 * slot[j];
+                o[0] = x[j]; o[1] = y[j]; o[2] = z[j];
+                if (out_col) {
+                    const double h = __ddiv_rn(__dsub_rn(z[j], P.zmin), P.zden);
+                    double* c = out_col + 3 * slot[j];
+                    c[0] = h;
+                    c[1] = __dmul_rn(0.5, __dsub_rn(1.0, h));
+                    c[2] = 0.5;
+                }
+            }
+    }
+    if (guard_local) atomicAdd(guard, (unsigned long long)guard_local);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ground split: plane moments over z <= thr, compaction of z > thr
+// ------------------------------------------------------------------------------------------------
+constexpr int kPlaneMaxBlocks = 1024;
+struct PlaneWs {
+    double partial[kPlaneMaxBlocks][10];
+    unsigned int ticket;
+};
+
+__global__ void __launch_bounds__(kCmpThreads)
+ground_split_kernel(const double* __restrict__ pts, int64_t n, double thr, double cx, double cy, double cz,
+                    double* __restrict__ out_pts, int32_t* __restrict__ out_index, int64_t* __restrict__ count,
+                    double* __restrict__ plane_out10, unsigned long long* __restrict__ guard, double tol,
+                    unsigned long long* tile_desc, CompactCtrl* ctrl, PlaneWs* pw, int n_tiles) {
+    __shared__ int s_tile;
+    // {n, Sx, Sy, Sz, Sxx, Sxy, Syy, Sxz, Syz, unused} about the centre (cx,cy,cz)
+    double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned guard_local = 0;
+    while (true) {
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ctrl->ticket, 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= n_tiles) break;
+        const int64_t base = (int64_t)tile * kCmpTile;
+        double x[kCmpRows], y[kCmpRows], z[kCmpRows];
+        bool keep[kCmpRows];
+#pragma unroll
+        for (int j = 0; j < kCmpRows; ++j) {
+            const int64_t i = base + (int64_t)j * kCmpThreads + threadIdx.x;
+            keep[j] = false;
+            if (i < n) {
+                x[j] = __ldg(pts + 3 * i);
+                y[j] = __ldg(pts + 3 * i + 1);
+                z[j] = __ldg(pts + 3 * i + 2);
+                const bool ground = z[j] <= thr;
+                keep[j] = !ground;
+                if (fabs(z[j] - thr) <= tol && z[j] != thr) ++guard_local;
+                if (ground) {
+                    const double dx = x[j] - cx, dy = y[j] - cy, dz = z[j] - cz;
+                    s[0] += 1.0; s[1] += dx; s[2] += dy; s[3] += dz;
+                    s[4] += dx * dx; s[5] += dx * dy; s[6] += dy * dy; s[7] += dx * dz; s[8] += dy * dz;
+                }
+            }
+        }
+        long long slot[kCmpRows];
+        compact_slots(keep, tile, tile_desc, slot, reinterpret_cast<unsigned long long*>(count), tile == n_tiles - 1);
+#pragma unroll
+        for (int j = 0; j < kCmpRows; ++j)
+            if (slot[j] >= 0) {
+                double* o = out_pts + 3 * slot[j];
+                o[0] = x[j]; o[1] = y[j]; o[2] = z[j];
+                out_index[slot[j]] = (int32_t)(base + (int64_t)j * kCmpThreads + threadIdx.x);
+            }
+    }
+    if (guard_local) atomicAdd(guard, (unsigned long long)guard_local);
+    // deterministic fold of the plane moments: warp tree, CTA partial, last CTA folds in CTA order
+    __shared__ double s_p[kCmpThreads / 32][9];
+    __shared__ bool s_last;
+    const int warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) s[c] = warp_sum(s[c]);
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) s_p[warp][c] = s[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        double v = 0;
+        for (int w = 0; w < kCmpThreads / 32; ++w) v += s_p[w][threadIdx.x];
+        pw->partial[blockIdx.x][threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&pw->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < 9) {
+        double v = 0;
+        for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(&pw->partial[b][threadIdx.x]);
+        plane_out10[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) { plane_out10[9] = 0.0; pw->ticket = 0u; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// radix select on fp64 keys (8 passes of 8 bits), state kept on the device
+// ------------------------------------------------------------------------------------------------
+struct SelectState {
+    unsigned long long prefix;   // key bits fixed so far (high bits)
+    long long k;                 // rank still to find inside the current bucket
+    unsigned int hist[256];
+    unsigned int ticket;
+    unsigned int pad;
+    // second order statistic
+    unsigned long long count_le; // #elements <= kth
+    unsigned long long min_gt;   // smallest key > kth (key space)
+};
+
+__device__ __forceinline__ unsigned long long f64_key(double d) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(unsigned long long k) {
+    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+constexpr int kSelThreads = 256;
+
+__global__ void __launch_bounds__(kSelThreads)
+select_pass_kernel(const double* __restrict__ col, int64_t stride_el, int64_t n, int pass, SelectState* st) {
+    __shared__ unsigned s_hist[256];
+    __shared__ bool s_last;
+    s_hist[threadIdx.x] = 0;  // kSelThreads == 256
+    __syncthreads();
+    const unsigned long long prefix = st->prefix;
+    const int shift = 56 - 8 * pass;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const unsigned long long key = f64_key(__ldg(col + i * stride_el));
+        const bool match = pass == 0 ? true : ((key >> (shift + 8)) == prefix);
+        if (match) atomicAdd(&s_hist[(key >> shift) & 0xff], 1u);
+    }
+    __syncthreads();
+    if (s_hist[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], s_hist[threadIdx.x]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        long long k = st->k;
+        int d = 0;
+        for (; d < 256; ++d) {
+            const long long c = (long long)((volatile unsigned*)st->hist)[d];
+            if (k < c) break;
+            k -= c;
+        }
+        if (d > 255) d = 255;
+        st->k = k;
+        st->prefix = (prefix << 8) | (unsigned long long)d;
+        for (int j = 0; j < 256; ++j) st->hist[j] = 0;
+        st->ticket = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_next_kernel(const double* __restrict__ col, int64_t stride_el, int64_t n, int64_t k, SelectState* st,
+                   double* __restrict__ out2) {
+    __shared__ unsigned long long s_cnt[kSelThreads / 32];
+    __shared__ unsigned long long s_min[kSelThreads / 32];
+    __shared__ bool s_last;
+    const unsigned long long kth = st->prefix;
+    unsigned long long cnt = 0, mn = ~0ull;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const unsigned long long key = f64_key(__ldg(col + i * stride_el));
+        if (key <= kth) ++cnt;
+        else if (key < mn) mn = key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, mn, o);
+        mn = t < mn ? t : mn;
+    }
+    if (lane_id() == 0) { s_cnt[threadIdx.x >> 5] = cnt; s_min[threadIdx.x >> 5] = mn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kSelThreads / 32; ++w) { cnt += s_cnt[w]; mn = s_min[w] < mn ? s_min[w] : mn; }
+        atomicAdd(&st->count_le, cnt);
+        atomicMin(&st->min_gt, mn);
+        __threadfence();
+        s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x != 0) return;
+    __threadfence();
+    const unsigned long long cle = *((volatile unsigned long long*)&st->count_le);
+    const unsigned long long mgt = *((volatile unsigned long long*)&st->min_gt);
+    out2[0] = key_f64(kth);
+    out2[1] = ((long long)cle >= k + 2 || mgt == ~0ull) ? key_f64(kth) : key_f64(mgt);
+    st->ticket = 0;
+}
+
+__global__ void select_init_kernel(SelectState* st, int64_t k) {
+    if (threadIdx.x < 256) st->hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        st->prefix = 0; st->k = k; st->ticket = 0; st->pad = 0; st->count_le = 0; st->min_gt = ~0ull;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void standardize_kernel(const double* __restrict__ in, int64_t n3, double m0, double m1, double m2,
+                                   double s0, double s1, double s2, double* __restrict__ out) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += step) {
+        const int c = (int)(i % 3);
+        const double m = c == 0 ? m0 : (c == 1 ? m1 : m2);
+        const double s = c == 0 ? s0 : (c == 1 ? s1 : s2);
+        out[i] = __ddiv_rn(__dsub_rn(in[i], m), s);   // X -= mean; X /= scale
+    }
+}
+
+__global__ void scatter_labels_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ index,
+                                      int64_t m, long long* __restrict__ full) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += step)
+        full[index[i]] = (long long)labels[i];
+}
+__global__ void fill_i64_kernel(long long* __restrict__ p, int64_t n, long long v) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) p[i] = v;
+}
+
+static int ew_grid(int64_t n) {
+    int64_t want = (n + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+struct PreLayout {
+    size_t off_ctrl, off_desc, off_plane, off_guard, total;
+    int64_t tiles;
+};
+static PreLayout pre_layout(int64_t n) {
+    PreLayout L;
+    const CompactLayout C = compact_layout(n);
+    L.tiles = C.tiles;
+    L.off_ctrl = C.off_ctrl;
+    L.off_desc = C.off_desc;
+    L.off_plane = ws_align(C.total);
+    L.off_guard = ws_align(L.off_plane + sizeof(PlaneWs));
+    L.total = ws_align(L.off_guard + 256);
+    return L;
+}
+
+}  // namespace lidar
+
+using namespace lidar;
+
+extern "C" {
+
+size_t lidar_preprocess_workspace_bytes(int64_t n) {
+    size_t a = pre_layout(n < 0 ? 0 : n).total;
+    size_t b = ws_align(sizeof(SelectState));
+    return a > b ? a : b;
+}
+
+int lidar_sigma_filter(const double* d_points, int64_t n, const double* h_mean3, const double* h_thr3,
+                       const double* h_tol3, double zmin, double zden, uint8_t* d_mask, double* d_out_points,
+                       double* d_out_colors, int64_t* d_count, uint64_t* d_guard, void* d_ws, size_t ws_bytes,
+                       void* stream) {
+    LIDAR_REQUIRE(n >= 0 && h_mean3 && h_thr3 && h_tol3 && d_count && d_guard, LIDAR_ERR_INVALID,
+                  "lidar_sigma_filter: bad argument");
+    LIDAR_REQUIRE(n == 0 || (d_points && d_out_points), LIDAR_ERR_INVALID, "lidar_sigma_filter: NULL points");
+    const PreLayout L = pre_layout(n);
+    LIDAR_REQUIRE(d_ws && ws_bytes >= L.total, LIDAR_ERR_WORKSPACE, "lidar_sigma_filter: workspace too small (%zu < %zu)",
+                  ws_bytes, L.total);
+    cudaStream_t st = as_stream(stream);
+    char* ws = static_cast<char*>(d_ws);
+    LIDAR_CUDA_TRY(cudaMemsetAsync(ws, 0, ws_align(L.off_desc + sizeof(unsigned long long) * L.tiles), st));
+    LIDAR_CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+    LIDAR_CUDA_TRY(cudaMemsetAsync(d_guard, 0, sizeof(uint64_t), st));
+    if (n == 0) return LIDAR_OK;
+    SigmaParams P;
+    for (int c = 0; c < 3; ++c) { P.mean[c] = h_mean3[c]; P.thr[c] = h_thr3[c]; P.tol[c] = h_tol3[c]; }
+    P.zmin = zmin; P.zden = zden;
+    int grid = sm_count() * 4;
+    if ((int64_t)grid > L.tiles) grid = (int)L.tiles;
+    sigma_filter_kernel<<<grid, kCmpThreads, 0, st>>>(d_points, n, P, d_mask, d_out_points, d_out_colors, d_count,
+        reinterpret_cast<unsigned long long*>(d_guard), reinterpret_cast<unsigned long long*>(ws + L.off_desc),
+        reinterpret_cast<CompactCtrl*>(ws + L.off_ctrl), (int)L.tiles);
+    LIDAR_CHECK_LAUNCH();
+    return LIDAR_OK;
+}
+
+int lidar_ground_split(const double* d_points, int64_t n, double z_threshold, const double* h_center3, double tol,
+                       double* d_out_points, int32_t* d_out_index, int64_t* d_count, double* d_plane10,
+                       uint64_t* d_guard, void* d_ws, size_t ws_bytes, void* stream) {
+    LIDAR_REQUIRE(n >= 0 && h_center3 && d_count && d_plane10 && d_guard, LIDAR_ERR_INVALID,
+                  "lidar_ground_split: bad argument");
+    LIDAR_REQUIRE(n == 0 || (d_points && d_out_points && d_out_index), LIDAR_ERR_INVALID,
+                  "lidar_ground_split: NULL points");
+    LIDAR_REQUIRE(n < (1ll << 31), LIDAR_ERR_INVALID, "lidar_ground_split: n must be < 2^31");
+    const PreLayout L = pre_layout(n);
+    LIDAR_REQUIRE(d_ws && ws_bytes >= L.total, LIDAR_ERR_WORKSPACE, "lidar_ground_split: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    char* ws = static_cast<char*>(d_ws);
+    LIDAR_CUDA_TRY(cudaMemsetAsync(ws, 0, ws_align(L.off_desc + sizeof(unsigned long long) * L.tiles), st));
+    LIDAR_CUDA_TRY(cudaMemsetAsync(ws + L.off_plane + offsetof(PlaneWs, ticket), 0, sizeof(unsigned), st));
+    LIDAR_CUDA_TRY(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+    LIDAR_CUDA_TRY(cudaMemsetAsync(d_guard, 0, sizeof(uint64_t), st));
+    LIDAR_CUDA_TRY(cudaMemsetAsync(d_plane10, 0, sizeof(double) * 10, st));
+    if (n == 0) return LIDAR_OK;
+    int grid = sm_count() * 4;
+    if ((int64_t)grid > L.tiles) grid = (int)L.tiles;
+    if (grid > kPlaneMaxBlocks) grid = kPlaneMaxBlocks;
+    ground_split_kernel<<<grid, kCmpThreads, 0, st>>>(d_points, n, z_threshold, h_center3[0], h_center3[1],
+        h_center3[2], d_out_points, d_out_index, d_count, d_plane10, reinterpret_cast<unsigned long long*>(d_guard),
+        tol, reinterpret_cast<unsigned long long*>(ws + L.off_desc), reinterpret_cast<CompactCtrl*>(ws + L.off_ctrl),
+        reinterpret_cast<PlaneWs*>(ws + L.off_plane), (int)L.tiles);
+    LIDAR_CHECK_LAUNCH();
+    return LIDAR_OK;
+}
+
+int lidar_select_kth(const double* d_column, int64_t stride_elems, int64_t n, int64_t k, double* d_out2,
+                     void* d_ws, size_t ws_bytes, void* stream) {
+    LIDAR_REQUIRE(n > 0 && k >= 0 && k < n, LIDAR_ERR_INVALID, "lidar_select_kth: need 0 <= k < n (k=%lld n=%lld)",
+                  (long long)k, (long long)n);
+    LIDAR_REQUIRE(d_column && d_out2 && stride_elems > 0, LIDAR_ERR_INVALID, "lidar_select_kth: bad argument");
+    LIDAR_REQUIRE(d_ws && ws_bytes >= sizeof(SelectState), LIDAR_ERR_WORKSPACE, "lidar_select_kth: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    SelectState* S = static_cast<SelectState*>(d_ws);
+    select_init_kernel<<<1, 256, 0, st>>>(S, k);
+    LIDAR_CHECK_LAUNCH();
+    int grid = (int)((n + kSelThreads * 8 - 1) / (kSelThreads * 8));
+    const int cap = sm_count() * 8;
+    grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
+    for (int pass = 0; pass < 8; ++pass) {
+        select_pass_kernel<<<grid, kSelThreads, 0, st>>>(d_column, stride_elems, n, pass, S);
+        LIDAR_CHECK_LAUNCH();
+    }
+    select_next_kernel<<<grid, kSelThreads, 0, st>>>(d_column, stride_elems, n, k, S, d_out2);
+    LIDAR_CHECK_LAUNCH();
+    return LIDAR_OK;
+}
+
+int lidar_standardize(const double* d_points, int64_t n, const double* h_mean3, const double* h_scale3,
+                      double* d_out, void* stream) {
+    LIDAR_REQUIRE(n >= 0 && h_mean3 && h_scale3, LIDAR_ERR_INVALID, "lidar_standardize: bad argument");
+    if (n == 0) return LIDAR_OK;
+    LIDAR_REQUIRE(d_points && d_out, LIDAR_ERR_INVALID, "lidar_standardize: NULL points");
+    standardize_kernel<<<ew_grid(n * 3), 256, 0, as_stream(stream)>>>(d_points, n * 3, h_mean3[0], h_mean3[1],
+        h_mean3[2], h_scale3[0], h_scale3[1], h_scale3[2], d_out);
+    LIDAR_CHECK_LAUNCH();
+    return LIDAR_OK;
+}
+
+int lidar_scatter_labels(const int32_t* d_labels, const int32_t* d_index, int64_t m, int64_t* d_full, int64_t n,
+                         void* stream) {
+    LIDAR_REQUIRE(m >= 0 && n >= 0, LIDAR_ERR_INVALID, "lidar_scatter_labels: bad sizes");
+    if (n == 0) return LIDAR_OK;
+    LIDAR_REQUIRE(d_full, LIDAR_ERR_INVALID, "lidar_scatter_labels: NULL output");
+    cudaStream_t st = as_stream(stream);
+    fill_i64_kernel<<<ew_grid(n), 256, 0, st>>>(reinterpret_cast<long long*>(d_full), n, -1ll);
+    LIDAR_CHECK_LAUNCH();
+    if (m > 0) {
+        LIDAR_REQUIRE(d_labels && d_index, LIDAR_ERR_INVALID, "lidar_scatter_labels: NULL labels");
+        scatter_labels_kernel<<<ew_grid(m), 256, 0, st>>>(d_labels, d_index, m, reinterpret_cast<long long*>(d_full));
+        LIDAR_CHECK_LAUNCH();
+    }
+    return LIDAR_OK;
+}
+
+}  // extern "C"

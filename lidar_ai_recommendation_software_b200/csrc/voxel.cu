@@ -30,8 +30,9 @@
 namespace lidar {
 
 constexpr int kFrameThreads = 256;
-constexpr int kScanWordsPerThread = 8;                                // 256-bit group per thread
-constexpr int kScanTileWords = kFrameThreads * kScanWordsPerThread;   // 2048 words = 65536 bits
+constexpr int kScanWordsPerThread = 8;                                // one 256-bit group = 8 words
+constexpr int kScanGroupsPerThread = 4;                               // each thread scans 4 adjacent groups
+constexpr int kScanTileWords = kFrameThreads * kScanWordsPerThread * kScanGroupsPerThread;   // 8192 words
 
 struct FrameWsLayout {
     size_t off_partial, off_ctrl, off_bitmap, off_group_prefix, off_tile_desc, off_acc, off_cnt, total;
@@ -105,10 +106,10 @@ __device__ void derive_desc(const FrameParams& P, const double* bb, lidar_frame_
     D->dims[3] = 0;
     D->key_space = ks;
     if (ks > P.max_key_space || ks >= (1ll << 31)) status = status ? status : LIDAR_ERR_CAPACITY;
-    // fixed point: |p - corner| < 2*voxel, n members at most  ->  2*voxel * 2^k * n < 2^62
+    // fixed point: |p - ref| < 2*voxel + 2^-24, n members at most  ->  that * 2^k * n < 2^62
     {
         int e;
-        frexp(P.voxel * 2.0, &e);  // voxel*2 < 2^e
+        frexp(P.voxel * 2.0 + 0x1p-24, &e);  // bound < 2^e
         D->fix_scale_xyz = ldexp(1.0, P.fix_bits_budget - e);
         double wmax = fmax(fabs(bb[3]), fabs(bb[7]));
         if (!(wmax > 0.0) || !isfinite(wmax)) wmax = 1.0;
@@ -198,14 +199,29 @@ k_frame_bbox(FrameParams P, double* __restrict__ partial, FrameCtrl* __restrict_
     if (!s_last) return;
     __threadfence();
     __shared__ double s_bb[8];
-    if (threadIdx.x < 8) {
-        const bool is_max = threadIdx.x >= 4;
+    {
+        // all 256 threads fold the per-CTA partials: thread t owns channel t&7 of CTAs t>>3, +32, ...
+        const int ch = threadIdx.x & 7;
+        const bool is_max = ch >= 4;
         double v = is_max ? -INFINITY : INFINITY;
-        for (unsigned b = 0; b < gridDim.x; ++b) {
-            const double q = ((volatile double*)partial)[(size_t)b * 8 + threadIdx.x];
+        for (unsigned b = threadIdx.x >> 3; b < gridDim.x; b += kFrameThreads / 8) {
+            const double q = __ldcg(partial + (size_t)b * 8 + ch);
             v = is_max ? fmax(v, q) : fmin(v, q);
         }
-        s_bb[threadIdx.x] = v;
+        // lanes with equal (lane & 7) hold the same channel: xor-shuffle over 8 and 16
+        for (int o = 8; o < 32; o <<= 1) {
+            const double q = __shfl_xor_sync(0xffffffffu, v, o);
+            v = is_max ? fmax(v, q) : fmin(v, q);
+        }
+        __shared__ double s_part[kFrameThreads / 32][8];
+        if (lane_id() < 8) s_part[warp][lane_id()] = v;
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            double r = s_part[0][threadIdx.x];
+            for (int w = 1; w < kFrameThreads / 32; ++w)
+                r = (threadIdx.x >= 4) ? fmax(r, s_part[w][threadIdx.x]) : fmin(r, s_part[w][threadIdx.x]);
+            s_bb[threadIdx.x] = r;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -215,15 +231,35 @@ k_frame_bbox(FrameParams P, double* __restrict__ partial, FrameCtrl* __restrict_
     }
 }
 
+// floor(fl(d / v)) without the DDIV sequence on the fast path: d * fl(1/v) is within 1.5 ulp of d/v,
+// so unless it lands within 4 ulp of an integer its floor equals the floor of the correctly rounded
+// quotient; the (astronomically rare) near-integer case takes the real division.
+__device__ __forceinline__ int floor_div_exact(double d, double v, double rinv) {
+    const double qh = __dmul_rn(d, rinv);
+    const double fl = floor(qh);
+    const double fr = __dsub_rn(qh, fl);
+    const double tol = __dadd_rn(__dmul_rn(fabs(qh), 0x1p-50), 1e-300);
+    if (fr > tol && __dsub_rn(1.0, fr) > tol) return (int)fl;
+    return (int)floor(__ddiv_rn(d, v));
+}
+
+// Accumulation reference of a voxel: its corner snapped to a multiple of 2^-24 m.  p is an fp32 value
+// and ref a multiple of 2^-24, so (p - ref) is exact in fp64 and (p - ref) * 2^k is an exact integer
+// for every |p| >= 2^-(k-23): the integer sums below are then the EXACT sums of the members.
+__device__ __forceinline__ double voxel_ref(double o, int i, double v) {
+    const double c = __dadd_rn(o, __dmul_rn((double)i, v));
+    return __dmul_rn(nearbyint(__dmul_rn(c, 16777216.0)), 1.0 / 16777216.0);
+}
+
 // analytic arange edge (DOUBLE_fill): e(0)=a, e(1)=fl(a+g), e(i)=fl(a + fl(i*delta))
 __device__ __forceinline__ double arange_edge(double a, double e1, double d, int i) {
     return i == 0 ? a : (i == 1 ? e1 : __dadd_rn(a, __dmul_rn((double)i, d)));
 }
-__device__ __forceinline__ int arange_bin(double x, double a, double e1, double d, int nb) {
+__device__ __forceinline__ int arange_bin(double x, double a, double e1, double d, double rd, int nb) {
     const double hi = arange_edge(a, e1, d, nb);
     if (!(x >= a) || !(x <= hi)) return -1;
     if (x == hi) return nb - 1;
-    int k = (int)floor(__ddiv_rn(__dsub_rn(x, a), d));
+    int k = (int)floor(__dmul_rn(__dsub_rn(x, a), rd));   // guess; corrected against the exact edges
     k = k < 0 ? 0 : (k > nb - 1 ? nb - 1 : k);
     while (x < arange_edge(a, e1, d, k)) --k;
     while (x >= arange_edge(a, e1, d, k + 1)) ++k;
@@ -244,20 +280,22 @@ k_frame_mark(const float4* __restrict__ pts, const lidar_frame_desc* __restrict_
     const int Dy = D.dims[1], Dz = D.dims[2];
     const bool do_grid = D.grid > 0.0;
     const int ny = D.ny;
+    const double rv = __ddiv_rn(1.0, v);
+    const double rdx = do_grid ? __ddiv_rn(1.0, D.exd) : 0.0, rdy = do_grid ? __ddiv_rn(1.0, D.eyd) : 0.0;
     LoadF32x4 L{pts};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float4 q = L.raw(i);
         const double x = (double)q.x, y = (double)q.y, z = (double)q.z;
-        const int ix = (int)floor(__ddiv_rn(__dsub_rn(x, ox), v));
-        const int iy = (int)floor(__ddiv_rn(__dsub_rn(y, oy), v));
-        const int iz = (int)floor(__ddiv_rn(__dsub_rn(z, oz), v));
+        const int ix = floor_div_exact(__dsub_rn(x, ox), v, rv);
+        const int iy = floor_div_exact(__dsub_rn(y, oy), v, rv);
+        const int iz = floor_div_exact(__dsub_rn(z, oz), v, rv);
         const int key = (ix * Dy + iy) * Dz + iz;
         voxel_key[i] = key;
         atomicOr(&bitmap[key >> 5], 1u << (key & 31));
         if (do_grid) {
-            const int bx = arange_bin(x, D.ex0, D.ex1, D.exd, D.nx);
-            const int by = arange_bin(y, D.ey0, D.ey1, D.eyd, ny);
+            const int bx = arange_bin(x, D.ex0, D.ex1, D.exd, rdx, D.nx);
+            const int by = arange_bin(y, D.ey0, D.ey1, D.eyd, rdy, ny);
             if (bx >= 0 && by >= 0) atomicAdd(&grid_out[bx * ny + by], 1);
         }
     }
@@ -282,9 +320,19 @@ k_frame_scan(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ group_p
         const int tile = s_tile;
         if (tile >= n_tiles) break;
         // the workspace bitmap is padded to whole tiles, so the loads never run off the end
-        const uint4* src = reinterpret_cast<const uint4*>(bitmap + (size_t)tile * kScanTileWords) + threadIdx.x * 2;
-        const uint4 a = src[0], b = src[1];
-        const unsigned cnt = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+        const uint4* src = reinterpret_cast<const uint4*>(bitmap + (size_t)tile * kScanTileWords) +
+                           threadIdx.x * (2 * kScanGroupsPerThread);
+        unsigned gcnt[kScanGroupsPerThread];
+        unsigned cnt = 0;
+        uint4 w[2 * kScanGroupsPerThread];
+#pragma unroll
+        for (int g = 0; g < 2 * kScanGroupsPerThread; ++g) w[g] = src[g];
+#pragma unroll
+        for (int g = 0; g < kScanGroupsPerThread; ++g) {
+            const uint4 a = w[2 * g], b = w[2 * g + 1];
+            gcnt[g] = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+            cnt += gcnt[g];
+        }
         // exclusive scan over the CTA
         unsigned inc = cnt;
 #pragma unroll
@@ -296,10 +344,10 @@ k_frame_scan(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ group_p
         __syncthreads();
         unsigned warp_off = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < kFrameThreads / 32; ++w) {
-            const unsigned s = s_warp_sum[w];
-            if (w < warp) warp_off += s;
-            total += s;
+        for (int w2 = 0; w2 < kFrameThreads / 32; ++w2) {
+            const unsigned sv = s_warp_sum[w2];
+            if (w2 < warp) warp_off += sv;
+            total += sv;
         }
         if (warp == 0) {
             const unsigned long long ex = scan_lookback_warp(tile_desc, tile, (unsigned long long)total);
@@ -309,7 +357,15 @@ k_frame_scan(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ group_p
             }
         }
         __syncthreads();
-        group_prefix[(size_t)tile * kFrameThreads + threadIdx.x] = (unsigned)s_excl + warp_off + (inc - cnt);
+        {
+            unsigned run = (unsigned)s_excl + warp_off + (inc - cnt);
+            uint4 o4;
+            o4.x = run; run += gcnt[0];
+            o4.y = run; run += gcnt[1];
+            o4.z = run; run += gcnt[2];
+            o4.w = run;
+            reinterpret_cast<uint4*>(group_prefix + (size_t)tile * (kFrameThreads * kScanGroupsPerThread))[threadIdx.x] = o4;
+        }
         __syncthreads();
     }
 }
@@ -350,9 +406,9 @@ k_frame_rank(const float4* __restrict__ pts, const lidar_frame_desc* __restrict_
         const int t = key / Dz;
         const int iy = t % Dy;
         const int ix = t / Dy;
-        const double cx = __dadd_rn(ox, __dmul_rn((double)ix, v));
-        const double cy = __dadd_rn(oy, __dmul_rn((double)iy, v));
-        const double cz = __dadd_rn(oz, __dmul_rn((double)iz, v));
+        const double cx = voxel_ref(ox, ix, v);
+        const double cy = voxel_ref(oy, iy, v);
+        const double cz = voxel_ref(oz, iz, v);
         const long long fx = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.x, cx), sxyz));
         const long long fy = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.y, cy), sxyz));
         const long long fz = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.z, cz), sxyz));
@@ -392,9 +448,9 @@ k_frame_finalize(const lidar_frame_desc* __restrict__ Dg, long long* __restrict_
         const int iy = t % Dy;
         const int ix = t / Dy;
         const double dc = (double)c;
-        const double cx = __dadd_rn(ox, __dmul_rn((double)ix, v));
-        const double cy = __dadd_rn(oy, __dmul_rn((double)iy, v));
-        const double cz = __dadd_rn(oz, __dmul_rn((double)iz, v));
+        const double cx = voxel_ref(ox, ix, v);
+        const double cy = voxel_ref(oy, iy, v);
+        const double cz = voxel_ref(oz, iz, v);
         float4 o;
         o.x = (float)__dadd_rn(cx, __ddiv_rn(__dmul_rn((double)s01.x, isx), dc));
         o.y = (float)__dadd_rn(cy, __ddiv_rn(__dmul_rn((double)s01.y, isx), dc));

@@ -60,6 +60,8 @@ def test_grid_density_counts_bit_exact(ops, synth, mode, g):
     xr = (xyz[:, 0].min(), xyz[:, 0].max())
     yr = (xyz[:, 1].min(), xyz[:, 1].max())
     want, ex, ey = ref_path.grid_density_counts(xyz[:, :2], xr, yr, g)
+    if mode == 2 and want.size * 4 > 200 * 1024:
+        pytest.skip("grid does not fit a CTA's shared memory: SHARED mode is refused by design")
     d = dev(xyz)
     got = ops.hist2d_counts(d[:, 0], d[:, 1], ops.arange_edges(*xr, g), ops.arange_edges(*yr, g), mode=mode)
     assert np.array_equal(ops.arange_edges(*xr, g), ex)
