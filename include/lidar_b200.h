@@ -94,6 +94,102 @@ int lidar_roi_crop(const void* d_points, int fmt, int64_t n, const double* h_lo3
                    void* stream);
 
 /* ------------------------------------------------------------------------------------------- *
+ * K2-K4  per-point stages of preprocess_lidar_data (utils/data_processing.py:127-229) and
+ *        preprocess_point_cloud (app_simplified.py:76-137) on (n,3) float64 clouds.
+ * ------------------------------------------------------------------------------------------- */
+size_t lidar_preprocess_workspace_bytes(int64_t n);
+
+/* 3-sigma inlier filter + compaction + height colours (data_processing.py:143-157).
+ *   keep <=> |p - mean| < thr on every axis (thr = 3*std, computed by the caller in fp64).
+ *   colours: h = (z - zmin)/zden ; (h, 0.5*(1-h), 0.5)   (zden = zmax - zmin + 1e-10)
+ *   d_guard: #points within tol of a threshold — the knife-edge certificate (0 => mask is exact even
+ *   though mean/std come from a parallel reduction).
+ *   d_mask uint8[n] (may be NULL); d_out_colors may be NULL. */
+int lidar_sigma_filter(const double* d_points, int64_t n, const double* h_mean3, const double* h_thr3,
+                       const double* h_tol3, double zmin, double zden, uint8_t* d_mask, double* d_out_points,
+                       double* d_out_colors, int64_t* d_count, uint64_t* d_guard, void* d_ws, size_t ws_bytes,
+                       void* stream);
+
+/* k-th and (k+1)-th smallest of a strided fp64 column (radix select, exact): the two order statistics
+ * np.percentile(z, 30) interpolates (data_processing.py:164).  d_out2 = {x_(k), x_(k+1)} (0-based;
+ * x_(k+1) = x_(k) when k = n-1). */
+int lidar_select_kth(const double* d_column, int64_t stride_elems, int64_t n, int64_t k, double* d_out2,
+                     void* d_ws, size_t ws_bytes, void* stream);
+
+/* ground split (data_processing.py:165-188): ground <=> z <= z_threshold.
+ *   d_plane10 = {n, Sx, Sy, Sz, Sxx, Sxy, Syy, Sxz, Syz, 0} over the ground points about h_center3
+ *   (normal equations of the lstsq plane z = ax + by + c);
+ *   non-ground points are compacted (order preserving) into d_out_points with their row index in
+ *   d_out_index (int32).  d_guard counts |z - thr| <= tol, z != thr. */
+int lidar_ground_split(const double* d_points, int64_t n, double z_threshold, const double* h_center3, double tol,
+                       double* d_out_points, int32_t* d_out_index, int64_t* d_count, double* d_plane10,
+                       uint64_t* d_guard, void* d_ws, size_t ws_bytes, void* stream);
+
+/* StandardScaler.transform (data_processing.py:190-191): out = (x - mean) / scale, fp64, IEEE ops */
+int lidar_standardize(const double* d_points, int64_t n, const double* h_mean3, const double* h_scale3,
+                      double* d_out, void* stream);
+
+/* d_dst[i] = d_src[d_index[i]] for k rows of row_bytes bytes (multiple of 4): the gather behind
+ * downsample_point_cloud (utils/data_processing.py:247-249).  Indices are not range checked. */
+int lidar_gather_rows(const void* d_src, int64_t n_rows, int row_bytes, const int64_t* d_index, int64_t k,
+                      void* d_dst, void* stream);
+
+/* full_labels = -1; full_labels[index[j]] = labels[j]  (data_processing.py:203-204), int64 output */
+int lidar_scatter_labels(const int32_t* d_labels, const int32_t* d_index, int64_t m, int64_t* d_full, int64_t n,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
+ * K7  DBSCAN with scikit-learn-identical labels (sklearn 1.9.0 DBSCAN(eps, min_samples).fit(X).labels_;
+ *     data_processing.py:197, app_simplified.py:107).  d_points (m,3) fp64; h_min3/h_max3 = bbox of
+ *     the points; d_labels int32[m] (-1 noise); d_n_clusters int32; d_guard = knife-edge pairs within
+ *     tol of eps^2 (pass tol = 0 when X is the raw data: fp64 rdist is then exact).
+ * K8  per-cluster mean (extract_people_positions, data_processing.py:251-280): exact integer sums.
+ *     d_labels int32 or int64 (labels_are_i64), ids outside [0, n_clusters) are skipped;
+ *     d_centroids3 (C,3) fp64; d_counts int64[C] (may be NULL).
+ * ------------------------------------------------------------------------------------------- */
+size_t lidar_dbscan_workspace_bytes(int64_t m, double eps, const double* h_min3, const double* h_max3);
+int lidar_dbscan(const double* d_points, int64_t m, double eps, int min_samples, double tol,
+                 const double* h_min3, const double* h_max3, int32_t* d_labels, int32_t* d_n_clusters,
+                 uint64_t* d_guard, void* d_ws, size_t ws_bytes, void* stream);
+size_t lidar_centroid_workspace_bytes(int n_clusters);
+int lidar_cluster_centroids(const double* d_points, const void* d_labels, int labels_are_i64, int64_t n,
+                            int n_clusters, double* d_centroids3, int64_t* d_counts, void* d_ws, size_t ws_bytes,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
+ * K9  lattice flow field and bottleneck scoring (models/crowd_flow_model.py:88-279,
+ *     app_simplified.py:348-447).  Lattice = meshgrid(x_grid, y_grid) row-major with y outer.
+ *     lidar_flow_field: unit vector to (exit_x, exit_y) rotated by sin(x*freq)*cos(y*freq)*amp, slowed
+ *       inside up to 3 discs of radius 3 m (h_discs_xy = x0,y0,x1,y1,...: drawn by the caller from the
+ *       legacy MT19937 stream), scaled by speed_span / max|v|; magnitudes optionally clipped.
+ *       d_sums4 = {sum |v|, sum vx, sum vy, bits of max|v| before scaling}.
+ *     lidar_flow_bottlenecks: variant A severity (5*gradient + 5*convergence)/2 per node, 0 if the node
+ *       does not qualify (speed <= 0.5, >= 5 nodes within 3 m inclusive, >= 3 in the 3..5 m ring).
+ *     lidar_flow_box_max: variant B: max speed in the open +-3 m box around nodes slower than slow_below
+ *       (-1 elsewhere).
+ *     lidar_radius_count: number of centres within `radius` (inclusive) of every (qx[i], qy[j]); output
+ *       int32 [nqy][nqx]  (KDTree.query_radius per cell centre, app_simplified.py:266-281).
+ * K10 frame-to-frame flow (NEW op): nearest previous centroid (fp32, lowest
+ *     index on ties) gated at `gate`, velocity = displacement / dt; lattice field = mean velocity of
+ *     the matched people within `radius` (inclusive) of each node.
+ * ------------------------------------------------------------------------------------------- */
+int lidar_flow_field(const double* d_xgrid, int nx, const double* d_ygrid, int ny, double exit_x, double exit_y,
+                     double freq, double amp, const double* h_discs_xy, int n_discs, double speed_span, int clip,
+                     double clip_lo, double clip_hi, double* d_positions, double* d_vectors, double* d_magnitudes,
+                     double* d_sums4, void* stream);
+int lidar_flow_bottlenecks(int nx, int ny, const double* d_positions, const double* d_vectors,
+                           const double* d_magnitudes, double* d_severity, void* stream);
+int lidar_flow_box_max(int nx, int ny, const double* d_positions, const double* d_magnitudes, double slow_below,
+                       double* d_box_max, void* stream);
+int lidar_radius_count(const double* d_centres_xy, int n_centres, const double* d_qx, int nqx, const double* d_qy,
+                       int nqy, double radius, int32_t* d_counts, void* stream);
+int lidar_frame_flow_match(const float* d_prev_xy, int n_prev, const float* d_cur_xy, int n_cur, float dt, float gate,
+                           int32_t* d_match, float* d_velocity, void* stream);
+int lidar_frame_flow_field(const double* d_lattice_xy, int n_lattice, const float* d_cur_xy, const int32_t* d_match,
+                           const float* d_velocity, int n_cur, double radius, double* d_vectors, double* d_magnitudes,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
  * K5  voxel downsample (NEW op).
  *     i_axis = floor((f64(p_axis) - origin_axis) / voxel) ; key = (ix*Dy + iy)*Dz + iz.
  *     Voxels come out in ascending key order.  All integer outputs are bit-exact and run-to-run

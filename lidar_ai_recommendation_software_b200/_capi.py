@@ -80,6 +80,27 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_compact_workspace_bytes": (_sz, [_i64]),
     "lidar_roi_crop": (_i32, [_vp, _i32, _i64, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp, _vp,
                               _vp, _sz, _vp]),
+    "lidar_preprocess_workspace_bytes": (_sz, [_i64]),
+    "lidar_sigma_filter": (_i32, [_vp, _i64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                  _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "lidar_select_kth": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "lidar_ground_split": (_i32, [_vp, _i64, _dbl, C.POINTER(C.c_double), _dbl, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _sz, _vp]),
+    "lidar_standardize": (_i32, [_vp, _i64, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp]),
+    "lidar_gather_rows": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp]),
+    "lidar_scatter_labels": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp]),
+    "lidar_dbscan_workspace_bytes": (_sz, [_i64, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "lidar_dbscan": (_i32, [_vp, _i64, _dbl, _i32, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp,
+                            _vp, _vp, _sz, _vp]),
+    "lidar_centroid_workspace_bytes": (_sz, [_i32]),
+    "lidar_cluster_centroids": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "lidar_flow_field": (_i32, [_vp, _i32, _vp, _i32, _dbl, _dbl, _dbl, _dbl, C.POINTER(C.c_double), _i32, _dbl,
+                                _i32, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp]),
+    "lidar_flow_bottlenecks": (_i32, [_i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "lidar_flow_box_max": (_i32, [_i32, _i32, _vp, _vp, _dbl, _vp, _vp]),
+    "lidar_radius_count": (_i32, [_vp, _i32, _vp, _i32, _vp, _i32, _dbl, _vp, _vp]),
+    "lidar_frame_flow_match": (_i32, [_vp, _i32, _vp, _i32, C.c_float, C.c_float, _vp, _vp, _vp]),
+    "lidar_frame_flow_field": (_i32, [_vp, _i32, _vp, _vp, _vp, _i32, _dbl, _vp, _vp, _vp]),
     "lidar_frame_workspace_bytes": (_sz, [C.POINTER(FrameCaps)]),
     "lidar_frame_workspace_init": (_i32, [_vp, _sz, C.POINTER(FrameCaps), _vp]),
     "lidar_frame_voxel_density": (_i32, [_vp, _i64, _dbl, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double),

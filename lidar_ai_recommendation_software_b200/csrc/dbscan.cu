@@ -1,0 +1,433 @@
+// K7 — DBSCAN with scikit-learn-identical labels, and K8 — per-cluster centroids.
+//
+// Replaces sklearn.cluster.DBSCAN(eps, min_samples=5).fit(X).labels_ at
+//   utils/data_processing.py:197  (variant A: on StandardScaler output, eps ~ 0.5 sigma)
+//   app_simplified.py:107         (variant B: raw metres, eps = 0.3)
+// and the per-cluster mean of extract_people_positions (utils/data_processing.py:251-280,
+// app_simplified.py:249-255, 328-331).
+//
+// sklearn's labels are a pure function of the data, restated here as:
+//   neighbour  <=>  rdist = ((dx*dx) + dy*dy) + dz*dz  <=  eps*eps   (fp64, inclusive, self counts)
+//   core       <=>  #neighbours >= min_samples
+//   clusters    =   connected components of the core-core neighbour graph, numbered by the rank of
+//                   their smallest core index (dbscan_inner seeds clusters in ascending index order)
+//   border      =   non-core point with a core neighbour: smallest cluster id among them
+//   noise       =   -1
+// GPU plan: uniform cell list with cell edge >= eps (counting sort by cell), thread per point walking
+// the 3x3 (x,y) columns whose z-runs are contiguous in the sorted order; lock-free union-find that
+// always links the larger root under the smaller one, so every component's root IS its smallest
+// core index; an exclusive scan over "is root" in original index order numbers the clusters.
+// Every output is order independent, hence deterministic although the cell sort uses atomics.
+//
+// Knife-edge certificate (variant A only): X went through a scaler whose mean/scale come from a
+// parallel reduction, so rdist can differ from sklearn's in the last bits.  Pairs with
+// |rdist - eps^2| <= tol that could change a decision are counted in *d_guard; tests assert 0.
+#include "device_scan.cuh"
+
+namespace lidar {
+
+constexpr int kDbThreads = 128;
+
+struct CellGrid {
+    double min[3];
+    double cell;
+    int g[3];
+    int ncell;
+};
+
+__device__ __forceinline__ int cell_coord(double p, double mn, double cell, int g) {
+    int c = (int)floor(__ddiv_rn(__dsub_rn(p, mn), cell));
+    return c < 0 ? 0 : (c >= g ? g - 1 : c);
+}
+__device__ __forceinline__ int cell_id(const CellGrid& G, int cx, int cy, int cz) {
+    return (cx * G.g[1] + cy) * G.g[2] + cz;
+}
+
+__global__ void db_cell_assign(const double* __restrict__ pts, int m, CellGrid G, int* __restrict__ cell,
+                               int* __restrict__ slot, unsigned* __restrict__ cell_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int cx = cell_coord(pts[3 * i], G.min[0], G.cell, G.g[0]);
+    const int cy = cell_coord(pts[3 * i + 1], G.min[1], G.cell, G.g[1]);
+    const int cz = cell_coord(pts[3 * i + 2], G.min[2], G.cell, G.g[2]);
+    const int c = cell_id(G, cx, cy, cz);
+    cell[i] = c;
+    slot[i] = (int)atomicAdd(&cell_count[c], 1u);
+}
+
+__global__ void db_scatter(const double* __restrict__ pts, int m, const int* __restrict__ cell,
+                           const int* __restrict__ slot, const unsigned* __restrict__ cell_start,
+                           int* __restrict__ sidx, int* __restrict__ scell, double* __restrict__ sx,
+                           double* __restrict__ sy, double* __restrict__ sz, int* __restrict__ parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int c = cell[i];
+    const int pos = (int)cell_start[c] + slot[i];
+    sidx[pos] = i;
+    scell[pos] = c;
+    sx[pos] = pts[3 * i];
+    sy[pos] = pts[3 * i + 1];
+    sz[pos] = pts[3 * i + 2];
+    parent[i] = i;
+}
+
+// Walk every candidate j of sorted point `pos` (the 3x3x3 cell neighbourhood); f(j, rdist) returns
+// false to stop early.
+template <class F>
+__device__ __forceinline__ void for_each_candidate(const CellGrid& G, const unsigned* __restrict__ cell_start,
+                                                   const double* __restrict__ sx, const double* __restrict__ sy,
+                                                   const double* __restrict__ sz, int c, double x, double y,
+                                                   double z, F&& f) {
+    const int cz = c % G.g[2];
+    const int t = c / G.g[2];
+    const int cy = t % G.g[1];
+    const int cx = t / G.g[1];
+    const int z0 = cz > 0 ? cz - 1 : 0;
+    const int z1 = cz < G.g[2] - 1 ? cz + 1 : G.g[2] - 1;
+    for (int ax = (cx > 0 ? cx - 1 : 0); ax <= (cx < G.g[0] - 1 ? cx + 1 : G.g[0] - 1); ++ax)
+        for (int ay = (cy > 0 ? cy - 1 : 0); ay <= (cy < G.g[1] - 1 ? cy + 1 : G.g[1] - 1); ++ay) {
+            const int j0 = (int)cell_start[cell_id(G, ax, ay, z0)];
+            const int j1 = (int)cell_start[cell_id(G, ax, ay, z1) + 1];
+            for (int j = j0; j < j1; ++j) {
+                const double dx = __dsub_rn(x, sx[j]), dy = __dsub_rn(y, sy[j]), dz = __dsub_rn(z, sz[j]);
+                double r = __dmul_rn(dx, dx);
+                r = __dadd_rn(r, __dmul_rn(dy, dy));
+                r = __dadd_rn(r, __dmul_rn(dz, dz));
+                if (!f(j, r)) return;
+            }
+        }
+}
+
+__global__ void __launch_bounds__(kDbThreads)
+db_core(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* __restrict__ scell,
+        const int* __restrict__ sidx, const double* __restrict__ sx, const double* __restrict__ sy,
+        const double* __restrict__ sz, double eps2, double tol, int min_samples, uint8_t* __restrict__ core_s,
+        uint8_t* __restrict__ core_o, unsigned long long* __restrict__ guard) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= m) return;
+    int cnt = 0, band_in = 0, band_out = 0;
+    for_each_candidate(G, cell_start, sx, sy, sz, scell[pos], sx[pos], sy[pos], sz[pos], [&](int, double r) {
+        const bool in = r <= eps2;
+        cnt += in;
+        if (fabs(r - eps2) <= tol && tol > 0.0) { band_in += in; band_out += !in; }
+        return (cnt - band_in) < min_samples;  // certain core: stop
+    });
+    const bool core = cnt >= min_samples;
+    if (((cnt - band_in) >= min_samples) != ((cnt + band_out) >= min_samples)) atomicAdd(guard, 1ull);
+    core_s[pos] = core;
+    core_o[sidx[pos]] = core;
+}
+
+__device__ __forceinline__ int uf_find(int* parent, int x) {
+    int p = ((volatile int*)parent)[x];
+    while (p != x) {
+        const int gp = ((volatile int*)parent)[p];
+        if (gp != p) parent[x] = gp;  // path halving (benign race: only ever moves toward the root)
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }  // a > b: hang a under the smaller root b
+        const int old = atomicMin(&parent[a], b);
+        if (old == a) return;   // a was still a root: linked
+        a = old;                // somebody re-parented a meanwhile: unite that root with b
+    }
+}
+
+__global__ void __launch_bounds__(kDbThreads)
+db_union(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* __restrict__ scell,
+         const int* __restrict__ sidx, const double* __restrict__ sx, const double* __restrict__ sy,
+         const double* __restrict__ sz, double eps2, double tol, const uint8_t* __restrict__ core_s,
+         int* __restrict__ parent, unsigned long long* __restrict__ guard) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= m || !core_s[pos]) return;
+    const int oi = sidx[pos];
+    unsigned band = 0;
+    for_each_candidate(G, cell_start, sx, sy, sz, scell[pos], sx[pos], sy[pos], sz[pos], [&](int j, double r) {
+        if (core_s[j]) {
+            if (tol > 0.0 && fabs(r - eps2) <= tol) ++band;
+            if (r <= eps2) {
+                const int oj = sidx[j];
+                if (oj < oi) uf_union(parent, oi, oj);
+            }
+        }
+        return true;
+    });
+    if (band) atomicAdd(guard, (unsigned long long)band);
+}
+
+__global__ void db_roots(int m, const uint8_t* __restrict__ core_o, int* __restrict__ parent,
+                         unsigned* __restrict__ is_root) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    unsigned r = 0;
+    if (core_o[i]) {
+        const int root = uf_find(parent, i);
+        r = (root == i);
+        if (root != i) parent[i] = root;
+    }
+    is_root[i] = r;
+}
+
+__global__ void db_label_core(int m, const int* __restrict__ sidx, const uint8_t* __restrict__ core_s,
+                              int* __restrict__ parent, const unsigned* __restrict__ root_rank,
+                              int* __restrict__ label_s, int* __restrict__ labels) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= m) return;
+    int lab = -1;
+    if (core_s[pos]) {
+        const int oi = sidx[pos];
+        const int root = uf_find(parent, oi);
+        lab = (int)root_rank[root];
+        labels[oi] = lab;
+    }
+    label_s[pos] = lab;
+}
+
+__global__ void __launch_bounds__(kDbThreads)
+db_border(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* __restrict__ scell,
+          const int* __restrict__ sidx, const double* __restrict__ sx, const double* __restrict__ sy,
+          const double* __restrict__ sz, double eps2, double tol, const uint8_t* __restrict__ core_s,
+          const int* __restrict__ label_s, int* __restrict__ labels, unsigned long long* __restrict__ guard) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= m || core_s[pos]) return;
+    int best = 0x7fffffff;
+    unsigned band = 0;
+    for_each_candidate(G, cell_start, sx, sy, sz, scell[pos], sx[pos], sy[pos], sz[pos], [&](int j, double r) {
+        if (core_s[j]) {
+            if (tol > 0.0 && fabs(r - eps2) <= tol) ++band;
+            if (r <= eps2) { const int l = label_s[j]; best = l < best ? l : best; }
+        }
+        return true;
+    });
+    labels[sidx[pos]] = best == 0x7fffffff ? -1 : best;
+    if (band) atomicAdd(guard, (unsigned long long)band);
+}
+
+struct DbLayout {
+    size_t off_cell, off_slot, off_count, off_start, off_sidx, off_scell, off_sx, off_sy, off_sz, off_parent,
+        off_core_s, off_core_o, off_isroot, off_rank, off_label_s, off_scan, total;
+};
+static DbLayout db_layout(int64_t m, int64_t ncell) {
+    DbLayout L;
+    size_t o = 0;
+    auto take = [&](size_t b) { size_t a = ws_align(o); o = a + b; return a; };
+    L.off_cell = take(4 * m); L.off_slot = take(4 * m);
+    L.off_count = take(4 * (ncell + 1)); L.off_start = take(4 * (ncell + 2));
+    L.off_sidx = take(4 * m); L.off_scell = take(4 * m);
+    L.off_sx = take(8 * m); L.off_sy = take(8 * m); L.off_sz = take(8 * m);
+    L.off_parent = take(4 * m); L.off_core_s = take(m); L.off_core_o = take(m);
+    L.off_isroot = take(4 * (m + 1)); L.off_rank = take(4 * (m + 2)); L.off_label_s = take(4 * m);
+    const int64_t big = m > ncell ? m : ncell;
+    L.off_scan = take(scan_workspace_bytes(big + 1));
+    L.total = ws_align(o);
+    return L;
+}
+
+constexpr int64_t kDbMaxCells = 1ll << 24;
+
+static bool make_grid(const double* mn, const double* mx, double eps, CellGrid* G) {
+    double cell = eps * (1.0 + 1e-9);
+    if (!(cell > 0.0)) return false;
+    for (int iter = 0; iter < 64; ++iter) {
+        double prod = 1.0;
+        for (int c = 0; c < 3; ++c) {
+            const double ext = mx[c] - mn[c];
+            if (!(ext >= 0.0) || !(ext < 1e300)) return false;
+            const double g = floor(ext / cell) + 1.0;
+            prod *= g;
+        }
+        if (prod <= (double)kDbMaxCells) break;
+        cell *= cbrt(prod / (double)kDbMaxCells) * 1.01;
+    }
+    G->cell = cell;
+    int64_t n = 1;
+    for (int c = 0; c < 3; ++c) {
+        G->min[c] = mn[c];
+        const double g = floor((mx[c] - mn[c]) / cell) + 1.0;
+        if (g > 2.0e9) return false;
+        G->g[c] = (int)g;
+        n *= G->g[c];
+    }
+    if (n > kDbMaxCells * 2) return false;
+    G->ncell = (int)n;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8 cluster centroids: exact two-limb integer sums, warp-aggregated by label
+//   value = hi * 2^-20 + lo * 2^-60   (hi = rint(v * 2^20), lo = rint((v - hi*2^-20) * 2^60))
+// Integer adds commute, so the result does not depend on the order in which atomics land.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+centroid_accumulate(const double* __restrict__ pts, const long long* __restrict__ labels64,
+                    const int* __restrict__ labels32, int64_t n, int n_clusters,
+                    long long* __restrict__ acc /*[C][6]*/, unsigned* __restrict__ cnt) {
+    const int64_t n_round = ((n + 31) / 32) * 32;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += step) {
+        int lab = -1;
+        long long v[6] = {0, 0, 0, 0, 0, 0};
+        if (i < n) {
+            lab = labels64 ? (int)labels64[i] : labels32[i];
+            if (lab >= n_clusters) lab = -1;
+            if (lab >= 0) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const double p = pts[3 * i + c];
+                    const double hi = nearbyint(__dmul_rn(p, 1048576.0));
+                    const double lo = __dsub_rn(p, __dmul_rn(hi, 1.0 / 1048576.0));
+                    v[2 * c] = __double2ll_rn(hi);
+                    v[2 * c + 1] = __double2ll_rn(__dmul_rn(lo, 1152921504606846976.0));
+                }
+            }
+        }
+        const unsigned act = __activemask();
+        const unsigned peers = __match_any_sync(act, lab);
+        const int leader = __ffs(peers) - 1;
+        // reduce inside each peer group by walking its members
+        unsigned rem = peers;
+        long long sum[6] = {0, 0, 0, 0, 0, 0};
+        while (rem) {
+            const int src = __ffs(rem) - 1;
+            rem &= rem - 1;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) sum[c] += __shfl_sync(peers, v[c], src);
+        }
+        if (lab >= 0 && (int)lane_id() == leader) {
+            unsigned long long* A = reinterpret_cast<unsigned long long*>(acc + (size_t)lab * 6);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) atomicAdd(A + c, (unsigned long long)sum[c]);
+            atomicAdd(cnt + lab, (unsigned)__popc(peers));
+        }
+    }
+}
+
+__global__ void centroid_finalize(int n_clusters, const long long* __restrict__ acc, const unsigned* __restrict__ cnt,
+                                  double* __restrict__ out /*[C][3]*/, long long* __restrict__ counts) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_clusters) return;
+    const double k = (double)cnt[c];
+    for (int a = 0; a < 3; ++a) {
+        const double hi = __dmul_rn((double)acc[(size_t)c * 6 + 2 * a], 1.0 / 1048576.0);
+        const double lo = __dmul_rn((double)acc[(size_t)c * 6 + 2 * a + 1], 1.0 / 1152921504606846976.0);
+        out[(size_t)c * 3 + a] = cnt[c] ? __ddiv_rn(__dadd_rn(hi, lo), k) : 0.0;
+    }
+    if (counts) counts[c] = (long long)cnt[c];
+}
+
+}  // namespace lidar
+
+using namespace lidar;
+
+extern "C" {
+
+size_t lidar_dbscan_workspace_bytes(int64_t m, double eps, const double* h_min3, const double* h_max3) {
+    if (m < 0 || !h_min3 || !h_max3) return 0;
+    CellGrid G;
+    if (!make_grid(h_min3, h_max3, eps, &G)) return 0;
+    return db_layout(m, G.ncell).total;
+}
+
+int lidar_dbscan(const double* d_points, int64_t m, double eps, int min_samples, double tol,
+                 const double* h_min3, const double* h_max3, int32_t* d_labels, int32_t* d_n_clusters,
+                 uint64_t* d_guard, void* d_ws, size_t ws_bytes, void* stream) {
+    LIDAR_REQUIRE(m >= 0 && m < (1ll << 31) - 64, LIDAR_ERR_INVALID, "lidar_dbscan: m out of range");
+    LIDAR_REQUIRE(eps > 0.0 && min_samples >= 1 && tol >= 0.0, LIDAR_ERR_INVALID, "lidar_dbscan: bad eps/min_samples/tol");
+    LIDAR_REQUIRE(d_n_clusters && d_guard, LIDAR_ERR_INVALID, "lidar_dbscan: NULL output");
+    cudaStream_t st = as_stream(stream);
+    LIDAR_CUDA_TRY(cudaMemsetAsync(d_n_clusters, 0, sizeof(int32_t), st));
+    LIDAR_CUDA_TRY(cudaMemsetAsync(d_guard, 0, sizeof(uint64_t), st));
+    if (m == 0) return LIDAR_OK;
+    LIDAR_REQUIRE(d_points && d_labels && h_min3 && h_max3, LIDAR_ERR_INVALID, "lidar_dbscan: NULL argument");
+    CellGrid G;
+    LIDAR_REQUIRE(make_grid(h_min3, h_max3, eps, &G), LIDAR_ERR_INVALID, "lidar_dbscan: cannot build a cell grid for this bbox");
+    const DbLayout L = db_layout(m, G.ncell);
+    LIDAR_REQUIRE(d_ws && ws_bytes >= L.total, LIDAR_ERR_WORKSPACE, "lidar_dbscan: workspace too small (%zu < %zu)",
+                  ws_bytes, L.total);
+    char* ws = static_cast<char*>(d_ws);
+    int* cell = reinterpret_cast<int*>(ws + L.off_cell);
+    int* slot = reinterpret_cast<int*>(ws + L.off_slot);
+    unsigned* cell_count = reinterpret_cast<unsigned*>(ws + L.off_count);
+    unsigned* cell_start = reinterpret_cast<unsigned*>(ws + L.off_start);
+    int* sidx = reinterpret_cast<int*>(ws + L.off_sidx);
+    int* scell = reinterpret_cast<int*>(ws + L.off_scell);
+    double* sx = reinterpret_cast<double*>(ws + L.off_sx);
+    double* sy = reinterpret_cast<double*>(ws + L.off_sy);
+    double* sz = reinterpret_cast<double*>(ws + L.off_sz);
+    int* parent = reinterpret_cast<int*>(ws + L.off_parent);
+    uint8_t* core_s = reinterpret_cast<uint8_t*>(ws + L.off_core_s);
+    uint8_t* core_o = reinterpret_cast<uint8_t*>(ws + L.off_core_o);
+    unsigned* is_root = reinterpret_cast<unsigned*>(ws + L.off_isroot);
+    unsigned* root_rank = reinterpret_cast<unsigned*>(ws + L.off_rank);
+    int* label_s = reinterpret_cast<int*>(ws + L.off_label_s);
+    void* scan_ws = ws + L.off_scan;
+    unsigned long long* guard = reinterpret_cast<unsigned long long*>(d_guard);
+
+    const int mi = (int)m;
+    const int g256 = (mi + 255) / 256;
+    const int gdb = (mi + kDbThreads - 1) / kDbThreads;
+    const double eps2 = eps * eps;
+    LIDAR_CUDA_TRY(cudaMemsetAsync(cell_count, 0, sizeof(unsigned) * (G.ncell + 1), st));
+    db_cell_assign<<<g256, 256, 0, st>>>(d_points, mi, G, cell, slot, cell_count);
+    LIDAR_CHECK_LAUNCH();
+    LIDAR_CUDA_TRY(launch_exclusive_scan(cell_count, cell_start, (int64_t)G.ncell, nullptr, scan_ws, st));
+    db_scatter<<<g256, 256, 0, st>>>(d_points, mi, cell, slot, cell_start, sidx, scell, sx, sy, sz, parent);
+    LIDAR_CHECK_LAUNCH();
+    db_core<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, min_samples, core_s,
+                                         core_o, guard);
+    LIDAR_CHECK_LAUNCH();
+    db_union<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard);
+    LIDAR_CHECK_LAUNCH();
+    db_roots<<<g256, 256, 0, st>>>(mi, core_o, parent, is_root);
+    LIDAR_CHECK_LAUNCH();
+    LIDAR_CUDA_TRY(launch_exclusive_scan(is_root, root_rank, (int64_t)mi, nullptr, scan_ws, st));
+    LIDAR_CUDA_TRY(cudaMemcpyAsync(d_n_clusters, root_rank + mi, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    db_label_core<<<g256, 256, 0, st>>>(mi, sidx, core_s, parent, root_rank, label_s, d_labels);
+    LIDAR_CHECK_LAUNCH();
+    db_border<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, label_s,
+                                           d_labels, guard);
+    LIDAR_CHECK_LAUNCH();
+    return LIDAR_OK;
+}
+
+size_t lidar_centroid_workspace_bytes(int n_clusters) {
+    if (n_clusters < 0) return 0;
+    return ws_align(sizeof(long long) * 6 * (size_t)n_clusters) + ws_align(sizeof(unsigned) * (size_t)n_clusters);
+}
+
+int lidar_cluster_centroids(const double* d_points, const void* d_labels, int labels_are_i64, int64_t n,
+                            int n_clusters, double* d_centroids3, int64_t* d_counts, void* d_ws, size_t ws_bytes,
+                            void* stream) {
+    LIDAR_REQUIRE(n >= 0 && n_clusters >= 0, LIDAR_ERR_INVALID, "lidar_cluster_centroids: bad sizes");
+    if (n_clusters == 0) return LIDAR_OK;
+    LIDAR_REQUIRE(d_centroids3 && (n == 0 || (d_points && d_labels)), LIDAR_ERR_INVALID,
+                  "lidar_cluster_centroids: NULL argument");
+    const size_t need = lidar_centroid_workspace_bytes(n_clusters);
+    LIDAR_REQUIRE(d_ws && ws_bytes >= need, LIDAR_ERR_WORKSPACE, "lidar_cluster_centroids: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    LIDAR_CUDA_TRY(cudaMemsetAsync(d_ws, 0, need, st));
+    long long* acc = static_cast<long long*>(d_ws);
+    unsigned* cnt = reinterpret_cast<unsigned*>(static_cast<char*>(d_ws) + ws_align(sizeof(long long) * 6 * (size_t)n_clusters));
+    if (n > 0) {
+        int64_t want = (n + 255) / 256;
+        const int64_t cap = (int64_t)sm_count() * 8;
+        const int grid = (int)(want < cap ? want : cap);
+        centroid_accumulate<<<grid, 256, 0, st>>>(d_points, labels_are_i64 ? static_cast<const long long*>(d_labels) : nullptr,
+                                                  labels_are_i64 ? nullptr : static_cast<const int*>(d_labels), n,
+                                                  n_clusters, acc, cnt);
+        LIDAR_CHECK_LAUNCH();
+    }
+    centroid_finalize<<<(n_clusters + 127) / 128, 128, 0, st>>>(n_clusters, acc, cnt, d_centroids3,
+                                                                reinterpret_cast<long long*>(d_counts));
+    LIDAR_CHECK_LAUNCH();
+    return LIDAR_OK;
+}
+
+}  // extern "C"

@@ -297,6 +297,18 @@ __global__ void fill_i64_kernel(long long* __restrict__ p, int64_t n, long long 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) p[i] = v;
 }
 
+// out[i] = in[idx[i]] for rows of `row_words` 4-byte words (downsample_point_cloud's fancy index)
+__global__ void gather_rows_kernel(const uint32_t* __restrict__ in, int row_words, const long long* __restrict__ idx,
+                                   int64_t k, uint32_t* __restrict__ out) {
+    const int64_t total = k * row_words;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += step) {
+        const int64_t r = t / row_words;
+        const int w = (int)(t - r * row_words);
+        out[t] = in[idx[r] * row_words + w];
+    }
+}
+
 static int ew_grid(int64_t n) {
     int64_t want = (n + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 8;
@@ -418,6 +430,19 @@ int lidar_standardize(const double* d_points, int64_t n, const double* h_mean3, 
     LIDAR_REQUIRE(d_points && d_out, LIDAR_ERR_INVALID, "lidar_standardize: NULL points");
     standardize_kernel<<<ew_grid(n * 3), 256, 0, as_stream(stream)>>>(d_points, n * 3, h_mean3[0], h_mean3[1],
         h_mean3[2], h_scale3[0], h_scale3[1], h_scale3[2], d_out);
+    LIDAR_CHECK_LAUNCH();
+    return LIDAR_OK;
+}
+
+int lidar_gather_rows(const void* d_src, int64_t n_rows, int row_bytes, const int64_t* d_index, int64_t k,
+                      void* d_dst, void* stream) {
+    LIDAR_REQUIRE(k >= 0 && n_rows >= 0 && row_bytes > 0 && row_bytes % 4 == 0, LIDAR_ERR_INVALID,
+                  "lidar_gather_rows: row_bytes must be a positive multiple of 4");
+    if (k == 0) return LIDAR_OK;
+    LIDAR_REQUIRE(d_src && d_index && d_dst, LIDAR_ERR_INVALID, "lidar_gather_rows: NULL argument");
+    gather_rows_kernel<<<ew_grid(k * (row_bytes / 4)), 256, 0, as_stream(stream)>>>(
+        static_cast<const uint32_t*>(d_src), row_bytes / 4, reinterpret_cast<const long long*>(d_index), k,
+        static_cast<uint32_t*>(d_dst));
     LIDAR_CHECK_LAUNCH();
     return LIDAR_OK;
 }

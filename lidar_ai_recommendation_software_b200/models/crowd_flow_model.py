@@ -1,0 +1,67 @@
+"""Drop-in for the reference's models/crowd_flow_model.py (CrowdFlowModel), CUDA-backed.
+
+`analyze(processed_data)` returns the same keys as models/crowd_flow_model.py:28-86.  The reference's
+flow field is a closed-form simulation (its `prev_positions` slot is dead code, :16-17); that behaviour
+is reproduced, and the dead slot is filled in by `analyze_sequence_frame`, which uses the real
+frame-to-frame displacement (NEW op) once a previous frame exists.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import flow as _flow
+from ..utils.data_processing import extract_people_positions
+
+
+class CrowdFlowModel:
+    def __init__(self):
+        self.prev_positions = None
+        self.flow_vectors = None
+        self.simulation_params = {
+            "flow_field_complexity": 2,
+            "bottleneck_count": 3,
+            "flow_speed_range": (0.2, 1.5),
+            "random_seed": 42,
+        }
+
+    @staticmethod
+    def _empty():
+        return {
+            "flow_vectors": {"positions": np.zeros((0, 2)), "vectors": np.zeros((0, 2)), "magnitudes": np.zeros(0)},
+            "avg_speed": 0.0, "dominant_direction": "N/A", "bottlenecks": [],
+        }
+
+    def analyze(self, processed_data):
+        """models/crowd_flow_model.py:28-86."""
+        people_positions = extract_people_positions(processed_data)
+        if len(people_positions) == 0:
+            return self._empty()
+        dims = processed_data["dimensions"]
+        p = self.simulation_params
+        flow, handles, avg_speed, direction = _flow.simulated_flow(
+            dims["x_range"], dims["y_range"], variant="A", complexity=p["flow_field_complexity"],
+            count=p["bottleneck_count"], speed_range=p["flow_speed_range"], seed=p["random_seed"])
+        return {"flow_vectors": flow, "avg_speed": avg_speed, "dominant_direction": direction,
+                "bottlenecks": _flow.bottlenecks_a(flow, handles)}
+
+    def analyze_sequence_frame(self, processed_data, dt=0.1, gate=1.5):
+        """Frame of a sequence: the first call behaves like `analyze`; later calls replace the simulated
+        field by the measured displacement field of the people matched against the previous frame."""
+        people_positions = extract_people_positions(processed_data)
+        if len(people_positions) == 0:
+            self.prev_positions = None
+            return self._empty()
+        if self.prev_positions is None or len(self.prev_positions) == 0:
+            self.prev_positions = people_positions
+            return self.analyze(processed_data)
+        dims = processed_data["dimensions"]
+        flow, match, _ = _flow.frame_flow(self.prev_positions, people_positions, dt, dims["x_range"],
+                                          dims["y_range"], gate=gate)
+        self.prev_positions = people_positions
+        self.flow_vectors = flow
+        vectors, magnitudes = flow["vectors"], flow["magnitudes"]
+        avg_vector = np.mean(vectors, axis=0)
+        angle = np.arctan2(avg_vector[1], avg_vector[0]) * 180 / np.pi
+        direction = _flow._DIRECTIONS[int((angle + 22.5) % 360 / 45)]
+        return {"flow_vectors": flow, "avg_speed": np.mean(magnitudes), "dominant_direction": direction,
+                "bottlenecks": [], "matches": match}

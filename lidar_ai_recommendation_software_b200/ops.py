@@ -415,3 +415,220 @@ def voxel_downsample(points: torch.Tensor, voxel_size: float, origin=None, max_k
     pipe = FramePipeline(max(n, 1), voxel_size, 0.0, max_key_space=max_key_space, device=points.device)
     pipe.enqueue(points, origin=origin)
     return pipe.result()
+
+
+# ------------------------------------------------------------------------------------------------
+# K2-K4 preprocess stages, K7 DBSCAN, K8 centroids  (all (n,3) float64 CUDA tensors)
+# ------------------------------------------------------------------------------------------------
+def _d3(v):
+    return (C.c_double * 3)(*[float(x) for x in v])
+
+
+def _check_f64x3(points: torch.Tensor):
+    if point_format(points) != FMT_F64X3:
+        raise ValueError("expected an (n,3) float64 CUDA tensor")
+
+
+def sigma_filter(points: torch.Tensor, mean, thr, tol, zmin: float, zden: float, want_colors: bool = True,
+                 want_mask: bool = False):
+    """3-sigma inlier filter (utils/data_processing.py:151-157) fused with the height colours (:143-147).
+
+    Returns (inliers (n',3), colors (n',3) | None, mask uint8 | None, guard:int)."""
+    _check_f64x3(points)
+    dev, n = points.device, points.shape[0]
+    out = torch.empty_like(points)
+    col = torch.empty_like(points) if want_colors else None
+    mask = torch.empty(n, dtype=torch.uint8, device=dev) if want_mask else None
+    cnt = torch.zeros(2, dtype=torch.int64, device=dev)   # [count, guard]
+    ws = _scratch.get("pre", lib.lidar_preprocess_workspace_bytes(n), dev)
+    check(lib.lidar_sigma_filter(_ptr(points), n, _d3(mean), _d3(thr), _d3(tol), float(zmin), float(zden),
+                                 _ptr(mask), _ptr(out), _ptr(col), _ptr(cnt), _ptr(cnt[1:]), _ptr(ws), ws.numel(),
+                                 _stream_ptr()))
+    kept, guard = (int(v) for v in cnt.tolist())
+    return out[:kept], (col[:kept] if col is not None else None), mask, guard
+
+
+def select_kth(column: torch.Tensor, k: int):
+    """(x_(k), x_(k+1)) of a 1-D float64 CUDA view (any stride) — exact radix select."""
+    if column.dtype != torch.float64 or column.dim() != 1 or not column.is_cuda:
+        raise ValueError("select_kth expects a 1-D float64 CUDA tensor")
+    n = column.shape[0]
+    dev = column.device
+    out = torch.empty(2, dtype=torch.float64, device=dev)
+    ws = _scratch.get("pre", lib.lidar_preprocess_workspace_bytes(n), dev)
+    stride = column.stride(0) if n > 1 else 1
+    check(lib.lidar_select_kth(_ptr(column), stride, n, int(k), _ptr(out), _ptr(ws), ws.numel(), _stream_ptr()))
+    a, b = out.tolist()
+    return a, b
+
+
+def ground_split(points: torch.Tensor, z_threshold: float, center, tol: float = 0.0):
+    """z <= thr split (utils/data_processing.py:165-188).
+
+    Returns (non_ground (m,3), non_ground_index int32 (m,), plane_sums (10,) numpy, guard:int)."""
+    _check_f64x3(points)
+    dev, n = points.device, points.shape[0]
+    out = torch.empty_like(points)
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    plane = torch.zeros(10, dtype=torch.float64, device=dev)
+    ws = _scratch.get("pre", lib.lidar_preprocess_workspace_bytes(n), dev)
+    check(lib.lidar_ground_split(_ptr(points), n, float(z_threshold), _d3(center), float(tol), _ptr(out), _ptr(idx),
+                                 _ptr(cnt), _ptr(plane), _ptr(cnt[1:]), _ptr(ws), ws.numel(), _stream_ptr()))
+    m, guard = (int(v) for v in cnt.tolist())
+    return out[:m], idx[:m], plane.cpu().numpy(), guard
+
+
+def standardize(points: torch.Tensor, mean, scale) -> torch.Tensor:
+    """(x - mean) / scale — StandardScaler.transform (utils/data_processing.py:190-191)."""
+    _check_f64x3(points)
+    out = torch.empty_like(points)
+    check(lib.lidar_standardize(_ptr(points), points.shape[0], _d3(mean), _d3(scale), _ptr(out), _stream_ptr()))
+    return out
+
+
+def scatter_labels(labels: torch.Tensor, index: torch.Tensor, n: int) -> torch.Tensor:
+    """int64 (n,) = -1 everywhere, labels at `index` (utils/data_processing.py:203-204)."""
+    dev = labels.device
+    full = torch.empty(n, dtype=torch.int64, device=dev)
+    check(lib.lidar_scatter_labels(_ptr(labels), _ptr(index), labels.shape[0], _ptr(full), n, _stream_ptr()))
+    return full
+
+
+def dbscan(points: torch.Tensor, eps: float, min_samples: int = 5, tol: float = 0.0, bounds=None):
+    """sklearn-identical DBSCAN labels (int32 (m,)), number of clusters, knife-edge guard count."""
+    _check_f64x3(points)
+    dev, m = points.device, points.shape[0]
+    labels = torch.empty(m, dtype=torch.int32, device=dev)
+    if m == 0:
+        return labels, 0, 0
+    if bounds is None:
+        bb = bbox(points).cpu().numpy()
+        bounds = (bb[:3], bb[4:7])
+    lo, hi = _d3(bounds[0]), _d3(bounds[1])
+    nb = lib.lidar_dbscan_workspace_bytes(m, float(eps), lo, hi)
+    if nb == 0:
+        raise _capi.LidarError(-1, "lidar_dbscan: cannot build a cell grid for this bbox / eps")
+    ws = _scratch.get("dbscan", nb, dev)
+    info = torch.zeros(2, dtype=torch.int64, device=dev)   # [n_clusters (int32 in low word), guard]
+    check(lib.lidar_dbscan(_ptr(points), m, float(eps), int(min_samples), float(tol), lo, hi, _ptr(labels),
+                           _ptr(info), _ptr(info[1:]), _ptr(ws), ws.numel(), _stream_ptr()))
+    nc, guard = (int(v) for v in info.tolist())
+    return labels, nc & 0xffffffff, guard
+
+
+def cluster_centroids(points: torch.Tensor, labels: torch.Tensor, n_clusters: int):
+    """Per-cluster mean of the member points, exact integer accumulation (extract_people_positions,
+    utils/data_processing.py:251-280).  Returns ((C,3) float64, (C,) int64 counts)."""
+    _check_f64x3(points)
+    if labels.dtype not in (torch.int32, torch.int64) or not labels.is_contiguous():
+        raise ValueError("labels must be contiguous int32 or int64")
+    dev = points.device
+    cent = torch.zeros((n_clusters, 3), dtype=torch.float64, device=dev)
+    counts = torch.zeros(n_clusters, dtype=torch.int64, device=dev)
+    if n_clusters == 0:
+        return cent, counts
+    ws = _scratch.get("centroid", lib.lidar_centroid_workspace_bytes(n_clusters), dev)
+    check(lib.lidar_cluster_centroids(_ptr(points), _ptr(labels), int(labels.dtype == torch.int64), points.shape[0],
+                                      n_clusters, _ptr(cent), _ptr(counts), _ptr(ws), ws.numel(), _stream_ptr()))
+    return cent, counts
+
+
+def gather_rows(points, indices):
+    """points[indices] on the device (downsample_point_cloud, utils/data_processing.py:247-249).
+    numpy in -> numpy out (same dtype); CUDA tensor in -> CUDA tensor out."""
+    dev = require_cuda()
+    is_np = not isinstance(points, torch.Tensor)
+    src = torch.from_numpy(np.ascontiguousarray(points)).to(dev) if is_np else points.contiguous()
+    idx = torch.as_tensor(np.asarray(indices, dtype=np.int64)).to(dev) if not isinstance(indices, torch.Tensor) \
+        else indices.to(device=dev, dtype=torch.int64).contiguous()
+    n = src.shape[0]
+    if idx.numel() and (int(idx.min()) < -n or int(idx.max()) >= n):
+        raise IndexError("index out of bounds")
+    idx = torch.where(idx < 0, idx + n, idx) if idx.numel() else idx
+    row_bytes = src[0].numel() * src.element_size() if n else src.element_size()
+    if row_bytes % 4:
+        raise ValueError("row size must be a multiple of 4 bytes")
+    out = torch.empty((idx.numel(),) + tuple(src.shape[1:]), dtype=src.dtype, device=dev)
+    check(lib.lidar_gather_rows(_ptr(src), n, row_bytes, _ptr(idx), idx.numel(), _ptr(out), _stream_ptr()))
+    return out.cpu().numpy() if is_np else out
+
+
+# ------------------------------------------------------------------------------------------------
+# K9 / K10 flow
+# ------------------------------------------------------------------------------------------------
+def _f64_dev(a, dev) -> torch.Tensor:
+    if isinstance(a, torch.Tensor):
+        return a.to(device=dev, dtype=torch.float64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+
+
+def flow_field(x_grid, y_grid, exit_xy, freq: float, amp: float, discs, speed_span: float, clip=None):
+    """Lattice flow field (models/crowd_flow_model.py:88-184).  Returns device tensors
+    (positions (G,2), vectors (G,2), magnitudes (G,), sums (3,) = [sum|v|, sum vx, sum vy])."""
+    dev = require_cuda()
+    xg, yg = _f64_dev(x_grid, dev), _f64_dev(y_grid, dev)
+    nx, ny = xg.numel(), yg.numel()
+    g = nx * ny
+    pos = torch.empty((g, 2), dtype=torch.float64, device=dev)
+    vec = torch.empty((g, 2), dtype=torch.float64, device=dev)
+    mag = torch.empty(g, dtype=torch.float64, device=dev)
+    sums = torch.zeros(4, dtype=torch.float64, device=dev)
+    flat = [float(v) for d in discs for v in d]
+    darr = (C.c_double * max(len(flat), 1))(*flat) if flat else None
+    lo, hi = (clip if clip is not None else (0.0, 0.0))
+    check(lib.lidar_flow_field(_ptr(xg), nx, _ptr(yg), ny, float(exit_xy[0]), float(exit_xy[1]), float(freq),
+                               float(amp), darr, len(discs), float(speed_span), int(clip is not None), float(lo),
+                               float(hi), _ptr(pos), _ptr(vec), _ptr(mag), _ptr(sums), _stream_ptr()))
+    return pos, vec, mag, sums[:3], (nx, ny)
+
+
+def flow_bottleneck_severity(nxy, pos, vec, mag) -> torch.Tensor:
+    sev = torch.empty_like(mag)
+    check(lib.lidar_flow_bottlenecks(nxy[0], nxy[1], _ptr(pos), _ptr(vec), _ptr(mag), _ptr(sev), _stream_ptr()))
+    return sev
+
+
+def flow_box_max(nxy, pos, mag, slow_below: float) -> torch.Tensor:
+    out = torch.empty_like(mag)
+    check(lib.lidar_flow_box_max(nxy[0], nxy[1], _ptr(pos), _ptr(mag), float(slow_below), _ptr(out), _stream_ptr()))
+    return out
+
+
+def radius_count(centres, qx, qy, radius: float) -> torch.Tensor:
+    """int32 (len(qy), len(qx)): #centres within `radius` (inclusive) of every (qx[i], qy[j])."""
+    dev = require_cuda()
+    c = _f64_dev(centres, dev).reshape(-1, 2)
+    x, y = _f64_dev(qx, dev), _f64_dev(qy, dev)
+    out = torch.empty((y.numel(), x.numel()), dtype=torch.int32, device=dev)
+    check(lib.lidar_radius_count(_ptr(c), c.shape[0], _ptr(x), x.numel(), _ptr(y), y.numel(), float(radius), _ptr(out),
+                                 _stream_ptr()))
+    return out
+
+
+def frame_flow_match(prev_xy, cur_xy, dt: float, gate: float = 1.5):
+    """B.3 association: (match int32 (C2,), velocity float32 (C2,2)) on the device."""
+    dev = require_cuda()
+
+    def f32(a):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=dev, dtype=torch.float32).contiguous().reshape(-1, 2)
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev).reshape(-1, 2)
+
+    p, c = f32(prev_xy), f32(cur_xy)
+    match = torch.empty(c.shape[0], dtype=torch.int32, device=dev)
+    vel = torch.zeros((c.shape[0], 2), dtype=torch.float32, device=dev)
+    check(lib.lidar_frame_flow_match(_ptr(p), p.shape[0], _ptr(c), c.shape[0], float(dt), float(gate), _ptr(match),
+                                     _ptr(vel), _stream_ptr()))
+    return match, vel, c
+
+
+def frame_flow_field(lattice, cur_f32, match, vel, radius: float = 3.0):
+    dev = require_cuda()
+    lat = _f64_dev(lattice, dev).reshape(-1, 2)
+    g = lat.shape[0]
+    vec = torch.zeros((g, 2), dtype=torch.float64, device=dev)
+    mag = torch.zeros(g, dtype=torch.float64, device=dev)
+    check(lib.lidar_frame_flow_field(_ptr(lat), g, _ptr(cur_f32), _ptr(match), _ptr(vel), cur_f32.shape[0],
+                                     float(radius), _ptr(vec), _ptr(mag), _stream_ptr()))
+    return vec, mag

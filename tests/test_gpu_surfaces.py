@@ -1,0 +1,280 @@
+"""GPU parity tests of the two drop-in call surfaces against the golden outputs of the UNMODIFIED
+reference (tests/golden/*.npz, produced by make_golden.py from /root/reference) and the CPU oracle.
+
+Surface A: utils.data_processing + models.crowd_density_model + models.crowd_flow_model
+Surface B: the functions inlined in app_simplified.py / app_with_db.py
+"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import new_ops, np_semantics as nps, ref_path
+
+pytestmark = pytest.mark.gpu
+
+CASE_NAMES = ["ref_sample_10k", "crowd_20k", "crowd_100k"]
+
+
+def sha(a) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def _hot(hs, key="density"):
+    return np.array([[h["x"], h["y"], h[key]] for h in hs], dtype=np.float64).reshape(-1, 3)
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import lidar_ai_recommendation_software_b200 as p
+    from lidar_ai_recommendation_software_b200 import apps, ops, preprocess
+    from lidar_ai_recommendation_software_b200.models.crowd_density_model import CrowdDensityModel
+    from lidar_ai_recommendation_software_b200.models.crowd_flow_model import CrowdFlowModel
+    from lidar_ai_recommendation_software_b200.utils import data_processing
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.apps, ns.ops, ns.pre, ns.dp = apps, ops, preprocess, data_processing
+    ns.CDM, ns.CFM = CrowdDensityModel, CrowdFlowModel
+    return ns
+
+
+@pytest.fixture(scope="module")
+def processed_a(pkg, case_points):
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = pkg.dp.preprocess_lidar_data(case_points(name))
+        return cache[name]
+
+    return get
+
+
+@pytest.fixture(scope="module")
+def processed_b(pkg, case_points):
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = pkg.apps.preprocess_point_cloud(case_points(name))
+        return cache[name]
+
+    return get
+
+
+# ---- surface A ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_preprocess_lidar_data_matches_reference(name, pkg, golden, processed_a):
+    g, out = golden(name), processed_a(name)
+    guards = out[pkg.pre.DEVICE_KEY].guards
+    assert guards["sigma"] == 0 and guards["dbscan"] == 0, f"knife-edge certificate failed: {guards}"
+    assert list(k for k in out if not k.startswith("_")) == ["points", "colors", "normals", "clusters",
+                                                              "ground_plane", "dimensions"]
+    assert out["points"].dtype == np.float64 and out["clusters"].dtype == np.int64
+    assert len(out["points"]) == int(g["a_n_inliers"])
+    assert sha(out["points"]) == str(g["a_points_sha"])                      # mask + compaction bit-exact
+    assert sha(out["colors"]) == str(g["a_colors_sha"])                      # colours bit-exact
+    assert np.array_equal(out["clusters"], g["a_clusters"])                  # DBSCAN labels bit-exact
+    assert np.allclose(out["ground_plane"], g["a_plane"], rtol=1e-9, atol=1e-12)
+    d = out["dimensions"]
+    dims = np.array([*d["x_range"], *d["y_range"], *d["z_range"], d["width"], d["length"], d["height"]])
+    assert np.array_equal(dims, g["a_dims"])
+    assert np.array_equal(out["normals"][:, 2], np.ones(len(out["points"]))) and not out["normals"][:, :2].any()
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_people_positions_and_grid_density(name, pkg, golden, processed_a):
+    g, pa = golden(name), processed_a(name)
+    pos = pkg.dp.extract_people_positions(pa)
+    assert pos.shape == g["a_people"].shape
+    assert np.allclose(pos, g["a_people"], rtol=1e-12, atol=0)
+    # a dict rebuilt by a caller (no device cache) goes through the upload path and agrees
+    plain = {"points": pa["points"].copy(), "clusters": pa["clusters"].copy()}
+    assert np.array_equal(pkg.dp.extract_people_positions(plain), pos)
+    d = pa["dimensions"]
+    for gs in (1.0, 0.5):
+        gx, gy, dens = pkg.dp.calculate_grid_density(pa["points"][:, :2], d["x_range"], d["y_range"], gs)
+        assert np.array_equal(np.rint(dens * gs * gs).astype(np.int32), g[f"a_grid_counts_g{gs}"])
+        assert np.array_equal(gx, g[f"a_grid_x_g{gs}"]) and np.array_equal(gy, g[f"a_grid_y_g{gs}"])
+        assert dens.dtype == np.float64
+    assert pkg.dp.calculate_grid_density(np.zeros((0, 2)), (0, 1), (0, 1)) == (None, None, None)
+    hist, ex, ey = pkg.apps.density_heatmap_counts(pa, bins=100)
+    assert np.array_equal(hist.astype(np.int32), g["heat_counts"])
+    assert np.array_equal(ex, g["heat_ex"]) and np.array_equal(ey, g["heat_ey"])
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_crowd_density_model(name, pkg, golden, processed_a):
+    g = golden(name)
+    model = pkg.CDM()
+    ra = model.analyze(processed_a(name))
+    assert list(ra) == ["total_people", "avg_density", "max_density", "density_map", "grid_coordinates",
+                        "density_values", "hotspots"]
+    assert np.array_equal([ra["total_people"], ra["avg_density"], ra["max_density"]], g["a_density_scalars"])
+    assert np.array_equal(ra["density_map"], g["a_density_map"])
+    assert np.array_equal(_hot(ra["hotspots"]), g["a_hotspots"])
+    assert [model.calculate_risk_level(v) for v in (0.5, 1.0, 2.5, 4.0)] == ["Low", "Moderate", "High", "Critical"]
+    empty = model.analyze({"points": np.zeros((5, 3)), "clusters": -np.ones(5, dtype=np.int64),
+                           "dimensions": {"x_range": (0, 1), "y_range": (0, 1)}})
+    assert empty["total_people"] == 0 and empty["density_map"].shape == (1, 1) and empty["hotspots"] == []
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_crowd_flow_model(name, pkg, golden, processed_a):
+    g = golden(name)
+    np.random.seed(123)
+    fa = pkg.CFM().analyze(processed_a(name))
+    # the reference re-seeds the GLOBAL legacy RNG with 42 and draws 6 uniforms: observable side effect
+    state_after = np.random.uniform()
+    np.random.seed(42)
+    [np.random.uniform() for _ in range(6)]
+    assert state_after == np.random.uniform()
+    assert sha(fa["flow_vectors"]["positions"]) == str(g["a_flow_positions_sha"])
+    assert np.allclose(fa["flow_vectors"]["vectors"], g["a_flow_vectors"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(fa["flow_vectors"]["magnitudes"], g["a_flow_magnitudes"], rtol=1e-9)
+    assert np.isclose(fa["avg_speed"], g["a_flow_scalars"][0], rtol=1e-9)
+    assert fa["dominant_direction"] == str(g["a_flow_direction"])
+    assert np.allclose(_hot(fa["bottlenecks"], "severity"), g["a_bottlenecks"], rtol=1e-12)
+    empty = pkg.CFM().analyze({"points": np.zeros((5, 3)), "clusters": -np.ones(5, dtype=np.int64),
+                               "dimensions": {"x_range": (0, 1), "y_range": (0, 1)}})
+    assert empty["dominant_direction"] == "N/A" and empty["flow_vectors"]["positions"].shape == (0, 2)
+
+
+# ---- surface B ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_preprocess_point_cloud_matches_reference(name, pkg, golden, processed_b):
+    g, out = golden(name), processed_b(name)
+    assert list(k for k in out if not k.startswith("_")) == ["points", "colors", "clusters", "dimensions"]
+    assert out[pkg.pre.DEVICE_KEY].guards["sigma"] == 0
+    assert len(out["points"]) == int(g["b_n_inliers"])
+    assert sha(out["colors"]) == str(g["b_colors_sha"])
+    assert np.array_equal(out["clusters"], g["b_clusters"])                  # 100s of clusters, bit-exact
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_analyze_crowd_density_b(name, pkg, golden, processed_b):
+    g = golden(name)
+    rb = pkg.apps.analyze_crowd_density(processed_b(name))
+    assert list(rb) == ["total_people", "avg_density", "max_density", "density_grid", "hotspots"]
+    assert np.allclose([rb["total_people"], rb["avg_density"], rb["max_density"]], g["b_density_scalars"], rtol=1e-12)
+    assert np.array_equal(rb["density_grid"], g["b_density_grid"])          # integer radius counts / 4
+    assert np.allclose(_hot(rb["hotspots"]), g["b_hotspots"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_analyze_crowd_flow_b(name, pkg, golden, processed_b):
+    g = golden(name)
+    fb = pkg.apps.analyze_crowd_flow(processed_b(name))
+    assert np.allclose(fb["flow_vectors"]["vectors"], g["b_flow_vectors"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(fb["flow_vectors"]["magnitudes"], g["b_flow_magnitudes"], rtol=1e-9)
+    assert np.isclose(fb["avg_speed"], g["b_flow_scalars"][0], rtol=1e-9)
+    assert fb["dominant_direction"] == str(g["b_flow_direction"])
+    assert np.allclose(_hot(fb["bottlenecks"], "severity"), g["b_bottlenecks"], rtol=1e-12)
+
+
+# ---- stage-level parity vs the oracle ------------------------------------------------------------
+def test_select_kth_matches_sort(pkg):
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 7, 1000, 100001):
+        x = rng.normal(size=(n, 3))
+        x[: n // 3, 2] = x[0, 2]          # ties
+        x[n // 2:, 2] *= -1.0             # both signs
+        d = torch.from_numpy(x).cuda()
+        s = np.sort(x[:, 2])
+        for k in sorted({0, n // 3, max(n - 2, 0), n - 1}):
+            a, b = pkg.ops.select_kth(d[:, 2], k)
+            assert a == s[k] and b == s[min(k + 1, n - 1)]
+        thr = pkg.pre.percentile_from_order_stats(*pkg.ops.select_kth(d[:, 2], int(np.floor((n - 1) * 0.3))), n, 30)
+        assert thr == float(np.percentile(x[:, 2], 30))
+
+
+@pytest.mark.parametrize("eps,seed", [(0.3, 0), (0.5, 1), (0.15, 2), (1.5, 3)])
+def test_dbscan_labels_match_oracle(pkg, eps, seed):
+    r = np.random.default_rng(seed)
+    centres = r.uniform(-5, 5, (40, 3))
+    X = np.concatenate([centres[r.integers(0, 40, 6000)] + r.normal(0, 0.15, (6000, 3)), r.uniform(-6, 6, (1500, 3))])
+    X = X[r.permutation(len(X))]
+    want = nps.dbscan_labels(X, eps, 5)
+    labels, nc, guard = pkg.ops.dbscan(torch.from_numpy(X).cuda(), eps, 5)
+    assert guard == 0
+    assert np.array_equal(labels.cpu().numpy().astype(np.int64), want)
+    assert nc == (want.max() + 1 if (want >= 0).any() else 0)
+
+
+def test_dbscan_degenerate_inputs(pkg):
+    # all points identical, fewer than min_samples, exactly on the eps boundary (inclusive)
+    same = np.zeros((10, 3))
+    lab, nc, _ = pkg.ops.dbscan(torch.from_numpy(same).cuda(), 0.3, 5)
+    assert nc == 1 and np.array_equal(lab.cpu().numpy(), np.zeros(10))
+    few = np.arange(12, dtype=np.float64).reshape(4, 3)
+    lab, nc, _ = pkg.ops.dbscan(torch.from_numpy(few).cuda(), 0.3, 5)
+    assert nc == 0 and np.all(lab.cpu().numpy() == -1)
+    line = np.zeros((6, 3))
+    line[:, 0] = np.arange(6) * 0.25       # neighbours exactly 0.25 and 0.5 apart, eps = 0.5 inclusive
+    want = nps.dbscan_labels(line, 0.5, 5)
+    lab, _, _ = pkg.ops.dbscan(torch.from_numpy(line).cuda(), 0.5, 5)
+    assert np.array_equal(lab.cpu().numpy().astype(np.int64), want)
+
+
+def test_cluster_centroids_exact(pkg):
+    rng = np.random.default_rng(1)
+    pts = rng.uniform(-80, 80, (50000, 3))
+    lab = rng.integers(-1, 37, 50000).astype(np.int64)
+    cent, counts = pkg.ops.cluster_centroids(torch.from_numpy(pts).cuda(), torch.from_numpy(lab).cuda(), 37)
+    want = np.array([pts[lab == c].mean(0) for c in range(37)])
+    assert np.allclose(cent.cpu().numpy(), want, rtol=1e-13, atol=1e-13)
+    assert np.array_equal(counts.cpu().numpy(), np.bincount(lab[lab >= 0], minlength=37))
+    # deterministic run to run
+    c2, _ = pkg.ops.cluster_centroids(torch.from_numpy(pts).cuda(), torch.from_numpy(lab).cuda(), 37)
+    assert torch.equal(cent, c2)
+
+
+def test_downsample_point_cloud_contract(pkg):
+    pts = np.random.default_rng(0).normal(size=(1000, 3))
+    out = pkg.dp.downsample_point_cloud(pts, 0.1)
+    assert out.shape == (100, 3) and out.dtype == pts.dtype
+    rows = {tuple(r) for r in pts}
+    assert all(tuple(r) in rows for r in out) and len({tuple(r) for r in out}) == 100
+    assert pkg.dp.downsample_point_cloud(pts, 1.0) is pts
+    assert pkg.dp.downsample_point_cloud(pts, 1e-9).shape == (1, 3)
+
+
+def test_frame_flow_matches_oracle(pkg):
+    rng = np.random.default_rng(2)
+    prev = rng.uniform(-20, 20, (300, 2))
+    cur = prev[rng.permutation(300)[:280]] + rng.normal(0.08, 0.03, (280, 2))
+    cur = np.concatenate([cur, rng.uniform(-20, 20, (15, 2))])
+    flow, match, vel = pkg.CFM.__module__ and __import__(
+        "lidar_ai_recommendation_software_b200.flow", fromlist=["frame_flow"]).frame_flow(
+        prev, cur, 0.1, (-20.0, 20.0), (-20.0, 20.0))
+    wm, wv = new_ops.frame_flow_match(prev, cur, 0.1, 1.5)
+    assert np.array_equal(match, wm)                                        # indices bit-exact
+    assert np.array_equal(vel, wv)
+    wvec, wmag = new_ops.frame_flow_field(flow["positions"], cur, wm, wv, 3.0)
+    assert np.allclose(flow["vectors"], wvec, rtol=1e-3, atol=1e-9)
+    assert np.allclose(flow["magnitudes"], wmag, rtol=1e-3, atol=1e-9)
+
+
+def test_sequence_model_uses_previous_frame(pkg, processed_b):
+    pb = processed_b("crowd_20k")
+    model = pkg.CFM()
+    first = model.analyze_sequence_frame(pb)
+    assert first["dominant_direction"] != "N/A" and model.prev_positions is not None
+    moved = dict(pb)
+    moved.pop(pkg.pre.DEVICE_KEY)
+    moved["points"] = pb["points"] + np.array([0.1, 0.0, 0.0])              # everybody walks +x at 1 m/s
+    second = model.analyze_sequence_frame(moved, dt=0.1)
+    assert second["dominant_direction"] == "E"
+    m = second["flow_vectors"]["magnitudes"]
+    assert np.allclose(m[m > 0], 1.0, rtol=1e-3)
+
+
+def test_errors_are_python_exceptions(pkg):
+    with pytest.raises(Exception):
+        pkg.dp.preprocess_lidar_data(np.zeros((0, 3)))
+    with pytest.raises(Exception):
+        pkg.dp.load_lidar_data("/nonexistent/file.xyz")

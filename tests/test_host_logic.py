@@ -1,0 +1,66 @@
+"""CPU tests of host-side logic that needs no GPU: loader contract, percentile lerp, plane solve."""
+import numpy as np
+import pytest
+
+
+def test_percentile_from_order_stats_matches_numpy():
+    from lidar_ai_recommendation_software_b200.preprocess import percentile_from_order_stats
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 10, 11, 1000, 7919):
+        x = np.sort(rng.normal(size=n))
+        lo = int(np.floor((n - 1) * 0.3))
+        got = percentile_from_order_stats(x[lo], x[min(lo + 1, n - 1)], n, 30)
+        assert got == float(np.percentile(x, 30))
+
+
+def test_plane_from_sums_matches_lstsq():
+    from lidar_ai_recommendation_software_b200.preprocess import _plane_from_sums
+    rng = np.random.default_rng(1)
+    g = rng.uniform(-50, 50, (5000, 3))
+    g[:, 2] = 0.01 * g[:, 0] - 0.02 * g[:, 1] + 0.3 + rng.normal(0, 0.01, 5000)
+    c = g.mean(0) + 0.5
+    d = g - c
+    s = np.array([len(g), d[:, 0].sum(), d[:, 1].sum(), d[:, 2].sum(), (d[:, 0] ** 2).sum(), (d[:, 0] * d[:, 1]).sum(),
+                  (d[:, 1] ** 2).sum(), (d[:, 0] * d[:, 2]).sum(), (d[:, 1] * d[:, 2]).sum(), 0.0])
+    A = np.column_stack((g[:, 0], g[:, 1], np.ones(len(g))))
+    want = np.linalg.lstsq(A, g[:, 2], rcond=None)[0]
+    got = _plane_from_sums(s, c)
+    assert np.allclose([got[0], got[1], got[3]], want, rtol=1e-9) and got[2] == -1
+
+
+def test_loader_formats(tmp_path):
+    from lidar_ai_recommendation_software_b200.io import load_lidar_data
+    pts = np.random.default_rng(0).normal(size=(50, 3))
+    np.save(tmp_path / "a.npy", np.column_stack([pts, np.ones(50)]))
+    assert np.array_equal(load_lidar_data(str(tmp_path / "a.npy")), pts)
+    np.savetxt(tmp_path / "a.xyz", pts)
+    assert np.allclose(load_lidar_data(str(tmp_path / "a.xyz")), pts)
+    np.savetxt(tmp_path / "a.txt", pts)
+    assert np.allclose(load_lidar_data(str(tmp_path / "a.txt")), pts)
+    with open(tmp_path / "a.csv", "w") as f:
+        f.write("intensity,Y,x,z\n")
+        for p in pts:
+            f.write(f"1.0,{float(p[1])!r},{float(p[0])!r},{float(p[2])!r}\n")
+    got = load_lidar_data(str(tmp_path / "a.csv"))       # columns in file order: Y, x, z (reference behaviour)
+    assert np.allclose(got, pts[:, [1, 0, 2]])
+    with open(tmp_path / "a.pcd", "w") as f:
+        f.write("# .PCD v0.7\nVERSION 0.7\nFIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 50\nHEIGHT 1\n"
+                "POINTS 50\nDATA ascii\n")
+        for p in pts:
+            f.write(f"{float(p[0])!r} {float(p[1])!r} {float(p[2])!r}\n")
+    assert np.allclose(load_lidar_data(str(tmp_path / "a.pcd")), pts)
+    with open(tmp_path / "b.pcd", "wb") as f:
+        f.write(b"VERSION 0.7\nFIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\nWIDTH 50\nHEIGHT 1\n"
+                b"POINTS 50\nDATA binary\n")
+        f.write(np.column_stack([pts, np.ones(50)]).astype(np.float32).tobytes())
+    assert np.allclose(load_lidar_data(str(tmp_path / "b.pcd")), pts.astype(np.float32))
+    with open(tmp_path / "a.ply", "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex 50\nproperty float x\nproperty float y\nproperty float z\n"
+                "element face 0\nend_header\n")
+        for p in pts:
+            f.write(f"{float(p[0])!r} {float(p[1])!r} {float(p[2])!r}\n")
+    assert np.allclose(load_lidar_data(str(tmp_path / "a.ply")), pts)
+    with pytest.raises(Exception, match="Failed to load point cloud file"):
+        load_lidar_data(str(tmp_path / "nope.xyz"))
+    with pytest.raises(Exception, match="Unsupported file format"):
+        load_lidar_data(str(tmp_path / "a.bin"))
