@@ -37,7 +37,7 @@ VOXEL = 0.05
 GRID = 0.5
 EXTENT = 50.0
 POOL = 16          # distinct frames cycled through: 16 x 16 MB = 256 MB > 126 MB of L2
-KERNELS = ["k_frame_bbox", "k_frame_mark", "k_frame_scan", "k_frame_rank", "k_frame_finalize"]
+KERNELS = ["k_frame_prep", "k_frame_mark", "k_frame_scan", "k_frame_rank", "k_frame_finalize"]
 
 
 def peaks():
@@ -148,6 +148,9 @@ def main():
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ctas-per-sm", type=int, default=0, help="frame kernel grid cap (0 = library default)")
+    ap.add_argument("--streams", type=int, default=4,
+                    help="independent frame pipelines in flight (frames round-robin over CUDA streams)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -175,9 +178,28 @@ def main():
     # every rank owns its own frames (frames shard across GPUs: weak scaling, no collective)
     host_frames = [synth.crowd_frame(n, seed=rank * 1000 + s, extent=EXTENT) for s in range(POOL)]
     frames = [torch.from_numpy(f).to(dev) for f in host_frames]
-    pipe = ops.FramePipeline(max_points=n, voxel_size=VOXEL, grid_size=GRID, max_key_space=1 << 28,
-                             max_nx=256, max_ny=256, device=dev)
+    if args.ctas_per_sm:
+        from lidar_ai_recommendation_software_b200 import _capi
+        _capi.check(_capi.lib.lidar_frame_set_ctas_per_sm(args.ctas_per_sm))
+    S = max(1, args.streams)
+    pipes = [ops.FramePipeline(max_points=n, voxel_size=VOXEL, grid_size=GRID, max_key_space=1 << 28,
+                               max_nx=256, max_ny=256, device=dev) for _ in range(S)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
+    pipe = pipes[0]
     torch.cuda.synchronize()
+
+    def run_frames(count):
+        """`count` frames, round-robin over the S pipelines/streams; returns after enqueueing, with the
+        current stream made to wait for all of them."""
+        cur = torch.cuda.current_stream()
+        for st in streams:
+            st.wait_stream(cur)
+        for s_ in range(count):
+            k = s_ % S
+            with torch.cuda.stream(streams[k]):
+                pipes[k].enqueue(frames[s_ % POOL])
+        for st in streams:
+            cur.wait_stream(st)
 
     def barrier():
         if world > 1:
@@ -187,21 +209,21 @@ def main():
     # ---- device-resident throughput ------------------------------------------------------------
     clocks = ClockSampler(local_rank)
     clocks.start()
-    for w in range(args.warmup):
-        pipe.enqueue(frames[w % POOL])
+    run_frames(args.warmup)
+    torch.cuda.synchronize()
     res = pipe.result()
     v_over_n = res.n_voxels / n
     barrier()
     clocks.rows.clear()   # keep only samples taken during the timed region
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for s in range(args.steps):
-        pipe.enqueue(frames[s % POOL])
+    run_frames(args.steps)
     ev1.record()
     barrier()
     clk = clocks.stop()
     ms = ev0.elapsed_time(ev1)
-    pipe.result()  # raises if any frame overflowed its capacities
+    for p_ in pipes:
+        p_.result()  # raises if any frame overflowed its capacities
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -222,13 +244,13 @@ def main():
     dom = int(np.argmax(per_kernel))
     hbm_peak, peak_src = peaks()
     # algorithmic bytes per point of each kernel
-    ks_bytes = float(res.desc.key_space) / 8.0
+    n_groups = float(res.desc.key_space) / 224.0          # one 32 B occupancy group per 224 voxel cells
     alg = {
-        "k_frame_bbox": 16.0 * n,
-        "k_frame_mark": (16.0 + 4.0) * n,
-        "k_frame_scan": ks_bytes + ks_bytes / 8.0,
-        "k_frame_rank": (16.0 + 4.0 + 4.0) * n,
-        "k_frame_finalize": (16.0 + 4.0 + 4.0) * res.n_voxels,
+        "k_frame_prep": 16.0 * n,                               # read every point once
+        "k_frame_mark": (16.0 + 4.0) * n,                       # read point, write voxel key
+        "k_frame_scan": n_groups * (32.0 + 4.0),                # read every group, write its prefix
+        "k_frame_rank": (16.0 + 4.0 + 4.0) * n + 32.0 * res.n_voxels,   # point, key, inverse + voxel record
+        "k_frame_finalize": 4.0 * res.n_voxels,                 # sweep of the member counters
     }
     step_bytes = (20.0 + 20.0 * v_over_n) * n      # 20 + 20*V/N bytes per point
     dom_name = KERNELS[dom]
@@ -287,6 +309,7 @@ def main():
                        "points_per_frame": n, "voxel_m": VOXEL, "grid_m": GRID, "voxels_per_point": v_over_n,
                        "key_space": int(res.desc.key_space),
                        "l2": f"inputs rotate over {POOL} distinct frames ({POOL * n * 16 / 1e6:.0f} MB > 126 MB L2)",
+                       "streams": S,
                        "sharding": "independent frames per rank, no collective"},
             "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": 5 * args.steps, "clocks": clk,

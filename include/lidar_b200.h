@@ -220,6 +220,14 @@ typedef struct lidar_frame_desc {
     int32_t pad;
 } lidar_frame_desc;
 
+/* one output voxel = one 32-byte sector, so a voxel is written with a single full-sector store */
+typedef struct lidar_voxel {
+    float x, y, z, intensity; /* centroid and mean intensity                                   */
+    int32_t count;            /* member points                                                 */
+    int32_t key;              /* (ix*Dy + iy)*Dz + iz                                          */
+    int32_t pad[2];
+} lidar_voxel;
+
 /* capacities chosen by the caller once per stream of frames */
 typedef struct lidar_frame_caps {
     int64_t max_points;
@@ -228,6 +236,9 @@ typedef struct lidar_frame_caps {
 } lidar_frame_caps;
 
 size_t lidar_frame_workspace_bytes(const lidar_frame_caps* caps);
+/* tuning knob: cap of the per-point frame kernels' grids in CTAs per SM (1..8, default 8).  Smaller
+ * grids leave room for the kernels of other frames (other streams) to run concurrently. */
+int lidar_frame_set_ctas_per_sm(int ctas_per_sm);
 /* one-time (or after an error): zero the persistent parts of the workspace */
 int lidar_frame_workspace_init(void* d_ws, size_t ws_bytes, const lidar_frame_caps* caps, void* stream);
 
@@ -239,26 +250,22 @@ int lidar_frame_workspace_init(void* d_ws, size_t ws_bytes, const lidar_frame_ca
  *                  utils/data_processing.py:282-328)
  *   d_voxel_key   int32[n]   per-point voxel key (B.1 voxel_idx)
  *   d_inverse     int32[n]   rank of the point's voxel
- *   d_centroids   float4[cap n]   (x,y,z,mean intensity) per voxel, ascending key
- *   d_counts      int32[cap n]
- *   d_unique_keys int32[cap n]
+ *   d_voxels      lidar_voxel[cap n]  centroid (x,y,z,mean intensity), count and key per voxel,
+ *                 ascending key
  *   d_grid        int32[max_nx*max_ny] laid out [nx][ny] with the ACTUAL ny from the descriptor
  *   d_desc        device lidar_frame_desc (read it back after the stream is synchronised)
  */
 int lidar_frame_voxel_density(const void* d_points, int64_t n, double voxel_size, double grid_size,
-                              const double* h_origin3, const double* h_xy_range4,
-                              int32_t* d_voxel_key, int32_t* d_inverse, void* d_centroids,
-                              int32_t* d_counts, int32_t* d_unique_keys, int32_t* d_grid,
-                              lidar_frame_desc* d_desc, const lidar_frame_caps* caps, void* d_ws,
-                              size_t ws_bytes, void* stream);
+                              const double* h_origin3, const double* h_xy_range4, int32_t* d_voxel_key,
+                              int32_t* d_inverse, lidar_voxel* d_voxels, int32_t* d_grid, lidar_frame_desc* d_desc,
+                              const lidar_frame_caps* caps, void* d_ws, size_t ws_bytes, void* stream);
 
 /* Same call, additionally recording six caller-created cudaEvent_t (passed as void*) on `stream`:
- * before k_frame_bbox, then after each of bbox, mark, scan, rank, finalize — so a benchmark can
+ * before k_frame_prep, then after each of prep, mark, scan, rank, finalize — so a benchmark can
  * attribute device time to each kernel without a profiler. */
 int lidar_frame_voxel_density_timed(const void* d_points, int64_t n, double voxel_size, double grid_size,
-                                    const double* h_origin3, const double* h_xy_range4,
-                                    int32_t* d_voxel_key, int32_t* d_inverse, void* d_centroids,
-                                    int32_t* d_counts, int32_t* d_unique_keys, int32_t* d_grid,
+                                    const double* h_origin3, const double* h_xy_range4, int32_t* d_voxel_key,
+                                    int32_t* d_inverse, lidar_voxel* d_voxels, int32_t* d_grid,
                                     lidar_frame_desc* d_desc, const lidar_frame_caps* caps, void* d_ws,
                                     size_t ws_bytes, void* stream, void** h_events6);
 

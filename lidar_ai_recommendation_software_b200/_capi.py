@@ -101,13 +101,13 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_radius_count": (_i32, [_vp, _i32, _vp, _i32, _vp, _i32, _dbl, _vp, _vp]),
     "lidar_frame_flow_match": (_i32, [_vp, _i32, _vp, _i32, C.c_float, C.c_float, _vp, _vp, _vp]),
     "lidar_frame_flow_field": (_i32, [_vp, _i32, _vp, _vp, _vp, _i32, _dbl, _vp, _vp, _vp]),
+    "lidar_frame_set_ctas_per_sm": (_i32, [_i32]),
     "lidar_frame_workspace_bytes": (_sz, [C.POINTER(FrameCaps)]),
     "lidar_frame_workspace_init": (_i32, [_vp, _sz, C.POINTER(FrameCaps), _vp]),
     "lidar_frame_voxel_density": (_i32, [_vp, _i64, _dbl, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double),
-                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(FrameCaps), _vp, _sz,
-                                         _vp]),
+                                         _vp, _vp, _vp, _vp, _vp, C.POINTER(FrameCaps), _vp, _sz, _vp]),
     "lidar_frame_voxel_density_timed": (_i32, [_vp, _i64, _dbl, _dbl, C.POINTER(C.c_double),
-                                               C.POINTER(C.c_double), _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                               C.POINTER(C.c_double), _vp, _vp, _vp, _vp, _vp,
                                                C.POINTER(FrameCaps), _vp, _sz, _vp, C.POINTER(C.c_void_p)]),
 }
 

@@ -6,22 +6,25 @@
 // binning (Appendix A.1), counts indexed [x][y].
 //
 // Design: "occupancy-bitmap ranking" instead of a key sort.
-//   The voxel key space (Dx*Dy*Dz cells) is held as a bitmap (1 bit per cell, 22 MB for a
+//   The voxel key space (Dx*Dy*Dz cells) is held as a bitmap (1 bit per cell, 20 MB for a
 //   100 m x 100 m x 2 m frame at 0.05 m — L2 resident on B200).  The rank of a voxel in ascending
 //   key order is the number of occupied cells before it, i.e. a popcount prefix over the bitmap.
 //   That yields exactly the output order of a stable sort-by-key + segmented reduce, without
 //   moving a single point, and every step is order independent:
-//     k_frame_bbox      min/max of x,y,z,intensity; the last CTA derives the frame descriptor
-//                       (origin, dims, key space, fixed-point scales, histogram edges) ON DEVICE
-//     k_frame_mark      per point: voxel key -> d_voxel_key, atomicOr into the bitmap,
+//     k_frame_prep      min/max of x,y,z,intensity; zeroes what the previous frame dirtied (bitmap,
+//                       duplicate filter, grid); the last CTA derives the frame descriptor (origin,
+//                       dims, key space, fixed-point scales, histogram edges) ON DEVICE
+//     k_frame_mark      per point: voxel key -> d_voxel_key, atomicOr into the bitmap (a second hit
+//                       on the same bit flags the voxel in a 512 KB hashed duplicate filter),
 //                       density bin -> RED.ADD into the grid              (reads 16 B, writes 4 B)
-//     k_frame_scan      single-pass chained scan of bitmap popcounts -> prefix per 256-bit group
-//     k_frame_rank      per point: rank = prefix + popc(bits below) -> d_inverse; integer
-//                       accumulation of (p - voxel_corner) in 2^-k fixed point and of counts
-//     k_frame_finalize  per voxel: centroid = corner + sum/count, count, key; restores the
-//                       all-zero invariant of bitmap and accumulators for the next frame
+//     k_frame_scan      one-wave scan of bitmap popcounts -> prefix per 256-bit group
+//     k_frame_rank      per point: rank = prefix + popc(bits below) -> d_inverse.  Voxels not in
+//                       the duplicate filter hold exactly one point (94 % of a crowd frame): the
+//                       point IS the centroid and is stored directly.  The rest accumulate
+//                       (p - ref) in 2^-k fixed point with integer atomics and enlist the voxel.
+//     k_frame_finalize  enlisted voxels only: centroid = ref + sum/count; re-zeroes accumulators
 //   Integer accumulation makes centroids independent of the order in which atomics land:
-//   bit-identical run to run, and equal to the fp64 mean to ~2^-46 m before the fp32 rounding.
+//   bit-identical run to run, and (p - ref)*2^k is an exact integer, so the sums are exact.
 //
 // Nothing in a frame needs the host: capacities are fixed per stream of frames, the descriptor is
 // read back together with the results.
@@ -30,39 +33,46 @@
 namespace lidar {
 
 constexpr int kFrameThreads = 256;
-constexpr int kScanWordsPerThread = 8;                                // one 256-bit group = 8 words
+// Occupancy groups: one 32-byte sector = {prefix, 7 x 32 occupancy bits} = 224 voxels.  Packing the
+// popcount prefix next to the bits means the rank of a point costs ONE random sector read.
+constexpr int kGroupVoxels = 224;
 constexpr int kScanGroupsPerThread = 4;                               // each thread scans 4 adjacent groups
-constexpr int kScanTileWords = kFrameThreads * kScanWordsPerThread * kScanGroupsPerThread;   // 8192 words
+constexpr int kScanTileGroups = kFrameThreads * kScanGroupsPerThread; // 1024 groups = 229 376 voxels per tile
+
+constexpr int kFilterBits = 22;                                       // duplicate filter: 2^22 bits = 512 KB
+constexpr int kFilterWords = 1 << (kFilterBits - 5);
 
 struct FrameWsLayout {
-    size_t off_partial, off_ctrl, off_bitmap, off_group_prefix, off_tile_desc, off_acc, off_cnt, total;
-    int64_t bitmap_words, groups, tiles;
+    size_t off_partial, off_ctrl, off_groups, off_tile_desc, off_acc, off_cnt, off_filter, total;
+    int64_t groups, tiles;
 };
 
 struct FrameCtrl {
     unsigned int bbox_ticket;
     unsigned int scan_ticket;
     unsigned int pad[2];
+    unsigned long long dirty_groups;  // occupancy groups the previous frame may have set
 };
+
+__device__ __forceinline__ unsigned filter_slot(int key) { return ((unsigned)key * 2654435761u) >> (32 - kFilterBits); }
 
 constexpr int kBboxMaxBlocks = 1024;
 
 static FrameWsLayout frame_layout(const lidar_frame_caps& c) {
     FrameWsLayout L;
-    L.bitmap_words = (c.max_key_space + 31) / 32;
+    L.groups = (c.max_key_space + kGroupVoxels - 1) / kGroupVoxels;
     // round up to whole tiles so the scan never needs a ragged tail
-    L.tiles = (L.bitmap_words + kScanTileWords - 1) / kScanTileWords;
-    L.bitmap_words = L.tiles * kScanTileWords;
-    L.groups = L.bitmap_words / kScanWordsPerThread;
+    L.tiles = (L.groups + kScanTileGroups - 1) / kScanTileGroups;
+    L.groups = L.tiles * kScanTileGroups;
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t a = ws_align(o); o = a + bytes; return a; };
     L.off_partial = take(sizeof(double) * 8 * kBboxMaxBlocks);
     L.off_ctrl = take(sizeof(FrameCtrl));
-    L.off_bitmap = take(sizeof(uint32_t) * L.bitmap_words);
-    L.off_group_prefix = take(sizeof(uint32_t) * L.groups);
+    L.off_groups = take(sizeof(uint32_t) * 8 * L.groups);
     L.off_tile_desc = take(sizeof(unsigned long long) * L.tiles);
     L.off_acc = take(sizeof(long long) * 4 * c.max_points);
     L.off_cnt = take(sizeof(int32_t) * c.max_points);
+    L.off_filter = take(sizeof(uint32_t) * kFilterWords);
     L.total = ws_align(o);
     return L;
 }
@@ -147,28 +157,41 @@ __device__ void derive_desc(const FrameParams& P, const double* bb, lidar_frame_
     D->pad = 0;
 }
 
-// ---- k_frame_bbox -----------------------------------------------------------------------------
+// ---- k_frame_prep -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFrameThreads)
-k_frame_bbox(FrameParams P, double* __restrict__ partial, FrameCtrl* __restrict__ ctrl,
+k_frame_prep(FrameParams P, double* __restrict__ partial, FrameCtrl* __restrict__ ctrl,
              lidar_frame_desc* __restrict__ D, int32_t* __restrict__ grid_out, int grid_cap,
-             unsigned long long* __restrict__ tile_desc, int64_t tiles) {
-    // zero the per-frame scratch that later kernels accumulate into
-    {
-        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-        const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        for (int64_t i = t0; i < grid_cap; i += stride) grid_out[i] = 0;
-        for (int64_t i = t0; i < tiles; i += stride) tile_desc[i] = 0ull;
-    }
+             unsigned long long* __restrict__ tile_desc, int64_t tiles, uint32_t* __restrict__ groups,
+             int64_t groups_cap, uint32_t* __restrict__ filter) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // issue this thread's point loads first so they are in flight while the zeroing stores drain
+    LoadF32x4 L{P.pts};
     float mn[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
     float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    LoadF32x4 L{P.pts};
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-        float4 v = L.raw(i);
+    auto fold = [&](const float4& v) {
         mn[0] = fminf(mn[0], v.x); mx[0] = fmaxf(mx[0], v.x);
         mn[1] = fminf(mn[1], v.y); mx[1] = fmaxf(mx[1], v.y);
         mn[2] = fminf(mn[2], v.z); mx[2] = fmaxf(mx[2], v.z);
         mn[3] = fminf(mn[3], v.w); mx[3] = fmaxf(mx[3], v.w);
+    };
+    int64_t i = t0;
+    for (; i + 3 * stride < P.n; i += 4 * stride) {
+        const float4 a = L.raw(i), b = L.raw(i + stride), c = L.raw(i + 2 * stride), d = L.raw(i + 3 * stride);
+        fold(a); fold(b); fold(c); fold(d);
+    }
+    for (; i < P.n; i += stride) fold(L.raw(i));
+    // zero what the previous frame dirtied and what later kernels accumulate into
+    {
+        int64_t dirty = (int64_t)ctrl->dirty_groups;
+        if (dirty > groups_cap) dirty = groups_cap;
+        uint4* b4 = reinterpret_cast<uint4*>(groups);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int64_t k = t0; k < dirty * 2; k += stride) b4[k] = z;
+        uint4* f4 = reinterpret_cast<uint4*>(filter);
+        for (int64_t k = t0; k < kFilterWords / 4; k += stride) f4[k] = z;
+        for (int64_t k = t0; k < grid_cap; k += stride) grid_out[k] = 0;
+        for (int64_t k = t0; k < tiles; k += stride) tile_desc[k] = 0ull;
     }
     __shared__ float s_v[kFrameThreads / 32][8];
     __shared__ bool s_last;
@@ -228,6 +251,10 @@ k_frame_bbox(FrameParams P, double* __restrict__ partial, FrameCtrl* __restrict_
         derive_desc(P, s_bb, D);
         ctrl->bbox_ticket = 0u;
         ctrl->scan_ticket = 0u;
+        // groups this frame may set (whole scan tiles), remembered for the next frame's zeroing
+        const long long ng = (D->key_space + kGroupVoxels - 1) / kGroupVoxels;
+        const long long tiles_used = (ng + kScanTileGroups - 1) / kScanTileGroups;
+        ctrl->dirty_groups = D->status == 0 && P.n > 0 ? (unsigned long long)(tiles_used * kScanTileGroups) : 0ull;
     }
 }
 
@@ -266,52 +293,87 @@ __device__ __forceinline__ int arange_bin(double x, double a, double e1, double 
     return k;
 }
 
+// streaming accesses: every point / key / inverse entry is touched once per pass, keep them from
+// evicting the L2-resident working set (occupancy groups, voxel records)
+__device__ __forceinline__ unsigned long long evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ int ld_stream_s32(const int* p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;"
+                 : "=r"(v) : "l"(p), "l"(evict_first_policy()));
+    return v;
+}
+__device__ __forceinline__ void st_stream_s32(int* p, int v) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.s32 [%0], %1, %2;"
+                 ::"l"(p), "r"(v), "l"(evict_first_policy()) : "memory");
+}
+
 // ---- k_frame_mark -----------------------------------------------------------------------------
+__device__ __forceinline__ void mark_point(const float4& q, const lidar_frame_desc& D, double rv, double rdx,
+                                           double rdy, bool do_grid, int64_t i, int32_t* __restrict__ voxel_key,
+                                           uint32_t* __restrict__ groups, uint32_t* __restrict__ filter,
+                                           int32_t* __restrict__ grid_out) {
+    const double x = (double)q.x, y = (double)q.y, z = (double)q.z;
+    const int ix = floor_div_exact(__dsub_rn(x, D.origin[0]), D.voxel, rv);
+    const int iy = floor_div_exact(__dsub_rn(y, D.origin[1]), D.voxel, rv);
+    const int iz = floor_div_exact(__dsub_rn(z, D.origin[2]), D.voxel, rv);
+    const int key = (ix * D.dims[1] + iy) * D.dims[2] + iz;
+    st_stream_s32(voxel_key + i, key);
+    const unsigned g = (unsigned)key / kGroupVoxels, b = (unsigned)key - g * kGroupVoxels;
+    const unsigned bit = 1u << (b & 31);
+    const unsigned old = atomicOr(&groups[(size_t)g * 8 + 1 + (b >> 5)], bit);
+    if (old & bit) {   // the voxel already had a point: flag it as multi-member
+        const unsigned h = filter_slot(key);
+        atomicOr(&filter[h >> 5], 1u << (h & 31));
+    }
+    if (do_grid) {
+        const int bx = arange_bin(x, D.ex0, D.ex1, D.exd, rdx, D.nx);
+        const int by = arange_bin(y, D.ey0, D.ey1, D.eyd, rdy, D.ny);
+        if (bx >= 0 && by >= 0) atomicAdd(&grid_out[bx * D.ny + by], 1);
+    }
+}
+
 __global__ void __launch_bounds__(kFrameThreads)
 k_frame_mark(const float4* __restrict__ pts, const lidar_frame_desc* __restrict__ Dg,
-             int32_t* __restrict__ voxel_key, uint32_t* __restrict__ bitmap,
+             int32_t* __restrict__ voxel_key, uint32_t* __restrict__ groups, uint32_t* __restrict__ filter,
              int32_t* __restrict__ grid_out) {
     __shared__ lidar_frame_desc D;
+    LoadF32x4 L{pts};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (threadIdx.x == 0) D = *Dg;
     __syncthreads();
     if (D.status != 0) return;
     const int64_t n = D.n_points;
-    const double ox = D.origin[0], oy = D.origin[1], oz = D.origin[2], v = D.voxel;
-    const int Dy = D.dims[1], Dz = D.dims[2];
     const bool do_grid = D.grid > 0.0;
-    const int ny = D.ny;
-    const double rv = __ddiv_rn(1.0, v);
+    const double rv = __ddiv_rn(1.0, D.voxel);
     const double rdx = do_grid ? __ddiv_rn(1.0, D.exd) : 0.0, rdy = do_grid ? __ddiv_rn(1.0, D.eyd) : 0.0;
-    LoadF32x4 L{pts};
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float4 q = L.raw(i);
-        const double x = (double)q.x, y = (double)q.y, z = (double)q.z;
-        const int ix = floor_div_exact(__dsub_rn(x, ox), v, rv);
-        const int iy = floor_div_exact(__dsub_rn(y, oy), v, rv);
-        const int iz = floor_div_exact(__dsub_rn(z, oz), v, rv);
-        const int key = (ix * Dy + iy) * Dz + iz;
-        voxel_key[i] = key;
-        atomicOr(&bitmap[key >> 5], 1u << (key & 31));
-        if (do_grid) {
-            const int bx = arange_bin(x, D.ex0, D.ex1, D.exd, rdx, D.nx);
-            const int by = arange_bin(y, D.ey0, D.ey1, D.eyd, rdy, ny);
-            if (bx >= 0 && by >= 0) atomicAdd(&grid_out[bx * ny + by], 1);
-        }
+    int64_t i = t0;
+    for (; i + stride < n; i += 2 * stride) {
+        const float4 a = L.raw(i), b = L.raw(i + stride);
+        mark_point(a, D, rv, rdx, rdy, do_grid, i, voxel_key, groups, filter, grid_out);
+        mark_point(b, D, rv, rdx, rdy, do_grid, i + stride, voxel_key, groups, filter, grid_out);
     }
+    if (i < n) mark_point(L.raw(i), D, rv, rdx, rdy, do_grid, i, voxel_key, groups, filter, grid_out);
 }
 
 // ---- k_frame_scan -----------------------------------------------------------------------------
+// All tiles of a frame run in ONE wave, so the classic chained look-back would degenerate into a
+// serial chain.  Instead every CTA publishes its tile total and then sums the totals of ALL earlier
+// tiles with its 256 threads (spinning only on totals not yet published).  The exclusive prefix of
+// every group is stored in word 0 of the group itself.
 __global__ void __launch_bounds__(kFrameThreads)
-k_frame_scan(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ group_prefix,
-             unsigned long long* __restrict__ tile_desc, FrameCtrl* __restrict__ ctrl,
-             lidar_frame_desc* __restrict__ Dg) {
+k_frame_scan(uint32_t* __restrict__ groups, unsigned long long* __restrict__ tile_desc,
+             FrameCtrl* __restrict__ ctrl, lidar_frame_desc* __restrict__ Dg) {
     __shared__ int s_tile;
     __shared__ unsigned s_warp_sum[kFrameThreads / 32];
-    __shared__ unsigned long long s_excl;
+    __shared__ unsigned long long s_look[kFrameThreads / 32];
     if (Dg->status != 0) return;
-    const int64_t words = (Dg->key_space + 31) / 32;
-    const int n_tiles = (int)((words + kScanTileWords - 1) / kScanTileWords);
+    const int64_t ng = (Dg->key_space + kGroupVoxels - 1) / kGroupVoxels;
+    const int n_tiles = (int)((ng + kScanTileGroups - 1) / kScanTileGroups);
     const unsigned lane = lane_id();
     const int warp = threadIdx.x >> 5;
     while (true) {
@@ -319,9 +381,9 @@ k_frame_scan(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ group_p
         __syncthreads();
         const int tile = s_tile;
         if (tile >= n_tiles) break;
-        // the workspace bitmap is padded to whole tiles, so the loads never run off the end
-        const uint4* src = reinterpret_cast<const uint4*>(bitmap + (size_t)tile * kScanTileWords) +
-                           threadIdx.x * (2 * kScanGroupsPerThread);
+        // the group array is padded to whole tiles, so the loads never run off the end
+        uint32_t* base = groups + ((size_t)tile * kScanTileGroups + (size_t)threadIdx.x * kScanGroupsPerThread) * 8;
+        const uint4* src = reinterpret_cast<const uint4*>(base);
         unsigned gcnt[kScanGroupsPerThread];
         unsigned cnt = 0;
         uint4 w[2 * kScanGroupsPerThread];
@@ -329,11 +391,10 @@ k_frame_scan(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ group_p
         for (int g = 0; g < 2 * kScanGroupsPerThread; ++g) w[g] = src[g];
 #pragma unroll
         for (int g = 0; g < kScanGroupsPerThread; ++g) {
-            const uint4 a = w[2 * g], b = w[2 * g + 1];
-            gcnt[g] = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
+            const uint4 a = w[2 * g], b = w[2 * g + 1];   // a.x is the (still zero) prefix slot
+            gcnt[g] = __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
             cnt += gcnt[g];
         }
-        // exclusive scan over the CTA
         unsigned inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -349,86 +410,107 @@ k_frame_scan(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ group_p
             if (w2 < warp) warp_off += sv;
             total += sv;
         }
-        if (warp == 0) {
-            const unsigned long long ex = scan_lookback_warp(tile_desc, tile, (unsigned long long)total);
-            if (lane == 0) {
-                s_excl = ex;
-                if (tile == n_tiles - 1) Dg->n_voxels = (int64_t)(ex + total);
-            }
+        if (threadIdx.x == 0) st_relaxed_u64(tile_desc + tile, kScanAgg | (unsigned long long)total);
+        unsigned long long look = 0ull;
+        for (int t = threadIdx.x; t < tile; t += kFrameThreads) {
+            unsigned long long d;
+            do { d = ld_relaxed_u64(tile_desc + t); } while ((d >> 62) == 0ull);
+            look += d & kScanValMask;
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) look += __shfl_xor_sync(0xffffffffu, look, o);
+        if (lane == 0) s_look[warp] = look;
         __syncthreads();
-        {
-            unsigned run = (unsigned)s_excl + warp_off + (inc - cnt);
-            uint4 o4;
-            o4.x = run; run += gcnt[0];
-            o4.y = run; run += gcnt[1];
-            o4.z = run; run += gcnt[2];
-            o4.w = run;
-            reinterpret_cast<uint4*>(group_prefix + (size_t)tile * (kFrameThreads * kScanGroupsPerThread))[threadIdx.x] = o4;
+        unsigned long long excl = 0ull;
+#pragma unroll
+        for (int w2 = 0; w2 < kFrameThreads / 32; ++w2) excl += s_look[w2];
+        if (threadIdx.x == 0 && tile == n_tiles - 1) Dg->n_voxels = (int64_t)(excl + total);
+        unsigned run = (unsigned)excl + warp_off + (inc - cnt);
+#pragma unroll
+        for (int g = 0; g < kScanGroupsPerThread; ++g) {
+            base[g * 8] = run;
+            run += gcnt[g];
         }
         __syncthreads();
     }
 }
 
 // ---- k_frame_rank -----------------------------------------------------------------------------
+__device__ __forceinline__ void rank_point(const float4& q, int key, const lidar_frame_desc& D, int64_t i,
+                                           const uint32_t* __restrict__ groups,
+                                           const uint32_t* __restrict__ filter, int32_t* __restrict__ inverse,
+                                           long long* __restrict__ acc, int32_t* __restrict__ cnt,
+                                           lidar_voxel* __restrict__ voxels) {
+    const unsigned g = (unsigned)key / kGroupVoxels, b = (unsigned)key - g * kGroupVoxels;
+    const uint4* gw = reinterpret_cast<const uint4*>(groups + (size_t)g * 8);
+    const uint4 a4 = gw[0], b4 = gw[1];
+    const unsigned w[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
+    const int wi = 1 + (int)(b >> 5);
+    unsigned r = w[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        if (k < wi) r += __popc(w[k]);
+        else if (k == wi) r += __popc(w[k] & ((1u << (b & 31)) - 1u));
+    }
+    st_stream_s32(inverse + i, (int)r);
+    const unsigned h = filter_slot(key);
+    const bool multi = (__ldg(filter + (h >> 5)) >> (h & 31)) & 1u;
+    if (!multi) {
+        // exactly one point in this voxel: it is the centroid.  One full 32-byte sector store.
+        float4* rec = reinterpret_cast<float4*>(voxels + r);
+        rec[0] = q;
+        rec[1] = make_float4(__int_as_float(1), __int_as_float(key), 0.f, 0.f);
+        return;
+    }
+    const int iz = key % D.dims[2];
+    const int t = key / D.dims[2];
+    const int iy = t % D.dims[1];
+    const int ix = t / D.dims[1];
+    const double cx = voxel_ref(D.origin[0], ix, D.voxel);
+    const double cy = voxel_ref(D.origin[1], iy, D.voxel);
+    const double cz = voxel_ref(D.origin[2], iz, D.voxel);
+    const long long fx = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.x, cx), D.fix_scale_xyz));
+    const long long fy = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.y, cy), D.fix_scale_xyz));
+    const long long fz = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.z, cz), D.fix_scale_xyz));
+    const long long fw = __double2ll_rn(__dmul_rn((double)q.w, D.fix_scale_w));
+    unsigned long long* A = reinterpret_cast<unsigned long long*>(acc + (size_t)r * 4);
+    // results unused: these compile to RED (fire and forget), nothing in the warp waits on them
+    atomicAdd(A + 0, (unsigned long long)fx);
+    atomicAdd(A + 1, (unsigned long long)fy);
+    atomicAdd(A + 2, (unsigned long long)fz);
+    atomicAdd(A + 3, (unsigned long long)fw);
+    atomicAdd(cnt + r, 1);
+    voxels[r].key = key;   // every member stores the same value
+}
+
 __global__ void __launch_bounds__(kFrameThreads)
 k_frame_rank(const float4* __restrict__ pts, const lidar_frame_desc* __restrict__ Dg,
-             const int32_t* __restrict__ voxel_key, const uint32_t* __restrict__ bitmap,
-             const uint32_t* __restrict__ group_prefix, int32_t* __restrict__ inverse,
-             long long* __restrict__ acc, int32_t* __restrict__ cnt, int32_t* __restrict__ unique_keys) {
+             const int32_t* __restrict__ voxel_key, const uint32_t* __restrict__ groups,
+             const uint32_t* __restrict__ filter, int32_t* __restrict__ inverse, long long* __restrict__ acc,
+             int32_t* __restrict__ cnt, lidar_voxel* __restrict__ voxels) {
     __shared__ lidar_frame_desc D;
     if (threadIdx.x == 0) D = *Dg;
     __syncthreads();
     if (D.status != 0) return;
     const int64_t n = D.n_points;
-    const double ox = D.origin[0], oy = D.origin[1], oz = D.origin[2], v = D.voxel;
-    const double sxyz = D.fix_scale_xyz, sw = D.fix_scale_w;
-    const int Dy = D.dims[1], Dz = D.dims[2];
     LoadF32x4 L{pts};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int key = __ldg(voxel_key + i);
-        const float4 q = L.raw(i);
-        const int g = key >> 8;
-        const uint4* gw = reinterpret_cast<const uint4*>(bitmap + (size_t)g * 8);
-        const uint4 a = gw[0], b = gw[1];
-        const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        const int wi = (key >> 5) & 7;
-        unsigned r = __ldg(group_prefix + g);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (k < wi) r += __popc(w[k]);
-            else if (k == wi) r += __popc(w[k] & ((1u << (key & 31)) - 1u));
-        }
-        inverse[i] = (int)r;
-        // decode the voxel corner and accumulate the offset in fixed point
-        const int iz = key % Dz;
-        const int t = key / Dz;
-        const int iy = t % Dy;
-        const int ix = t / Dy;
-        const double cx = voxel_ref(ox, ix, v);
-        const double cy = voxel_ref(oy, iy, v);
-        const double cz = voxel_ref(oz, iz, v);
-        const long long fx = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.x, cx), sxyz));
-        const long long fy = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.y, cy), sxyz));
-        const long long fz = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.z, cz), sxyz));
-        const long long fw = __double2ll_rn(__dmul_rn((double)q.w, sw));
-        unsigned long long* A = reinterpret_cast<unsigned long long*>(acc + (size_t)r * 4);
-        atomicAdd(A + 0, (unsigned long long)fx);
-        atomicAdd(A + 1, (unsigned long long)fy);
-        atomicAdd(A + 2, (unsigned long long)fz);
-        atomicAdd(A + 3, (unsigned long long)fw);
-        atomicAdd(cnt + r, 1);
-        unique_keys[r] = key;  // every member stores the same value
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n; i += 2 * stride) {
+        const int k0 = ld_stream_s32(voxel_key + i), k1 = ld_stream_s32(voxel_key + i + stride);
+        const float4 a = L.raw(i), b = L.raw(i + stride);
+        rank_point(a, k0, D, i, groups, filter, inverse, acc, cnt, voxels);
+        rank_point(b, k1, D, i + stride, groups, filter, inverse, acc, cnt, voxels);
     }
+    if (i < n) rank_point(L.raw(i), ld_stream_s32(voxel_key + i), D, i, groups, filter, inverse, acc, cnt, voxels);
 }
 
 // ---- k_frame_finalize -------------------------------------------------------------------------
+// cnt[r] != 0 exactly for the voxels that went through the accumulators (multi-member voxels and the
+// few singletons that collided in the duplicate filter): a coalesced sweep over cnt finds them.
 __global__ void __launch_bounds__(kFrameThreads)
-k_frame_finalize(const lidar_frame_desc* __restrict__ Dg, long long* __restrict__ acc,
-                 int32_t* __restrict__ cnt, const int32_t* __restrict__ unique_keys,
-                 uint32_t* __restrict__ bitmap, float4* __restrict__ centroids,
-                 int32_t* __restrict__ counts) {
+k_frame_finalize(const lidar_frame_desc* __restrict__ Dg, long long* __restrict__ acc, int32_t* __restrict__ cnt,
+                 lidar_voxel* __restrict__ voxels) {
     __shared__ lidar_frame_desc D;
     if (threadIdx.x == 0) D = *Dg;
     __syncthreads();
@@ -439,8 +521,9 @@ k_frame_finalize(const lidar_frame_desc* __restrict__ Dg, long long* __restrict_
     const int Dy = D.dims[1], Dz = D.dims[2];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < V; r += stride) {
-        const int key = unique_keys[r];
         const int c = cnt[r];
+        if (c == 0) continue;
+        const int key = voxels[r].key;
         longlong2* A = reinterpret_cast<longlong2*>(acc + (size_t)r * 4);
         const longlong2 s01 = A[0], s23 = A[1];
         const int iz = key % Dz;
@@ -456,20 +539,22 @@ k_frame_finalize(const lidar_frame_desc* __restrict__ Dg, long long* __restrict_
         o.y = (float)__dadd_rn(cy, __ddiv_rn(__dmul_rn((double)s01.y, isx), dc));
         o.z = (float)__dadd_rn(cz, __ddiv_rn(__dmul_rn((double)s23.x, isx), dc));
         o.w = (float)__ddiv_rn(__dmul_rn((double)s23.y, isw), dc);
-        centroids[r] = o;
-        counts[r] = c;
-        // restore the all-zero invariant for the next frame
+        float4* rec = reinterpret_cast<float4*>(voxels + r);
+        rec[0] = o;
+        rec[1] = make_float4(__int_as_float(c), __int_as_float(key), 0.f, 0.f);
+        // restore the all-zero invariant of the accumulators for the next frame
         A[0] = make_longlong2(0, 0);
         A[1] = make_longlong2(0, 0);
         cnt[r] = 0;
-        bitmap[key >> 5] = 0u;  // racing stores of the same value
     }
 }
+
+static int g_ctas_per_sm = 8;   // grid cap of the per-point frame kernels, in CTAs per SM (tuning knob)
 
 static int frame_grid(int64_t n, int per_thread) {
     int64_t want = (n + (int64_t)kFrameThreads * per_thread - 1) / ((int64_t)kFrameThreads * per_thread);
     if (want < 1) want = 1;
-    const int64_t cap = (int64_t)sm_count() * 8;
+    const int64_t cap = (int64_t)sm_count() * g_ctas_per_sm;
     return (int)(want < cap ? want : cap);
 }
 
@@ -478,6 +563,12 @@ static int frame_grid(int64_t n, int per_thread) {
 using namespace lidar;
 
 extern "C" {
+
+int lidar_frame_set_ctas_per_sm(int ctas_per_sm) {
+    LIDAR_REQUIRE(ctas_per_sm >= 1 && ctas_per_sm <= 8, LIDAR_ERR_INVALID, "lidar_frame_set_ctas_per_sm: 1..8");
+    g_ctas_per_sm = ctas_per_sm;
+    return LIDAR_OK;
+}
 
 size_t lidar_frame_workspace_bytes(const lidar_frame_caps* caps) {
     if (!caps || caps->max_points < 0 || caps->max_key_space <= 0) return 0;
@@ -495,8 +586,7 @@ int lidar_frame_workspace_init(void* d_ws, size_t ws_bytes, const lidar_frame_ca
 
 static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxel_size, double grid_size,
                               const double* h_origin3, const double* h_xy_range4,
-                              int32_t* d_voxel_key, int32_t* d_inverse, void* d_centroids,
-                              int32_t* d_counts, int32_t* d_unique_keys, int32_t* d_grid,
+                              int32_t* d_voxel_key, int32_t* d_inverse, lidar_voxel* d_voxels, int32_t* d_grid,
                               lidar_frame_desc* d_desc, const lidar_frame_caps* caps, void* d_ws,
                               size_t ws_bytes, void* stream, void** events) {
     LIDAR_REQUIRE(caps != nullptr, LIDAR_ERR_INVALID, "lidar_frame_voxel_density: caps is NULL");
@@ -509,22 +599,23 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
     LIDAR_REQUIRE(grid_size >= 0.0, LIDAR_ERR_INVALID, "lidar_frame_voxel_density: grid_size must be >= 0");
     LIDAR_REQUIRE(caps->max_key_space > 0 && caps->max_key_space < (1ll << 31), LIDAR_ERR_INVALID,
                   "lidar_frame_voxel_density: caps.max_key_space must be in (0, 2^31)");
-    LIDAR_REQUIRE(d_desc && d_voxel_key && d_inverse && d_centroids && d_counts && d_unique_keys,
-                  LIDAR_ERR_INVALID, "lidar_frame_voxel_density: NULL output");
+    LIDAR_REQUIRE(d_desc && d_voxel_key && d_inverse && d_voxels, LIDAR_ERR_INVALID,
+                  "lidar_frame_voxel_density: NULL output");
     LIDAR_REQUIRE(grid_size == 0.0 || (d_grid && caps->max_nx > 0 && caps->max_ny > 0), LIDAR_ERR_INVALID,
                   "lidar_frame_voxel_density: density grid requested without d_grid / capacities");
     LIDAR_REQUIRE(n == 0 || d_points, LIDAR_ERR_INVALID, "lidar_frame_voxel_density: NULL points");
     const FrameWsLayout L = frame_layout(*caps);
     LIDAR_REQUIRE(d_ws && ws_bytes >= L.total, LIDAR_ERR_WORKSPACE,
                   "lidar_frame_voxel_density: workspace too small (%zu < %zu)", ws_bytes, L.total);
+    LIDAR_REQUIRE(L.tiles <= 65536, LIDAR_ERR_CAPACITY, "lidar_frame_voxel_density: caps.max_key_space too large");
     char* ws = static_cast<char*>(d_ws);
     double* partial = reinterpret_cast<double*>(ws + L.off_partial);
     FrameCtrl* ctrl = reinterpret_cast<FrameCtrl*>(ws + L.off_ctrl);
-    uint32_t* bitmap = reinterpret_cast<uint32_t*>(ws + L.off_bitmap);
-    uint32_t* group_prefix = reinterpret_cast<uint32_t*>(ws + L.off_group_prefix);
+    uint32_t* groups = reinterpret_cast<uint32_t*>(ws + L.off_groups);
     unsigned long long* tile_desc = reinterpret_cast<unsigned long long*>(ws + L.off_tile_desc);
     long long* acc = reinterpret_cast<long long*>(ws + L.off_acc);
     int32_t* cnt = reinterpret_cast<int32_t*>(ws + L.off_cnt);
+    uint32_t* filter = reinterpret_cast<uint32_t*>(ws + L.off_filter);
 
     FrameParams P;
     P.pts = static_cast<const float4*>(d_points);
@@ -548,57 +639,54 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
     };
     const int grid_cap = grid_size > 0.0 ? caps->max_nx * caps->max_ny : 0;
     LIDAR_CUDA_TRY(mark(0));
-    int bgrid = frame_grid(n, 4);
+    int bgrid = frame_grid(n > 0 ? n : 1, 4);
+    if (bgrid < sm_count()) bgrid = sm_count();   // enough CTAs to zero the bitmap quickly
     if (bgrid > kBboxMaxBlocks) bgrid = kBboxMaxBlocks;
-    k_frame_bbox<<<bgrid, kFrameThreads, 0, st>>>(P, partial, ctrl, d_desc, d_grid, grid_cap, tile_desc, L.tiles);
+    k_frame_prep<<<bgrid, kFrameThreads, 0, st>>>(P, partial, ctrl, d_desc, d_grid, grid_cap, tile_desc, L.tiles,
+                                                  groups, L.groups, filter);
     LIDAR_CHECK_LAUNCH();
     LIDAR_CUDA_TRY(mark(1));
     if (n == 0) {
         for (int i = 2; i <= 5; ++i) LIDAR_CUDA_TRY(mark(i));
         return LIDAR_OK;
     }
-    k_frame_mark<<<frame_grid(n, 2), kFrameThreads, 0, st>>>(P.pts, d_desc, d_voxel_key, bitmap, d_grid);
+    k_frame_mark<<<frame_grid(n, 2), kFrameThreads, 0, st>>>(P.pts, d_desc, d_voxel_key, groups, filter, d_grid);
     LIDAR_CHECK_LAUNCH();
     LIDAR_CUDA_TRY(mark(2));
     {
-        int sgrid = sm_count() * 4;
+        // one CTA per tile when they all fit in a single wave, so nobody spins on an unscheduled tile
+        int sgrid = sm_count() * 8;
         if ((int64_t)sgrid > L.tiles) sgrid = (int)L.tiles;
-        k_frame_scan<<<sgrid, kFrameThreads, 0, st>>>(bitmap, group_prefix, tile_desc, ctrl, d_desc);
+        k_frame_scan<<<sgrid, kFrameThreads, 0, st>>>(groups, tile_desc, ctrl, d_desc);
         LIDAR_CHECK_LAUNCH();
     }
     LIDAR_CUDA_TRY(mark(3));
-    k_frame_rank<<<frame_grid(n, 2), kFrameThreads, 0, st>>>(P.pts, d_desc, d_voxel_key, bitmap, group_prefix,
-                                                              d_inverse, acc, cnt, d_unique_keys);
+    k_frame_rank<<<frame_grid(n, 2), kFrameThreads, 0, st>>>(P.pts, d_desc, d_voxel_key, groups, filter, d_inverse,
+                                                              acc, cnt, d_voxels);
     LIDAR_CHECK_LAUNCH();
     LIDAR_CUDA_TRY(mark(4));
-    k_frame_finalize<<<frame_grid(n, 2), kFrameThreads, 0, st>>>(d_desc, acc, cnt, d_unique_keys, bitmap,
-                                                                  static_cast<float4*>(d_centroids), d_counts);
+    k_frame_finalize<<<frame_grid(n, 4), kFrameThreads, 0, st>>>(d_desc, acc, cnt, d_voxels);
     LIDAR_CHECK_LAUNCH();
     LIDAR_CUDA_TRY(mark(5));
     return LIDAR_OK;
 }
 
 int lidar_frame_voxel_density(const void* d_points, int64_t n, double voxel_size, double grid_size,
-                              const double* h_origin3, const double* h_xy_range4,
-                              int32_t* d_voxel_key, int32_t* d_inverse, void* d_centroids,
-                              int32_t* d_counts, int32_t* d_unique_keys, int32_t* d_grid,
-                              lidar_frame_desc* d_desc, const lidar_frame_caps* caps, void* d_ws,
-                              size_t ws_bytes, void* stream) {
+                              const double* h_origin3, const double* h_xy_range4, int32_t* d_voxel_key,
+                              int32_t* d_inverse, lidar_voxel* d_voxels, int32_t* d_grid, lidar_frame_desc* d_desc,
+                              const lidar_frame_caps* caps, void* d_ws, size_t ws_bytes, void* stream) {
     return frame_voxel_density_impl(d_points, n, voxel_size, grid_size, h_origin3, h_xy_range4, d_voxel_key,
-                                    d_inverse, d_centroids, d_counts, d_unique_keys, d_grid, d_desc, caps,
-                                    d_ws, ws_bytes, stream, nullptr);
+                                    d_inverse, d_voxels, d_grid, d_desc, caps, d_ws, ws_bytes, stream, nullptr);
 }
 
 int lidar_frame_voxel_density_timed(const void* d_points, int64_t n, double voxel_size, double grid_size,
-                                    const double* h_origin3, const double* h_xy_range4,
-                                    int32_t* d_voxel_key, int32_t* d_inverse, void* d_centroids,
-                                    int32_t* d_counts, int32_t* d_unique_keys, int32_t* d_grid,
+                                    const double* h_origin3, const double* h_xy_range4, int32_t* d_voxel_key,
+                                    int32_t* d_inverse, lidar_voxel* d_voxels, int32_t* d_grid,
                                     lidar_frame_desc* d_desc, const lidar_frame_caps* caps, void* d_ws,
                                     size_t ws_bytes, void* stream, void** h_events6) {
     LIDAR_REQUIRE(h_events6 != nullptr, LIDAR_ERR_INVALID, "lidar_frame_voxel_density_timed: events is NULL");
     return frame_voxel_density_impl(d_points, n, voxel_size, grid_size, h_origin3, h_xy_range4, d_voxel_key,
-                                    d_inverse, d_centroids, d_counts, d_unique_keys, d_grid, d_desc, caps,
-                                    d_ws, ws_bytes, stream, h_events6);
+                                    d_inverse, d_voxels, d_grid, d_desc, caps, d_ws, ws_bytes, stream, h_events6);
 }
 
 }  // extern "C"

@@ -236,9 +236,11 @@ class FramePipeline:
         n = int(max_points)
         self.voxel_key = torch.empty(n, dtype=torch.int32, device=dev)
         self.inverse = torch.empty(n, dtype=torch.int32, device=dev)
-        self.centroids = torch.empty((n, 4), dtype=torch.float32, device=dev)
-        self.counts = torch.empty(n, dtype=torch.int32, device=dev)
-        self.unique_keys = torch.empty(n, dtype=torch.int32, device=dev)
+        # lidar_voxel records (32 B): float x,y,z,intensity; int32 count, key, pad[2]
+        self.voxels = torch.empty((n, 8), dtype=torch.float32, device=dev)
+        self.centroids = self.voxels[:, :4]
+        self.counts = self.voxels.view(torch.int32)[:, 4]
+        self.unique_keys = self.voxels.view(torch.int32)[:, 5]
         self.grid = (torch.empty(int(max_nx) * int(max_ny), dtype=torch.int32, device=dev)
                      if grid_size > 0 else None)
         self.desc_dev = torch.zeros(C.sizeof(FrameDesc), dtype=torch.uint8, device=dev)
@@ -262,9 +264,8 @@ class FramePipeline:
         r4 = (C.c_double * 4)(*[float(v) for v in xy_range]) if xy_range is not None else None
         self._n = n
         args = (_ptr(points), n, self.voxel_size, self.grid_size, o3, r4, _ptr(self.voxel_key),
-                _ptr(self.inverse), _ptr(self.centroids), _ptr(self.counts), _ptr(self.unique_keys),
-                _ptr(self.grid), _ptr(self.desc_dev), C.byref(self.caps), _ptr(self.ws), self.ws.numel(),
-                _stream_ptr())
+                _ptr(self.inverse), _ptr(self.voxels), _ptr(self.grid), _ptr(self.desc_dev), C.byref(self.caps),
+                _ptr(self.ws), self.ws.numel(), _stream_ptr())
         try:
             if events is None:
                 check(lib.lidar_frame_voxel_density(*args))
@@ -320,8 +321,7 @@ class HostFramePipeline:
                 "pipe": pipe, "stream": st, "n": 0,
                 "h_in": torch.empty((n, 4), dtype=torch.float32).pin_memory(),
                 "d_in": torch.empty((n, 4), dtype=torch.float32, device=self.device),
-                "h_cent": torch.empty((n, 4), dtype=torch.float32).pin_memory(),
-                "h_cnt": torch.empty(n, dtype=torch.int32).pin_memory(),
+                "h_vox": torch.empty((n, 8), dtype=torch.float32).pin_memory(),
                 "h_inv": torch.empty(n, dtype=torch.int32).pin_memory() if per_point_outputs else None,
                 "h_key": torch.empty(n, dtype=torch.int32).pin_memory() if per_point_outputs else None,
                 "h_grid": (torch.empty(pipe.grid.numel(), dtype=torch.int32).pin_memory()
@@ -337,7 +337,7 @@ class HostFramePipeline:
 
     def d2h_bytes(self, n: int) -> int:
         s = self.slots[0]
-        b = n * 16 + n * 4 + C.sizeof(FrameDesc)
+        b = n * 32 + C.sizeof(FrameDesc)
         if self.per_point_outputs:
             b += 2 * n * 4
         if s["h_grid"] is not None:
@@ -363,8 +363,7 @@ class HostFramePipeline:
             slot["d_in"][:n].copy_(h_in, non_blocking=True)
             pipe.enqueue(slot["d_in"][:n], origin=origin, xy_range=xy_range)
             pipe.desc_host.copy_(pipe.desc_dev, non_blocking=True)
-            slot["h_cent"][:n].copy_(pipe.centroids[:n], non_blocking=True)
-            slot["h_cnt"][:n].copy_(pipe.counts[:n], non_blocking=True)
+            slot["h_vox"][:n].copy_(pipe.voxels[:n], non_blocking=True)
             if self.per_point_outputs:
                 slot["h_inv"][:n].copy_(pipe.inverse[:n], non_blocking=True)
                 slot["h_key"][:n].copy_(pipe.voxel_key[:n], non_blocking=True)
@@ -383,9 +382,10 @@ class HostFramePipeline:
             raise _capi.LidarError(int(desc.status), "frame exceeded its capacities")
         n, v = slot["n"], int(desc.n_voxels)
         cp = (lambda a: a.copy()) if copy else (lambda a: a)
+        rec = slot["h_vox"].numpy()[:v]
         out = {
-            "centroids": cp(slot["h_cent"].numpy()[:v]), "counts": cp(slot["h_cnt"].numpy()[:v]),
-            "n_voxels": v, "dims": tuple(desc.dims[:3]), "origin": tuple(desc.origin[:3]), "desc": desc,
+            "centroids": cp(rec[:, :4]), "counts": cp(rec.view(np.int32)[:, 4]),
+            "unique_keys": cp(rec.view(np.int32)[:, 5]), "n_voxels": v, "dims": tuple(desc.dims[:3]), "origin": tuple(desc.origin[:3]), "desc": desc,
         }
         if self.per_point_outputs:
             out["inverse"] = cp(slot["h_inv"].numpy()[:n])
