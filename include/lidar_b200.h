@@ -44,6 +44,11 @@ extern "C" {
 #define LIDAR_HIST_GLOBAL 1 /* one RED.ADD per point straight into the L2-resident grid          */
 #define LIDAR_HIST_SHARED 2 /* CTA-private shared-memory grid, warp-aggregated, flushed at the end */
 
+/* shared-MLP implementation selector (lidar_shared_mlp_maxpool) */
+#define LIDAR_MLP_AUTO 0    /* tcgen05 when the shape is 3-64-64-128 / k = 32 with fused gather, else SIMT */
+#define LIDAR_MLP_SIMT 1    /* fp32 CUDA-core kernel, any widths                                           */
+#define LIDAR_MLP_TCGEN05 2 /* 5th-gen tensor cores (bf16 hi/lo split operands, fp32 accumulate in TMEM)   */
+
 const char* lidar_last_error(void);
 int lidar_abi_version(void);
 /* sm_count, compute capability (major*10+minor), opt-in shared memory per block of `device` */
@@ -188,6 +193,34 @@ int lidar_frame_flow_match(const float* d_prev_xy, int n_prev, const float* d_cu
 int lidar_frame_flow_field(const double* d_lattice_xy, int n_lattice, const float* d_cur_xy, const int32_t* d_match,
                            const float* d_velocity, int n_cur, double radius, double* d_vectors, double* d_magnitudes,
                            void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
+ * K11-K13  PointNet++-style set abstraction (NEW ops; the reference only
+ *          names a classifier in windows_design.md:65 and contains no such code).
+ *   lidar_fps             (B,N,3) f32 -> (B,M) int32.  idx[0] = 0, fp32 ((dx*dx+dy*dy)+dz*dz), running min
+ *                         initialised to 1e10, lowest index of the maximum: bit-exact.  One thread-block
+ *                         cluster per cloud (N <= 16384), points resident on chip.
+ *   lidar_ball_query      first k indices (ascending) with d2 < r2 (strict, fp32); the first hit pre-fills
+ *                         all k slots; no hit leaves zeros: bit-exact.  (B,M,k) int32.
+ *   lidar_group_points    out[b,:3,m,j] = xyz[b,idx[b,m,j]] - new_xyz[b,m]; feature channels gathered
+ *                         unchanged after them.  (B,3+C,M,k) f32, exact.
+ *   lidar_gather_points   new_xyz[b,m] = xyz[b,idx[b,m]]   (the centres FPS selected)
+ *   lidar_shared_mlp_maxpool   relu(W3 relu(W2 relu(W1 g + b1) + b2) + b3), max over k -> (B,c3,M) f32.
+ *                         Input is either a materialised grouped tensor d_grouped (B,c_in,M,k) or the
+ *                         fused gather (d_xyz, d_idx, d_new_xyz[, d_feats]) with d_grouped = NULL.
+ *                         W1 (c1,c_in), W2 (c2,c1), W3 (c3,c2) row-major fp32, BatchNorm pre-folded.
+ * ------------------------------------------------------------------------------------------- */
+size_t lidar_fps_workspace_bytes(int b, int n);
+int lidar_fps(const float* d_xyz, int b, int n, int m, int32_t* d_idx, void* d_ws, size_t ws_bytes, void* stream);
+int lidar_ball_query(const float* d_xyz, const float* d_new_xyz, int b, int n, int m, float radius, int k,
+                     int32_t* d_idx, void* stream);
+int lidar_group_points(const float* d_xyz, const float* d_feats, const int32_t* d_idx, const float* d_new_xyz, int b,
+                       int n, int m, int k, int c_feat, float* d_out, void* stream);
+int lidar_gather_points(const float* d_xyz, const int32_t* d_idx, int b, int n, int m, float* d_out, void* stream);
+int lidar_shared_mlp_maxpool(const float* d_xyz, const float* d_feats, const int32_t* d_idx, const float* d_new_xyz,
+                             const float* d_grouped, int b, int n, int m, int k, int c_in, int c1, int c2, int c3,
+                             const float* d_w1, const float* d_b1, const float* d_w2, const float* d_b2,
+                             const float* d_w3, const float* d_b3, float* d_out, int impl, void* stream);
 
 /* ------------------------------------------------------------------------------------------- *
  * K5  voxel downsample (NEW op).

@@ -19,6 +19,7 @@ LIDAR_OK = 0
 FMT_F32X4 = 0
 FMT_F64X3 = 1
 HIST_AUTO, HIST_GLOBAL, HIST_SHARED = 0, 1, 2
+MLP_AUTO, MLP_SIMT, MLP_TCGEN05 = 0, 1, 2
 
 ERR_NAMES = {-1: "LIDAR_ERR_INVALID", -2: "LIDAR_ERR_CUDA", -3: "LIDAR_ERR_WORKSPACE", -4: "LIDAR_ERR_CAPACITY"}
 
@@ -101,6 +102,13 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_radius_count": (_i32, [_vp, _i32, _vp, _i32, _vp, _i32, _dbl, _vp, _vp]),
     "lidar_frame_flow_match": (_i32, [_vp, _i32, _vp, _i32, C.c_float, C.c_float, _vp, _vp, _vp]),
     "lidar_frame_flow_field": (_i32, [_vp, _i32, _vp, _vp, _vp, _i32, _dbl, _vp, _vp, _vp]),
+    "lidar_fps_workspace_bytes": (_sz, [_i32, _i32]),
+    "lidar_fps": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "lidar_ball_query": (_i32, [_vp, _vp, _i32, _i32, _i32, C.c_float, _i32, _vp, _vp]),
+    "lidar_group_points": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "lidar_gather_points": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "lidar_shared_mlp_maxpool": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "lidar_frame_set_ctas_per_sm": (_i32, [_i32]),
     "lidar_frame_workspace_bytes": (_sz, [C.POINTER(FrameCaps)]),
     "lidar_frame_workspace_init": (_i32, [_vp, _sz, C.POINTER(FrameCaps), _vp]),

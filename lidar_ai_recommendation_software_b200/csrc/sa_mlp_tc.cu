@@ -1,0 +1,274 @@
+// K13 (tensor-core path) — fused gather + shared MLP 3-64-64-128 + max-pool over k = 32 on the
+// 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).  NEW op, SURVEY.md Appendix B.7.
+//
+// One CTA tile = 128 rows = 4 centres x 32 neighbours, so TMEM lane r / thread r / warp w line up with
+// (neighbour r % 32 of centre w): the max-pool over the neighbours is a warp REDUX, no shared memory.
+//   layer 1 (K = 3)        CUDA cores, straight from the gathered (xyz[idx] - centre)
+//   layer 2 (128x64x64)    tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM columns 0..63)
+//   layer 3 (128x128x64)   tcgen05.mma kind::f16 (TMEM columns 64..191)
+// Precision: rtol 1e-3 is not reachable with plain bf16 (or tf32) operands, so every operand is split
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi) and each GEMM is issued as hi*hi + hi*lo + lo*hi
+// (the dropped lo*lo term is ~2^-16 relative) — three MMAs per K step, still tensor-bound trivial.
+// Operands are K-major, un-swizzled "interleaved" core matrices (8 rows x 16 B), built directly by the
+// producing threads with 16-byte shared stores:
+//     offset(row, k) = (row/8)*1024 + (k/8)*128 + (row%8)*16 + (k%8)*2      [SBO = 1024 B, LBO = 128 B]
+// Descriptor / instruction-descriptor bit layouts follow the PTX ISA tcgen05 matrix-descriptor tables.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace lidar {
+
+constexpr int kTcThreads = 128;
+constexpr int kTcRows = 128;
+constexpr int kTcK = 32;            // neighbours per centre
+constexpr int kC1 = 64, kC2 = 64, kC3 = 128;
+constexpr int kTmemCols = 256;      // 64 (layer 2) + 128 (layer 3) rounded up to a power of two
+
+// shared-memory carve-up (bytes)
+constexpr int kOffAh = 0;                       // activations hi  [128 x 64] bf16
+constexpr int kOffAl = kOffAh + 128 * 64 * 2;   // activations lo
+constexpr int kOffW2h = kOffAl + 128 * 64 * 2;  // W2 hi [64 x 64]
+constexpr int kOffW2l = kOffW2h + 64 * 64 * 2;
+constexpr int kOffW3h = kOffW2l + 64 * 64 * 2;  // W3 hi [128 x 64]
+constexpr int kOffW3l = kOffW3h + 128 * 64 * 2;
+constexpr int kOffW1 = kOffW3l + 128 * 64 * 2;  // fp32 [64][3]
+constexpr int kOffB1 = kOffW1 + 64 * 3 * 4;
+constexpr int kOffB2 = kOffB1 + 64 * 4;
+constexpr int kOffB3 = kOffB2 + 64 * 4;
+constexpr int kOffBar = kOffB3 + 128 * 4;       // mbarrier (8 B) + TMEM base (4 B)
+constexpr int kTcSmem = kOffBar + 16;
+
+__device__ __forceinline__ unsigned s_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (sm_100 version bit set)
+__device__ __forceinline__ unsigned long long umma_desc(unsigned smem_byte_addr) {
+    const unsigned long long lbo = 128 >> 4, sbo = 1024 >> 4;
+    return (unsigned long long)((smem_byte_addr >> 4) & 0x3FFF) | (lbo << 16) | (sbo << 32) | (1ull << 46);
+}
+// instruction descriptor: D = F32, A = B = BF16, both K-major, M x N
+__device__ __forceinline__ unsigned umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(unsigned tmem_d, unsigned long long a, unsigned long long b, unsigned idesc,
+                                         unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(s_addr(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
+    unsigned r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// split 8 fp32 values into bf16 hi / lo and store them as one 16-byte K chunk each
+__device__ __forceinline__ void store_chunk(unsigned char* smem, int row, int kc, const float (&x)[8]) {
+    unsigned hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+        hi[i] = (unsigned)__bfloat16_as_ushort(h0) | ((unsigned)__bfloat16_as_ushort(h1) << 16);
+        lo[i] = (unsigned)__bfloat16_as_ushort(l0) | ((unsigned)__bfloat16_as_ushort(l1) << 16);
+    }
+    const int off = (row >> 3) * 1024 + kc * 128 + (row & 7) * 16;
+    *reinterpret_cast<uint4*>(smem + kOffAh + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(smem + kOffAl + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// stage an fp32 [rows x 64] row-major weight matrix as bf16 hi / lo core matrices
+__device__ __forceinline__ void stage_weights(const float* __restrict__ W, int rows, unsigned char* hi_base,
+                                              unsigned char* lo_base) {
+    for (int e = threadIdx.x; e < rows * 64; e += kTcThreads) {
+        const int r = e >> 6, k = e & 63;
+        const float x = W[e];
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+        const int off = (r >> 3) * 1024 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(hi_base + off) = h;
+        *reinterpret_cast<__nv_bfloat16*>(lo_base + off) = l;
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads)
+shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx, const float* __restrict__ new_xyz,
+                     int n, int m, int n_centres, const float* __restrict__ W1, const float* __restrict__ B1,
+                     const float* __restrict__ W2, const float* __restrict__ B2, const float* __restrict__ W3,
+                     const float* __restrict__ B3, float* __restrict__ out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float* sW1 = reinterpret_cast<float*>(smem + kOffW1);
+    float* sB1 = reinterpret_cast<float*>(smem + kOffB1);
+    float* sB2 = reinterpret_cast<float*>(smem + kOffB2);
+    float* sB3 = reinterpret_cast<float*>(smem + kOffB3);
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + kOffBar);
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + kOffBar + 8);
+    const int warp = threadIdx.x >> 5;
+    const unsigned lane = lane_id();
+
+    // ---- one-time setup: weights, barrier, TMEM ------------------------------------------------
+    stage_weights(W2, kC2, smem + kOffW2h, smem + kOffW2l);
+    stage_weights(W3, kC3, smem + kOffW3h, smem + kOffW3l);
+    for (int i = threadIdx.x; i < kC1 * 3; i += kTcThreads) sW1[i] = W1[i];
+    for (int i = threadIdx.x; i < kC1; i += kTcThreads) sB1[i] = B1[i];
+    for (int i = threadIdx.x; i < kC2; i += kTcThreads) sB2[i] = B2[i];
+    for (int i = threadIdx.x; i < kC3; i += kTcThreads) sB3[i] = B3[i];
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_addr(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_addr(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_base = *tmem_slot;
+    const unsigned tmem_lane = tmem_base + ((unsigned)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+    const unsigned sbase = s_addr(smem);
+    const unsigned idesc2 = umma_idesc(kTcRows, kC2), idesc3 = umma_idesc(kTcRows, kC3);
+    unsigned phase = 0;
+
+    const int n_tiles = (n_centres + 3) / 4;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int centre = tile * 4 + warp;           // global centre index b*m + mm
+        const bool live = centre < n_centres;
+        const int row = threadIdx.x;
+        // ---- gather + layer 1 (fp32 CUDA cores) -> A (hi, lo) ------------------------------------
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+        if (live) {
+            const int b = centre / m;
+            const int src = idx[(size_t)centre * kTcK + lane];
+            const float* p = xyz + ((size_t)b * n + src) * 3;
+            const float* c = new_xyz + (size_t)centre * 3;
+            g0 = __fsub_rn(p[0], c[0]); g1 = __fsub_rn(p[1], c[1]); g2 = __fsub_rn(p[2], c[2]);
+        }
+#pragma unroll
+        for (int kc = 0; kc < 8; ++kc) {
+            float h[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int o = kc * 8 + i;
+                float a = sB1[o];
+                a = fmaf(sW1[o * 3], g0, a);
+                a = fmaf(sW1[o * 3 + 1], g1, a);
+                a = fmaf(sW1[o * 3 + 2], g2, a);
+                h[i] = fmaxf(a, 0.f);
+            }
+            store_chunk(smem, row, kc, h);
+        }
+        // generic-proxy smem writes -> visible to the tensor core (async proxy); TMEM reads of the previous
+        // tile are complete (tcgen05.wait::ld) and ordered before the MMAs that overwrite the accumulators
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        // ---- layer 2: D2[128x64] = A1 * W2^T ----------------------------------------------------
+        if (threadIdx.x == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {   // K = 64 in steps of 16 (two 16-byte chunks = 256 B)
+                const unsigned long long ah = umma_desc(sbase + kOffAh + j * 256), al = umma_desc(sbase + kOffAl + j * 256);
+                const unsigned long long wh = umma_desc(sbase + kOffW2h + j * 256), wl = umma_desc(sbase + kOffW2l + j * 256);
+                umma_f16(tmem_base, ah, wh, idesc2, j > 0);
+                umma_f16(tmem_base, ah, wl, idesc2, 1);
+                umma_f16(tmem_base, al, wh, idesc2, 1);
+            }
+            umma_commit(bar);
+        }
+        bar_wait(bar, phase);
+        phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- epilogue 2: bias + ReLU, re-split, becomes the A operand of layer 3 -----------------
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float v[16];
+            tmem_ld16(tmem_lane + q * 16, v);
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                float h[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) h[i] = fmaxf(v[hlf * 8 + i] + sB2[q * 16 + hlf * 8 + i], 0.f);
+                store_chunk(smem, row, q * 2 + hlf, h);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        // ---- layer 3: D3[128x128] = A2 * W3^T ---------------------------------------------------
+        if (threadIdx.x == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned long long ah = umma_desc(sbase + kOffAh + j * 256), al = umma_desc(sbase + kOffAl + j * 256);
+                const unsigned long long wh = umma_desc(sbase + kOffW3h + j * 256), wl = umma_desc(sbase + kOffW3l + j * 256);
+                umma_f16(tmem_base + kC2, ah, wh, idesc3, j > 0);
+                umma_f16(tmem_base + kC2, ah, wl, idesc3, 1);
+                umma_f16(tmem_base + kC2, al, wh, idesc3, 1);
+            }
+            umma_commit(bar);
+        }
+        bar_wait(bar, phase);
+        phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- epilogue 3: bias + ReLU + max over the 32 neighbours (= the 32 lanes of this warp) ----
+        const int b = live ? centre / m : 0, mm = live ? centre % m : 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float v[16];
+            tmem_ld16(tmem_lane + kC2 + q * 16, v);
+            float keep = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float a = fmaxf(v[i] + sB3[q * 16 + i], 0.f);
+                const unsigned mx = __reduce_max_sync(0xffffffffu, __float_as_uint(a));   // a >= 0: uint order = float order
+                if ((int)lane == i) keep = __uint_as_float(mx);
+            }
+            if (live && lane < 16) out[((size_t)b * kC3 + q * 16 + lane) * m + mm] = keep;
+        }
+    }
+    // ---- teardown ----------------------------------------------------------------------------------
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+int launch_shared_mlp_tc(const float* xyz, const int* idx, const float* new_xyz, int b, int n, int m, int k,
+                         const float* W1, const float* B1, const float* W2, const float* B2, const float* W3,
+                         const float* B3, float* out, cudaStream_t st) {
+    (void)k;
+    LIDAR_CUDA_TRY(cudaFuncSetAttribute(shared_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+    const int n_centres = b * m;
+    const int n_tiles = (n_centres + 3) / 4;
+    int grid = sm_count() * 2;   // 2 CTAs per SM: 2 x 256 TMEM columns, 2 x 82 KB of shared memory
+    if (grid > n_tiles) grid = n_tiles;
+    shared_mlp_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(xyz, idx, new_xyz, n, m, n_centres, W1, B1, W2, B2, W3, B3, out);
+    LIDAR_CHECK_LAUNCH();
+    return LIDAR_OK;
+}
+
+}  // namespace lidar
