@@ -250,7 +250,10 @@ typedef struct lidar_frame_desc {
     int64_t n_points;
     int64_t n_voxels;
     int32_t status;       /* 0 ok, LIDAR_ERR_CAPACITY if key_space / grid exceeded capacities  */
-    int32_t pad;
+    int32_t fast_f32;     /* 1: origin is fp32-exact, the fp32 index guess may be used         */
+    /* exact division of a key (< 2^31) by Dz and by Dy: q = (key * magic) >> (31 + shift)     */
+    uint32_t magic_dz, magic_dy;
+    int32_t shift_dz, shift_dy;
 } lidar_frame_desc;
 
 /* one output voxel = one 32-byte sector, so a voxel is written with a single full-sector store */

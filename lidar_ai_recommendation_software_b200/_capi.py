@@ -51,7 +51,9 @@ class FrameDesc(C.Structure):
         ("n_points", C.c_int64),
         ("n_voxels", C.c_int64),
         ("status", C.c_int32),
-        ("pad", C.c_int32),
+        ("fast_f32", C.c_int32),
+        ("magic_dz", C.c_uint32), ("magic_dy", C.c_uint32),
+        ("shift_dz", C.c_int32), ("shift_dy", C.c_int32),
     ]
 
 

@@ -43,16 +43,19 @@ constexpr int kFilterBits = 22;                                       // duplica
 constexpr int kFilterWords = 1 << (kFilterBits - 5);
 
 struct FrameWsLayout {
-    size_t off_partial, off_ctrl, off_groups, off_tile_desc, off_acc, off_cnt, off_filter, total;
+    size_t off_partial, off_ctrl, off_groups, off_tile_desc, off_acc, off_cnt, off_filter, off_cta_desc, total;
     int64_t groups, tiles;
 };
 
 struct FrameCtrl {
     unsigned int bbox_ticket;
     unsigned int scan_ticket;
-    unsigned int pad[2];
+    unsigned int grid_bar;     // fused kernel: grid-barrier arrival counter (reset by the last CTA to exit)
+    unsigned int exit_ticket;  // fused kernel: CTAs that have passed the last barrier
     unsigned long long dirty_groups;  // occupancy groups the previous frame may have set
 };
+
+constexpr int kFusedMaxCtas = 1024;   // cap of the fused kernel's grid (one slot of cta_desc each)
 
 __device__ __forceinline__ unsigned filter_slot(int key) { return ((unsigned)key * 2654435761u) >> (32 - kFilterBits); }
 
@@ -73,6 +76,7 @@ static FrameWsLayout frame_layout(const lidar_frame_caps& c) {
     L.off_acc = take(sizeof(long long) * 4 * c.max_points);
     L.off_cnt = take(sizeof(int32_t) * c.max_points);
     L.off_filter = take(sizeof(uint32_t) * kFilterWords);
+    L.off_cta_desc = take(sizeof(unsigned long long) * kFusedMaxCtas);
     L.total = ws_align(o);
     return L;
 }
@@ -154,7 +158,32 @@ __device__ void derive_desc(const FrameParams& P, const double* bb, lidar_frame_
     }
     if (P.n == 0) status = 0;
     D->status = status;
-    D->pad = 0;
+    // the fp32 index guess needs an origin that fp32 represents exactly (true for a bbox-derived origin)
+    int fast = 1;
+    for (int c = 0; c < 3; ++c)
+        if ((double)(float)D->origin[c] != D->origin[c]) fast = 0;
+    if ((double)(float)P.voxel == 0.0) fast = 0;
+    D->fast_f32 = fast;
+    // Granlund-Montgomery: for 0 <= n < 2^31 and 2^(l-1) < d <= 2^l,  n / d == (n * ceil(2^(31+l)/d)) >> (31+l)
+    for (int c = 0; c < 2; ++c) {
+        const unsigned long long d = (unsigned long long)(c == 0 ? D->dims[2] : D->dims[1]);
+        int l = 0;
+        while ((1ull << l) < d) ++l;
+        const unsigned long long num = 1ull << (31 + l);
+        const unsigned m = (unsigned)((num + d - 1) / d);
+        if (c == 0) { D->magic_dz = m; D->shift_dz = l; } else { D->magic_dy = m; D->shift_dy = l; }
+    }
+}
+
+__device__ __forceinline__ int magic_div(int n, unsigned magic, int shift) {
+    return (int)(((unsigned long long)(unsigned)n * magic) >> (31 + shift));
+}
+// key -> (ix, iy, iz) without integer division instructions
+__device__ __forceinline__ void decode_key(int key, const lidar_frame_desc& D, int& ix, int& iy, int& iz) {
+    const int t = magic_div(key, D.magic_dz, D.shift_dz);
+    iz = key - t * D.dims[2];
+    ix = magic_div(t, D.magic_dy, D.shift_dy);
+    iy = t - ix * D.dims[1];
 }
 
 // ---- k_frame_prep -----------------------------------------------------------------------------
@@ -293,6 +322,29 @@ __device__ __forceinline__ int arange_bin(double x, double a, double e1, double 
     return k;
 }
 
+// fp32 guess of floor((p - o) / v), accepted only when the fractional part is farther from an integer
+// than the worst-case fp32 error; returns false when the exact fp64 path must decide
+__device__ __forceinline__ bool fast_voxel_index(float p, float of, float rvf, int& k) {
+    const float q = __fmul_rn(__fsub_rn(p, of), rvf);
+    const float kf = floorf(q);
+    const float fr = __fsub_rn(q, kf);
+    const float eps = fmaf(q, 4.0e-7f, 2.0e-6f);     // 3 roundings of 2^-24 each, with margin
+    k = (int)kf;
+    return fr > eps && fr < 1.0f - eps && q < 1.0e6f;
+}
+// fp32 guess of the histogram bin, VERIFIED against the exact fp64 edges; falls back to arange_bin
+__device__ __forceinline__ int fast_arange_bin(float xf, double x, float af, float rdf, double a, double e1, double d,
+                                               double rd, int nb) {
+    int k = (int)floorf(__fmul_rn(__fsub_rn(xf, af), rdf));
+    k = k < 0 ? 0 : (k > nb - 1 ? nb - 1 : k);
+    double lo = __dadd_rn(a, __dmul_rn((double)k, d));
+    double hi = __dadd_rn(a, __dmul_rn((double)(k + 1), d));
+    lo = k == 1 ? e1 : lo;
+    hi = k == 0 ? e1 : hi;
+    if (x >= lo && x < hi) return k;
+    return arange_bin(x, a, e1, d, rd, nb);
+}
+
 // streaming accesses: every point / key / inverse entry is touched once per pass, keep them from
 // evicting the L2-resident working set (occupancy groups, voxel records)
 __device__ __forceinline__ unsigned long long evict_first_policy() {
@@ -312,27 +364,36 @@ __device__ __forceinline__ void st_stream_s32(int* p, int v) {
 }
 
 // ---- k_frame_mark -----------------------------------------------------------------------------
-__device__ __forceinline__ void mark_point(const float4& q, const lidar_frame_desc& D, double rv, double rdx,
-                                           double rdy, bool do_grid, int64_t i, int32_t* __restrict__ voxel_key,
+struct MarkConst {
+    float of[3], rvf, axf, ayf, rdxf, rdyf;
+    double rv, rdx, rdy;
+    int fast;
+};
+
+__device__ __forceinline__ void mark_point(const float4& q, const lidar_frame_desc& D, const MarkConst& K,
+                                           bool do_grid, int64_t i, int32_t* __restrict__ voxel_key,
                                            uint32_t* __restrict__ groups, uint32_t* __restrict__ filter,
                                            int32_t* __restrict__ grid_out) {
-    const double x = (double)q.x, y = (double)q.y, z = (double)q.z;
-    const int ix = floor_div_exact(__dsub_rn(x, D.origin[0]), D.voxel, rv);
-    const int iy = floor_div_exact(__dsub_rn(y, D.origin[1]), D.voxel, rv);
-    const int iz = floor_div_exact(__dsub_rn(z, D.origin[2]), D.voxel, rv);
+    int ix, iy, iz;
+    const bool fx = K.fast && fast_voxel_index(q.x, K.of[0], K.rvf, ix);
+    const bool fy = K.fast && fast_voxel_index(q.y, K.of[1], K.rvf, iy);
+    const bool fz = K.fast && fast_voxel_index(q.z, K.of[2], K.rvf, iz);
+    if (!fx) ix = floor_div_exact(__dsub_rn((double)q.x, D.origin[0]), D.voxel, K.rv);
+    if (!fy) iy = floor_div_exact(__dsub_rn((double)q.y, D.origin[1]), D.voxel, K.rv);
+    if (!fz) iz = floor_div_exact(__dsub_rn((double)q.z, D.origin[2]), D.voxel, K.rv);
     const int key = (ix * D.dims[1] + iy) * D.dims[2] + iz;
     st_stream_s32(voxel_key + i, key);
     const unsigned g = (unsigned)key / kGroupVoxels, b = (unsigned)key - g * kGroupVoxels;
     const unsigned bit = 1u << (b & 31);
     const unsigned old = atomicOr(&groups[(size_t)g * 8 + 1 + (b >> 5)], bit);
+    if (do_grid) {
+        const int bx = fast_arange_bin(q.x, (double)q.x, K.axf, K.rdxf, D.ex0, D.ex1, D.exd, K.rdx, D.nx);
+        const int by = fast_arange_bin(q.y, (double)q.y, K.ayf, K.rdyf, D.ey0, D.ey1, D.eyd, K.rdy, D.ny);
+        if (bx >= 0 && by >= 0) atomicAdd(&grid_out[bx * D.ny + by], 1);
+    }
     if (old & bit) {   // the voxel already had a point: flag it as multi-member
         const unsigned h = filter_slot(key);
         atomicOr(&filter[h >> 5], 1u << (h & 31));
-    }
-    if (do_grid) {
-        const int bx = arange_bin(x, D.ex0, D.ex1, D.exd, rdx, D.nx);
-        const int by = arange_bin(y, D.ey0, D.ey1, D.eyd, rdy, D.ny);
-        if (bx >= 0 && by >= 0) atomicAdd(&grid_out[bx * D.ny + by], 1);
     }
 }
 
@@ -349,15 +410,21 @@ k_frame_mark(const float4* __restrict__ pts, const lidar_frame_desc* __restrict_
     if (D.status != 0) return;
     const int64_t n = D.n_points;
     const bool do_grid = D.grid > 0.0;
-    const double rv = __ddiv_rn(1.0, D.voxel);
-    const double rdx = do_grid ? __ddiv_rn(1.0, D.exd) : 0.0, rdy = do_grid ? __ddiv_rn(1.0, D.eyd) : 0.0;
+    MarkConst K;
+    K.rv = __ddiv_rn(1.0, D.voxel);
+    K.rdx = do_grid ? __ddiv_rn(1.0, D.exd) : 0.0;
+    K.rdy = do_grid ? __ddiv_rn(1.0, D.eyd) : 0.0;
+    K.of[0] = (float)D.origin[0]; K.of[1] = (float)D.origin[1]; K.of[2] = (float)D.origin[2];
+    K.rvf = (float)K.rv;
+    K.axf = (float)D.ex0; K.ayf = (float)D.ey0; K.rdxf = (float)K.rdx; K.rdyf = (float)K.rdy;
+    K.fast = D.fast_f32;
     int64_t i = t0;
     for (; i + stride < n; i += 2 * stride) {
         const float4 a = L.raw(i), b = L.raw(i + stride);
-        mark_point(a, D, rv, rdx, rdy, do_grid, i, voxel_key, groups, filter, grid_out);
-        mark_point(b, D, rv, rdx, rdy, do_grid, i + stride, voxel_key, groups, filter, grid_out);
+        mark_point(a, D, K, do_grid, i, voxel_key, groups, filter, grid_out);
+        mark_point(b, D, K, do_grid, i + stride, voxel_key, groups, filter, grid_out);
     }
-    if (i < n) mark_point(L.raw(i), D, rv, rdx, rdy, do_grid, i, voxel_key, groups, filter, grid_out);
+    if (i < n) mark_point(L.raw(i), D, K, do_grid, i, voxel_key, groups, filter, grid_out);
 }
 
 // ---- k_frame_scan -----------------------------------------------------------------------------
@@ -436,11 +503,41 @@ k_frame_scan(uint32_t* __restrict__ groups, unsigned long long* __restrict__ til
 }
 
 // ---- k_frame_rank -----------------------------------------------------------------------------
-__device__ __forceinline__ void rank_point(const float4& q, int key, const lidar_frame_desc& D, int64_t i,
-                                           const uint32_t* __restrict__ groups,
-                                           const uint32_t* __restrict__ filter, int32_t* __restrict__ inverse,
-                                           long long* __restrict__ acc, int32_t* __restrict__ cnt,
-                                           lidar_voxel* __restrict__ voxels) {
+// The accumulate path is needed by ~12 % of the points but, taken in place, would be executed by almost
+// every warp (divergence).  Each warp therefore parks those points in a private shared-memory ring and
+// drains it 32 at a time with all lanes active.
+struct MultiItem {
+    float4 q;
+    int key;
+    unsigned r;
+    int pad[2];
+};
+constexpr int kRingSize = 64;
+
+__device__ __forceinline__ void accumulate_multi(const MultiItem& it, const lidar_frame_desc& D,
+                                                 long long* __restrict__ acc, int32_t* __restrict__ cnt,
+                                                 lidar_voxel* __restrict__ voxels) {
+    int ix, iy, iz;
+    decode_key(it.key, D, ix, iy, iz);
+    const double cx = voxel_ref(D.origin[0], ix, D.voxel);
+    const double cy = voxel_ref(D.origin[1], iy, D.voxel);
+    const double cz = voxel_ref(D.origin[2], iz, D.voxel);
+    const long long fx = __double2ll_rn(__dmul_rn(__dsub_rn((double)it.q.x, cx), D.fix_scale_xyz));
+    const long long fy = __double2ll_rn(__dmul_rn(__dsub_rn((double)it.q.y, cy), D.fix_scale_xyz));
+    const long long fz = __double2ll_rn(__dmul_rn(__dsub_rn((double)it.q.z, cz), D.fix_scale_xyz));
+    const long long fw = __double2ll_rn(__dmul_rn((double)it.q.w, D.fix_scale_w));
+    unsigned long long* A = reinterpret_cast<unsigned long long*>(acc + (size_t)it.r * 4);
+    // results unused: these compile to RED (fire and forget), nothing in the warp waits on them
+    atomicAdd(A + 0, (unsigned long long)fx);
+    atomicAdd(A + 1, (unsigned long long)fy);
+    atomicAdd(A + 2, (unsigned long long)fz);
+    atomicAdd(A + 3, (unsigned long long)fw);
+    atomicAdd(cnt + it.r, 1);
+    voxels[it.r].key = it.key;   // every member stores the same value
+}
+
+// returns the rank and whether the voxel is (possibly) multi-member
+__device__ __forceinline__ unsigned rank_of(int key, const uint32_t* __restrict__ groups) {
     const unsigned g = (unsigned)key / kGroupVoxels, b = (unsigned)key - g * kGroupVoxels;
     const uint4* gw = reinterpret_cast<const uint4*>(groups + (size_t)g * 8);
     const uint4 a4 = gw[0], b4 = gw[1];
@@ -452,35 +549,7 @@ __device__ __forceinline__ void rank_point(const float4& q, int key, const lidar
         if (k < wi) r += __popc(w[k]);
         else if (k == wi) r += __popc(w[k] & ((1u << (b & 31)) - 1u));
     }
-    st_stream_s32(inverse + i, (int)r);
-    const unsigned h = filter_slot(key);
-    const bool multi = (__ldg(filter + (h >> 5)) >> (h & 31)) & 1u;
-    if (!multi) {
-        // exactly one point in this voxel: it is the centroid.  One full 32-byte sector store.
-        float4* rec = reinterpret_cast<float4*>(voxels + r);
-        rec[0] = q;
-        rec[1] = make_float4(__int_as_float(1), __int_as_float(key), 0.f, 0.f);
-        return;
-    }
-    const int iz = key % D.dims[2];
-    const int t = key / D.dims[2];
-    const int iy = t % D.dims[1];
-    const int ix = t / D.dims[1];
-    const double cx = voxel_ref(D.origin[0], ix, D.voxel);
-    const double cy = voxel_ref(D.origin[1], iy, D.voxel);
-    const double cz = voxel_ref(D.origin[2], iz, D.voxel);
-    const long long fx = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.x, cx), D.fix_scale_xyz));
-    const long long fy = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.y, cy), D.fix_scale_xyz));
-    const long long fz = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.z, cz), D.fix_scale_xyz));
-    const long long fw = __double2ll_rn(__dmul_rn((double)q.w, D.fix_scale_w));
-    unsigned long long* A = reinterpret_cast<unsigned long long*>(acc + (size_t)r * 4);
-    // results unused: these compile to RED (fire and forget), nothing in the warp waits on them
-    atomicAdd(A + 0, (unsigned long long)fx);
-    atomicAdd(A + 1, (unsigned long long)fy);
-    atomicAdd(A + 2, (unsigned long long)fz);
-    atomicAdd(A + 3, (unsigned long long)fw);
-    atomicAdd(cnt + r, 1);
-    voxels[r].key = key;   // every member stores the same value
+    return r;
 }
 
 __global__ void __launch_bounds__(kFrameThreads)
@@ -489,64 +558,114 @@ k_frame_rank(const float4* __restrict__ pts, const lidar_frame_desc* __restrict_
              const uint32_t* __restrict__ filter, int32_t* __restrict__ inverse, long long* __restrict__ acc,
              int32_t* __restrict__ cnt, lidar_voxel* __restrict__ voxels) {
     __shared__ lidar_frame_desc D;
+    __shared__ MultiItem s_ring[kFrameThreads / 32][kRingSize];
     if (threadIdx.x == 0) D = *Dg;
     __syncthreads();
     if (D.status != 0) return;
     const int64_t n = D.n_points;
     LoadF32x4 L{pts};
+    const unsigned lane = lane_id();
+    MultiItem* ring = s_ring[threadIdx.x >> 5];
+    unsigned head = 0, count = 0;     // warp-uniform
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + stride < n; i += 2 * stride) {
-        const int k0 = ld_stream_s32(voxel_key + i), k1 = ld_stream_s32(voxel_key + i + stride);
-        const float4 a = L.raw(i), b = L.raw(i + stride);
-        rank_point(a, k0, D, i, groups, filter, inverse, acc, cnt, voxels);
-        rank_point(b, k1, D, i + stride, groups, filter, inverse, acc, cnt, voxels);
+    const int64_t n_round = ((n + 31) / 32) * 32;   // keep whole warps in the loop for the ballots
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool live = i < n;
+        bool multi = false;
+        MultiItem it;
+        if (live) {
+            it.key = ld_stream_s32(voxel_key + i);
+            it.q = L.raw(i);
+            it.r = rank_of(it.key, groups);
+            st_stream_s32(inverse + i, (int)it.r);
+            const unsigned h = filter_slot(it.key);
+            multi = (__ldg(filter + (h >> 5)) >> (h & 31)) & 1u;
+            if (!multi) {
+                // exactly one point in this voxel: it is the centroid.  One full 32-byte sector store.
+                float4* rec = reinterpret_cast<float4*>(voxels + it.r);
+                rec[0] = it.q;
+                rec[1] = make_float4(__int_as_float(1), __int_as_float(it.key), 0.f, 0.f);
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, multi);
+        if (m) {
+            if (multi) ring[(head + count + __popc(m & lanemask_lt())) % kRingSize] = it;
+            count += __popc(m);
+            __syncwarp();
+            if (count >= 32) {
+                accumulate_multi(ring[(head + lane) % kRingSize], D, acc, cnt, voxels);
+                head = (head + 32) % kRingSize;
+                count -= 32;
+                __syncwarp();
+            }
+        }
     }
-    if (i < n) rank_point(L.raw(i), ld_stream_s32(voxel_key + i), D, i, groups, filter, inverse, acc, cnt, voxels);
+    if (lane < count) accumulate_multi(ring[(head + lane) % kRingSize], D, acc, cnt, voxels);
 }
 
 // ---- k_frame_finalize -------------------------------------------------------------------------
 // cnt[r] != 0 exactly for the voxels that went through the accumulators (multi-member voxels and the
-// few singletons that collided in the duplicate filter): a coalesced sweep over cnt finds them.
+// few singletons that collided in the duplicate filter): a coalesced sweep over cnt finds them; the
+// ~6 % of hits are parked in a per-warp ring and finished 32 at a time, so the fp64 divisions run with
+// full warps instead of being executed, mostly masked, by every warp.
+__device__ __forceinline__ void finalize_voxel(unsigned r, const lidar_frame_desc& D, double isx, double isw,
+                                               long long* __restrict__ acc, int32_t* __restrict__ cnt,
+                                               lidar_voxel* __restrict__ voxels) {
+    const int c = cnt[r];
+    const int key = voxels[r].key;
+    longlong2* A = reinterpret_cast<longlong2*>(acc + (size_t)r * 4);
+    const longlong2 s01 = A[0], s23 = A[1];
+    int ix, iy, iz;
+    decode_key(key, D, ix, iy, iz);
+    const double dc = (double)c;
+    const double cx = voxel_ref(D.origin[0], ix, D.voxel);
+    const double cy = voxel_ref(D.origin[1], iy, D.voxel);
+    const double cz = voxel_ref(D.origin[2], iz, D.voxel);
+    float4 o;
+    o.x = (float)__dadd_rn(cx, __ddiv_rn(__dmul_rn((double)s01.x, isx), dc));
+    o.y = (float)__dadd_rn(cy, __ddiv_rn(__dmul_rn((double)s01.y, isx), dc));
+    o.z = (float)__dadd_rn(cz, __ddiv_rn(__dmul_rn((double)s23.x, isx), dc));
+    o.w = (float)__ddiv_rn(__dmul_rn((double)s23.y, isw), dc);
+    float4* rec = reinterpret_cast<float4*>(voxels + r);
+    rec[0] = o;
+    rec[1] = make_float4(__int_as_float(c), __int_as_float(key), 0.f, 0.f);
+    // restore the all-zero invariant of the accumulators for the next frame
+    A[0] = make_longlong2(0, 0);
+    A[1] = make_longlong2(0, 0);
+    cnt[r] = 0;
+}
+
 __global__ void __launch_bounds__(kFrameThreads)
 k_frame_finalize(const lidar_frame_desc* __restrict__ Dg, long long* __restrict__ acc, int32_t* __restrict__ cnt,
                  lidar_voxel* __restrict__ voxels) {
     __shared__ lidar_frame_desc D;
+    __shared__ unsigned s_ring[kFrameThreads / 32][kRingSize];
     if (threadIdx.x == 0) D = *Dg;
     __syncthreads();
     if (D.status != 0) return;
     const int64_t V = D.n_voxels;
-    const double ox = D.origin[0], oy = D.origin[1], oz = D.origin[2], v = D.voxel;
     const double isx = 1.0 / D.fix_scale_xyz, isw = 1.0 / D.fix_scale_w;  // powers of two: exact
-    const int Dy = D.dims[1], Dz = D.dims[2];
+    const unsigned lane = lane_id();
+    unsigned* ring = s_ring[threadIdx.x >> 5];
+    unsigned head = 0, count = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < V; r += stride) {
-        const int c = cnt[r];
-        if (c == 0) continue;
-        const int key = voxels[r].key;
-        longlong2* A = reinterpret_cast<longlong2*>(acc + (size_t)r * 4);
-        const longlong2 s01 = A[0], s23 = A[1];
-        const int iz = key % Dz;
-        const int t = key / Dz;
-        const int iy = t % Dy;
-        const int ix = t / Dy;
-        const double dc = (double)c;
-        const double cx = voxel_ref(ox, ix, v);
-        const double cy = voxel_ref(oy, iy, v);
-        const double cz = voxel_ref(oz, iz, v);
-        float4 o;
-        o.x = (float)__dadd_rn(cx, __ddiv_rn(__dmul_rn((double)s01.x, isx), dc));
-        o.y = (float)__dadd_rn(cy, __ddiv_rn(__dmul_rn((double)s01.y, isx), dc));
-        o.z = (float)__dadd_rn(cz, __ddiv_rn(__dmul_rn((double)s23.x, isx), dc));
-        o.w = (float)__ddiv_rn(__dmul_rn((double)s23.y, isw), dc);
-        float4* rec = reinterpret_cast<float4*>(voxels + r);
-        rec[0] = o;
-        rec[1] = make_float4(__int_as_float(c), __int_as_float(key), 0.f, 0.f);
-        // restore the all-zero invariant of the accumulators for the next frame
-        A[0] = make_longlong2(0, 0);
-        A[1] = make_longlong2(0, 0);
-        cnt[r] = 0;
+    const int64_t v_round = ((V + 31) / 32) * 32;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < v_round; r += stride) {
+        const bool hit = r < V && __ldg(cnt + r) != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+            if (hit) ring[(head + count + __popc(m & lanemask_lt())) % kRingSize] = (unsigned)r;
+            count += __popc(m);
+            __syncwarp();
+            if (count >= 32) {
+                finalize_voxel(ring[(head + lane) % kRingSize], D, isx, isw, acc, cnt, voxels);
+                head = (head + 32) % kRingSize;
+                count -= 32;
+                __syncwarp();
+            }
+        }
     }
+    if (lane < count) finalize_voxel(ring[(head + lane) % kRingSize], D, isx, isw, acc, cnt, voxels);
 }
 
 static int g_ctas_per_sm = 8;   // grid cap of the per-point frame kernels, in CTAs per SM (tuning knob)
