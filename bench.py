@@ -109,30 +109,56 @@ def time_cpu(frame: np.ndarray, budget_s: float = 12.0, max_reps: int = 5):
     return best, reps
 
 
+def _ref_worker(seed, n, steps, warmup, barrier, q):
+    """One host core: its own frame, `warmup` untimed + `steps` timed oracle steps after a common start."""
+    from lidar_ai_recommendation_software_b200 import synth
+    frame = synth.crowd_frame(n, seed=seed, extent=EXTENT)
+    for _ in range(warmup):
+        cpu_oracle_step(frame)
+    barrier.wait()
+    for _ in range(steps):
+        cpu_oracle_step(frame)
+    q.put(time.time())
+
+
 def run_reference(args, rank: int):
-    """--impl reference: the reference-side CPU path on this box's host cores (rank 0 only)."""
+    """--impl reference: the reference-side CPU path on ALL of this box's host cores (rank 0 only).
+
+    The reference has no voxel op, so the CPU arm is the oracle port (numpy restatement of Appendix B.1)
+    plus the reference's own calculate_grid_density arithmetic; numpy runs it on one thread, so every
+    core gets its own frame (independent frames, exactly how the GPU arm shards them)."""
     if rank != 0:
         return
-    from lidar_ai_recommendation_software_b200 import synth
+    import multiprocessing as mp
     n = args.points
-    frames = [synth.crowd_frame(n, seed=s, extent=EXTENT) for s in range(2)]
-    for w in range(min(args.warmup, 1)):
-        cpu_oracle_step(frames[w % 2])
-    steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for s in range(steps):
-        cpu_oracle_step(frames[s % 2])
-    dt = time.perf_counter() - t0
-    val = n * steps / dt / 1e6
+    procs = max(1, os.cpu_count() or 1)
+    steps = max(1, min(args.steps, 4))
+    warmup = min(args.warmup, 1)
+    ctx = mp.get_context("fork")
+    barrier = ctx.Barrier(procs + 1)
+    q = ctx.Queue()
+    ws = [ctx.Process(target=_ref_worker, args=(1000 + i, n, steps, warmup, barrier, q)) for i in range(procs)]
+    for w in ws:
+        w.start()
+    barrier.wait()
+    t0 = time.time()
+    ends = [q.get() for _ in ws]
+    for w in ws:
+        w.join()
+    dt = max(ends) - t0
+    val = n * steps * procs / dt / 1e6
     line = {
         "impl": "reference", "metric": "Mpoints/s voxelize+density", "value": val, "unit": "Mpoints/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / steps * 1e3,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{n}-point crowd frame, {VOXEL} m voxel downsample + {GRID} m density histogram",
-                   "points_per_frame": n, "voxel_m": VOXEL, "grid_m": GRID},
-        "cpu_baseline": {"value": val, "unit": "Mpoints/s", "cores": 1, "kind": "port",
-                         "sample": f"{steps} x {n}-point frame; numpy restatement of voxel downsample (absent upstream) "
-                                   "+ the reference's np.histogram2d grid density; single-threaded numpy"},
+        "config": {"workload": f"{n}-point crowd frame, {VOXEL} m voxel downsample + {GRID} m "
+                               "calculate_grid_density histogram (BASELINE configs[1])",
+                   "points_per_frame": n, "voxel_m": VOXEL, "grid_m": GRID,
+                   "frames_per_step": procs},
+        "cpu_baseline": {"value": val, "unit": "Mpoints/s", "cores": procs, "kind": "port",
+                         "sample": f"{steps} steps x {procs} frames of {n} points, one frame per host core in "
+                                   "parallel processes; numpy restatement of voxel downsample (absent upstream) "
+                                   "+ the reference's np.histogram2d grid density"},
         "e2e": {"value": val, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -149,8 +175,15 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="frame kernel grid cap (0 = library default)")
-    ap.add_argument("--streams", type=int, default=4,
+    ap.add_argument("--streams", type=int, default=0,
                     help="independent frame pipelines in flight (frames round-robin over CUDA streams)")
+    ap.add_argument("--mode", default="fused", choices=["fused", "multikernel"],
+                    help="frame back end: one persistent cooperative kernel, or five dependent kernels")
+    ap.add_argument("--fused-threads", type=int, default=0)
+    ap.add_argument("--fused-ctas-per-sm", type=int, default=0)
+    ap.add_argument("--fused-smem-kb", type=int, default=0)
+    ap.add_argument("--fused-plain-launch", action="store_true",
+                    help="experiment: ordinary instead of cooperative launch (lets frames of different streams overlap)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -181,7 +214,15 @@ def main():
     if args.ctas_per_sm:
         from lidar_ai_recommendation_software_b200 import _capi
         _capi.check(_capi.lib.lidar_frame_set_ctas_per_sm(args.ctas_per_sm))
-    S = max(1, args.streams)
+    fused = args.mode == "fused"
+    if args.fused_plain_launch:
+        from lidar_ai_recommendation_software_b200 import _capi
+        _capi.check(_capi.lib.lidar_frame_set_fused_plain_launch(1))
+    ops.set_frame_mode(ops.FRAME_FUSED if fused else ops.FRAME_MULTIKERNEL, args.fused_threads,
+                       args.fused_ctas_per_sm, args.fused_smem_kb)
+    # the fused kernel fills the device by itself (frames of other streams would only queue behind it);
+    # the five-kernel path leaves gaps that frames on other streams fill
+    S = args.streams if args.streams > 0 else (1 if fused else 4)
     pipes = [ops.FramePipeline(max_points=n, voxel_size=VOXEL, grid_size=GRID, max_key_space=1 << 28,
                                max_nx=256, max_ny=256, device=dev) for _ in range(S)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
@@ -241,8 +282,29 @@ def main():
         for k in range(5):
             per_kernel[k] += evs[s][k].elapsed_time(evs[s][k + 1])
     per_kernel /= ksteps  # ms
-    dom = int(np.argmax(per_kernel))
     hbm_peak, peak_src = peaks()
+    step_ms = ms / args.steps
+    step_bytes = (20.0 + 20.0 * v_over_n) * n      # SURVEY.md §8(d): 20 + 20*V/N bytes per point
+    phases = None
+    if fused:
+        # one launch per frame: the kernel's algorithmic bytes are the step's; phases from %globaltimer
+        kms = float(per_kernel.sum())
+        last = pipe.result()
+        ph = [int(x) for x in last.desc.trace_ns]
+        assert ph[15] > 0, "the fused kernel did not run"
+        names = ["load_bbox", "bar1", "desc", "mark", "bar2", "scan_popc", "scan_wait", "scan_prefix", "bar3",
+                 "rank", "bar4", "clean_finalize"]
+        phases = {k + "_us": ph[i] / 1e3 for i, k in enumerate(names)}
+        phases["ctas"] = ph[15]
+        gbs = step_bytes / (kms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_frame_fused", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": step_bytes, "launch_ms": kms,
+                    "note": "launch_ms = one frame alone on the device (CUDA events around the launch)"}
+        roofline_step = {"bytes_per_point": step_bytes / n, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak,
+                         "kernel_ms": {"k_frame_fused": kms}, "phases_of_one_frame": phases}
+    dom = int(np.argmax(per_kernel))
     # algorithmic bytes per point of each kernel
     n_groups = float(res.desc.key_space) / 224.0          # one 32 B occupancy group per 224 voxel cells
     alg = {
@@ -252,16 +314,15 @@ def main():
         "k_frame_rank": (16.0 + 4.0 + 4.0) * n + 32.0 * res.n_voxels,   # point, key, inverse + voxel record
         "k_frame_finalize": 4.0 * res.n_voxels,                 # sweep of the member counters
     }
-    step_bytes = (20.0 + 20.0 * v_over_n) * n      # SURVEY.md §8(d): 20 + 20*V/N bytes per point
-    dom_name = KERNELS[dom]
-    dom_gbs = alg[dom_name] / (per_kernel[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": dom_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg[dom_name], "launch_ms": float(per_kernel[dom])}
-    step_ms = ms / args.steps
-    roofline_step = {"bytes_per_point": step_bytes / n, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
-                     "peak": hbm_peak, "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak,
-                     "kernel_ms": {k: float(v) for k, v in zip(KERNELS, per_kernel)}}
+    if not fused:
+        dom_name = KERNELS[dom]
+        dom_gbs = alg[dom_name] / (per_kernel[dom] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom_name, "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": dom_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg[dom_name], "launch_ms": float(per_kernel[dom])}
+        roofline_step = {"bytes_per_point": step_bytes / n, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak,
+                         "kernel_ms": {k: float(v) for k, v in zip(KERNELS, per_kernel)}}
 
     # ---- end to end through the host-buffer API ------------------------------------------------
     hp = ops.HostFramePipeline(max_points=n, voxel_size=VOXEL, grid_size=GRID, slots=2, max_key_space=1 << 28,
@@ -309,10 +370,10 @@ def main():
                        "points_per_frame": n, "voxel_m": VOXEL, "grid_m": GRID, "voxels_per_point": v_over_n,
                        "key_space": int(res.desc.key_space),
                        "l2": f"inputs rotate over {POOL} distinct frames ({POOL * n * 16 / 1e6:.0f} MB > 126 MB L2)",
-                       "streams": S,
+                       "streams": S, "backend": args.mode,
                        "sharding": "independent frames per rank, no collective"},
             "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": 5 * args.steps, "clocks": clk,
+            "gpu_launches": (1 if fused else 5) * args.steps, "clocks": clk,
         }
         print(json.dumps(line))
     if world > 1:

@@ -254,6 +254,12 @@ typedef struct lidar_frame_desc {
     /* exact division of a key (< 2^31) by Dz and by Dy: q = (key * magic) >> (31 + shift)     */
     uint32_t magic_dz, magic_dy;
     int32_t shift_dz, shift_dy;
+    /* fused kernel only — timeline of CTA 0 (ns between consecutive %globaltimer stamps):
+     *  [0] load+zero+bbox  [1] barrier 1   [2] descriptor   [3] mark        [4] barrier 2
+     *  [5] scan popcounts  [6] wait totals [7] prefixes     [8] barrier 3   [9] rank
+     *  [10] barrier 4      [11] clean+finalize              [15] = CTAs of the grid.
+     * All zero when the five-kernel path ran.                                                 */
+    uint32_t trace_ns[16];
 } lidar_frame_desc;
 
 /* one output voxel = one 32-byte sector, so a voxel is written with a single full-sector store */
@@ -272,6 +278,25 @@ typedef struct lidar_frame_caps {
 } lidar_frame_caps;
 
 size_t lidar_frame_workspace_bytes(const lidar_frame_caps* caps);
+/* How lidar_frame_voxel_density runs a frame.
+ *   LIDAR_FRAME_FUSED        one persistent cooperative kernel (k_frame_fused): the frame is pulled
+ *                            into shared memory once (TMA bulk copies) and all five phases run on
+ *                            the resident points, separated by grid barriers
+ *   LIDAR_FRAME_MULTIKERNEL  five dependent kernels (prep, mark, scan, rank, finalize)
+ *   LIDAR_FRAME_AUTO         fused, falling back to the five kernels if the cooperative launch is
+ *                            refused
+ * threads / ctas_per_sm / smem_kb tune the fused kernel (0 keeps the current value; smem_kb 0 =
+ * as much as the frame needs).  Both paths produce identical outputs.  Process-wide setting. */
+enum { LIDAR_FRAME_AUTO = 0, LIDAR_FRAME_MULTIKERNEL = 1, LIDAR_FRAME_FUSED = 2 };
+int lidar_frame_set_fused(int mode, int threads, int ctas_per_sm, int smem_kb);
+/* EXPERIMENT knob, off by default: launch k_frame_fused with an ordinary launch instead of a
+ * cooperative one.  Cooperative launches of different streams do not overlap on the device; ordinary
+ * ones do, but then co-residency of the grid is the caller's responsibility: the grid must fit the
+ * device next to whatever else is running (the kernel traps after spinning for two seconds). */
+int lidar_frame_set_fused_plain_launch(int on);
+/* diagnostics: byte offset inside the workspace of uint64 stamps[ctas][16] (%globaltimer, ns) that
+ * every CTA of the last k_frame_fused launch wrote at its 13 trace points (see trace_ns). */
+size_t lidar_frame_trace_offset(const lidar_frame_caps* caps);
 /* tuning knob: cap of the per-point frame kernels' grids in CTAs per SM (1..8, default 8).  Smaller
  * grids leave room for the kernels of other frames (other streams) to run concurrently. */
 int lidar_frame_set_ctas_per_sm(int ctas_per_sm);

@@ -54,6 +54,7 @@ class FrameDesc(C.Structure):
         ("fast_f32", C.c_int32),
         ("magic_dz", C.c_uint32), ("magic_dy", C.c_uint32),
         ("shift_dz", C.c_int32), ("shift_dy", C.c_int32),
+        ("trace_ns", C.c_uint32 * 16),
     ]
 
 
@@ -112,6 +113,9 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_shared_mlp_maxpool": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "lidar_frame_set_ctas_per_sm": (_i32, [_i32]),
+    "lidar_frame_set_fused": (_i32, [_i32, _i32, _i32, _i32]),
+    "lidar_frame_set_fused_plain_launch": (_i32, [_i32]),
+    "lidar_frame_trace_offset": (_sz, [C.POINTER(FrameCaps)]),
     "lidar_frame_workspace_bytes": (_sz, [C.POINTER(FrameCaps)]),
     "lidar_frame_workspace_init": (_i32, [_vp, _sz, C.POINTER(FrameCaps), _vp]),
     "lidar_frame_voxel_density": (_i32, [_vp, _i64, _dbl, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double),

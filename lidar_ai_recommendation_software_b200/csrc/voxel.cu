@@ -6,25 +6,30 @@
 // binning (Appendix A.1), counts indexed [x][y].
 //
 // Design: "occupancy-bitmap ranking" instead of a key sort.
-//   The voxel key space (Dx*Dy*Dz cells) is held as a bitmap (1 bit per cell, 20 MB for a
+//   The voxel key space (Dx*Dy*Dz cells) is held as a bitmap (1 bit per cell, 22 MB for a
 //   100 m x 100 m x 2 m frame at 0.05 m — L2 resident on B200).  The rank of a voxel in ascending
 //   key order is the number of occupied cells before it, i.e. a popcount prefix over the bitmap.
 //   That yields exactly the output order of a stable sort-by-key + segmented reduce, without
 //   moving a single point, and every step is order independent:
-//     k_frame_prep      min/max of x,y,z,intensity; zeroes what the previous frame dirtied (bitmap,
-//                       duplicate filter, grid); the last CTA derives the frame descriptor (origin,
-//                       dims, key space, fixed-point scales, histogram edges) ON DEVICE
-//     k_frame_mark      per point: voxel key -> d_voxel_key, atomicOr into the bitmap (a second hit
-//                       on the same bit flags the voxel in a 512 KB hashed duplicate filter),
-//                       density bin -> RED.ADD into the grid              (reads 16 B, writes 4 B)
-//     k_frame_scan      one-wave scan of bitmap popcounts -> prefix per 256-bit group
-//     k_frame_rank      per point: rank = prefix + popc(bits below) -> d_inverse.  Voxels not in
-//                       the duplicate filter hold exactly one point (94 % of a crowd frame): the
-//                       point IS the centroid and is stored directly.  The rest accumulate
-//                       (p - ref) in 2^-k fixed point with integer atomics and enlist the voxel.
-//     k_frame_finalize  enlisted voxels only: centroid = ref + sum/count; re-zeroes accumulators
+//     prep      min/max of x,y,z,intensity; the frame descriptor (origin, dims, key space, fixed-point
+//               scales, histogram edges) is derived ON DEVICE
+//     mark      per point: voxel key, atomicOr into the bitmap, density bin -> RED.ADD into the grid.
+//               The atomicOr returns the old word: a point that finds its bit already set is a LATER
+//               member of its voxel ("dup"); the flag travels with the key (bit 31).
+//     scan      scan of bitmap popcounts -> exclusive prefix stored inside each 32-byte group
+//     rank      per point: rank = prefix + popc(bits below) -> inverse.  The FIRST member of a voxel
+//               (94 % of the points of a crowd frame are the only member) stores itself as the voxel
+//               record with one 32-byte store; dup members accumulate (p - ref) in 2^-k fixed point
+//               with integer atomics.
+//     finalize  voxels with dup members only: centroid = ref + (first + sum)/count; re-zeroes accumulators
 //   Integer accumulation makes centroids independent of the order in which atomics land:
 //   bit-identical run to run, and (p - ref)*2^k is an exact integer, so the sums are exact.
+//
+// Two back ends with identical arithmetic (shared device functions) and identical outputs:
+//   k_frame_fused   ONE persistent cooperative kernel: the frame is pulled into shared memory once by
+//                   the TMA bulk-copy engine and all phases run on the resident points, separated by
+//                   grid barriers (default)
+//   k_frame_prep/mark/scan/rank/finalize   five dependent kernels (any frame size, no co-residency)
 //
 // Nothing in a frame needs the host: capacities are fixed per stream of frames, the descriptor is
 // read back together with the results.
@@ -39,11 +44,8 @@ constexpr int kGroupVoxels = 224;
 constexpr int kScanGroupsPerThread = 4;                               // each thread scans 4 adjacent groups
 constexpr int kScanTileGroups = kFrameThreads * kScanGroupsPerThread; // 1024 groups = 229 376 voxels per tile
 
-constexpr int kFilterBits = 22;                                       // duplicate filter: 2^22 bits = 512 KB
-constexpr int kFilterWords = 1 << (kFilterBits - 5);
-
 struct FrameWsLayout {
-    size_t off_partial, off_ctrl, off_groups, off_tile_desc, off_acc, off_cnt, off_filter, off_cta_desc, total;
+    size_t off_partial, off_ctrl, off_groups, off_tile_desc, off_acc, off_cnt, off_cta_desc, off_trace, off_grid_rep, total;
     int64_t groups, tiles;
 };
 
@@ -56,8 +58,12 @@ struct FrameCtrl {
 };
 
 constexpr int kFusedMaxCtas = 1024;   // cap of the fused kernel's grid (one slot of cta_desc each)
-
-__device__ __forceinline__ unsigned filter_slot(int key) { return ((unsigned)key * 2654435761u) >> (32 - kFilterBits); }
+// The density REDs of a 1 M-point frame land in a 166 KB grid: same-sector atomics serialise in L2
+// (micro-benchmark: 16.4 us for 1 M REDs into one grid, 11.2 us into 8 replicas).  The fused kernel
+// spreads them over up to 8 private replicas (CTA b uses replica b % R) and merges them after the mark
+// phase.  The replica area is all-zero between frames.
+constexpr int kGridRepCells = 1 << 19;   // 2 MB
+constexpr int kGridRepMax = 8;
 
 constexpr int kBboxMaxBlocks = 1024;
 
@@ -75,8 +81,9 @@ static FrameWsLayout frame_layout(const lidar_frame_caps& c) {
     L.off_tile_desc = take(sizeof(unsigned long long) * L.tiles);
     L.off_acc = take(sizeof(long long) * 4 * c.max_points);
     L.off_cnt = take(sizeof(int32_t) * c.max_points);
-    L.off_filter = take(sizeof(uint32_t) * kFilterWords);
     L.off_cta_desc = take(sizeof(unsigned long long) * kFusedMaxCtas);
+    L.off_trace = take(sizeof(unsigned long long) * 16 * kFusedMaxCtas);
+    L.off_grid_rep = take(sizeof(int32_t) * kGridRepCells);
     L.total = ws_align(o);
     return L;
 }
@@ -93,35 +100,42 @@ struct FrameParams {
     int fix_bits_budget;  // 62 - ceil(log2(n))
 };
 
-// ---- descriptor derivation (one thread) -------------------------------------------------------
-__device__ void derive_desc(const FrameParams& P, const double* bb, lidar_frame_desc* D) {
-    int status = 0;
-    for (int c = 0; c < 4; ++c) {
-        D->bbox_min[c] = bb[c];
-        D->bbox_max[c] = bb[4 + c];
-    }
-    D->voxel = P.voxel;
-    D->n_points = P.n;
-    D->n_voxels = 0;
-    long long ks = 1;
-    for (int c = 0; c < 3; ++c) {
+// ---- descriptor derivation --------------------------------------------------------------------
+// Called by ALL threads of a CTA (>= 128 threads) with the frame's bounding box in shared memory: the
+// independent pieces (three voxel axes, two histogram axes, fixed-point scales, two magic divisors) run
+// on different warps instead of one after the other on one thread (~3 us -> ~1 us on the critical path
+// of every frame).  `s_stat` is 8 ints of shared scratch.  Ends with a __syncthreads().
+__device__ __forceinline__ int first_error(int a, int b) { return a ? a : b; }
+
+__device__ void derive_desc_cta(const FrameParams& P, const double* bb, lidar_frame_desc* D, int* s_stat) {
+    const int tid = threadIdx.x;
+    const int part = ((tid & 31) < 2 && (tid >> 5) < 4) ? (tid >> 5) + 4 * (tid & 31) : -1;   // 0..7
+    if (part >= 0) s_stat[part] = 0;
+    if (part >= 0 && part < 3) {
+        // voxel axis c: origin, extent in voxels
+        const int c = part;
+        int status = 0;
         const double o = P.has_origin ? P.origin[c] : bb[c];
         D->origin[c] = o;
         if (bb[c] < o) status = LIDAR_ERR_INVALID;  // a point below the origin would index < 0
         const double span = floor(__ddiv_rn(__dsub_rn(bb[4 + c], o), P.voxel));
         long long d = (span >= 0.0 && span < 2147483000.0) ? (long long)span + 1 : 0;
-        if (d <= 0) { d = 1; if (P.n > 0) status = status ? status : LIDAR_ERR_CAPACITY; }
+        if (d <= 0) { d = 1; if (P.n > 0) status = first_error(status, LIDAR_ERR_CAPACITY); }
         D->dims[c] = (int)d;
-        // overflow-safe product
-        if (ks > (1ll << 40)) status = status ? status : LIDAR_ERR_CAPACITY;
-        ks *= d;
-    }
-    D->origin[3] = 0.0;
-    D->dims[3] = 0;
-    D->key_space = ks;
-    if (ks > P.max_key_space || ks >= (1ll << 31)) status = status ? status : LIDAR_ERR_CAPACITY;
-    // fixed point: |p - ref| < 2*voxel + 2^-24, n members at most  ->  that * 2^k * n < 2^62
-    {
+        s_stat[part] = status;
+    } else if (part == 3) {
+        for (int c = 0; c < 4; ++c) {
+            D->bbox_min[c] = bb[c];
+            D->bbox_max[c] = bb[4 + c];
+        }
+        D->voxel = P.voxel;
+        D->n_points = P.n;
+        D->n_voxels = 0;
+        for (int k = 0; k < 16; ++k) D->trace_ns[k] = 0u;
+        D->origin[3] = 0.0;
+        D->dims[3] = 0;
+        D->grid = P.grid;
+        // fixed point: |p - ref| < 2*voxel + 2^-24, n members at most  ->  that * 2^k * n < 2^62
         int e;
         frexp(P.voxel * 2.0 + 0x1p-24, &e);  // bound < 2^e
         D->fix_scale_xyz = ldexp(1.0, P.fix_bits_budget - e);
@@ -129,43 +143,54 @@ __device__ void derive_desc(const FrameParams& P, const double* bb, lidar_frame_
         if (!(wmax > 0.0) || !isfinite(wmax)) wmax = 1.0;
         frexp(wmax, &e);
         D->fix_scale_w = ldexp(1.0, P.fix_bits_budget - e - 1);
-    }
-    // density grid edges, numpy arange rule (data_processing.py:305-313)
-    D->grid = P.grid;
-    D->nx = D->ny = 0;
-    D->ex0 = D->ex1 = D->exd = D->ey0 = D->ey1 = D->eyd = 0.0;
-    if (P.grid > 0.0) {
-        const double g = P.grid;
-        const double margin = __dmul_rn(g, 2.0);
-        double lo[2], hi[2];
-        lo[0] = P.has_range ? P.xyr[0] : bb[0];
-        hi[0] = P.has_range ? P.xyr[1] : bb[4];
-        lo[1] = P.has_range ? P.xyr[2] : bb[1];
-        hi[1] = P.has_range ? P.xyr[3] : bb[5];
-        for (int c = 0; c < 2; ++c) {
-            const double a = __dsub_rn(lo[c], margin);
-            const double stop = __dadd_rn(__dadd_rn(hi[c], margin), g);
+    } else if (part == 4 || part == 5) {
+        // density grid edges of axis c, numpy arange rule (data_processing.py:305-313)
+        const int c = part - 4;
+        int status = 0;
+        double a = 0.0, e1 = 0.0, delta = 0.0;
+        int nb = 0;
+        if (P.grid > 0.0) {
+            const double g = P.grid;
+            const double margin = __dmul_rn(g, 2.0);
+            const double lo = P.has_range ? P.xyr[2 * c] : bb[c];
+            const double hi = P.has_range ? P.xyr[2 * c + 1] : bb[4 + c];
+            a = __dsub_rn(lo, margin);
+            const double stop = __dadd_rn(__dadd_rn(hi, margin), g);
             const double len = ceil(__ddiv_rn(__dsub_rn(stop, a), g));
-            int nedges = (len > 0.0 && len < 1.0e9) ? (int)len : 0;
-            const double e1 = __dadd_rn(a, g);
-            const double delta = __dsub_rn(e1, a);
-            int nb = nedges - 1;
-            if (nb < 1) { nb = 0; if (P.n > 0) status = status ? status : LIDAR_ERR_CAPACITY; }
-            if (c == 0) { D->ex0 = a; D->ex1 = e1; D->exd = delta; D->nx = nb; }
-            else        { D->ey0 = a; D->ey1 = e1; D->eyd = delta; D->ny = nb; }
+            const int nedges = (len > 0.0 && len < 1.0e9) ? (int)len : 0;
+            e1 = __dadd_rn(a, g);
+            delta = __dsub_rn(e1, a);
+            nb = nedges - 1;
+            if (nb < 1) { nb = 0; if (P.n > 0) status = LIDAR_ERR_CAPACITY; }
+            if (nb > (c == 0 ? P.max_nx : P.max_ny)) status = first_error(status, LIDAR_ERR_CAPACITY);
         }
-        if (D->nx > P.max_nx || D->ny > P.max_ny) status = status ? status : LIDAR_ERR_CAPACITY;
+        if (c == 0) { D->ex0 = a; D->ex1 = e1; D->exd = delta; D->nx = nb; }
+        else        { D->ey0 = a; D->ey1 = e1; D->eyd = delta; D->ny = nb; }
+        s_stat[part] = status;
     }
-    if (P.n == 0) status = 0;
-    D->status = status;
-    // the fp32 index guess needs an origin that fp32 represents exactly (true for a bbox-derived origin)
-    int fast = 1;
-    for (int c = 0; c < 3; ++c)
-        if ((double)(float)D->origin[c] != D->origin[c]) fast = 0;
-    if ((double)(float)P.voxel == 0.0) fast = 0;
-    D->fast_f32 = fast;
-    // Granlund-Montgomery: for 0 <= n < 2^31 and 2^(l-1) < d <= 2^l,  n / d == (n * ceil(2^(31+l)/d)) >> (31+l)
-    for (int c = 0; c < 2; ++c) {
+    __syncthreads();
+    if (part == 0) {
+        // key space (overflow-safe product) and the combined status, first error in axis order wins
+        int status = first_error(first_error(s_stat[0], s_stat[1]), s_stat[2]);
+        long long ks = 1;
+        for (int c = 0; c < 3; ++c) {
+            if (ks > (1ll << 40)) status = first_error(status, LIDAR_ERR_CAPACITY);
+            ks *= (long long)D->dims[c];
+        }
+        D->key_space = ks;
+        if (ks > P.max_key_space || ks >= (1ll << 31)) status = first_error(status, LIDAR_ERR_CAPACITY);
+        status = first_error(status, first_error(s_stat[4], s_stat[5]));
+        if (P.n == 0) status = 0;
+        D->status = status;
+        // the fp32 index guess needs an origin that fp32 represents exactly (true for a bbox-derived origin)
+        int fast = 1;
+        for (int c = 0; c < 3; ++c)
+            if ((double)(float)D->origin[c] != D->origin[c]) fast = 0;
+        if ((double)(float)P.voxel == 0.0) fast = 0;
+        D->fast_f32 = fast;
+    } else if (part == 1 || part == 2) {
+        // Granlund-Montgomery: for 0 <= n < 2^31 and 2^(l-1) < d <= 2^l,  n / d == (n * ceil(2^(31+l)/d)) >> (31+l)
+        const int c = part - 1;
         const unsigned long long d = (unsigned long long)(c == 0 ? D->dims[2] : D->dims[1]);
         int l = 0;
         while ((1ull << l) < d) ++l;
@@ -173,6 +198,7 @@ __device__ void derive_desc(const FrameParams& P, const double* bb, lidar_frame_
         const unsigned m = (unsigned)((num + d - 1) / d);
         if (c == 0) { D->magic_dz = m; D->shift_dz = l; } else { D->magic_dy = m; D->shift_dy = l; }
     }
+    __syncthreads();
 }
 
 __device__ __forceinline__ int magic_div(int n, unsigned magic, int shift) {
@@ -191,7 +217,7 @@ __global__ void __launch_bounds__(kFrameThreads)
 k_frame_prep(FrameParams P, double* __restrict__ partial, FrameCtrl* __restrict__ ctrl,
              lidar_frame_desc* __restrict__ D, int32_t* __restrict__ grid_out, int grid_cap,
              unsigned long long* __restrict__ tile_desc, int64_t tiles, uint32_t* __restrict__ groups,
-             int64_t groups_cap, uint32_t* __restrict__ filter) {
+             int64_t groups_cap) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // issue this thread's point loads first so they are in flight while the zeroing stores drain
@@ -217,8 +243,6 @@ k_frame_prep(FrameParams P, double* __restrict__ partial, FrameCtrl* __restrict_
         uint4* b4 = reinterpret_cast<uint4*>(groups);
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
         for (int64_t k = t0; k < dirty * 2; k += stride) b4[k] = z;
-        uint4* f4 = reinterpret_cast<uint4*>(filter);
-        for (int64_t k = t0; k < kFilterWords / 4; k += stride) f4[k] = z;
         for (int64_t k = t0; k < grid_cap; k += stride) grid_out[k] = 0;
         for (int64_t k = t0; k < tiles; k += stride) tile_desc[k] = 0ull;
     }
@@ -276,8 +300,9 @@ k_frame_prep(FrameParams P, double* __restrict__ partial, FrameCtrl* __restrict_
         }
     }
     __syncthreads();
+    __shared__ int s_stat[8];
+    derive_desc_cta(P, s_bb, D, s_stat);
     if (threadIdx.x == 0) {
-        derive_desc(P, s_bb, D);
         ctrl->bbox_ticket = 0u;
         ctrl->scan_ticket = 0u;
         // groups this frame may set (whole scan tiles), remembered for the next frame's zeroing
@@ -363,17 +388,37 @@ __device__ __forceinline__ void st_stream_s32(int* p, int v) {
                  ::"l"(p), "r"(v), "l"(evict_first_policy()) : "memory");
 }
 
-// ---- k_frame_mark -----------------------------------------------------------------------------
+// fire-and-forget reductions: spelled in PTX so that ptxas emits REDG (no return path) and never
+// ATOMG with a discarded result
+__device__ __forceinline__ void red_add_s32(int32_t* p, int v) {
+    asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---- per-point arithmetic shared by both back ends -----------------------------------------------
 struct MarkConst {
     float of[3], rvf, axf, ayf, rdxf, rdyf;
     double rv, rdx, rdy;
-    int fast;
+    int fast, do_grid;
 };
 
-__device__ __forceinline__ void mark_point(const float4& q, const lidar_frame_desc& D, const MarkConst& K,
-                                           bool do_grid, int64_t i, int32_t* __restrict__ voxel_key,
-                                           uint32_t* __restrict__ groups, uint32_t* __restrict__ filter,
-                                           int32_t* __restrict__ grid_out) {
+__device__ __forceinline__ MarkConst make_mark_const(const lidar_frame_desc& D) {
+    MarkConst K;
+    K.do_grid = D.grid > 0.0;
+    K.rv = __ddiv_rn(1.0, D.voxel);
+    K.rdx = K.do_grid ? __ddiv_rn(1.0, D.exd) : 0.0;
+    K.rdy = K.do_grid ? __ddiv_rn(1.0, D.eyd) : 0.0;
+    K.of[0] = (float)D.origin[0]; K.of[1] = (float)D.origin[1]; K.of[2] = (float)D.origin[2];
+    K.rvf = (float)K.rv;
+    K.axf = (float)D.ex0; K.ayf = (float)D.ey0; K.rdxf = (float)K.rdx; K.rdyf = (float)K.rdy;
+    K.fast = D.fast_f32;
+    return K;
+}
+
+// B.1: key = (ix*Dy + iy)*Dz + iz with i = floor((f64(p) - origin) / voxel)
+__device__ __forceinline__ int voxel_key_of(const float4& q, const lidar_frame_desc& D, const MarkConst& K) {
     int ix, iy, iz;
     const bool fx = K.fast && fast_voxel_index(q.x, K.of[0], K.rvf, ix);
     const bool fy = K.fast && fast_voxel_index(q.y, K.of[1], K.rvf, iy);
@@ -381,26 +426,126 @@ __device__ __forceinline__ void mark_point(const float4& q, const lidar_frame_de
     if (!fx) ix = floor_div_exact(__dsub_rn((double)q.x, D.origin[0]), D.voxel, K.rv);
     if (!fy) iy = floor_div_exact(__dsub_rn((double)q.y, D.origin[1]), D.voxel, K.rv);
     if (!fz) iz = floor_div_exact(__dsub_rn((double)q.z, D.origin[2]), D.voxel, K.rv);
-    const int key = (ix * D.dims[1] + iy) * D.dims[2] + iz;
-    st_stream_s32(voxel_key + i, key);
-    const unsigned g = (unsigned)key / kGroupVoxels, b = (unsigned)key - g * kGroupVoxels;
-    const unsigned bit = 1u << (b & 31);
-    const unsigned old = atomicOr(&groups[(size_t)g * 8 + 1 + (b >> 5)], bit);
-    if (do_grid) {
-        const int bx = fast_arange_bin(q.x, (double)q.x, K.axf, K.rdxf, D.ex0, D.ex1, D.exd, K.rdx, D.nx);
-        const int by = fast_arange_bin(q.y, (double)q.y, K.ayf, K.rdyf, D.ey0, D.ey1, D.eyd, K.rdy, D.ny);
-        if (bx >= 0 && by >= 0) atomicAdd(&grid_out[bx * D.ny + by], 1);
-    }
-    if (old & bit) {   // the voxel already had a point: flag it as multi-member
-        const unsigned h = filter_slot(key);
-        atomicOr(&filter[h >> 5], 1u << (h & 31));
-    }
+    return (ix * D.dims[1] + iy) * D.dims[2] + iz;
+}
+// calculate_grid_density cell of a point ([x][y] layout), -1 when outside the edges
+__device__ __forceinline__ int grid_cell_of(const float4& q, const lidar_frame_desc& D, const MarkConst& K) {
+    const int bx = fast_arange_bin(q.x, (double)q.x, K.axf, K.rdxf, D.ex0, D.ex1, D.exd, K.rdx, D.nx);
+    const int by = fast_arange_bin(q.y, (double)q.y, K.ayf, K.rdyf, D.ey0, D.ey1, D.eyd, K.rdy, D.ny);
+    return (bx >= 0 && by >= 0) ? bx * D.ny + by : -1;
 }
 
+constexpr unsigned kDupFlag = 0x80000000u;   // keys are < 2^31: bit 31 carries "a later member of its voxel"
+
+// occupancy bit of a key: word address inside its group and the bit mask
+__device__ __forceinline__ uint32_t* occupancy_word(uint32_t* groups, int key, unsigned& bit) {
+    const unsigned g = (unsigned)key / kGroupVoxels, b = (unsigned)key - g * kGroupVoxels;
+    bit = 1u << (b & 31);
+    return groups + (size_t)g * 8 + 1 + (b >> 5);
+}
+
+// 256-bit global accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256): a whole 32-byte occupancy group or
+// voxel record moves with ONE request, i.e. one L1 wavefront per lane instead of two
+struct __align__(32) Word8 { unsigned w[8]; };
+__device__ __forceinline__ Word8 ld_cg_256(const void* p) {
+    Word8 v;
+    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]), "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7])
+                 : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_256(void* p, const Word8& v) {
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]), "r"(v.w[4]), "r"(v.w[5]), "r"(v.w[6]), "r"(v.w[7])
+                 : "memory");
+}
+__device__ __forceinline__ unsigned group_popc(const Word8& g) {
+    return __popc(g.w[1]) + __popc(g.w[2]) + __popc(g.w[3]) + __popc(g.w[4]) + __popc(g.w[5]) + __popc(g.w[6]) + __popc(g.w[7]);
+}
+// rank of a key = prefix of its group + occupied cells below it inside the group
+__device__ __forceinline__ unsigned rank_in_group(const Word8& g, unsigned b) {
+    const int wi = 1 + (int)(b >> 5);
+    unsigned r = g.w[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+        if (k < wi) r += __popc(g.w[k]);
+        else if (k == wi) r += __popc(g.w[k] & ((1u << (b & 31)) - 1u));
+    }
+    return r;
+}
+__device__ __forceinline__ unsigned rank_of(int key, const uint32_t* __restrict__ groups) {
+    const unsigned g = (unsigned)key / kGroupVoxels, b = (unsigned)key - g * kGroupVoxels;
+    return rank_in_group(ld_cg_256(groups + (size_t)g * 8), b);
+}
+// the first member of a voxel stores itself as the record (count 1): one full-sector store
+__device__ __forceinline__ void store_first_member(lidar_voxel* __restrict__ voxels, unsigned r, const float4& q, int key) {
+    Word8 rec;
+    rec.w[0] = __float_as_uint(q.x); rec.w[1] = __float_as_uint(q.y);
+    rec.w[2] = __float_as_uint(q.z); rec.w[3] = __float_as_uint(q.w);
+    rec.w[4] = 1u; rec.w[5] = (unsigned)key; rec.w[6] = 0u; rec.w[7] = 0u;
+    st_256(voxels + r, rec);
+}
+
+struct Fixed4 { long long x, y, z, w; };
+// (p - ref) * 2^k of a member of voxel `key`: an exact integer (see voxel_ref)
+__device__ __forceinline__ Fixed4 fixed_offsets(const float4& q, int key, const lidar_frame_desc& D) {
+    int ix, iy, iz;
+    decode_key(key, D, ix, iy, iz);
+    const double cx = voxel_ref(D.origin[0], ix, D.voxel);
+    const double cy = voxel_ref(D.origin[1], iy, D.voxel);
+    const double cz = voxel_ref(D.origin[2], iz, D.voxel);
+    Fixed4 f;
+    f.x = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.x, cx), D.fix_scale_xyz));
+    f.y = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.y, cy), D.fix_scale_xyz));
+    f.z = __double2ll_rn(__dmul_rn(__dsub_rn((double)q.z, cz), D.fix_scale_xyz));
+    f.w = __double2ll_rn(__dmul_rn((double)q.w, D.fix_scale_w));
+    return f;
+}
+// a later ("dup") member adds itself to the accumulators of its voxel; results unused => RED
+__device__ __forceinline__ void accumulate_dup(const float4& q, int key, unsigned r, const lidar_frame_desc& D,
+                                               long long* __restrict__ acc, int32_t* __restrict__ cnt) {
+    const Fixed4 f = fixed_offsets(q, key, D);
+    unsigned long long* A = reinterpret_cast<unsigned long long*>(acc + (size_t)r * 4);
+    red_add_u64(A + 0, (unsigned long long)f.x);
+    red_add_u64(A + 1, (unsigned long long)f.y);
+    red_add_u64(A + 2, (unsigned long long)f.z);
+    red_add_u64(A + 3, (unsigned long long)f.w);
+    red_add_s32(cnt + r, 1);
+}
+// voxel r has cnt[r] dup members plus the first member sitting in its record
+__device__ __forceinline__ void finalize_voxel(unsigned r, const lidar_frame_desc& D, double isx, double isw,
+                                               long long* __restrict__ acc, int32_t* __restrict__ cnt,
+                                               lidar_voxel* __restrict__ voxels) {
+    const int c = __ldcg(cnt + r) + 1;
+    Word8 rec = ld_cg_256(voxels + r);
+    const float4 first = make_float4(__uint_as_float(rec.w[0]), __uint_as_float(rec.w[1]), __uint_as_float(rec.w[2]),
+                                     __uint_as_float(rec.w[3]));
+    const int key = (int)rec.w[5];
+    const Fixed4 f = fixed_offsets(first, key, D);
+    longlong2* A = reinterpret_cast<longlong2*>(acc + (size_t)r * 4);
+    const longlong2 s01 = __ldcg(A), s23 = __ldcg(A + 1);
+    int ix, iy, iz;
+    decode_key(key, D, ix, iy, iz);
+    const double dc = (double)c;
+    const double cx = voxel_ref(D.origin[0], ix, D.voxel);
+    const double cy = voxel_ref(D.origin[1], iy, D.voxel);
+    const double cz = voxel_ref(D.origin[2], iz, D.voxel);
+    rec.w[0] = __float_as_uint((float)__dadd_rn(cx, __ddiv_rn(__dmul_rn((double)(s01.x + f.x), isx), dc)));
+    rec.w[1] = __float_as_uint((float)__dadd_rn(cy, __ddiv_rn(__dmul_rn((double)(s01.y + f.y), isx), dc)));
+    rec.w[2] = __float_as_uint((float)__dadd_rn(cz, __ddiv_rn(__dmul_rn((double)(s23.x + f.z), isx), dc)));
+    rec.w[3] = __float_as_uint((float)__ddiv_rn(__dmul_rn((double)(s23.y + f.w), isw), dc));
+    rec.w[4] = (unsigned)c;
+    st_256(voxels + r, rec);
+    // restore the all-zero invariant of the accumulators for the next frame
+    A[0] = make_longlong2(0, 0);
+    A[1] = make_longlong2(0, 0);
+    cnt[r] = 0;
+}
+
+// ---- k_frame_mark -----------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFrameThreads)
 k_frame_mark(const float4* __restrict__ pts, const lidar_frame_desc* __restrict__ Dg,
-             int32_t* __restrict__ voxel_key, uint32_t* __restrict__ groups, uint32_t* __restrict__ filter,
-             int32_t* __restrict__ grid_out) {
+             int32_t* __restrict__ voxel_key, uint32_t* __restrict__ groups, int32_t* __restrict__ grid_out) {
     __shared__ lidar_frame_desc D;
     LoadF32x4 L{pts};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -409,22 +554,30 @@ k_frame_mark(const float4* __restrict__ pts, const lidar_frame_desc* __restrict_
     __syncthreads();
     if (D.status != 0) return;
     const int64_t n = D.n_points;
-    const bool do_grid = D.grid > 0.0;
-    MarkConst K;
-    K.rv = __ddiv_rn(1.0, D.voxel);
-    K.rdx = do_grid ? __ddiv_rn(1.0, D.exd) : 0.0;
-    K.rdy = do_grid ? __ddiv_rn(1.0, D.eyd) : 0.0;
-    K.of[0] = (float)D.origin[0]; K.of[1] = (float)D.origin[1]; K.of[2] = (float)D.origin[2];
-    K.rvf = (float)K.rv;
-    K.axf = (float)D.ex0; K.ayf = (float)D.ey0; K.rdxf = (float)K.rdx; K.rdyf = (float)K.rdy;
-    K.fast = D.fast_f32;
-    int64_t i = t0;
-    for (; i + stride < n; i += 2 * stride) {
-        const float4 a = L.raw(i), b = L.raw(i + stride);
-        mark_point(a, D, K, do_grid, i, voxel_key, groups, filter, grid_out);
-        mark_point(b, D, K, do_grid, i + stride, voxel_key, groups, filter, grid_out);
+    const MarkConst K = make_mark_const(D);
+    // two points per trip: both atomicOr are in flight before either result is consumed
+    for (int64_t i = t0; i < n; i += 2 * stride) {
+        const bool two = i + stride < n;
+        const float4 a = L.raw(i);
+        const float4 b = two ? L.raw(i + stride) : a;
+        const int ka = voxel_key_of(a, D, K), kb = voxel_key_of(b, D, K);
+        unsigned bita, bitb, olda, oldb = 0u;
+        uint32_t* wa = occupancy_word(groups, ka, bita);
+        uint32_t* wb = occupancy_word(groups, kb, bitb);
+        olda = atomicOr(wa, bita);
+        if (two) oldb = atomicOr(wb, bitb);
+        if (K.do_grid) {
+            const int ca = grid_cell_of(a, D, K);
+            if (ca >= 0) red_add_s32(grid_out + ca, 1);
+            if (two) {
+                const int cb = grid_cell_of(b, D, K);
+                if (cb >= 0) red_add_s32(grid_out + cb, 1);
+            }
+        }
+        // the dup flag rides on the key; k_frame_rank strips it again
+        st_stream_s32(voxel_key + i, (int)((unsigned)ka | ((olda & bita) ? kDupFlag : 0u)));
+        if (two) st_stream_s32(voxel_key + i + stride, (int)((unsigned)kb | ((oldb & bitb) ? kDupFlag : 0u)));
     }
-    if (i < n) mark_point(L.raw(i), D, K, do_grid, i, voxel_key, groups, filter, grid_out);
 }
 
 // ---- k_frame_scan -----------------------------------------------------------------------------
@@ -503,10 +656,10 @@ k_frame_scan(uint32_t* __restrict__ groups, unsigned long long* __restrict__ til
 }
 
 // ---- k_frame_rank -----------------------------------------------------------------------------
-// The accumulate path is needed by ~12 % of the points but, taken in place, would be executed by almost
+// The accumulate path is needed by ~6 % of the points but, taken in place, would be executed by almost
 // every warp (divergence).  Each warp therefore parks those points in a private shared-memory ring and
 // drains it 32 at a time with all lanes active.
-struct MultiItem {
+struct DupItem {
     float4 q;
     int key;
     unsigned r;
@@ -514,127 +667,61 @@ struct MultiItem {
 };
 constexpr int kRingSize = 64;
 
-__device__ __forceinline__ void accumulate_multi(const MultiItem& it, const lidar_frame_desc& D,
-                                                 long long* __restrict__ acc, int32_t* __restrict__ cnt,
-                                                 lidar_voxel* __restrict__ voxels) {
-    int ix, iy, iz;
-    decode_key(it.key, D, ix, iy, iz);
-    const double cx = voxel_ref(D.origin[0], ix, D.voxel);
-    const double cy = voxel_ref(D.origin[1], iy, D.voxel);
-    const double cz = voxel_ref(D.origin[2], iz, D.voxel);
-    const long long fx = __double2ll_rn(__dmul_rn(__dsub_rn((double)it.q.x, cx), D.fix_scale_xyz));
-    const long long fy = __double2ll_rn(__dmul_rn(__dsub_rn((double)it.q.y, cy), D.fix_scale_xyz));
-    const long long fz = __double2ll_rn(__dmul_rn(__dsub_rn((double)it.q.z, cz), D.fix_scale_xyz));
-    const long long fw = __double2ll_rn(__dmul_rn((double)it.q.w, D.fix_scale_w));
-    unsigned long long* A = reinterpret_cast<unsigned long long*>(acc + (size_t)it.r * 4);
-    // results unused: these compile to RED (fire and forget), nothing in the warp waits on them
-    atomicAdd(A + 0, (unsigned long long)fx);
-    atomicAdd(A + 1, (unsigned long long)fy);
-    atomicAdd(A + 2, (unsigned long long)fz);
-    atomicAdd(A + 3, (unsigned long long)fw);
-    atomicAdd(cnt + it.r, 1);
-    voxels[it.r].key = it.key;   // every member stores the same value
-}
-
-// returns the rank and whether the voxel is (possibly) multi-member
-__device__ __forceinline__ unsigned rank_of(int key, const uint32_t* __restrict__ groups) {
-    const unsigned g = (unsigned)key / kGroupVoxels, b = (unsigned)key - g * kGroupVoxels;
-    const uint4* gw = reinterpret_cast<const uint4*>(groups + (size_t)g * 8);
-    const uint4 a4 = gw[0], b4 = gw[1];
-    const unsigned w[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
-    const int wi = 1 + (int)(b >> 5);
-    unsigned r = w[0];
-#pragma unroll
-    for (int k = 1; k < 8; ++k) {
-        if (k < wi) r += __popc(w[k]);
-        else if (k == wi) r += __popc(w[k] & ((1u << (b & 31)) - 1u));
-    }
-    return r;
-}
-
 __global__ void __launch_bounds__(kFrameThreads)
 k_frame_rank(const float4* __restrict__ pts, const lidar_frame_desc* __restrict__ Dg,
-             const int32_t* __restrict__ voxel_key, const uint32_t* __restrict__ groups,
-             const uint32_t* __restrict__ filter, int32_t* __restrict__ inverse, long long* __restrict__ acc,
+             int32_t* __restrict__ voxel_key, const uint32_t* __restrict__ groups,
+             int32_t* __restrict__ inverse, long long* __restrict__ acc,
              int32_t* __restrict__ cnt, lidar_voxel* __restrict__ voxels) {
     __shared__ lidar_frame_desc D;
-    __shared__ MultiItem s_ring[kFrameThreads / 32][kRingSize];
+    __shared__ DupItem s_ring[kFrameThreads / 32][kRingSize];
     if (threadIdx.x == 0) D = *Dg;
     __syncthreads();
     if (D.status != 0) return;
     const int64_t n = D.n_points;
     LoadF32x4 L{pts};
     const unsigned lane = lane_id();
-    MultiItem* ring = s_ring[threadIdx.x >> 5];
+    DupItem* ring = s_ring[threadIdx.x >> 5];
     unsigned head = 0, count = 0;     // warp-uniform
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n_round = ((n + 31) / 32) * 32;   // keep whole warps in the loop for the ballots
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         const bool live = i < n;
-        bool multi = false;
-        MultiItem it;
+        bool dup = false;
+        DupItem it;
         if (live) {
-            it.key = ld_stream_s32(voxel_key + i);
+            const unsigned fk = (unsigned)__ldcg(voxel_key + i);   // written by k_frame_mark, flag in bit 31
+            dup = (fk & kDupFlag) != 0u;
+            it.key = (int)(fk & ~kDupFlag);
             it.q = L.raw(i);
             it.r = rank_of(it.key, groups);
             st_stream_s32(inverse + i, (int)it.r);
-            const unsigned h = filter_slot(it.key);
-            multi = (__ldg(filter + (h >> 5)) >> (h & 31)) & 1u;
-            if (!multi) {
-                // exactly one point in this voxel: it is the centroid.  One full 32-byte sector store.
-                float4* rec = reinterpret_cast<float4*>(voxels + it.r);
-                rec[0] = it.q;
-                rec[1] = make_float4(__int_as_float(1), __int_as_float(it.key), 0.f, 0.f);
-            }
+            if (dup) voxel_key[i] = it.key;                          // strip the flag (6 % of the points)
+            else store_first_member(voxels, it.r, it.q, it.key);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, multi);
+        const unsigned m = __ballot_sync(0xffffffffu, dup);
         if (m) {
-            if (multi) ring[(head + count + __popc(m & lanemask_lt())) % kRingSize] = it;
+            if (dup) ring[(head + count + __popc(m & lanemask_lt())) % kRingSize] = it;
             count += __popc(m);
             __syncwarp();
             if (count >= 32) {
-                accumulate_multi(ring[(head + lane) % kRingSize], D, acc, cnt, voxels);
+                const DupItem& e = ring[(head + lane) % kRingSize];
+                accumulate_dup(e.q, e.key, e.r, D, acc, cnt);
                 head = (head + 32) % kRingSize;
                 count -= 32;
                 __syncwarp();
             }
         }
     }
-    if (lane < count) accumulate_multi(ring[(head + lane) % kRingSize], D, acc, cnt, voxels);
+    if (lane < count) {
+        const DupItem& e = ring[(head + lane) % kRingSize];
+        accumulate_dup(e.q, e.key, e.r, D, acc, cnt);
+    }
 }
 
 // ---- k_frame_finalize -------------------------------------------------------------------------
-// cnt[r] != 0 exactly for the voxels that went through the accumulators (multi-member voxels and the
-// few singletons that collided in the duplicate filter): a coalesced sweep over cnt finds them; the
-// ~6 % of hits are parked in a per-warp ring and finished 32 at a time, so the fp64 divisions run with
-// full warps instead of being executed, mostly masked, by every warp.
-__device__ __forceinline__ void finalize_voxel(unsigned r, const lidar_frame_desc& D, double isx, double isw,
-                                               long long* __restrict__ acc, int32_t* __restrict__ cnt,
-                                               lidar_voxel* __restrict__ voxels) {
-    const int c = cnt[r];
-    const int key = voxels[r].key;
-    longlong2* A = reinterpret_cast<longlong2*>(acc + (size_t)r * 4);
-    const longlong2 s01 = A[0], s23 = A[1];
-    int ix, iy, iz;
-    decode_key(key, D, ix, iy, iz);
-    const double dc = (double)c;
-    const double cx = voxel_ref(D.origin[0], ix, D.voxel);
-    const double cy = voxel_ref(D.origin[1], iy, D.voxel);
-    const double cz = voxel_ref(D.origin[2], iz, D.voxel);
-    float4 o;
-    o.x = (float)__dadd_rn(cx, __ddiv_rn(__dmul_rn((double)s01.x, isx), dc));
-    o.y = (float)__dadd_rn(cy, __ddiv_rn(__dmul_rn((double)s01.y, isx), dc));
-    o.z = (float)__dadd_rn(cz, __ddiv_rn(__dmul_rn((double)s23.x, isx), dc));
-    o.w = (float)__ddiv_rn(__dmul_rn((double)s23.y, isw), dc);
-    float4* rec = reinterpret_cast<float4*>(voxels + r);
-    rec[0] = o;
-    rec[1] = make_float4(__int_as_float(c), __int_as_float(key), 0.f, 0.f);
-    // restore the all-zero invariant of the accumulators for the next frame
-    A[0] = make_longlong2(0, 0);
-    A[1] = make_longlong2(0, 0);
-    cnt[r] = 0;
-}
-
+// cnt[r] != 0 exactly for the voxels with more than one member: a coalesced sweep over cnt finds them;
+// the ~6 % of hits are parked in a per-warp ring and finished 32 at a time, so the fp64 divisions run
+// with full warps instead of being executed, mostly masked, by every warp.
 __global__ void __launch_bounds__(kFrameThreads)
 k_frame_finalize(const lidar_frame_desc* __restrict__ Dg, long long* __restrict__ acc, int32_t* __restrict__ cnt,
                  lidar_voxel* __restrict__ voxels) {
@@ -651,7 +738,7 @@ k_frame_finalize(const lidar_frame_desc* __restrict__ Dg, long long* __restrict_
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t v_round = ((V + 31) / 32) * 32;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < v_round; r += stride) {
-        const bool hit = r < V && __ldg(cnt + r) != 0;
+        const bool hit = r < V && __ldcg(cnt + r) != 0;
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (m) {
             if (hit) ring[(head + count + __popc(m & lanemask_lt())) % kRingSize] = (unsigned)r;
@@ -668,7 +755,570 @@ k_frame_finalize(const lidar_frame_desc* __restrict__ Dg, long long* __restrict_
     if (lane < count) finalize_voxel(ring[(head + lane) % kRingSize], D, isx, isw, acc, cnt, voxels);
 }
 
+// ================================================================================================
+// k_frame_fused — the whole frame in ONE persistent cooperative kernel, points resident on chip.
+//
+// One CTA per SM (grid = a multiple of the SM count, all co-resident: cooperative launch).  Every CTA
+// owns a contiguous chunk of the frame and pulls it into shared memory ONCE with the TMA bulk-copy
+// engine (cp.async.bulk + mbarrier, SASS UBLKCP): 1 M points / 148 SMs = 6 757 points = 106 KB per SM —
+// a whole frame fits in the 33 MB of shared memory of the chip.  All later phases read the points (and
+// their voxel keys) from shared memory, so HBM sees the compulsory traffic only: 16 B/point in,
+// key + inverse + voxel records out.  Points beyond the shared-memory capacity of a CTA ("spill") are
+// re-read from global memory (L2) in each phase, so any frame size works.
+//
+//   phase 0  TMA load of the chunk; zero the density grid; min/max of the chunk -> partials
+//   -- grid barrier --   every CTA folds the partials and derives the frame descriptor redundantly
+//   phase 1  mark: voxel key (+dup flag) -> smem, key -> global, atomicOr occupancy bit, density RED;
+//            four points per thread in flight
+//   -- grid barrier --
+//   phase 2  scan: each CTA popcounts a contiguous range of occupancy groups (one 256-bit load per
+//            group, warps walk contiguous rows), publishes its total (flag + value), waits for the
+//            totals of ALL CTAs (co-resident => spinning is safe), writes the exclusive prefix into
+//            word 0 of each of its groups
+//   -- grid barrier --
+//   phase 3  rank: prefix + popc(bits below) -> inverse; first members store their record, dup
+//            members accumulate exact fixed-point sums
+//   -- grid barrier --
+//   phase 4  re-zero this CTA's range of the occupancy bitmap (clean for the next frame) and finalize
+//            the multi-member voxels (sweep of the member counters)
+//
+// Same arithmetic (device functions) as the five-kernel path => identical outputs.
+// ================================================================================================
+constexpr int kFusedMaxThreads = 512;     // 128 registers per thread: room for four points in flight
+constexpr int kFusedLoadStages = 4;       // the chunk arrives in 4 bulk copies, each with its own mbarrier
+constexpr int kFusedRing = 64;
+constexpr int kFusedBatch = 4;            // points per thread per trip in the mark and rank phases
+
+struct FusedArgs {
+    FrameParams P;
+    double* partial;
+    FrameCtrl* ctrl;
+    lidar_frame_desc* D;
+    int32_t* voxel_key;
+    int32_t* inverse;
+    lidar_voxel* voxels;
+    int32_t* grid_out;
+    int grid_cap;
+    uint32_t* groups;
+    int64_t groups_cap;
+    long long* acc;
+    int32_t* cnt;
+    unsigned long long* cta_desc;
+    unsigned long long* trace_all;   // [G][16] %globaltimer stamps of every CTA (diagnostics)
+    int32_t* grid_rep;               // kGridRepCells zeroed cells: private replicas of the density grid
+    int smem_points;      // resident points per CTA (shared-memory capacity)
+    int smem_groups;      // capacity of the per-group popcount cache (bytes) per CTA
+};
+
+__device__ __forceinline__ unsigned fused_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fused_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fused_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fused_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fused_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fused_mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(fused_smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fused_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(fused_smem_u32(dst)), "l"(src), "r"(bytes), "r"(fused_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// a spin that lasts two seconds means the grid is not co-resident (or a CTA died): kill the context
+// instead of hanging the device
+struct SpinGuard {
+    unsigned long long t0;
+    unsigned polls;
+    __device__ __forceinline__ SpinGuard() : t0(0ull), polls(0u) {}
+    __device__ __forceinline__ void tick() {
+        if ((++polls & 0x3ffu) == 0u) {
+            const unsigned long long t = global_timer_ns();
+            if (t0 == 0ull) t0 = t;
+            else if (t - t0 > 2000000000ull) __trap();
+        }
+    }
+};
+
+// All CTAs of the grid are co-resident (cooperative launch), so a counter barrier cannot deadlock.
+// `target` = arrivals expected so far = barrier ordinal * gridDim.x; the counter is reset to zero by
+// the last CTA to leave the kernel.
+__device__ __forceinline__ void fused_grid_barrier(unsigned* ctr, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        red_release_add_u32(ctr, 1u);
+        SpinGuard guard;
+        while (ld_acquire_u32(ctr) < target) guard.tick();
+    }
+    __syncthreads();
+}
+
+#define FUSED_TRACE(k) do { if (tid == 0) s_trace[k] = global_timer_ns(); } while (0)
+
+__global__ void __launch_bounds__(kFusedMaxThreads, 1)
+k_frame_fused(const FusedArgs A) {
+    extern __shared__ __align__(128) unsigned char fsm[];
+    __shared__ lidar_frame_desc D;
+    __shared__ __align__(8) unsigned long long s_bar[kFusedLoadStages];
+    __shared__ double s_red[kFusedMaxThreads / 32][8];
+    __shared__ double s_bb[8];
+    __shared__ unsigned s_wsum[kFusedMaxThreads / 32];
+    __shared__ unsigned long long s_wlook[kFusedMaxThreads / 32][2];
+    __shared__ unsigned long long s_base_total[2];
+    __shared__ unsigned long long s_trace[16];
+    __shared__ int s_stat[8];
+
+    const int T = blockDim.x;
+    const int tid = threadIdx.x;
+    const int nwarp = T >> 5;
+    const int warp = tid >> 5;
+    const unsigned lane = lane_id();
+    const int G = gridDim.x;
+    const int b = blockIdx.x;
+    const FrameParams& P = A.P;
+    const int64_t n = P.n;
+
+    // shared-memory carve-up: points | keys | ring (per warp) | group popcounts
+    float4* s_pts = reinterpret_cast<float4*>(fsm);
+    unsigned* s_key = reinterpret_cast<unsigned*>(fsm + (size_t)A.smem_points * 16);
+    uint2* s_ring = reinterpret_cast<uint2*>(fsm + (size_t)A.smem_points * 20);
+    unsigned char* s_gcnt = reinterpret_cast<unsigned char*>(s_ring + (size_t)nwarp * kFusedRing);
+
+    // this CTA's chunk of the frame: [c0, c0 + m), the first `res` points resident in shared memory
+    const int64_t per = ((n + G - 1) / G + 31) & ~(int64_t)31;   // multiple of 32: whole warps, 512-B aligned
+    const int64_t c0 = (int64_t)b * per < n ? (int64_t)b * per : n;
+    const int m = (int)((c0 + per <= n ? c0 + per : n) - c0);
+    const int res = m < A.smem_points ? m : A.smem_points;
+    const float4* gp = P.pts + c0;
+    const int stage_pts = ((res + kFusedLoadStages - 1) / kFusedLoadStages + 3) & ~3;
+
+    if (tid == 0) {
+        s_trace[0] = global_timer_ns();
+#pragma unroll
+        for (int s = 0; s < kFusedLoadStages; ++s) fused_mbar_init(&s_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int s = 0; s < kFusedLoadStages; ++s) {
+            const int p0 = s * stage_pts;
+            int cnt = res - p0;
+            cnt = cnt < 0 ? 0 : (cnt > stage_pts ? stage_pts : cnt);
+            if (cnt > 0) {
+                fused_mbar_expect_tx(&s_bar[s], (unsigned)cnt * 16u);
+                fused_bulk_g2s(s_pts + p0, gp + p0, (unsigned)cnt * 16u, &s_bar[s]);
+            }
+        }
+    }
+    // ---- phase 0b: zero the density grid and the scan flags; the occupancy bitmap is already clean
+    //      unless the previous frame of this workspace ran on the five-kernel path (dirty > 0) --------
+    {
+        const int64_t gt0 = (int64_t)b * T + tid, gstride = (int64_t)G * T;
+        int64_t dirty = (int64_t)A.ctrl->dirty_groups;
+        if (dirty > A.groups_cap) dirty = A.groups_cap;
+        uint4* b4 = reinterpret_cast<uint4*>(A.groups);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int64_t k = gt0; k < dirty * 2; k += gstride) b4[k] = z;
+        for (int64_t k = gt0; k < A.grid_cap; k += gstride) A.grid_out[k] = 0;
+        for (int64_t k = gt0; k < G; k += gstride) A.cta_desc[k] = 0ull;
+    }
+    __syncthreads();   // mbarrier init visible to every waiter
+    // ---- phase 0c: bounding box of the chunk -----------------------------------------------------
+    {
+        float mn[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        auto fold = [&](const float4& v) {
+            mn[0] = fminf(mn[0], v.x); mx[0] = fmaxf(mx[0], v.x);
+            mn[1] = fminf(mn[1], v.y); mx[1] = fmaxf(mx[1], v.y);
+            mn[2] = fminf(mn[2], v.z); mx[2] = fmaxf(mx[2], v.z);
+            mn[3] = fminf(mn[3], v.w); mx[3] = fmaxf(mx[3], v.w);
+        };
+        // spill points first: their global loads overlap the wait for the bulk copies
+        for (int j = res + tid; j < m; j += T) fold(__ldcg(gp + j));
+#pragma unroll
+        for (int s = 0; s < kFusedLoadStages; ++s) {
+            const int p0 = s * stage_pts;
+            int p1 = p0 + stage_pts;
+            p1 = p1 > res ? res : p1;
+            if (p0 < p1) {
+                fused_mbar_wait(&s_bar[s], 0);
+                for (int j = p0 + tid; j < p1; j += T) fold(s_pts[j]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+                mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { s_red[warp][c] = (double)mn[c]; s_red[warp][4 + c] = (double)mx[c]; }
+        }
+        __syncthreads();
+        if (tid < 8) {
+            const bool is_max = tid >= 4;
+            double v = is_max ? -INFINITY : INFINITY;
+            for (int w = 0; w < nwarp; ++w) v = is_max ? fmax(v, s_red[w][tid]) : fmin(v, s_red[w][tid]);
+            A.partial[(size_t)b * 8 + tid] = v;
+        }
+    }
+    FUSED_TRACE(1);
+    fused_grid_barrier(&A.ctrl->grid_bar, 1u * G);
+    FUSED_TRACE(2);
+    // ---- every CTA folds the G partials and derives the descriptor (identical in every CTA) ------
+    {
+        const int ch = tid & 7;
+        const bool is_max = ch >= 4;
+        double v = is_max ? -INFINITY : INFINITY;
+        for (int q = tid >> 3; q < G; q += T / 8) {
+            const double x = __ldcg(A.partial + (size_t)q * 8 + ch);
+            v = is_max ? fmax(v, x) : fmin(v, x);
+        }
+        for (int o = 8; o < 32; o <<= 1) {
+            const double x = __shfl_xor_sync(0xffffffffu, v, o);
+            v = is_max ? fmax(v, x) : fmin(v, x);
+        }
+        if (lane < 8) s_red[warp][lane] = v;   // the barrier above separates this from the earlier use
+        __syncthreads();
+        if (tid < 8) {
+            double r = s_red[0][tid];
+            for (int w = 1; w < nwarp; ++w) r = (tid >= 4) ? fmax(r, s_red[w][tid]) : fmin(r, s_red[w][tid]);
+            s_bb[tid] = r;
+        }
+        __syncthreads();
+        derive_desc_cta(P, s_bb, &D, s_stat);
+    }
+    FUSED_TRACE(3);
+    const bool ok = D.status == 0;
+    const int64_t ng = ok ? (D.key_space + kGroupVoxels - 1) / kGroupVoxels : 0;
+    // density grid replicas: R copies of nx*ny cells, CTA b adds into copy b % R
+    const int ncell = D.nx * D.ny;
+    int grid_reps = (ok && ncell > 0) ? kGridRepCells / ncell : 0;
+    grid_reps = grid_reps > kGridRepMax ? kGridRepMax : grid_reps;
+    int32_t* const grid_acc = grid_reps >= 2 ? A.grid_rep + (size_t)(b % grid_reps) * ncell : A.grid_out;
+
+    // ---- phase 1: mark ----------------------------------------------------------------------------
+    if (ok) {
+        const MarkConst K = make_mark_const(D);
+        // resident points: kFusedBatch points per thread per trip, all their atomicOr in flight together
+        for (int j0 = tid; j0 < res; j0 += kFusedBatch * T) {
+            float4 q[kFusedBatch];
+            int key[kFusedBatch];
+            unsigned bit[kFusedBatch], old[kFusedBatch];
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                const int j = j0 + u * T;
+                q[u] = s_pts[j < res ? j : j0];
+            }
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                key[u] = voxel_key_of(q[u], D, K);
+                uint32_t* w = occupancy_word(A.groups, key[u], bit[u]);
+                old[u] = 0u;
+                if (j0 + u * T < res) old[u] = atomicOr(w, bit[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                const int j = j0 + u * T;
+                if (j < res) {
+                    st_stream_s32(A.voxel_key + c0 + j, key[u]);
+                    if (K.do_grid) {
+                        const int cell = grid_cell_of(q[u], D, K);
+                        if (cell >= 0) red_add_s32(grid_acc + cell, 1);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                const int j = j0 + u * T;
+                if (j < res) s_key[j] = (unsigned)key[u] | ((old[u] & bit[u]) ? kDupFlag : 0u);
+            }
+        }
+        // spill points: the flagged key goes to global memory, phase 3 strips the flag
+        for (int j = res + tid; j < m; j += T) {
+            const float4 q = __ldcg(gp + j);
+            const int key = voxel_key_of(q, D, K);
+            unsigned bit;
+            uint32_t* w = occupancy_word(A.groups, key, bit);
+            const unsigned old = atomicOr(w, bit);
+            if (K.do_grid) {
+                const int cell = grid_cell_of(q, D, K);
+                if (cell >= 0) red_add_s32(grid_acc + cell, 1);
+            }
+            A.voxel_key[c0 + j] = (int)((unsigned)key | ((old & bit) ? kDupFlag : 0u));
+        }
+    }
+    FUSED_TRACE(4);
+    fused_grid_barrier(&A.ctrl->grid_bar, 2u * G);
+    FUSED_TRACE(5);
+
+    // ---- phase 2: scan of the occupancy groups ----------------------------------------------------
+    // CTA b owns groups [g0, g1); warp w owns the contiguous segment [w0, w1) and walks it in rows of 32
+    // groups (1 KB, one 256-bit load per lane)
+    const int64_t gpc = (ng + G - 1) / G;
+    const int64_t g0 = (int64_t)b * gpc < ng ? (int64_t)b * gpc : ng;
+    const int64_t g1 = g0 + gpc < ng ? g0 + gpc : ng;
+    const int64_t wseg = (((gpc + nwarp - 1) / nwarp) + 31) & ~(int64_t)31;
+    const int64_t w0 = g0 + (int64_t)warp * wseg < g1 ? g0 + (int64_t)warp * wseg : g1;
+    const int64_t w1 = w0 + wseg < g1 ? w0 + wseg : g1;
+    unsigned long long n_voxels = 0ull;
+    if (ok) {
+        const bool cache = gpc <= (int64_t)A.smem_groups;
+        unsigned mine = 0;
+        for (int64_t row = w0; row < w1; row += 32 * kFusedBatch) {
+            Word8 gw[kFusedBatch];
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {          // kFusedBatch rows (1 KB each) in flight per warp
+                const int64_t g = row + u * 32 + lane;
+                if (g < w1) gw[u] = ld_cg_256(A.groups + (size_t)g * 8);
+            }
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                const int64_t g = row + u * 32 + lane;
+                if (g < w1) {
+                    const unsigned pc = group_popc(gw[u]);
+                    if (cache) s_gcnt[g - g0] = (unsigned char)pc;
+                    mine += pc;
+                }
+            }
+        }
+        mine = warp_sum_u32(mine);
+        if (lane == 0) s_wsum[warp] = mine;
+        __syncthreads();
+        unsigned total = 0;
+        for (int w = 0; w < nwarp; ++w) total += s_wsum[w];
+        if (tid == 0) A.cta_desc[b] = (unsigned long long)total;
+        FUSED_TRACE(6);
+    }
+    // totals of ALL CTAs: earlier ones give this CTA's base, all of them give the voxel count.  (One
+    // poller per CTA on the barrier counter; polling the G totals directly puts G*G threads on a few lines.)
+    fused_grid_barrier(&A.ctrl->grid_bar, 3u * G);
+    if (ok) {
+        const bool cache = gpc <= (int64_t)A.smem_groups;
+        unsigned long long before = 0ull, all = 0ull;
+        for (int c = tid; c < G; c += T) {
+            const unsigned long long d = __ldcg(A.cta_desc + c);
+            all += d;
+            if (c < b) before += d;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            before += __shfl_xor_sync(0xffffffffu, before, o);
+            all += __shfl_xor_sync(0xffffffffu, all, o);
+        }
+        if (lane == 0) { s_wlook[warp][0] = before; s_wlook[warp][1] = all; }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long bs = 0ull, al = 0ull;
+            for (int w = 0; w < nwarp; ++w) { bs += s_wlook[w][0]; al += s_wlook[w][1]; }
+            s_base_total[0] = bs;
+            s_base_total[1] = al;
+            D.n_voxels = (int64_t)al;
+        }
+        __syncthreads();
+        FUSED_TRACE(7);
+        unsigned warp_off = 0;
+        for (int w = 0; w < warp; ++w) warp_off += s_wsum[w];
+        n_voxels = s_base_total[1];
+        unsigned run = (unsigned)s_base_total[0] + warp_off;
+        for (int64_t row = w0; row < w1; row += 32) {
+            const int64_t g = row + lane;
+            unsigned pc = 0;
+            if (g < w1) pc = cache ? (unsigned)s_gcnt[g - g0] : group_popc(ld_cg_256(A.groups + (size_t)g * 8));
+            unsigned inc = pc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (unsigned)o) inc += t;
+            }
+            if (g < w1) A.groups[(size_t)g * 8] = run + inc - pc;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+    FUSED_TRACE(8);
+    fused_grid_barrier(&A.ctrl->grid_bar, 4u * G);
+    FUSED_TRACE(9);
+
+    // ---- phase 3: rank ----------------------------------------------------------------------------
+    if (ok) {
+        uint2* ring = s_ring + (size_t)warp * kFusedRing;
+        unsigned head = 0, count = 0;   // warp-uniform
+        auto drain = [&](unsigned slot) {
+            const uint2 e = ring[slot];
+            const int j = (int)e.x;
+            float4 q;
+            int key;
+            if (j < res) { q = s_pts[j]; key = (int)(s_key[j] & ~kDupFlag); }
+            else { q = __ldcg(gp + j); key = __ldcg(A.voxel_key + c0 + j); }   // flag already stripped
+            accumulate_dup(q, key, e.y, D, A.acc, A.cnt);
+        };
+        const int m_round = (m + 31) & ~31;
+        for (int j0 = tid; j0 < m_round; j0 += kFusedBatch * T) {
+            float4 q[kFusedBatch];
+            unsigned fk[kFusedBatch], r[kFusedBatch];
+            bool live[kFusedBatch];
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                const int j = j0 + u * T;
+                live[u] = j < m;
+                fk[u] = 0u;
+                r[u] = 0u;
+                if (live[u]) {
+                    if (j < res) { q[u] = s_pts[j]; fk[u] = s_key[j]; }
+                    else { q[u] = __ldcg(gp + j); fk[u] = (unsigned)__ldcg(A.voxel_key + c0 + j); }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u)
+                if (live[u]) r[u] = rank_of((int)(fk[u] & ~kDupFlag), A.groups);
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                const int j = j0 + u * T;
+                const bool dup = live[u] && (fk[u] & kDupFlag) != 0u;
+                if (live[u]) {
+                    const int key = (int)(fk[u] & ~kDupFlag);
+                    st_stream_s32(A.inverse + c0 + j, (int)r[u]);
+                    if (!dup) store_first_member(A.voxels, r[u], q[u], key);
+                    else if (j >= res) A.voxel_key[c0 + j] = key;      // strip the flag of a spilled key
+                }
+                const unsigned mm = __ballot_sync(0xffffffffu, dup);
+                if (mm) {
+                    if (dup) ring[(head + count + __popc(mm & lanemask_lt())) % kFusedRing] = make_uint2((unsigned)j, r[u]);
+                    count += __popc(mm);
+                    __syncwarp();
+                    if (count >= 32) {
+                        drain((head + lane) % kFusedRing);
+                        head = (head + 32) % kFusedRing;
+                        count -= 32;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        if (lane < count) drain((head + lane) % kFusedRing);
+    }
+    FUSED_TRACE(10);
+    fused_grid_barrier(&A.ctrl->grid_bar, 5u * G);
+    FUSED_TRACE(11);
+
+    // ---- phase 4: clean the bitmap for the next frame, finalize the multi-member voxels -----------
+    if (grid_reps >= 2) {
+        // merge the density replicas (complete since barrier 2) into the output grid and leave them zeroed
+        // for the next frame; placed here because this phase is latency-bound and has the slack
+        for (int k = b * T + tid; k < ncell; k += G * T) {
+            int v[kGridRepMax];
+#pragma unroll
+            for (int r = 0; r < kGridRepMax; ++r)      // all replica loads in flight before the first store
+                v[r] = r < grid_reps ? __ldcg(A.grid_rep + (size_t)r * ncell + k) : 0;
+            int sum = 0;
+#pragma unroll
+            for (int r = 0; r < kGridRepMax; ++r) {
+                sum += v[r];
+                if (r < grid_reps) A.grid_rep[(size_t)r * ncell + k] = 0;
+            }
+            A.grid_out[k] = sum;
+        }
+    }
+    if (ok) {
+        Word8 z;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) z.w[k] = 0u;
+        for (int64_t row = w0; row < w1; row += 32) {
+            const int64_t g = row + lane;
+            if (g < w1) st_256(A.groups + (size_t)g * 8, z);
+        }
+        unsigned* ring = reinterpret_cast<unsigned*>(s_ring + (size_t)warp * kFusedRing);
+        unsigned head = 0, count = 0;
+        const double isx = 1.0 / D.fix_scale_xyz, isw = 1.0 / D.fix_scale_w;
+        const int64_t V = (int64_t)n_voxels;
+        const int64_t vper = ((V + G - 1) / G + 31) & ~(int64_t)31;
+        const int64_t v0 = (int64_t)b * vper;
+        const int64_t v1 = v0 + vper;   // whole warps; bounds-checked against V below
+        for (int64_t r0 = v0 + tid; r0 < v1; r0 += (int64_t)kFusedBatch * T) {
+            int c[kFusedBatch];
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                const int64_t r = r0 + (int64_t)u * T;
+                c[u] = (r < v1 && r < V) ? __ldcg(A.cnt + r) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                const int64_t r = r0 + (int64_t)u * T;
+                const bool hit = c[u] != 0;
+                const unsigned mm = __ballot_sync(0xffffffffu, hit);
+                if (mm) {
+                    if (hit) ring[(head + count + __popc(mm & lanemask_lt())) % kFusedRing] = (unsigned)r;
+                    count += __popc(mm);
+                    __syncwarp();
+                    if (count >= 32) {
+                        finalize_voxel(ring[(head + lane) % kFusedRing], D, isx, isw, A.acc, A.cnt, A.voxels);
+                        head = (head + 32) % kFusedRing;
+                        count -= 32;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        if (lane < count) finalize_voxel(ring[(head + lane) % kFusedRing], D, isx, isw, A.acc, A.cnt, A.voxels);
+    }
+    // ---- epilogue: descriptor out, counters reset by the last CTA to leave -------------------------
+    __syncthreads();
+    if (tid == 0) {
+        s_trace[12] = global_timer_ns();
+        for (int k = 0; k < 13; ++k) A.trace_all[(size_t)b * 16 + k] = s_trace[k];
+        if (b == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) D.trace_ns[k] = (uint32_t)(s_trace[k + 1] - s_trace[k]);
+            D.trace_ns[15] = (uint32_t)G;
+            *A.D = D;
+        }
+        __threadfence();
+        if (atomicAdd(&A.ctrl->exit_ticket, 1u) == (unsigned)G - 1u) {
+            A.ctrl->grid_bar = 0u;
+            A.ctrl->exit_ticket = 0u;
+            A.ctrl->dirty_groups = 0ull;     // phase 4 left the bitmap clean
+        }
+    }
+}
+
 static int g_ctas_per_sm = 8;   // grid cap of the per-point frame kernels, in CTAs per SM (tuning knob)
+
+// fused-kernel configuration (lidar_frame_set_fused)
+static int g_fused_mode = LIDAR_FRAME_AUTO;
+static int g_fused_threads = 512;
+static int g_fused_ctas_per_sm = 1;
+static int g_fused_smem_kb = 0;          // 0 = as much as the chunk needs, up to the opt-in maximum
+static int g_fused_plain_launch = 0;     // experiment: ordinary launch instead of cooperative (see header)
+static bool g_fused_attr_set = false;
+static size_t g_fused_attr_bytes = 0;
 
 static int frame_grid(int64_t n, int per_thread) {
     int64_t want = (n + (int64_t)kFrameThreads * per_thread - 1) / ((int64_t)kFrameThreads * per_thread);
@@ -682,6 +1332,30 @@ static int frame_grid(int64_t n, int per_thread) {
 using namespace lidar;
 
 extern "C" {
+
+int lidar_frame_set_fused(int mode, int threads, int ctas_per_sm, int smem_kb) {
+    LIDAR_REQUIRE(mode == LIDAR_FRAME_AUTO || mode == LIDAR_FRAME_MULTIKERNEL || mode == LIDAR_FRAME_FUSED,
+                  LIDAR_ERR_INVALID, "lidar_frame_set_fused: unknown mode %d", mode);
+    LIDAR_REQUIRE(threads == 0 || (threads >= 128 && threads <= kFusedMaxThreads && threads % 32 == 0),
+                  LIDAR_ERR_INVALID, "lidar_frame_set_fused: threads must be a multiple of 32 in [128, 512]");
+    LIDAR_REQUIRE(ctas_per_sm >= 0 && ctas_per_sm <= 4, LIDAR_ERR_INVALID, "lidar_frame_set_fused: ctas_per_sm 0..4");
+    LIDAR_REQUIRE(smem_kb >= 0 && smem_kb <= 227, LIDAR_ERR_INVALID, "lidar_frame_set_fused: smem_kb 0..227");
+    g_fused_mode = mode;
+    if (threads) g_fused_threads = threads;
+    if (ctas_per_sm) g_fused_ctas_per_sm = ctas_per_sm;
+    g_fused_smem_kb = smem_kb;
+    return LIDAR_OK;
+}
+
+size_t lidar_frame_trace_offset(const lidar_frame_caps* caps) {
+    if (!caps || caps->max_points < 0 || caps->max_key_space <= 0) return 0;
+    return frame_layout(*caps).off_trace;
+}
+
+int lidar_frame_set_fused_plain_launch(int on) {
+    g_fused_plain_launch = on ? 1 : 0;
+    return LIDAR_OK;
+}
 
 int lidar_frame_set_ctas_per_sm(int ctas_per_sm) {
     LIDAR_REQUIRE(ctas_per_sm >= 1 && ctas_per_sm <= 8, LIDAR_ERR_INVALID, "lidar_frame_set_ctas_per_sm: 1..8");
@@ -734,7 +1408,6 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
     unsigned long long* tile_desc = reinterpret_cast<unsigned long long*>(ws + L.off_tile_desc);
     long long* acc = reinterpret_cast<long long*>(ws + L.off_acc);
     int32_t* cnt = reinterpret_cast<int32_t*>(ws + L.off_cnt);
-    uint32_t* filter = reinterpret_cast<uint32_t*>(ws + L.off_filter);
 
     FrameParams P;
     P.pts = static_cast<const float4*>(d_points);
@@ -758,18 +1431,83 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
     };
     const int grid_cap = grid_size > 0.0 ? caps->max_nx * caps->max_ny : 0;
     LIDAR_CUDA_TRY(mark(0));
+    if (n > 0 && g_fused_mode != LIDAR_FRAME_MULTIKERNEL) {
+        // ---- the whole frame as one persistent cooperative kernel -----------------------------
+        const int T = g_fused_threads;
+        const int G = sm_count() * g_fused_ctas_per_sm;
+        LIDAR_REQUIRE(G <= kFusedMaxCtas, LIDAR_ERR_CAPACITY, "lidar_frame_voxel_density: fused grid too large");
+        const size_t ring_bytes = (size_t)(T / 32) * kFusedRing * sizeof(uint2);
+        const size_t static_bytes = 4096;    // static __shared__ of k_frame_fused, rounded up
+        size_t budget = g_fused_smem_kb ? (size_t)g_fused_smem_kb * 1024 : smem_optin();
+        if (budget > smem_optin()) budget = smem_optin();
+        LIDAR_REQUIRE(budget > static_bytes + ring_bytes + 4096, LIDAR_ERR_INVALID,
+                      "lidar_frame_voxel_density: fused shared-memory budget too small");
+        budget -= static_bytes;
+        const int64_t per = (((n + G - 1) / G) + 31) & ~(int64_t)31;
+        const int64_t gpc = (L.groups + G - 1) / G;     // worst case (capacity), so the layout is per pipeline
+        // group popcount cache first (1 B per group, capped at 16 KB), the rest holds points (20 B each)
+        size_t gbytes = (size_t)((gpc + 127) & ~(int64_t)127);
+        if (gbytes > 16384) gbytes = 0;
+        int64_t room = ((int64_t)budget - (int64_t)ring_bytes - (int64_t)gbytes) / 20;
+        room &= ~(int64_t)31;
+        int64_t spts = per < room ? per : room;
+        if (spts < 0) spts = 0;
+        const size_t dyn = (size_t)spts * 20 + ring_bytes + gbytes;
+        if (!g_fused_attr_set || dyn > g_fused_attr_bytes) {
+            LIDAR_CUDA_TRY(cudaFuncSetAttribute(k_frame_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(smem_optin() - static_bytes)));
+            g_fused_attr_set = true;
+            g_fused_attr_bytes = smem_optin() - static_bytes;
+        }
+        FusedArgs A;
+        A.P = P;
+        A.partial = partial;
+        A.ctrl = ctrl;
+        A.D = d_desc;
+        A.voxel_key = d_voxel_key;
+        A.inverse = d_inverse;
+        A.voxels = d_voxels;
+        A.grid_out = d_grid;
+        A.grid_cap = grid_cap;
+        A.groups = groups;
+        A.groups_cap = L.groups;
+        A.acc = acc;
+        A.cnt = cnt;
+        A.cta_desc = reinterpret_cast<unsigned long long*>(ws + L.off_cta_desc);
+        A.trace_all = reinterpret_cast<unsigned long long*>(ws + L.off_trace);
+        A.grid_rep = reinterpret_cast<int32_t*>(ws + L.off_grid_rep);
+        A.smem_points = (int)spts;
+        A.smem_groups = (int)gbytes;
+        void* kargs[] = {&A};
+        cudaError_t le;
+        if (g_fused_plain_launch) {
+            k_frame_fused<<<G, T, dyn, st>>>(A);
+            le = cudaGetLastError();
+        } else {
+            le = cudaLaunchCooperativeKernel((const void*)k_frame_fused, dim3(G), dim3(T), kargs, dyn, st);
+        }
+        if (le == cudaSuccess) {
+            for (int i = 1; i <= 5; ++i) LIDAR_CUDA_TRY(mark(i));
+            return LIDAR_OK;
+        }
+        (void)cudaGetLastError();
+        LIDAR_REQUIRE(g_fused_mode == LIDAR_FRAME_AUTO, LIDAR_ERR_CUDA,
+                      "lidar_frame_voxel_density: cooperative launch of k_frame_fused failed: %s",
+                      cudaGetErrorString(le));
+        // AUTO: fall through to the five-kernel path (e.g. the grid cannot be co-resident)
+    }
     int bgrid = frame_grid(n > 0 ? n : 1, 4);
     if (bgrid < sm_count()) bgrid = sm_count();   // enough CTAs to zero the bitmap quickly
     if (bgrid > kBboxMaxBlocks) bgrid = kBboxMaxBlocks;
     k_frame_prep<<<bgrid, kFrameThreads, 0, st>>>(P, partial, ctrl, d_desc, d_grid, grid_cap, tile_desc, L.tiles,
-                                                  groups, L.groups, filter);
+                                                  groups, L.groups);
     LIDAR_CHECK_LAUNCH();
     LIDAR_CUDA_TRY(mark(1));
     if (n == 0) {
         for (int i = 2; i <= 5; ++i) LIDAR_CUDA_TRY(mark(i));
         return LIDAR_OK;
     }
-    k_frame_mark<<<frame_grid(n, 2), kFrameThreads, 0, st>>>(P.pts, d_desc, d_voxel_key, groups, filter, d_grid);
+    k_frame_mark<<<frame_grid(n, 2), kFrameThreads, 0, st>>>(P.pts, d_desc, d_voxel_key, groups, d_grid);
     LIDAR_CHECK_LAUNCH();
     LIDAR_CUDA_TRY(mark(2));
     {
@@ -780,7 +1518,7 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
         LIDAR_CHECK_LAUNCH();
     }
     LIDAR_CUDA_TRY(mark(3));
-    k_frame_rank<<<frame_grid(n, 2), kFrameThreads, 0, st>>>(P.pts, d_desc, d_voxel_key, groups, filter, d_inverse,
+    k_frame_rank<<<frame_grid(n, 2), kFrameThreads, 0, st>>>(P.pts, d_desc, d_voxel_key, groups, d_inverse,
                                                               acc, cnt, d_voxels);
     LIDAR_CHECK_LAUNCH();
     LIDAR_CUDA_TRY(mark(4));

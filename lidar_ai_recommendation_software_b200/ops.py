@@ -182,6 +182,17 @@ def roi_crop(points: torch.Tensor, lo, hi, return_mask: bool = True):
 # ------------------------------------------------------------------------------------------------
 # K5 (+K6) frame pipeline
 # ------------------------------------------------------------------------------------------------
+FRAME_AUTO, FRAME_MULTIKERNEL, FRAME_FUSED = 0, 1, 2
+
+
+def set_frame_mode(mode: int = FRAME_AUTO, threads: int = 0, ctas_per_sm: int = 0, smem_kb: int = 0) -> None:
+    """How `FramePipeline.enqueue` runs a frame (process-wide): one persistent cooperative kernel with
+    the frame resident in shared memory (FRAME_FUSED), five dependent kernels (FRAME_MULTIKERNEL), or
+    fused with fallback (FRAME_AUTO, default).  `threads`, `ctas_per_sm`, `smem_kb` tune the fused
+    kernel (0 = keep / as needed).  Outputs are identical in every mode."""
+    check(lib.lidar_frame_set_fused(int(mode), int(threads), int(ctas_per_sm), int(smem_kb)))
+
+
 @dataclass
 class FrameResult:
     desc: FrameDesc
