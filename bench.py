@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--e2e-slots", type=int, default=3, help="frames in flight in the end-to-end leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="frame kernel grid cap (0 = library default)")
     ap.add_argument("--streams", type=int, default=0,
@@ -325,8 +326,8 @@ def main():
                          "kernel_ms": {k: float(v) for k, v in zip(KERNELS, per_kernel)}}
 
     # ---- end to end through the host-buffer API ------------------------------------------------
-    hp = ops.HostFramePipeline(max_points=n, voxel_size=VOXEL, grid_size=GRID, slots=2, max_key_space=1 << 28,
-                               max_nx=256, max_ny=256)
+    hp = ops.HostFramePipeline(max_points=n, voxel_size=VOXEL, grid_size=GRID, slots=args.e2e_slots,
+                               max_key_space=1 << 28, max_nx=256, max_ny=256)
     pinned = [torch.from_numpy(f).pin_memory() for f in host_frames[:4]]
     torch.cuda.synchronize()
     for w in range(3):
@@ -334,11 +335,16 @@ def main():
     e2e_steps = max(4, min(args.e2e_steps, args.steps))
     barrier()
     t0 = time.perf_counter()
-    hp.submit(pinned[0])
-    for s in range(1, e2e_steps):
+    inflight = 0
+    for s in range(e2e_steps):
+        if inflight == args.e2e_slots:
+            out = hp.collect(copy=False)
+            inflight -= 1
         hp.submit(pinned[s % 4])
+        inflight += 1
+    while inflight:
         out = hp.collect(copy=False)
-    out = hp.collect(copy=False)
+        inflight -= 1
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     assert int(out["counts"].sum()) == n
@@ -348,7 +354,7 @@ def main():
     e2e_val = n * e2e_steps * world / float(te.item()) / 1e6
     e2e = {"value": e2e_val, "unit": "Mpoints/s", "h2d_bytes_per_step": hp.h2d_bytes(n),
            "d2h_bytes_per_step": hp.d2h_bytes(n), "steps": e2e_steps,
-           "api": "ops.HostFramePipeline.submit/collect (pinned numpy in, numpy out, 2 slots in flight)"}
+           "api": f"ops.HostFramePipeline.submit/collect (pinned numpy in, numpy out, {args.e2e_slots} slots in flight)"}
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------
     cpu = None

@@ -321,6 +321,13 @@ int lidar_frame_voxel_density(const void* d_points, int64_t n, double voxel_size
                               int32_t* d_inverse, lidar_voxel* d_voxels, int32_t* d_grid, lidar_frame_desc* d_desc,
                               const lidar_frame_caps* caps, void* d_ws, size_t ws_bytes, void* stream);
 
+/* Repack the first min(n_voxels, capacity) voxel records as structure-of-arrays for the trip to the
+ * host: d_centroids4 float[capacity*4] (x,y,z,mean intensity), d_counts int32[capacity], d_keys
+ * int32[capacity] or NULL.  n_voxels is read from the DEVICE descriptor (no host round trip).  This
+ * is the layout the numpy surface returns (centroids (V,4), counts (V,)). */
+int lidar_frame_pack_soa(const lidar_voxel* d_voxels, const lidar_frame_desc* d_desc, int64_t capacity,
+                         float* d_centroids4, int32_t* d_counts, int32_t* d_keys, void* stream);
+
 /* Same call, additionally recording six caller-created cudaEvent_t (passed as void*) on `stream`:
  * before k_frame_prep, then after each of prep, mark, scan, rank, finalize — so a benchmark can
  * attribute device time to each kernel without a profiler. */

@@ -117,6 +117,7 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_frame_set_fused_plain_launch": (_i32, [_i32]),
     "lidar_frame_trace_offset": (_sz, [C.POINTER(FrameCaps)]),
     "lidar_frame_workspace_bytes": (_sz, [C.POINTER(FrameCaps)]),
+    "lidar_frame_pack_soa": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "lidar_frame_workspace_init": (_i32, [_vp, _sz, C.POINTER(FrameCaps), _vp]),
     "lidar_frame_voxel_density": (_i32, [_vp, _i64, _dbl, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          _vp, _vp, _vp, _vp, _vp, C.POINTER(FrameCaps), _vp, _sz, _vp]),

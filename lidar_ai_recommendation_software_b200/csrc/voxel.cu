@@ -1309,6 +1309,25 @@ k_frame_fused(const FusedArgs A) {
     }
 }
 
+// ---- k_frame_pack -----------------------------------------------------------------------------
+// Host-bound results leave the device as structure-of-arrays: 16 B centroid + 4 B count (+ 4 B key) per
+// voxel instead of the 32-byte record, i.e. 37 % fewer bytes over PCIe for the same information.
+__global__ void __launch_bounds__(kFrameThreads)
+k_frame_pack(const lidar_voxel* __restrict__ voxels, const lidar_frame_desc* __restrict__ Dg, int64_t cap,
+             float4* __restrict__ centroids, int32_t* __restrict__ counts, int32_t* __restrict__ keys) {
+    if (Dg->status != 0) return;
+    int64_t V = Dg->n_voxels;
+    if (V > cap) V = cap;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < V; r += stride) {
+        const Word8 rec = ld_cg_256(voxels + r);
+        centroids[r] = make_float4(__uint_as_float(rec.w[0]), __uint_as_float(rec.w[1]), __uint_as_float(rec.w[2]),
+                                   __uint_as_float(rec.w[3]));
+        counts[r] = (int32_t)rec.w[4];
+        if (keys) keys[r] = (int32_t)rec.w[5];
+    }
+}
+
 static int g_ctas_per_sm = 8;   // grid cap of the per-point frame kernels, in CTAs per SM (tuning knob)
 
 // fused-kernel configuration (lidar_frame_set_fused)
@@ -1525,6 +1544,17 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
     k_frame_finalize<<<frame_grid(n, 4), kFrameThreads, 0, st>>>(d_desc, acc, cnt, d_voxels);
     LIDAR_CHECK_LAUNCH();
     LIDAR_CUDA_TRY(mark(5));
+    return LIDAR_OK;
+}
+
+int lidar_frame_pack_soa(const lidar_voxel* d_voxels, const lidar_frame_desc* d_desc, int64_t capacity,
+                         float* d_centroids4, int32_t* d_counts, int32_t* d_keys, void* stream) {
+    LIDAR_REQUIRE(d_voxels && d_desc && d_centroids4 && d_counts, LIDAR_ERR_INVALID, "lidar_frame_pack_soa: NULL argument");
+    LIDAR_REQUIRE(capacity >= 0, LIDAR_ERR_INVALID, "lidar_frame_pack_soa: negative capacity");
+    if (capacity == 0) return LIDAR_OK;
+    k_frame_pack<<<frame_grid(capacity, 4), kFrameThreads, 0, as_stream(stream)>>>(
+        d_voxels, d_desc, capacity, reinterpret_cast<float4*>(d_centroids4), d_counts, d_keys);
+    LIDAR_CHECK_LAUNCH();
     return LIDAR_OK;
 }
 

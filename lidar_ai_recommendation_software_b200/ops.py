@@ -314,25 +314,34 @@ class FramePipeline:
 class HostFramePipeline:
     """The call a user of the numpy surface makes: HOST float4 frame in, HOST numpy results out.
 
-    Pinned staging buffers, one H2D copy of the frame, the five frame kernels, one D2H copy per
-    output.  Two slots alternate on two streams so the copies of one frame overlap the kernels of
-    the next (`submit` / `collect`); `process` is the synchronous single-frame form.
+    Pinned staging buffers, one H2D copy of the frame, the frame kernel, a repack of the 32-byte voxel
+    records into the structure-of-arrays the numpy surface returns (16 B centroid + 4 B count per voxel:
+    fewer bytes over PCIe), one D2H copy per output.  Slots alternate on their own streams so the copies
+    of one frame overlap the kernels and copies of the next (`submit` / `collect`); `process` is the
+    synchronous single-frame form.
     """
 
     def __init__(self, max_points: int, voxel_size: float, grid_size: float = 0.0, slots: int = 2,
-                 per_point_outputs: bool = True, **caps):
+                 per_point_outputs: bool = True, unique_keys: bool = False, **caps):
         self.device = require_cuda()
         self.per_point_outputs = per_point_outputs
+        self.unique_keys = unique_keys
         self.slots = []
         n = int(max_points)
+        dev = self.device
         for _ in range(slots):
-            pipe = FramePipeline(n, voxel_size, grid_size, device=self.device, **caps)
-            st = torch.cuda.Stream(device=self.device)
+            pipe = FramePipeline(n, voxel_size, grid_size, device=dev, **caps)
+            st = torch.cuda.Stream(device=dev)
             slot = {
                 "pipe": pipe, "stream": st, "n": 0,
                 "h_in": torch.empty((n, 4), dtype=torch.float32).pin_memory(),
-                "d_in": torch.empty((n, 4), dtype=torch.float32, device=self.device),
-                "h_vox": torch.empty((n, 8), dtype=torch.float32).pin_memory(),
+                "d_in": torch.empty((n, 4), dtype=torch.float32, device=dev),
+                "d_cen": torch.empty((n, 4), dtype=torch.float32, device=dev),
+                "d_cnt": torch.empty(n, dtype=torch.int32, device=dev),
+                "d_ukey": torch.empty(n, dtype=torch.int32, device=dev) if unique_keys else None,
+                "h_cen": torch.empty((n, 4), dtype=torch.float32).pin_memory(),
+                "h_cnt": torch.empty(n, dtype=torch.int32).pin_memory(),
+                "h_ukey": torch.empty(n, dtype=torch.int32).pin_memory() if unique_keys else None,
                 "h_inv": torch.empty(n, dtype=torch.int32).pin_memory() if per_point_outputs else None,
                 "h_key": torch.empty(n, dtype=torch.int32).pin_memory() if per_point_outputs else None,
                 "h_grid": (torch.empty(pipe.grid.numel(), dtype=torch.int32).pin_memory()
@@ -347,8 +356,12 @@ class HostFramePipeline:
         return n * 16
 
     def d2h_bytes(self, n: int) -> int:
+        """Bytes copied device -> host per frame of n points (the voxel count is not known on the host
+        when the copies are enqueued, so the per-voxel arrays travel at their capacity n)."""
         s = self.slots[0]
-        b = n * 32 + C.sizeof(FrameDesc)
+        b = n * (16 + 4) + C.sizeof(FrameDesc)
+        if self.unique_keys:
+            b += n * 4
         if self.per_point_outputs:
             b += 2 * n * 4
         if s["h_grid"] is not None:
@@ -373,8 +386,13 @@ class HostFramePipeline:
         with torch.cuda.stream(slot["stream"]):
             slot["d_in"][:n].copy_(h_in, non_blocking=True)
             pipe.enqueue(slot["d_in"][:n], origin=origin, xy_range=xy_range)
+            check(lib.lidar_frame_pack_soa(_ptr(pipe.voxels), _ptr(pipe.desc_dev), n, _ptr(slot["d_cen"]),
+                                           _ptr(slot["d_cnt"]), _ptr(slot["d_ukey"]), _stream_ptr()))
             pipe.desc_host.copy_(pipe.desc_dev, non_blocking=True)
-            slot["h_vox"][:n].copy_(pipe.voxels[:n], non_blocking=True)
+            slot["h_cen"][:n].copy_(slot["d_cen"][:n], non_blocking=True)
+            slot["h_cnt"][:n].copy_(slot["d_cnt"][:n], non_blocking=True)
+            if self.unique_keys:
+                slot["h_ukey"][:n].copy_(slot["d_ukey"][:n], non_blocking=True)
             if self.per_point_outputs:
                 slot["h_inv"][:n].copy_(pipe.inverse[:n], non_blocking=True)
                 slot["h_key"][:n].copy_(pipe.voxel_key[:n], non_blocking=True)
@@ -393,11 +411,12 @@ class HostFramePipeline:
             raise _capi.LidarError(int(desc.status), "frame exceeded its capacities")
         n, v = slot["n"], int(desc.n_voxels)
         cp = (lambda a: a.copy()) if copy else (lambda a: a)
-        rec = slot["h_vox"].numpy()[:v]
         out = {
-            "centroids": cp(rec[:, :4]), "counts": cp(rec.view(np.int32)[:, 4]),
-            "unique_keys": cp(rec.view(np.int32)[:, 5]), "n_voxels": v, "dims": tuple(desc.dims[:3]), "origin": tuple(desc.origin[:3]), "desc": desc,
+            "centroids": cp(slot["h_cen"].numpy()[:v]), "counts": cp(slot["h_cnt"].numpy()[:v]),
+            "n_voxels": v, "dims": tuple(desc.dims[:3]), "origin": tuple(desc.origin[:3]), "desc": desc,
         }
+        if self.unique_keys:
+            out["unique_keys"] = cp(slot["h_ukey"].numpy()[:v])
         if self.per_point_outputs:
             out["inverse"] = cp(slot["h_inv"].numpy()[:n])
             out["voxel_key"] = cp(slot["h_key"].numpy()[:n])

@@ -128,3 +128,33 @@ def test_fused_two_streams_in_flight(ops, synth):
         want = ref[(2 * 19 + k) % 4]
         assert torch.equal(r.inverse, want[0]) and torch.equal(r.counts, want[1])
         assert torch.equal(r.centroids, want[2]) and torch.equal(r.grid_counts, want[3])
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_frame_pipeline_numpy_in_numpy_out(ops, synth, pinned):
+    """The host-buffer surface (what bench.py's e2e leg times): numpy frame in, numpy SoA results out,
+    two frames in flight; every integer output equals the oracle's."""
+    ops.set_frame_mode(ops.FRAME_AUTO, 512, 1, 0)
+    n = 60000
+    hp = ops.HostFramePipeline(max_points=n, voxel_size=0.05, grid_size=0.5, slots=2, unique_keys=True,
+                               max_nx=256, max_ny=256)
+    frames = [synth.crowd_frame(n - 1000 * s, seed=20 + s, extent=20.0) for s in range(3)]
+    srcs = [torch.from_numpy(f).pin_memory() if pinned else f for f in frames]
+    outs = []
+    hp.submit(srcs[0])
+    for s in (1, 2):
+        hp.submit(srcs[s])
+        outs.append(hp.collect())
+    outs.append(hp.collect())
+    for f, out in zip(frames, outs):
+        want = new_ops.voxel_downsample(f, 0.05)
+        assert out["n_voxels"] == len(want["unique_keys"])
+        assert np.array_equal(out["inverse"], want["inverse"])
+        assert np.array_equal(out["voxel_key"], want["voxel_key"])
+        assert np.array_equal(out["counts"], want["counts"])
+        assert np.array_equal(out["unique_keys"], want["unique_keys"])
+        assert np.allclose(out["centroids"], want["centroids"], rtol=1e-6, atol=1e-7)
+        xyz = f[:, :3].astype(np.float64)
+        wc, _, _ = ref_path.grid_density_counts(xyz[:, :2], (xyz[:, 0].min(), xyz[:, 0].max()),
+                                                (xyz[:, 1].min(), xyz[:, 1].max()), 0.5)
+        assert np.array_equal(out["grid_counts"], wc)
