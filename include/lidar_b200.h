@@ -151,7 +151,12 @@ int lidar_scatter_labels(const int32_t* d_labels, const int32_t* d_index, int64_
  * K8  per-cluster mean (extract_people_positions, data_processing.py:251-280): exact integer sums.
  *     d_labels int32 or int64 (labels_are_i64), ids outside [0, n_clusters) are skipped;
  *     d_centroids3 (C,3) fp64; d_counts int64[C] (may be NULL).
+ *     Two cell grids give the same labels: "dense" (cell diagonal < eps, 5x5x5 neighbourhood; full cells are
+ *     core without a distance test and merged cells are skipped) is used when tol == 0 and the directory
+ *     fits; "general" (cell edge >= eps, every pair tested) otherwise.  lidar_dbscan_set_dense(0) forces the
+ *     general grid (process-wide; used by the tests to cross-check the two).
  * ------------------------------------------------------------------------------------------- */
+int lidar_dbscan_set_dense(int on);
 size_t lidar_dbscan_workspace_bytes(int64_t m, double eps, const double* h_min3, const double* h_max3);
 int lidar_dbscan(const double* d_points, int64_t m, double eps, int min_samples, double tol,
                  const double* h_min3, const double* h_max3, int32_t* d_labels, int32_t* d_n_clusters,

@@ -93,6 +93,7 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_standardize": (_i32, [_vp, _i64, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp]),
     "lidar_gather_rows": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp]),
     "lidar_scatter_labels": (_i32, [_vp, _vp, _i64, _vp, _i64, _vp]),
+    "lidar_dbscan_set_dense": (_i32, [_i32]),
     "lidar_dbscan_workspace_bytes": (_sz, [_i64, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "lidar_dbscan": (_i32, [_vp, _i64, _dbl, _i32, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp,
                             _vp, _vp, _sz, _vp]),

@@ -28,111 +28,167 @@ namespace lidar {
 // FPS
 // ------------------------------------------------------------------------------------------------
 constexpr int kFpsThreads = 256;
-constexpr int kFpsPpt = 8;          // points per thread held in registers
+constexpr int kFpsPpt = 8;          // points per thread held in registers (a CONTIGUOUS run of the cloud)
 constexpr int kFpsMaxCluster = 8;
-
-struct FpsCand {
-    float val;
-    int idx;
-    float x, y, z;
-    int pad[3];
-};
+constexpr int kFpsWarps = kFpsThreads / 32;
 
 __device__ __forceinline__ bool cand_better(float v, int i, float bv, int bi) {
     return v > bv || (v == bv && i < bi);
 }
+__device__ __forceinline__ unsigned fps_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned fps_map_peer(unsigned local_addr, unsigned peer) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(peer));
+    return r;
+}
+// remote store + transaction-count signal on the peer's mbarrier: data and "it has arrived" travel together,
+// the receiver wakes from mbarrier.try_wait ~60 cycles after the last byte (a barrier.cluster round costs ~400-500)
+__device__ __forceinline__ void fps_send_cand(unsigned slot_addr, unsigned bar_addr, unsigned val, float x, float y, float z) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(slot_addr), "r"(val), "r"(__float_as_uint(x)), "r"(__float_as_uint(y)), "r"(__float_as_uint(z)),
+                 "r"(bar_addr) : "memory");
+}
+// (default .acquire.cta: shared memory is not cached in L1, and a cluster-scope acquire would add a CCTL.IVALL
+// to every iteration; the phase completion itself orders the peers' st.async data before this read)
+__device__ __forceinline__ void fps_mbar_wait(unsigned bar_addr, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar_addr), "r"(parity) : "memory");
+    } while (!done);
+}
 
-// kSmemPath: the slice lives in shared memory (any points-per-thread) instead of registers
+// index of the first of eight values equal to their maximum (all lanes compute it redundantly: a depth-3 max
+// tree and an equality mask cost ~60 cycles, a REDUX + ballot + shuffle round ~130)
+__device__ __forceinline__ int fps_first_max8(const unsigned (&v)[8], unsigned& mx) {
+    const unsigned a = max(v[0], v[1]), b = max(v[2], v[3]), c = max(v[4], v[5]), d = max(v[6], v[7]);
+    mx = max(max(a, b), max(c, d));
+    unsigned mask = 0u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mask |= (v[k] == mx ? 1u : 0u) << k;
+    return __ffs(mask) - 1;
+}
+
+// One thread-block cluster per cloud.
+//   * thread t of CTA r owns the contiguous indices [(r*256 + t)*8, +8): position order == index order at every
+//     level (lane, warp, CTA), so "lowest index among equals" is "lowest position": no index reduction, and the
+//     index does not even travel -- the CTA that owns the winner writes it out
+//   * distances are >= 0, so their fp32 bit patterns order like the values: the warp argmax is ONE REDUX.MAX
+//     plus a ballot (lowest lane holding the maximum writes the warp's entry)
+//   * CTA argmax: warp 0 folds the 8 warp entries and sends the CTA's 16-byte candidate {value bits, x, y, z} to
+//     EVERY CTA of the cluster (one st.async + complete_tx on the receiver's mbarrier; slots and barriers double
+//     buffered) -- one DSMEM transit and one mbarrier wake-up per iteration instead of a barrier.cluster round
+//   * 25 KB of shared memory per CTA (its own slice, for the coordinates of its candidate), so the 16 clusters of
+//     a 16-cloud batch are co-resident (with the whole cloud per CTA only 15 clusters fit: two waves)
 template <int kCluster>
 __global__ void __launch_bounds__(kFpsThreads)
 fps_cluster_kernel(const float* __restrict__ xyz, int n, int m, int* __restrict__ out) {
     cg::cluster_group cluster = cg::this_cluster();
-    const unsigned rank = kCluster > 1 ? cluster.block_rank() : 0;
+    const unsigned rank = cluster.block_rank();
     const int cloud = blockIdx.x / kCluster;
     const float* P = xyz + (size_t)cloud * n * 3;
     int* O = out + (size_t)cloud * m;
+    constexpr int per_cta = kFpsThreads * kFpsPpt;
+    static_assert(kFpsWarps == 8 && kFpsMaxCluster == 8, "fps_first_max8 folds exactly eight entries");
 
-    __shared__ FpsCand s_slots[2][kFpsMaxCluster];   // written by every CTA of the cluster (DSMEM)
-    __shared__ FpsCand s_warp[kFpsThreads / 32];
+    __shared__ float s_x[per_cta], s_y[per_cta], s_z[per_cta];   // this CTA's slice, SoA
+    __shared__ __align__(16) uint4 s_slots[2][kFpsMaxCluster];   // one candidate per CTA of the cluster (DSMEM)
+    __shared__ __align__(16) unsigned s_wval[2][kFpsWarps];      // per-warp candidates of this CTA
+    __shared__ __align__(16) unsigned s_widx[2][kFpsWarps];
+    __shared__ __align__(8) unsigned long long s_mbar[2];
 
-    // slice of this CTA: indices rank*per_cta + j*kFpsThreads + t
-    const int per_cta = kFpsThreads * kFpsPpt;
+    const int tid = threadIdx.x;
+    const unsigned lane = lane_id();
+    const int warp = tid >> 5;
+    const int slice0 = rank * per_cta;
+    for (int l = tid; l < per_cta; l += kFpsThreads) {
+        const int i = slice0 + l;
+        const bool live = i < n;
+        s_x[l] = live ? P[3 * i] : 0.f;
+        s_y[l] = live ? P[3 * i + 1] : 0.f;
+        s_z[l] = live ? P[3 * i + 2] : 0.f;
+    }
+    // slots of absent CTAs (kCluster < 8) stay at value 0: they sit after the real ones and never win a tie
+    if (tid < 2 * kFpsMaxCluster) (&s_slots[0][0])[tid] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
     float px[kFpsPpt], py[kFpsPpt], pz[kFpsPpt], md[kFpsPpt];
-    int base_idx = rank * per_cta + threadIdx.x;
+    const int base_idx = slice0 + tid * kFpsPpt;
 #pragma unroll
     for (int j = 0; j < kFpsPpt; ++j) {
-        const int i = base_idx + j * kFpsThreads;
-        if (i < n) {
-            px[j] = P[3 * i]; py[j] = P[3 * i + 1]; pz[j] = P[3 * i + 2];
-            md[j] = 1e10f;
-        } else {
-            px[j] = py[j] = pz[j] = 0.f;
-            md[j] = -1.f;   // padding never wins (real distances are >= 0)
-        }
+        const int l = tid * kFpsPpt + j;
+        px[j] = s_x[l]; py[j] = s_y[l]; pz[j] = s_z[l];
+        md[j] = slice0 + l < n ? 1e10f : -1.f;   // padding never wins (real distances are >= 0)
     }
     float sx = P[0], sy = P[1], sz = P[2];   // idx[0] = 0
-    if (rank == 0 && threadIdx.x == 0) O[0] = 0;
-    if (kCluster > 1) cluster.sync();
+    if (rank == 0 && tid == 0) O[0] = 0;
+    const unsigned bar0 = fps_smem_u32(&s_mbar[0]), bar1 = fps_smem_u32(&s_mbar[1]);
+    constexpr unsigned kTxBytes = kCluster * 16u;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0), "r"(kTxBytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar1), "r"(kTxBytes) : "memory");
+    }
+    cluster.sync();   // every peer's barriers and slots exist before the first remote store
+    // lane r of warp 0 talks to CTA r: this CTA's slot there, and that CTA's barriers
+    const unsigned peer = lane < (unsigned)kCluster ? lane : 0u;
+    const unsigned peer_slot0 = fps_map_peer(fps_smem_u32(&s_slots[0][rank]), peer);
+    const unsigned peer_slot1 = fps_map_peer(fps_smem_u32(&s_slots[1][rank]), peer);
+    const unsigned peer_bar0 = fps_map_peer(bar0, peer), peer_bar1 = fps_map_peer(bar1, peer);
 
     for (int it = 1; it < m; ++it) {
-        float bv = -2.f;
+        const int par = it & 1;
+        const unsigned phase = (unsigned)((it - 1) >> 1) & 1u;   // k-th use of barrier `par`
+        float bv = -1.f;
         int bi = 0x7fffffff;
-        float bx = 0.f, by = 0.f, bz = 0.f;
 #pragma unroll
         for (int j = 0; j < kFpsPpt; ++j) {
             const float dx = __fsub_rn(px[j], sx), dy = __fsub_rn(py[j], sy), dz = __fsub_rn(pz[j], sz);
             const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
             const float v = md[j] < 0.f ? md[j] : fminf(md[j], d);
             md[j] = v;
-            const int i = base_idx + j * kFpsThreads;
-            if (cand_better(v, i, bv, bi)) { bv = v; bi = i; bx = px[j]; by = py[j]; bz = pz[j]; }
+            if (v > bv) { bv = v; bi = base_idx + j; }    // ascending j: strict compare keeps the lowest index
         }
-        // warp argmax
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            const float ox = __shfl_xor_sync(0xffffffffu, bx, o);
-            const float oy = __shfl_xor_sync(0xffffffffu, by, o);
-            const float oz = __shfl_xor_sync(0xffffffffu, bz, o);
-            if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bx = ox; by = oy; bz = oz; }
-        }
-        if (lane_id() == 0) s_warp[threadIdx.x >> 5] = FpsCand{bv, bi, bx, by, bz, {0, 0, 0}};
+        // warp argmax: one REDUX over the value bits, the lowest lane holding the maximum writes the entry
+        const unsigned vb = bv < 0.f ? 0u : __float_as_uint(bv);
+        const unsigned wm = __reduce_max_sync(0xffffffffu, vb);
+        const unsigned holders = __ballot_sync(0xffffffffu, vb == wm);
+        if ((holders & lanemask_lt()) == 0u && vb == wm) { s_wval[par][warp] = wm; s_widx[par][warp] = (unsigned)bi; }
         __syncthreads();
-        const int par = it & 1;
-        if (threadIdx.x < 32) {
-            FpsCand c = threadIdx.x < kFpsThreads / 32 ? s_warp[threadIdx.x] : FpsCand{-2.f, 0x7fffffff, 0, 0, 0, {0, 0, 0}};
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, c.val, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, c.idx, o);
-                const float ox = __shfl_xor_sync(0xffffffffu, c.x, o);
-                const float oy = __shfl_xor_sync(0xffffffffu, c.y, o);
-                const float oz = __shfl_xor_sync(0xffffffffu, c.z, o);
-                if (cand_better(ov, oi, c.val, c.idx)) { c.val = ov; c.idx = oi; c.x = ox; c.y = oy; c.z = oz; }
-            }
-            // lane r publishes this CTA's candidate into CTA r's slot array (distributed shared memory)
-            if (kCluster > 1) {
-                if (threadIdx.x < kCluster) {
-                    FpsCand* peer = cluster.map_shared_rank(&s_slots[par][rank], threadIdx.x);
-                    *peer = c;
-                }
-            } else if (threadIdx.x == 0) {
-                s_slots[par][0] = c;
-            }
+        int my_ci = 0;
+        if (warp == 0) {
+            const uint4 a = *reinterpret_cast<const uint4*>(&s_wval[par][0]);
+            const uint4 b = *reinterpret_cast<const uint4*>(&s_wval[par][4]);
+            const unsigned v8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            unsigned cm;
+            const int pos = fps_first_max8(v8, cm);
+            my_ci = (int)s_widx[par][pos];
+            const int l = my_ci != 0x7fffffff ? my_ci - slice0 : 0;   // an all-padding CTA sends value 0
+            if (lane < (unsigned)kCluster)
+                fps_send_cand(par ? peer_slot1 : peer_slot0, par ? peer_bar1 : peer_bar0, cm, s_x[l], s_y[l], s_z[l]);
         }
-        if (kCluster > 1) cluster.sync(); else __syncthreads();
-        // every CTA picks the cluster-wide winner from its own (now complete) slot array
-        FpsCand w = s_slots[par][0];
+        fps_mbar_wait(par ? bar1 : bar0, phase);
+        // every thread folds the candidates of the cluster's CTAs (slot order == index order)
+        unsigned g8[8];
 #pragma unroll
-        for (int r = 1; r < kCluster; ++r) {
-            const FpsCand c = s_slots[par][r];
-            if (cand_better(c.val, c.idx, w.val, w.idx)) w = c;
+        for (int r = 0; r < 8; ++r) g8[r] = s_slots[par][r].x;
+        unsigned gm;
+        const int wp = fps_first_max8(g8, gm);
+        const uint4 w = s_slots[par][wp];
+        sx = __uint_as_float(w.y); sy = __uint_as_float(w.z); sz = __uint_as_float(w.w);
+        if (tid == 0) {
+            if (wp == (int)rank) O[it] = my_ci;     // the owner of the winner writes its index
+            // re-arm this barrier for its next use (iteration it + 2): peers cannot send for it + 2 before they
+            // have received this CTA's candidate of it + 1, which leaves after this point
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                         ::"r"(par ? bar1 : bar0), "r"(kTxBytes) : "memory");
         }
-        sx = w.x; sy = w.y; sz = w.z;
-        if (rank == 0 && threadIdx.x == 0) O[it] = w.idx;
     }
-    if (kCluster > 1) cluster.sync();   // nobody exits while a peer may still write into its slots
+    cluster.sync();   // nobody exits while a peer may still write into its slots
 }
 
 // generic fallback for clouds larger than one cluster's register capacity: one CTA per cloud, points

@@ -17,7 +17,7 @@ from . import _capi
 from ._capi import FMT_F32X4, FMT_F64X3, HIST_AUTO, FrameCaps, FrameDesc, check, lib
 
 __all__ = [
-    "require_cuda", "point_format", "bbox", "moments", "hist2d_counts", "hist2d_points_counts", "roi_crop",
+    "require_cuda", "point_format", "bbox", "moments", "hist2d_counts", "hist2d_points_counts", "roi_crop", "set_dbscan_dense",
     "FramePipeline", "HostFramePipeline", "voxel_downsample", "arange_edges", "linspace_edges",
 ]
 
@@ -523,6 +523,11 @@ def scatter_labels(labels: torch.Tensor, index: torch.Tensor, n: int) -> torch.T
     full = torch.empty(n, dtype=torch.int64, device=dev)
     check(lib.lidar_scatter_labels(_ptr(labels), _ptr(index), labels.shape[0], _ptr(full), n, _stream_ptr()))
     return full
+
+
+def set_dbscan_dense(on: bool = True) -> None:
+    """Process-wide: allow (default) or forbid the dense cell grid of lidar_dbscan (same labels either way)."""
+    check(lib.lidar_dbscan_set_dense(1 if on else 0))
 
 
 def dbscan(points: torch.Tensor, eps: float, min_samples: int = 5, tol: float = 0.0, bounds=None):

@@ -32,6 +32,8 @@ class DeviceCache:
     guards: dict = field(default_factory=dict)
 
     def matches(self, processed: dict) -> bool:
+        if self.ids is None:      # device-only dict (run(..., host_arrays=False)): nothing to go stale
+            return "points" not in processed and "clusters" not in processed
         return self.ids == (id(processed.get("points")), id(processed.get("clusters")))
 
 
@@ -65,15 +67,28 @@ def _plane_from_sums(s: np.ndarray, center) -> np.ndarray:
     return np.array([a, b, -1, c0])
 
 
-def run(points, variant: str = "A") -> dict:
+def run(points, variant: str = "A", host_arrays: bool = True) -> dict:
     """Full preprocess on the GPU; returns the reference's processed_data dict (numpy arrays) plus a
-    DeviceCache under DEVICE_KEY."""
+    DeviceCache under DEVICE_KEY.
+
+    `points` is the reference's (n,3) array, or an (n,3) float64 CUDA tensor that is already resident.
+    `host_arrays=False` is the sequence mode (BASELINE configs[3]): the per-point outputs (points, colors,
+    normals, clusters) stay on the device under DEVICE_KEY and are NOT copied back; the dict carries only
+    `dimensions` (+ `ground_plane`).  extract_people_positions / the density and flow models accept it."""
     dev = ops.require_cuda()
-    host = _as_f64x3(points)
-    n = host.shape[0]
+    if isinstance(points, torch.Tensor) and points.is_cuda:
+        if points.dim() != 2 or points.shape[1] != 3 or points.dtype != torch.float64:
+            raise ValueError("a CUDA input must be an (n,3) float64 tensor")
+        d_pts = points.contiguous()
+        n = d_pts.shape[0]
+    else:
+        host = _as_f64x3(points)
+        n = host.shape[0]
+        d_pts = None
     if n == 0:
         raise ValueError("zero-size array to reduction operation minimum which has no identity")
-    d_pts = torch.from_numpy(host).to(dev, non_blocking=False)
+    if d_pts is None:
+        d_pts = torch.from_numpy(host).to(dev, non_blocking=False)
 
     # --- colours need z min/max of the RAW cloud (data_processing.py:143) ---------------------
     bb = ops.bbox(d_pts).cpu().numpy()
@@ -87,7 +102,7 @@ def run(points, variant: str = "A") -> dict:
     std = np.sqrt(s2[3:] / n)
     thr = 3 * std
     tol = 1e-9 * std
-    inl, col, _, guard_sigma = ops.sigma_filter(d_pts, mean, thr, tol, zmin, zden, want_colors=True)
+    inl, col, _, guard_sigma = ops.sigma_filter(d_pts, mean, thr, tol, zmin, zden, want_colors=host_arrays)
     n_in = inl.shape[0]
     if n_in == 0:
         raise IndexError("index -1 is out of bounds for axis 0 with size 0")   # np.percentile of an empty array
@@ -141,6 +156,12 @@ def run(points, variant: str = "A") -> dict:
         "width": hi3[0] - lo3[0], "length": hi3[1] - lo3[1], "height": hi3[2] - lo3[2],
     }
 
+    if not host_arrays:
+        if variant == "A":
+            out["ground_plane"] = plane
+        out["dimensions"] = dims
+        out[DEVICE_KEY] = DeviceCache(inl, full, None, n_clusters, guards)
+        return out
     h_points = inl.cpu().numpy()
     h_clusters = full.cpu().numpy()
     out["points"] = h_points

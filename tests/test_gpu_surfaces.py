@@ -28,7 +28,7 @@ def _hot(hs, key="density"):
 @pytest.fixture(scope="module")
 def pkg():
     import lidar_ai_recommendation_software_b200 as p
-    from lidar_ai_recommendation_software_b200 import apps, ops, preprocess
+    from lidar_ai_recommendation_software_b200 import apps, ops, preprocess, synth
     from lidar_ai_recommendation_software_b200.models.crowd_density_model import CrowdDensityModel
     from lidar_ai_recommendation_software_b200.models.crowd_flow_model import CrowdFlowModel
     from lidar_ai_recommendation_software_b200.utils import data_processing
@@ -37,7 +37,7 @@ def pkg():
         pass
 
     ns = NS()
-    ns.apps, ns.ops, ns.pre, ns.dp = apps, ops, preprocess, data_processing
+    ns.apps, ns.ops, ns.pre, ns.dp, ns.synth = apps, ops, preprocess, data_processing, synth
     ns.CDM, ns.CFM = CrowdDensityModel, CrowdFlowModel
     return ns
 
@@ -203,6 +203,49 @@ def test_dbscan_labels_match_oracle(pkg, eps, seed):
     assert guard == 0
     assert np.array_equal(labels.cpu().numpy().astype(np.int64), want)
     assert nc == (want.max() + 1 if (want >= 0).any() else 0)
+
+
+@pytest.mark.parametrize("eps,min_samples", [(0.3, 5), (0.12, 3), (0.6, 8)])
+def test_dbscan_dense_grid_equals_general_grid_and_oracle(pkg, eps, min_samples):
+    """Scan-ordered, very dense returns (hundreds of points per eps-ball, like a 128-beam frame near the
+    sensor) mixed with sparse clutter: the dense cell grid (full cells are core without a distance test,
+    merged cells are skipped) must give sklearn's labels exactly, like the general grid."""
+    r = np.random.default_rng(7)
+    th = np.linspace(0, 2 * np.pi, 3000, endpoint=False)
+    rings = [np.stack([rad * np.cos(th), rad * np.sin(th), 0.02 * np.sin(7 * th) + r.normal(0, 0.004, th.size)], 1)
+             for rad in (1.0, 1.1, 1.25, 2.0)]
+    blobs = r.uniform(-3, 3, (25, 3)) * [1, 1, 0.3]
+    people = blobs[r.integers(0, 25, 3000)] + r.normal(0, 0.08, (3000, 3))
+    clutter = r.uniform(-3.5, 3.5, (1000, 3)) * [1, 1, 0.5]
+    X = np.concatenate(rings + [people, clutter])
+    want = nps.dbscan_labels(X, eps, min_samples)
+    d = torch.from_numpy(X).cuda()
+    try:
+        pkg.ops.set_dbscan_dense(True)
+        lab_d, nc_d, _ = pkg.ops.dbscan(d, eps, min_samples)
+        pkg.ops.set_dbscan_dense(False)
+        lab_g, nc_g, _ = pkg.ops.dbscan(d, eps, min_samples)
+    finally:
+        pkg.ops.set_dbscan_dense(True)
+    assert np.array_equal(lab_g.cpu().numpy().astype(np.int64), want)
+    assert np.array_equal(lab_d.cpu().numpy().astype(np.int64), want)
+    assert nc_d == nc_g == (want.max() + 1 if (want >= 0).any() else 0)
+
+
+def test_dbscan_dense_grid_ring_frame_equals_general_grid(pkg):
+    """A quarter-resolution 128-beam frame (too big for the CPU oracle in seconds): both grids must agree."""
+    f = pkg.synth.ring_sequence_frame(3, rings=64, azimuth_steps=8192)
+    X = np.ascontiguousarray(f[f[:, 2] > 0.15][:, :3], dtype=np.float64)
+    d = torch.from_numpy(X).cuda()
+    try:
+        pkg.ops.set_dbscan_dense(True)
+        lab_d, nc_d, _ = pkg.ops.dbscan(d, 0.3, 5)
+        pkg.ops.set_dbscan_dense(False)
+        lab_g, nc_g, _ = pkg.ops.dbscan(d, 0.3, 5)
+    finally:
+        pkg.ops.set_dbscan_dense(True)
+    assert nc_d == nc_g and nc_d > 10
+    assert torch.equal(lab_d, lab_g)
 
 
 def test_dbscan_degenerate_inputs(pkg):
