@@ -48,6 +48,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/ncu_traffic.json)."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if not p.exists():
+        return None
+    d = json.loads(p.read_text()).get(kernel)
+    return None if d is None else d["dram_read_bytes_per_launch"] + d["dram_write_bytes_per_launch"]
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -185,6 +194,11 @@ def main():
     ap.add_argument("--fused-smem-kb", type=int, default=0)
     ap.add_argument("--fused-plain-launch", action="store_true",
                     help="experiment: ordinary instead of cooperative launch (lets frames of different streams overlap)")
+    ap.add_argument("--pdl", type=int, default=-1,
+                    help="programmatic dependent launch of the fused kernel (1/0; default: library setting)")
+    ap.add_argument("--streaming", type=int, default=1,
+                    help="fused back end, one stream: ordinary launch + programmatic dependent launch for the "
+                         "device-resident leg (frames back to back on one stream); 0 = cooperative launches")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -219,6 +233,9 @@ def main():
     if args.fused_plain_launch:
         from lidar_ai_recommendation_software_b200 import _capi
         _capi.check(_capi.lib.lidar_frame_set_fused_plain_launch(1))
+    if args.pdl >= 0:
+        from lidar_ai_recommendation_software_b200 import _capi
+        _capi.check(_capi.lib.lidar_frame_set_fused_pdl(args.pdl))
     ops.set_frame_mode(ops.FRAME_FUSED if fused else ops.FRAME_MULTIKERNEL, args.fused_threads,
                        args.fused_ctas_per_sm, args.fused_smem_kb)
     # the fused kernel fills the device by itself (frames of other streams would only queue behind it);
@@ -228,6 +245,9 @@ def main():
                                max_nx=256, max_ny=256, device=dev) for _ in range(S)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     pipe = pipes[0]
+    streaming = bool(fused and S == 1 and args.streaming and not args.fused_plain_launch and args.pdl < 0)
+    if streaming:
+        ops.set_frame_streaming(True)
     torch.cuda.synchronize()
 
     def run_frames(count):
@@ -272,6 +292,8 @@ def main():
     ms = float(t.item())
     value = n * args.steps * world / (ms * 1e-3) / 1e6
 
+    if streaming:
+        ops.set_frame_streaming(False)   # the remaining legs (several pipelines / streams) use cooperative launches
     # ---- per-kernel device time (CUDA events on the launching stream) --------------------------
     ksteps = min(args.steps, 50)
     per_kernel = np.zeros(5)
@@ -299,7 +321,7 @@ def main():
         phases["ctas"] = ph[15]
         gbs = step_bytes / (kms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_frame_fused", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": gbs / hbm_peak, "traffic": ncu_traffic("k_frame_fused"), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": step_bytes, "launch_ms": kms,
                     "note": "launch_ms = one frame alone on the device (CUDA events around the launch)"}
         roofline_step = {"bytes_per_point": step_bytes / n, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
@@ -319,7 +341,7 @@ def main():
         dom_name = KERNELS[dom]
         dom_gbs = alg[dom_name] / (per_kernel[dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom_name, "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": dom_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": dom_gbs / hbm_peak, "traffic": ncu_traffic(dom_name), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg[dom_name], "launch_ms": float(per_kernel[dom])}
         roofline_step = {"bytes_per_point": step_bytes / n, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
                          "peak": hbm_peak, "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak,
@@ -377,6 +399,8 @@ def main():
                        "key_space": int(res.desc.key_space),
                        "l2": f"inputs rotate over {POOL} distinct frames ({POOL * n * 16 / 1e6:.0f} MB > 126 MB L2)",
                        "streams": S, "backend": args.mode,
+                       "launch": ("ordinary launch + programmatic dependent launch (one pipeline, one stream)"
+                                  if streaming else "cooperative launch" if fused else "five ordinary launches"),
                        "sharding": "independent frames per rank, no collective"},
             "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": (1 if fused else 5) * args.steps, "clocks": clk,

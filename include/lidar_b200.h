@@ -299,6 +299,12 @@ int lidar_frame_set_fused(int mode, int threads, int ctas_per_sm, int smem_kb);
  * ones do, but then co-residency of the grid is the caller's responsibility: the grid must fit the
  * device next to whatever else is running (the kernel traps after spinning for two seconds). */
 int lidar_frame_set_fused_plain_launch(int on);
+/* Programmatic dependent launch of k_frame_fused (off by default): when frames are enqueued back to back on
+ * one stream, the next frame's kernel may start on SMs the current one has left, and runs its TMA load and
+ * bounding box (which touch only its own input) under the current frame's tail; everything that touches the
+ * pipeline's workspace or outputs waits (griddepcontrol.wait) until the previous kernel has completed.
+ * Outputs are identical.  Process-wide setting. */
+int lidar_frame_set_fused_pdl(int on);
 /* diagnostics: byte offset inside the workspace of uint64 stamps[ctas][16] (%globaltimer, ns) that
  * every CTA of the last k_frame_fused launch wrote at its 13 trace points (see trace_ns). */
 size_t lidar_frame_trace_offset(const lidar_frame_caps* caps);

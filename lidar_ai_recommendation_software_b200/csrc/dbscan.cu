@@ -112,6 +112,28 @@ __device__ __forceinline__ void for_each_candidate(const CellGrid& G, const unsi
         }
 }
 
+// squared distance from p to the box of cell (ax, ay, az), shrunk by a relative 1e-9 so that rounding in the
+// cell assignment can only make the bound smaller (a pruned cell really has no point within eps)
+__device__ __forceinline__ double cell_box_dist2(const CellGrid& G, int ax, int ay, int az, double x, double y, double z) {
+    const double lo_x = G.min[0] + ax * G.cell, lo_y = G.min[1] + ay * G.cell, lo_z = G.min[2] + az * G.cell;
+    const double dx = fmax(0.0, fmax(lo_x - x, x - (lo_x + G.cell)));
+    const double dy = fmax(0.0, fmax(lo_y - y, y - (lo_y + G.cell)));
+    const double dz = fmax(0.0, fmax(lo_z - z, z - (lo_z + G.cell)));
+    return (dx * dx + dy * dy + dz * dz) * (1.0 - 1e-9) - 1e-300;
+}
+__device__ __forceinline__ double rdist_of(double x, double y, double z, double qx, double qy, double qz) {
+    const double dx = __dsub_rn(x, qx), dy = __dsub_rn(y, qy), dz = __dsub_rn(z, qz);
+    double r = __dmul_rn(dx, dx);
+    r = __dadd_rn(r, __dmul_rn(dy, dy));
+    return __dadd_rn(r, __dmul_rn(dz, dz));
+}
+// first core point of the sorted run [j0, j1), -1 if none (a full cell is all core: one load)
+__device__ __forceinline__ int first_core(const uint8_t* __restrict__ core_s, int j0, int j1) {
+    for (int j = j0; j < j1; ++j)
+        if (core_s[j]) return j;
+    return -1;
+}
+
 __global__ void __launch_bounds__(kDbThreads)
 db_core(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* __restrict__ scell,
         const int* __restrict__ sidx, const double* __restrict__ sx, const double* __restrict__ sy,
@@ -122,11 +144,41 @@ db_core(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* _
     if (G.dense) {
         // every point of the cell is a neighbour (cell diagonal < eps): a full cell is all core
         const int c = scell[pos];
-        if ((int)(cell_start[c + 1] - cell_start[c]) >= min_samples) {
-            core_s[pos] = 1;
-            core_o[sidx[pos]] = 1;
-            return;
+        const int own = (int)(cell_start[c + 1] - cell_start[c]);
+        bool core = own >= min_samples;
+        if (!core) {
+            // the own cell counts without a test; then the other cells, nearest columns first, pruned by their
+            // box distance, until min_samples neighbours are certain (tol == 0 on this grid: no band)
+            const double x = sx[pos], y = sy[pos], z = sz[pos];
+            const int cz = c % G.g[2];
+            const int t = c / G.g[2];
+            const int cy = t % G.g[1];
+            const int cx = t / G.g[1];
+            const int z0 = cz - 2 > 0 ? cz - 2 : 0;
+            const int z1 = cz + 2 < G.g[2] - 1 ? cz + 2 : G.g[2] - 1;
+            int cnt = own;
+            // 25 column offsets in rings of growing Chebyshev / Manhattan distance, packed as (dx+2)*5 + (dy+2)
+            constexpr unsigned char order[25] = {12, 7, 11, 13, 17, 6, 8, 16, 18, 2, 10, 14, 22, 1, 3, 5, 9, 15, 19, 21, 23, 0, 4, 20, 24};
+            for (int k = 0; k < 25 && !core; ++k) {
+                const int ax = cx + order[k] / 5 - 2, ay = cy + order[k] % 5 - 2;
+                if (ax < 0 || ay < 0 || ax >= G.g[0] || ay >= G.g[1]) continue;
+                const int col = cell_id(G, ax, ay, 0);
+                unsigned b1 = cell_start[col + z0];
+                for (int az = z0; az <= z1 && !core; ++az) {
+                    const unsigned b0 = b1;
+                    b1 = cell_start[col + az + 1];
+                    if (b0 == b1 || col + az == c) continue;
+                    if (cell_box_dist2(G, ax, ay, az, x, y, z) > eps2) continue;
+                    for (int j = (int)b0; j < (int)b1; ++j) {
+                        cnt += rdist_of(x, y, z, sx[j], sy[j], sz[j]) <= eps2;
+                        if (cnt >= min_samples) { core = true; break; }
+                    }
+                }
+            }
         }
+        core_s[pos] = core;
+        core_o[sidx[pos]] = core;
+        return;
     }
     int cnt = 0, band_in = 0, band_out = 0;
     for_each_candidate(G, cell_start, sx, sy, sz, scell[pos], sx[pos], sy[pos], sz[pos], [&](int, double r) {
@@ -186,28 +238,6 @@ db_union(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* 
 }
 
 // ---- dense grid ------------------------------------------------------------------------------------
-// squared distance from p to the box of cell (ax, ay, az), shrunk by a relative 1e-9 so that rounding in the
-// cell assignment can only make the bound smaller (a pruned cell really has no point within eps)
-__device__ __forceinline__ double cell_box_dist2(const CellGrid& G, int ax, int ay, int az, double x, double y, double z) {
-    const double lo_x = G.min[0] + ax * G.cell, lo_y = G.min[1] + ay * G.cell, lo_z = G.min[2] + az * G.cell;
-    const double dx = fmax(0.0, fmax(lo_x - x, x - (lo_x + G.cell)));
-    const double dy = fmax(0.0, fmax(lo_y - y, y - (lo_y + G.cell)));
-    const double dz = fmax(0.0, fmax(lo_z - z, z - (lo_z + G.cell)));
-    return (dx * dx + dy * dy + dz * dz) * (1.0 - 1e-9) - 1e-300;
-}
-__device__ __forceinline__ double rdist_of(double x, double y, double z, double qx, double qy, double qz) {
-    const double dx = __dsub_rn(x, qx), dy = __dsub_rn(y, qy), dz = __dsub_rn(z, qz);
-    double r = __dmul_rn(dx, dx);
-    r = __dadd_rn(r, __dmul_rn(dy, dy));
-    return __dadd_rn(r, __dmul_rn(dz, dz));
-}
-// first core point of the sorted run [j0, j1), -1 if none (a full cell is all core: one load)
-__device__ __forceinline__ int first_core(const uint8_t* __restrict__ core_s, int j0, int j1) {
-    for (int j = j0; j < j1; ++j)
-        if (core_s[j]) return j;
-    return -1;
-}
-
 __global__ void __launch_bounds__(kDbThreads)
 db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* __restrict__ scell,
                const int* __restrict__ sidx, const double* __restrict__ sx, const double* __restrict__ sy,

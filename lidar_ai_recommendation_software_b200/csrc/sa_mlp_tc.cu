@@ -83,33 +83,36 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi), two values per instruction: cvt.rn.bf16x2.f32 (F2FP, a
+// full-rate ALU op; the scalar F2F conversion runs at a quarter of that and was 21 % of the kernel's stall samples)
+__device__ __forceinline__ void split_pair(float a, float b, unsigned& hi, unsigned& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));           // low half <- a, high half <- b
+    const float ra = __fsub_rn(a, __uint_as_float(hi << 16)), rb = __fsub_rn(b, __uint_as_float(hi & 0xffff0000u));
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
 // split 8 fp32 values into bf16 hi / lo and store them as one 16-byte K chunk each
-__device__ __forceinline__ void store_chunk(unsigned char* smem, int row, int kc, const float (&x)[8]) {
+__device__ __forceinline__ void store_chunk_at(unsigned char* hi_base, unsigned char* lo_base, int row, int kc, const float (&x)[8]) {
     unsigned hi[4], lo[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
-        const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
-        hi[i] = (unsigned)__bfloat16_as_ushort(h0) | ((unsigned)__bfloat16_as_ushort(h1) << 16);
-        lo[i] = (unsigned)__bfloat16_as_ushort(l0) | ((unsigned)__bfloat16_as_ushort(l1) << 16);
-    }
+    for (int i = 0; i < 4; ++i) split_pair(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
     const int off = (row >> 3) * 1024 + kc * 128 + (row & 7) * 16;
-    *reinterpret_cast<uint4*>(smem + kOffAh + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(smem + kOffAl + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+__device__ __forceinline__ void store_chunk(unsigned char* smem, int row, int kc, const float (&x)[8]) {
+    store_chunk_at(smem + kOffAh, smem + kOffAl, row, kc, x);
 }
 
-// stage an fp32 [rows x 64] row-major weight matrix as bf16 hi / lo core matrices
+// stage an fp32 [rows x 64] row-major weight matrix as bf16 hi / lo core matrices: one 16-byte K chunk
+// (8 consecutive k of one row = two float4 loads) per thread and step
 __device__ __forceinline__ void stage_weights(const float* __restrict__ W, int rows, unsigned char* hi_base,
                                               unsigned char* lo_base) {
-    for (int e = threadIdx.x; e < rows * 64; e += kTcThreads) {
-        const int r = e >> 6, k = e & 63;
-        const float x = W[e];
-        const __nv_bfloat16 h = __float2bfloat16_rn(x);
-        const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
-        const int off = (r >> 3) * 1024 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2;
-        *reinterpret_cast<__nv_bfloat16*>(hi_base + off) = h;
-        *reinterpret_cast<__nv_bfloat16*>(lo_base + off) = l;
+    for (int e = threadIdx.x; e < rows * 8; e += kTcThreads) {
+        const int r = e >> 3, kc = e & 7;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(W + (size_t)r * 64 + kc * 8));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(W + (size_t)r * 64 + kc * 8) + 1);
+        const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        store_chunk_at(hi_base, lo_base, r, kc, x);
     }
 }
 
@@ -153,19 +156,28 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
     unsigned phase = 0;
 
     const int n_tiles = (n_centres + 3) / 4;
+    // gathered (neighbour - centre) of a tile: two dependent global loads (index, then point); the NEXT tile's
+    // are issued before the current tile's math so their latency hides under it
+    auto gather = [&](int t, float& a0, float& a1, float& a2) {
+        const int c_ = t * 4 + warp;
+        a0 = a1 = a2 = 0.f;
+        if (t < n_tiles && c_ < n_centres) {
+            const int b_ = c_ / m;
+            const int src = __ldg(idx + (size_t)c_ * kTcK + lane);
+            const float* p = xyz + ((size_t)b_ * n + src) * 3;
+            const float* c = new_xyz + (size_t)c_ * 3;
+            a0 = __fsub_rn(__ldg(p), __ldg(c)); a1 = __fsub_rn(__ldg(p + 1), __ldg(c + 1)); a2 = __fsub_rn(__ldg(p + 2), __ldg(c + 2));
+        }
+    };
+    float n0, n1, n2;
+    gather(blockIdx.x, n0, n1, n2);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int centre = tile * 4 + warp;           // global centre index b*m + mm
         const bool live = centre < n_centres;
         const int row = threadIdx.x;
         // ---- gather + layer 1 (fp32 CUDA cores) -> A (hi, lo) ------------------------------------
-        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-        if (live) {
-            const int b = centre / m;
-            const int src = idx[(size_t)centre * kTcK + lane];
-            const float* p = xyz + ((size_t)b * n + src) * 3;
-            const float* c = new_xyz + (size_t)centre * 3;
-            g0 = __fsub_rn(p[0], c[0]); g1 = __fsub_rn(p[1], c[1]); g2 = __fsub_rn(p[2], c[2]);
-        }
+        const float g0 = n0, g1 = n1, g2 = n2;
+        gather(tile + gridDim.x, n0, n1, n2);
 #pragma unroll
         for (int kc = 0; kc < 8; ++kc) {
             float h[8];

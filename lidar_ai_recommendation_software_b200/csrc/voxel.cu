@@ -935,18 +935,9 @@ k_frame_fused(const FusedArgs A) {
             }
         }
     }
-    // ---- phase 0b: zero the density grid and the scan flags; the occupancy bitmap is already clean
-    //      unless the previous frame of this workspace ran on the five-kernel path (dirty > 0) --------
-    {
-        const int64_t gt0 = (int64_t)b * T + tid, gstride = (int64_t)G * T;
-        int64_t dirty = (int64_t)A.ctrl->dirty_groups;
-        if (dirty > A.groups_cap) dirty = A.groups_cap;
-        uint4* b4 = reinterpret_cast<uint4*>(A.groups);
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (int64_t k = gt0; k < dirty * 2; k += gstride) b4[k] = z;
-        for (int64_t k = gt0; k < A.grid_cap; k += gstride) A.grid_out[k] = 0;
-        for (int64_t k = gt0; k < G; k += gstride) A.cta_desc[k] = 0ull;
-    }
+    // let the NEXT frame's kernel (programmatic dependent launch) start as SMs free up: its TMA load and
+    // bounding box touch nothing this kernel owns, everything else waits at its griddepcontrol.wait
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __syncthreads();   // mbarrier init visible to every waiter
     // ---- phase 0c: bounding box of the chunk -----------------------------------------------------
     {
@@ -983,12 +974,27 @@ k_frame_fused(const FusedArgs A) {
             for (int c = 0; c < 4; ++c) { s_red[warp][c] = (double)mn[c]; s_red[warp][4 + c] = (double)mx[c]; }
         }
         __syncthreads();
-        if (tid < 8) {
-            const bool is_max = tid >= 4;
-            double v = is_max ? -INFINITY : INFINITY;
-            for (int w = 0; w < nwarp; ++w) v = is_max ? fmax(v, s_red[w][tid]) : fmin(v, s_red[w][tid]);
-            A.partial[(size_t)b * 8 + tid] = v;
-        }
+    }
+    // ---- phase 0b: from here on the frame touches state shared with the previous frame of this pipeline
+    //      (workspace, outputs): wait for that kernel to have completed (no-op without a dependent launch).
+    //      Then zero the density grid and the scan flags; the occupancy bitmap is already clean unless the
+    //      previous frame of this workspace ran on the five-kernel path (dirty > 0) ---------------------
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    {
+        const int64_t gt0 = (int64_t)b * T + tid, gstride = (int64_t)G * T;
+        int64_t dirty = (int64_t)A.ctrl->dirty_groups;
+        if (dirty > A.groups_cap) dirty = A.groups_cap;
+        uint4* b4 = reinterpret_cast<uint4*>(A.groups);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int64_t k = gt0; k < dirty * 2; k += gstride) b4[k] = z;
+        for (int64_t k = gt0; k < A.grid_cap; k += gstride) A.grid_out[k] = 0;
+        for (int64_t k = gt0; k < G; k += gstride) A.cta_desc[k] = 0ull;
+    }
+    if (tid < 8) {
+        const bool is_max = tid >= 4;
+        double v = is_max ? -INFINITY : INFINITY;
+        for (int w = 0; w < nwarp; ++w) v = is_max ? fmax(v, s_red[w][tid]) : fmin(v, s_red[w][tid]);
+        A.partial[(size_t)b * 8 + tid] = v;
     }
     FUSED_TRACE(1);
     fused_grid_barrier(&A.ctrl->grid_bar, 1u * G);
@@ -1336,6 +1342,7 @@ static int g_fused_threads = 512;
 static int g_fused_ctas_per_sm = 1;
 static int g_fused_smem_kb = 0;          // 0 = as much as the chunk needs, up to the opt-in maximum
 static int g_fused_plain_launch = 0;     // experiment: ordinary launch instead of cooperative (see header)
+static int g_fused_pdl = 0;              // programmatic dependent launch: frame f+1 loads while frame f drains
 static bool g_fused_attr_set = false;
 static size_t g_fused_attr_bytes = 0;
 
@@ -1373,6 +1380,11 @@ size_t lidar_frame_trace_offset(const lidar_frame_caps* caps) {
 
 int lidar_frame_set_fused_plain_launch(int on) {
     g_fused_plain_launch = on ? 1 : 0;
+    return LIDAR_OK;
+}
+
+int lidar_frame_set_fused_pdl(int on) {
+    g_fused_pdl = on ? 1 : 0;
     return LIDAR_OK;
 }
 
@@ -1497,14 +1509,26 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
         A.grid_rep = reinterpret_cast<int32_t*>(ws + L.off_grid_rep);
         A.smem_points = (int)spts;
         A.smem_groups = (int)gbytes;
-        void* kargs[] = {&A};
-        cudaError_t le;
-        if (g_fused_plain_launch) {
-            k_frame_fused<<<G, T, dyn, st>>>(A);
-            le = cudaGetLastError();
-        } else {
-            le = cudaLaunchCooperativeKernel((const void*)k_frame_fused, dim3(G), dim3(T), kargs, dyn, st);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(G);
+        cfg.blockDim = dim3(T);
+        cfg.dynamicSmemBytes = dyn;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (!g_fused_plain_launch) {
+            attr[na].id = cudaLaunchAttributeCooperative;      // gang scheduling: the grid barriers cannot deadlock
+            attr[na].val.cooperative = 1;
+            ++na;
         }
+        if (g_fused_pdl) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        cfg.attrs = attr;
+        cfg.numAttrs = na;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, k_frame_fused, A);
         if (le == cudaSuccess) {
             for (int i = 1; i <= 5; ++i) LIDAR_CUDA_TRY(mark(i));
             return LIDAR_OK;

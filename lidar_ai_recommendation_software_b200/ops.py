@@ -17,7 +17,7 @@ from . import _capi
 from ._capi import FMT_F32X4, FMT_F64X3, HIST_AUTO, FrameCaps, FrameDesc, check, lib
 
 __all__ = [
-    "require_cuda", "point_format", "bbox", "moments", "hist2d_counts", "hist2d_points_counts", "roi_crop", "set_dbscan_dense",
+    "require_cuda", "point_format", "bbox", "moments", "hist2d_counts", "hist2d_points_counts", "roi_crop", "set_dbscan_dense", "set_frame_streaming",
     "FramePipeline", "HostFramePipeline", "voxel_downsample", "arange_edges", "linspace_edges",
 ]
 
@@ -191,6 +191,16 @@ def set_frame_mode(mode: int = FRAME_AUTO, threads: int = 0, ctas_per_sm: int = 
     fused with fallback (FRAME_AUTO, default).  `threads`, `ctas_per_sm`, `smem_kb` tune the fused
     kernel (0 = keep / as needed).  Outputs are identical in every mode."""
     check(lib.lidar_frame_set_fused(int(mode), int(threads), int(ctas_per_sm), int(smem_kb)))
+
+
+def set_frame_streaming(on: bool = True) -> None:
+    """Streaming mode of the fused frame kernel (process-wide, off by default): ordinary launch + programmatic
+    dependent launch, so that with frames enqueued back to back on ONE stream the launch gap disappears and the
+    next frame's TMA load runs under the current frame's tail.  Only for a single pipeline per device: two fused
+    kernels of different streams launched this way could each hold part of the SMs and wait for each other
+    (the cooperative launch of the default mode rules that out)."""
+    check(lib.lidar_frame_set_fused_plain_launch(1 if on else 0))
+    check(lib.lidar_frame_set_fused_pdl(1 if on else 0))
 
 
 @dataclass
