@@ -4,6 +4,7 @@
 bench.py is the contract line (configs[1]).  This script times the other named shapes on B200 and
 prints one JSON line per config; results are kept under profiles/.
 
+    python bench_configs.py --config surfaces  # cfg 1 shapes through the drop-in call surfaces A and B
     python bench_configs.py --config sa      # cfg 3: FPS 16384->1024, ball query r=0.2 k=32, MLP 64-64-128, batch 16
     python bench_configs.py --config seq     # cfg 4: 128-beam sequence (~2.6 M pts/frame), frames shard over ranks
     python bench_configs.py --config scan    # cfg 5: 50 M-point venue scan, points shard over ranks, allreduce of the grid
@@ -49,6 +50,59 @@ def ev_time(fn, reps, warm, torch):
         e1.synchronize()
         ts.append(e0.elapsed_time(e1))
     return float(np.median(ts)), float(np.min(ts))
+
+
+def run_surfaces(args, torch, dev):
+    """cfg 1 shapes through the drop-in call surfaces (numpy in -> numpy / dict out, copies included): the calls
+    the Streamlit apps make.  The reference-side CPU times of the same calls are in SURVEY.md §6 (measured with the
+    unmodified reference in the build container; /root/reference does not exist on the GPU box)."""
+    from lidar_ai_recommendation_software_b200 import apps, synth
+    from lidar_ai_recommendation_software_b200.models.crowd_density_model import CrowdDensityModel
+    from lidar_ai_recommendation_software_b200.models.crowd_flow_model import CrowdFlowModel
+    from lidar_ai_recommendation_software_b200.utils import data_processing as dp
+
+    def wall(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        return float(np.min(ts)) * 1e3
+
+    out = {}
+    for n in (100_000, 1_000_000):
+        f = synth.crowd_frame(n, seed=0, extent=50.0)
+        pts = np.ascontiguousarray(f[:, :3], dtype=np.float64)
+        tag = f"{n // 1000}k"
+        out[f"preprocess_lidar_data_{tag}_ms"] = wall(lambda: dp.preprocess_lidar_data(pts))
+        out[f"preprocess_point_cloud_{tag}_ms"] = wall(lambda: apps.preprocess_point_cloud(pts))
+        pa = dp.preprocess_lidar_data(pts)
+        pb = apps.preprocess_point_cloud(pts)
+        out[f"clusters_A_{tag}"] = int(pa["clusters"].max() + 1)
+        out[f"clusters_B_{tag}"] = int(pb["clusters"].max() + 1)
+        out[f"extract_people_positions_B_{tag}_ms"] = wall(lambda: dp.extract_people_positions(pb))
+        out[f"CrowdDensityModel.analyze_{tag}_ms"] = wall(lambda: CrowdDensityModel(grid_size=1.0).analyze(pb))
+        out[f"CrowdFlowModel.analyze_{tag}_ms"] = wall(lambda: CrowdFlowModel().analyze(pb))
+        out[f"analyze_crowd_density_B_{tag}_ms"] = wall(lambda: apps.analyze_crowd_density(pb))
+        out[f"analyze_crowd_flow_B_{tag}_ms"] = wall(lambda: apps.analyze_crowd_flow(pb))
+        out[f"density_heatmap_counts_{tag}_ms"] = wall(lambda: apps.density_heatmap_counts(pb))
+        xr = (pts[:, 0].min(), pts[:, 0].max())
+        yr = (pts[:, 1].min(), pts[:, 1].max())
+        out[f"calculate_grid_density_points_0.5m_{tag}_ms"] = wall(lambda: dp.calculate_grid_density(pts[:, :2], xr, yr, 0.5))
+        out[f"downsample_point_cloud_0.1_{tag}_ms"] = wall(lambda: dp.downsample_point_cloud(pts, 0.1))
+    line = {"config": "configs[0] shapes (and 1 M) through the drop-in surfaces A and B, numpy in -> numpy out, host wall clock, best of 5",
+            "n_gpus": 1, "data": "synthetic (Appendix C.1)", "ms": out,
+            "reference_cpu_ms_SURVEY_6": {"preprocess_lidar_data_100k": 4770.0, "preprocess_point_cloud_100k": 1060.0,
+                                          "CrowdDensityModel.analyze": 3.9, "analyze_crowd_density_B_100x100": 1010.0,
+                                          "CrowdFlowModel.analyze": "130-290", "calculate_grid_density_points_100k": 16.1,
+                                          "calculate_grid_density_points_1000k": 166.0, "histogram2d_bins100_1000k": 152.0,
+                                          "downsample_point_cloud_1000k": 38.0,
+                                          "preprocess_lidar_data_1000k": "infeasible (sklearn neighbour lists ~50 GB)"}}
+    print(json.dumps(line))
 
 
 def run_sa(args, torch, dev, rank, world):
@@ -251,7 +305,7 @@ def run_scan(args, torch, dev, rank, world, dist):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", required=True, choices=["sa", "seq", "scan"])
+    ap.add_argument("--config", required=True, choices=["sa", "seq", "scan", "surfaces"])
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic frames generated per rank (cycled)")
@@ -272,7 +326,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    if args.config == "sa":
+    if args.config == "surfaces":
+        if rank == 0:
+            run_surfaces(args, torch, dev)
+    elif args.config == "sa":
         if rank == 0:
             run_sa(args, torch, dev, rank, world)
     elif args.config == "seq":

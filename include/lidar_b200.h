@@ -152,8 +152,9 @@ int lidar_scatter_labels(const int32_t* d_labels, const int32_t* d_index, int64_
  *     d_labels int32 or int64 (labels_are_i64), ids outside [0, n_clusters) are skipped;
  *     d_centroids3 (C,3) fp64; d_counts int64[C] (may be NULL).
  *     Two cell grids give the same labels: "dense" (cell diagonal < eps, 5x5x5 neighbourhood; full cells are
- *     core without a distance test and merged cells are skipped) is used when tol == 0 and the directory
- *     fits; "general" (cell edge >= eps, every pair tested) otherwise.  lidar_dbscan_set_dense(0) forces the
+ *     core without a distance test and merged cells are skipped) is used when the directory fits and
+ *     tol <= 1e-7 eps^2 (decisions are then taken on pairs certainly within eps; those resting on a pair
+ *     inside the tol band are counted in d_guard); "general" (cell edge >= eps, every pair tested) otherwise.  lidar_dbscan_set_dense(0) forces the
  *     general grid (process-wide; used by the tests to cross-check the two).
  * ------------------------------------------------------------------------------------------- */
 int lidar_dbscan_set_dense(int on);

@@ -20,8 +20,7 @@
 // Every output is order independent, hence deterministic although the cell sort uses atomics.
 //
 // Two grids, same labels:
-//   general   cell edge >= eps, 3x3x3 neighbourhood, every candidate pair is tested (always used when
-//             tol > 0: the knife-edge certificate must see every pair)
+//   general   cell edge >= eps, 3x3x3 neighbourhood, every candidate pair is tested
 //   dense     cell edge = eps/sqrt(3) * (1 - 1e-6), 5x5x5 neighbourhood ("grid-exact" DBSCAN): the cell diagonal is
 //             shorter than eps, so all points of a cell are mutual neighbours.  A cell with >= min_samples points
 //             is all core without a single distance test, the core points of a cell always share a cluster, and
@@ -29,6 +28,9 @@
 //             is already in its set.  A 128-beam scan has ~1000 points inside a 0.3 m ball near the sensor:
 //             14.2 ms -> see DESIGN.md for a 1 M-point frame.  The margin 1e-6 dwarfs the fp64 rounding of the cell
 //             assignment and of rdist (~1e-15), so "same cell => rdist <= eps^2" holds in the reference's arithmetic.
+//             Certificate (tol > 0): a decision is taken on a pair that is CERTAINLY within eps whenever one
+//             exists; decisions that rest on a pair inside the band, and near misses, are counted in *d_guard.
+//             Pairs that are never examined (same cell, already merged cells) cannot change a certain decision.
 //
 // Knife-edge certificate (variant A only): X went through a scaler whose mean/scale come from a
 // parallel reduction, so rdist can differ from sklearn's in the last bits.  Pairs with
@@ -156,25 +158,32 @@ db_core(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* _
             const int cx = t / G.g[1];
             const int z0 = cz - 2 > 0 ? cz - 2 : 0;
             const int z1 = cz + 2 < G.g[2] - 1 ? cz + 2 : G.g[2] - 1;
-            int cnt = own;
+            // same-cell pairs are farther than 1e-6*eps^2 from the threshold: never inside the tol band
+            int cnt = own, band_in = 0, band_out = 0;
+            bool certain = false;
             // 25 column offsets in rings of growing Chebyshev / Manhattan distance, packed as (dx+2)*5 + (dy+2)
             constexpr unsigned char order[25] = {12, 7, 11, 13, 17, 6, 8, 16, 18, 2, 10, 14, 22, 1, 3, 5, 9, 15, 19, 21, 23, 0, 4, 20, 24};
-            for (int k = 0; k < 25 && !core; ++k) {
+            for (int k = 0; k < 25 && !certain; ++k) {
                 const int ax = cx + order[k] / 5 - 2, ay = cy + order[k] % 5 - 2;
                 if (ax < 0 || ay < 0 || ax >= G.g[0] || ay >= G.g[1]) continue;
                 const int col = cell_id(G, ax, ay, 0);
                 unsigned b1 = cell_start[col + z0];
-                for (int az = z0; az <= z1 && !core; ++az) {
+                for (int az = z0; az <= z1 && !certain; ++az) {
                     const unsigned b0 = b1;
                     b1 = cell_start[col + az + 1];
                     if (b0 == b1 || col + az == c) continue;
-                    if (cell_box_dist2(G, ax, ay, az, x, y, z) > eps2) continue;
+                    if (cell_box_dist2(G, ax, ay, az, x, y, z) > eps2 + tol) continue;
                     for (int j = (int)b0; j < (int)b1; ++j) {
-                        cnt += rdist_of(x, y, z, sx[j], sy[j], sz[j]) <= eps2;
-                        if (cnt >= min_samples) { core = true; break; }
+                        const double r = rdist_of(x, y, z, sx[j], sy[j], sz[j]);
+                        const bool in = r <= eps2;
+                        cnt += in;
+                        if (tol > 0.0 && fabs(r - eps2) <= tol) { band_in += in; band_out += !in; }
+                        if (cnt - band_in >= min_samples) { certain = true; break; }   // core whatever the band pairs do
                     }
                 }
             }
+            core = cnt >= min_samples;
+            if (((cnt - band_in) >= min_samples) != ((cnt + band_out) >= min_samples)) atomicAdd(guard, 1ull);
         }
         core_s[pos] = core;
         core_o[sidx[pos]] = core;
@@ -241,11 +250,13 @@ db_union(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* 
 __global__ void __launch_bounds__(kDbThreads)
 db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* __restrict__ scell,
                const int* __restrict__ sidx, const double* __restrict__ sx, const double* __restrict__ sy,
-               const double* __restrict__ sz, double eps2, const uint8_t* __restrict__ core_s, int* __restrict__ parent) {
+               const double* __restrict__ sz, double eps2, double tol, const uint8_t* __restrict__ core_s,
+               int* __restrict__ parent, unsigned long long* __restrict__ guard) {
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= m || !core_s[pos]) return;
     const int oi = sidx[pos];
     const int c = scell[pos];
+    unsigned band = 0;   // decisions of this point that rest on a pair inside the tol band (certificate)
     // (a) the core points of one cell are mutual neighbours: link to the first of them
     {
         const int jf = first_core(core_s, (int)cell_start[c], (int)cell_start[c + 1]);
@@ -270,27 +281,39 @@ db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const
                 const unsigned b0 = b1;
                 b1 = cell_start[col + az + 1];
                 if (col + az <= c || b0 == b1) continue;
-                if (cell_box_dist2(G, ax, ay, az, x, y, z) > eps2) continue;
+                if (cell_box_dist2(G, ax, ay, az, x, y, z) > eps2 + tol) continue;
                 const int jf = first_core(core_s, (int)b0, (int)b1);
                 if (jf < 0) continue;
                 if (uf_find(parent, sidx[jf]) == uf_find(parent, oi)) continue;
+                // merge on a pair that is certainly within eps; pairs inside the band are used only if no certain
+                // pair exists, and then count against the certificate (as do near misses)
+                int hit = -1, maybe = -1;
+                unsigned miss = 0;
                 for (int j = jf; j < (int)b1; ++j) {
-                    if (core_s[j] && rdist_of(x, y, z, sx[j], sy[j], sz[j]) <= eps2) {
-                        uf_union(parent, oi, sidx[j]);
-                        break;
-                    }
+                    if (!core_s[j]) continue;
+                    const double r = rdist_of(x, y, z, sx[j], sy[j], sz[j]);
+                    if (tol > 0.0 && fabs(r - eps2) <= tol) {
+                        if (r <= eps2) maybe = j; else ++miss;
+                    } else if (r <= eps2) { hit = j; break; }
+                }
+                if (hit >= 0) uf_union(parent, oi, sidx[hit]);
+                else {
+                    if (maybe >= 0) { uf_union(parent, oi, sidx[maybe]); ++band; }
+                    band += miss;
                 }
             }
         }
+    if (band) atomicAdd(guard, (unsigned long long)band);
 }
 
 __global__ void __launch_bounds__(kDbThreads)
 db_border_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* __restrict__ scell,
                 const int* __restrict__ sidx, const double* __restrict__ sx, const double* __restrict__ sy,
-                const double* __restrict__ sz, double eps2, const uint8_t* __restrict__ core_s,
-                const int* __restrict__ label_s, int* __restrict__ labels) {
+                const double* __restrict__ sz, double eps2, double tol, const uint8_t* __restrict__ core_s,
+                const int* __restrict__ label_s, int* __restrict__ labels, unsigned long long* __restrict__ guard) {
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= m || core_s[pos]) return;
+    unsigned band = 0;
     const int c = scell[pos];
     const double x = sx[pos], y = sy[pos], z = sz[pos];
     const int cz = c % G.g[2];
@@ -313,13 +336,25 @@ db_border_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, cons
                 if (jf < 0) continue;
                 const int lab = label_s[jf];          // every core point of a cell carries the same label
                 if (lab >= best) continue;
-                if (cell_box_dist2(G, ax, ay, az, x, y, z) > eps2) continue;
+                if (cell_box_dist2(G, ax, ay, az, x, y, z) > eps2 + tol) continue;
+                bool hit = false, maybe = false;
+                unsigned miss = 0;
                 for (int j = jf; j < (int)b1; ++j) {
-                    if (core_s[j] && rdist_of(x, y, z, sx[j], sy[j], sz[j]) <= eps2) { best = lab; break; }
+                    if (!core_s[j]) continue;
+                    const double r = rdist_of(x, y, z, sx[j], sy[j], sz[j]);
+                    if (tol > 0.0 && fabs(r - eps2) <= tol) {
+                        if (r <= eps2) maybe = true; else ++miss;
+                    } else if (r <= eps2) { hit = true; break; }
+                }
+                if (hit) best = lab;
+                else {
+                    if (maybe) { best = lab; ++band; }
+                    band += miss;
                 }
             }
         }
     labels[sidx[pos]] = best == 0x7fffffff ? -1 : best;
+    if (band) atomicAdd(guard, (unsigned long long)band);
 }
 
 __global__ void db_roots(int m, const uint8_t* __restrict__ core_o, int* __restrict__ parent,
@@ -543,8 +578,8 @@ int lidar_dbscan(const double* d_points, int64_t m, double eps, int min_samples,
     if (m == 0) return LIDAR_OK;
     LIDAR_REQUIRE(d_points && d_labels && h_min3 && h_max3, LIDAR_ERR_INVALID, "lidar_dbscan: NULL argument");
     CellGrid G;
-    // the certificate of variant A (tol > 0) must see every pair: general grid; otherwise the dense grid
-    LIDAR_REQUIRE(make_grid(h_min3, h_max3, eps, tol == 0.0 && g_db_dense, &G), LIDAR_ERR_INVALID,
+    // dense grid unless the tol band could reach same-cell pairs (they sit >= 2e-6 * eps^2 below the threshold)
+    LIDAR_REQUIRE(make_grid(h_min3, h_max3, eps, tol <= 1e-7 * eps * eps && g_db_dense, &G), LIDAR_ERR_INVALID,
                   "lidar_dbscan: cannot build a cell grid for this bbox");
     const DbLayout L = db_layout(m, G.ncell);
     LIDAR_REQUIRE(d_ws && ws_bytes >= L.total, LIDAR_ERR_WORKSPACE, "lidar_dbscan: workspace too small (%zu < %zu)",
@@ -581,7 +616,7 @@ int lidar_dbscan(const double* d_points, int64_t m, double eps, int min_samples,
     db_core<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, min_samples, core_s,
                                          core_o, guard);
     LIDAR_CHECK_LAUNCH();
-    if (G.dense) db_union_dense<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, core_s, parent);
+    if (G.dense) db_union_dense<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard);
     else db_union<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard);
     LIDAR_CHECK_LAUNCH();
     db_roots<<<g256, 256, 0, st>>>(mi, core_o, parent, is_root);
@@ -590,7 +625,7 @@ int lidar_dbscan(const double* d_points, int64_t m, double eps, int min_samples,
     LIDAR_CUDA_TRY(cudaMemcpyAsync(d_n_clusters, root_rank + mi, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     db_label_core<<<g256, 256, 0, st>>>(mi, sidx, core_s, parent, root_rank, label_s, d_labels);
     LIDAR_CHECK_LAUNCH();
-    if (G.dense) db_border_dense<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, core_s, label_s, d_labels);
+    if (G.dense) db_border_dense<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, label_s, d_labels, guard);
     else db_border<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, label_s,
                                                 d_labels, guard);
     LIDAR_CHECK_LAUNCH();
