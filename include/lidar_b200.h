@@ -162,6 +162,13 @@ size_t lidar_dbscan_workspace_bytes(int64_t m, double eps, const double* h_min3,
 int lidar_dbscan(const double* d_points, int64_t m, double eps, int min_samples, double tol,
                  const double* h_min3, const double* h_max3, int32_t* d_labels, int32_t* d_n_clusters,
                  uint64_t* d_guard, void* d_ws, size_t ws_bytes, void* stream);
+/* Local point density of the visualisation paths: sklearn KDTree(points).query_radius(points, r, count_only=True)
+ * (utils/visualization.py:43-45 and 167-168, app_simplified.py:158-159): d_counts[i] = number of points j, i itself
+ * included, with fp64 rdist(i,j) <= r*r.  d_points (m,3) fp64 (2-D projections: set the third column to 0);
+ * h_min3/h_max3 = bbox of the points; d_counts int64[m] (KDTree returns intp). */
+size_t lidar_ball_count_workspace_bytes(int64_t m, double radius, const double* h_min3, const double* h_max3);
+int lidar_ball_count(const double* d_points, int64_t m, double radius, const double* h_min3, const double* h_max3,
+                     int64_t* d_counts, void* d_ws, size_t ws_bytes, void* stream);
 size_t lidar_centroid_workspace_bytes(int n_clusters);
 int lidar_cluster_centroids(const double* d_points, const void* d_labels, int labels_are_i64, int64_t n,
                             int n_clusters, double* d_centroids3, int64_t* d_counts, void* d_ws, size_t ws_bytes,

@@ -97,6 +97,8 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_dbscan_workspace_bytes": (_sz, [_i64, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "lidar_dbscan": (_i32, [_vp, _i64, _dbl, _i32, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp,
                             _vp, _vp, _sz, _vp]),
+    "lidar_ball_count_workspace_bytes": (_sz, [_i64, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "lidar_ball_count": (_i32, [_vp, _i64, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp, _sz, _vp]),
     "lidar_centroid_workspace_bytes": (_sz, [_i32]),
     "lidar_cluster_centroids": (_i32, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "lidar_flow_field": (_i32, [_vp, _i32, _vp, _i32, _dbl, _dbl, _dbl, _dbl, C.POINTER(C.c_double), _i32, _dbl,

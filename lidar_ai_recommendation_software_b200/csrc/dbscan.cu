@@ -357,6 +357,50 @@ db_border_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, cons
     if (band) atomicAdd(guard, (unsigned long long)band);
 }
 
+// ---- local point density (visualisation) -------------------------------------------------------------
+// KDTree(points).query_radius(points, r, count_only=True)  (utils/visualization.py:43-45, 167-168;
+// app_simplified.py:158-159): per point, the number of points (itself included) with fp64 rdist <= r*r.
+// Same cell list as DBSCAN with cell edge r/2 and a 5x5x5 neighbourhood; a cell whose box lies entirely
+// inside the ball is counted wholesale (the k-d tree does the same with whole nodes), entirely outside is
+// skipped, the rest is tested point by point.  The box bounds are widened / shrunk by 1e-9 relative, so a
+// wholesale decision is never taken on a pair that rounding could flip.
+__global__ void __launch_bounds__(kDbThreads)
+db_ball_count(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* __restrict__ scell,
+              const int* __restrict__ sidx, const double* __restrict__ sx, const double* __restrict__ sy,
+              const double* __restrict__ sz, double r2, long long* __restrict__ counts) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= m) return;
+    const int c = scell[pos];
+    const double x = sx[pos], y = sy[pos], z = sz[pos];
+    const int cz = c % G.g[2];
+    const int t = c / G.g[2];
+    const int cy = t % G.g[1];
+    const int cx = t / G.g[1];
+    const int R = G.reach;
+    const int z0 = cz - R > 0 ? cz - R : 0;
+    const int z1 = cz + R < G.g[2] - 1 ? cz + R : G.g[2] - 1;
+    long long cnt = 0;
+    for (int ax = (cx - R > 0 ? cx - R : 0); ax <= (cx + R < G.g[0] - 1 ? cx + R : G.g[0] - 1); ++ax)
+        for (int ay = (cy - R > 0 ? cy - R : 0); ay <= (cy + R < G.g[1] - 1 ? cy + R : G.g[1] - 1); ++ay) {
+            const int col = cell_id(G, ax, ay, 0);
+            unsigned b1 = cell_start[col + z0];
+            for (int az = z0; az <= z1; ++az) {
+                const unsigned b0 = b1;
+                b1 = cell_start[col + az + 1];
+                if (b0 == b1) continue;
+                if (cell_box_dist2(G, ax, ay, az, x, y, z) > r2) continue;
+                // farthest corner of the cell box, widened
+                const double lo_x = G.min[0] + ax * G.cell, lo_y = G.min[1] + ay * G.cell, lo_z = G.min[2] + az * G.cell;
+                const double fx = fmax(fabs(x - lo_x), fabs(x - (lo_x + G.cell)));
+                const double fy = fmax(fabs(y - lo_y), fabs(y - (lo_y + G.cell)));
+                const double fz = fmax(fabs(z - lo_z), fabs(z - (lo_z + G.cell)));
+                if ((fx * fx + fy * fy + fz * fz) * (1.0 + 1e-9) <= r2) { cnt += (long long)(b1 - b0); continue; }
+                for (int j = (int)b0; j < (int)b1; ++j) cnt += rdist_of(x, y, z, sx[j], sy[j], sz[j]) <= r2;
+            }
+        }
+    counts[sidx[pos]] = cnt;
+}
+
 __global__ void db_roots(int m, const uint8_t* __restrict__ core_o, int* __restrict__ parent,
                          unsigned* __restrict__ is_root) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -478,6 +522,30 @@ static bool make_grid(const double* mn, const double* mx, double eps, bool want_
         n *= G->g[c];
     }
     if (n > kDbMaxCells * 2) return false;
+    G->ncell = (int)n;
+    return true;
+}
+
+// cell grid for a radius query: cell edge r/2 (reach 2) while the directory stays small, else cell >= r
+static bool make_grid_radius(const double* mn, const double* mx, double r, CellGrid* G) {
+    if (!(r > 0.0)) return false;
+    const double dc = r * 0.5 * (1.0 + 1e-9);
+    double prod = 1.0;
+    for (int c = 0; c < 3; ++c) {
+        const double ext = mx[c] - mn[c];
+        if (!(ext >= 0.0) || !(ext < 1e300)) return false;
+        prod *= floor(ext / dc) + 1.0;
+    }
+    if (prod > (double)kDbDenseMaxCells) return make_grid(mn, mx, r, false, G);
+    G->cell = dc;
+    G->reach = 2;
+    G->dense = 0;
+    int64_t n = 1;
+    for (int c = 0; c < 3; ++c) {
+        G->min[c] = mn[c];
+        G->g[c] = (int)(floor((mx[c] - mn[c]) / dc) + 1.0);
+        n *= G->g[c];
+    }
     G->ncell = (int)n;
     return true;
 }
@@ -628,6 +696,52 @@ int lidar_dbscan(const double* d_points, int64_t m, double eps, int min_samples,
     if (G.dense) db_border_dense<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, label_s, d_labels, guard);
     else db_border<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, label_s,
                                                 d_labels, guard);
+    LIDAR_CHECK_LAUNCH();
+    return LIDAR_OK;
+}
+
+size_t lidar_ball_count_workspace_bytes(int64_t m, double radius, const double* h_min3, const double* h_max3) {
+    if (m < 0 || !h_min3 || !h_max3) return 0;
+    CellGrid G;
+    if (!make_grid_radius(h_min3, h_max3, radius, &G)) return 0;
+    return db_layout(m, G.ncell).total;
+}
+
+int lidar_ball_count(const double* d_points, int64_t m, double radius, const double* h_min3, const double* h_max3,
+                     int64_t* d_counts, void* d_ws, size_t ws_bytes, void* stream) {
+    LIDAR_REQUIRE(m >= 0 && m < (1ll << 31) - 64, LIDAR_ERR_INVALID, "lidar_ball_count: m out of range");
+    LIDAR_REQUIRE(radius > 0.0, LIDAR_ERR_INVALID, "lidar_ball_count: radius must be > 0");
+    if (m == 0) return LIDAR_OK;
+    LIDAR_REQUIRE(d_points && d_counts && h_min3 && h_max3, LIDAR_ERR_INVALID, "lidar_ball_count: NULL argument");
+    CellGrid G;
+    LIDAR_REQUIRE(make_grid_radius(h_min3, h_max3, radius, &G), LIDAR_ERR_INVALID,
+                  "lidar_ball_count: cannot build a cell grid for this bbox");
+    const DbLayout L = db_layout(m, G.ncell);
+    LIDAR_REQUIRE(d_ws && ws_bytes >= L.total, LIDAR_ERR_WORKSPACE, "lidar_ball_count: workspace too small (%zu < %zu)",
+                  ws_bytes, L.total);
+    char* ws = static_cast<char*>(d_ws);
+    int* cell = reinterpret_cast<int*>(ws + L.off_cell);
+    int* slot = reinterpret_cast<int*>(ws + L.off_slot);
+    unsigned* cell_count = reinterpret_cast<unsigned*>(ws + L.off_count);
+    unsigned* cell_start = reinterpret_cast<unsigned*>(ws + L.off_start);
+    int* sidx = reinterpret_cast<int*>(ws + L.off_sidx);
+    int* scell = reinterpret_cast<int*>(ws + L.off_scell);
+    double* sx = reinterpret_cast<double*>(ws + L.off_sx);
+    double* sy = reinterpret_cast<double*>(ws + L.off_sy);
+    double* sz = reinterpret_cast<double*>(ws + L.off_sz);
+    int* parent = reinterpret_cast<int*>(ws + L.off_parent);
+    void* scan_ws = ws + L.off_scan;
+    cudaStream_t st = as_stream(stream);
+    const int mi = (int)m;
+    const int g256 = (mi + 255) / 256;
+    LIDAR_CUDA_TRY(cudaMemsetAsync(cell_count, 0, sizeof(unsigned) * (G.ncell + 1), st));
+    db_cell_assign<<<g256, 256, 0, st>>>(d_points, mi, G, cell, slot, cell_count);
+    LIDAR_CHECK_LAUNCH();
+    LIDAR_CUDA_TRY(launch_exclusive_scan(cell_count, cell_start, (int64_t)G.ncell, nullptr, scan_ws, st));
+    db_scatter<<<g256, 256, 0, st>>>(d_points, mi, cell, slot, cell_start, sidx, scell, sx, sy, sz, parent);
+    LIDAR_CHECK_LAUNCH();
+    db_ball_count<<<(mi + kDbThreads - 1) / kDbThreads, kDbThreads, 0, st>>>(
+        mi, G, cell_start, scell, sidx, sx, sy, sz, radius * radius, reinterpret_cast<long long*>(d_counts));
     LIDAR_CHECK_LAUNCH();
     return LIDAR_OK;
 }

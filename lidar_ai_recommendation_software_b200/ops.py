@@ -17,7 +17,7 @@ from . import _capi
 from ._capi import FMT_F32X4, FMT_F64X3, HIST_AUTO, FrameCaps, FrameDesc, check, lib
 
 __all__ = [
-    "require_cuda", "point_format", "bbox", "moments", "hist2d_counts", "hist2d_points_counts", "roi_crop", "set_dbscan_dense", "set_frame_streaming",
+    "require_cuda", "point_format", "bbox", "moments", "hist2d_counts", "hist2d_points_counts", "roi_crop", "ball_count", "set_dbscan_dense", "set_frame_streaming",
     "FramePipeline", "HostFramePipeline", "voxel_downsample", "arange_edges", "linspace_edges",
 ]
 
@@ -560,6 +560,27 @@ def dbscan(points: torch.Tensor, eps: float, min_samples: int = 5, tol: float = 
                            _ptr(info), _ptr(info[1:]), _ptr(ws), ws.numel(), _stream_ptr()))
     nc, guard = (int(v) for v in info.tolist())
     return labels, nc & 0xffffffff, guard
+
+
+def ball_count(points: torch.Tensor, radius: float, bounds=None) -> torch.Tensor:
+    """KDTree(points).query_radius(points, r=radius, count_only=True) on the device: int64 (n,) counts, the
+    point itself included, inclusive fp64 `rdist <= r*r` (utils/visualization.py:43-45, 167-168).
+    `points` is (n,3) float64 CUDA; for a 2-D projection pass the two coordinates and a zero third column."""
+    _check_f64x3(points)
+    dev, n = points.device, points.shape[0]
+    counts = torch.empty(n, dtype=torch.int64, device=dev)
+    if n == 0:
+        return counts
+    if bounds is None:
+        bb = bbox(points).cpu().numpy()
+        bounds = (bb[:3], bb[4:7])
+    lo, hi = _d3(bounds[0]), _d3(bounds[1])
+    nb = lib.lidar_ball_count_workspace_bytes(n, float(radius), lo, hi)
+    if nb == 0:
+        raise _capi.LidarError(-1, "lidar_ball_count: cannot build a cell grid for this bbox / radius")
+    ws = _scratch.get("dbscan", nb, dev)
+    check(lib.lidar_ball_count(_ptr(points), n, float(radius), lo, hi, _ptr(counts), _ptr(ws), ws.numel(), _stream_ptr()))
+    return counts
 
 
 def cluster_centroids(points: torch.Tensor, labels: torch.Tensor, n_clusters: int):

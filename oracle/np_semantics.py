@@ -181,3 +181,20 @@ def radius_count(centres: np.ndarray, queries: np.ndarray, r: float) -> np.ndarr
             d2 = d2 + dj * dj
         out[s:s + 4096] = (d2 <= r2).sum(1)
     return out
+
+
+# KDTree(points).query_radius(points, r, count_only=True) of the visualisation paths
+# (utils/visualization.py:43-45, 164-168; app_simplified.py:158-159): per point, the number of points
+# (itself included) with fp64 reduced distance <= r*r.  Brute force in chunks.
+def local_density_counts(points: np.ndarray, r: float) -> np.ndarray:
+    pts = np.asarray(points, dtype=np.float64)
+    out = np.zeros(len(pts), dtype=np.int64)
+    r2 = float(r) * float(r)
+    for s in range(0, len(pts), 512):
+        q = pts[s:s + 512]
+        d2 = np.zeros((len(q), len(pts)))
+        for j in range(pts.shape[1]):
+            dj = q[:, j, None] - pts[None, :, j]
+            d2 = d2 + dj * dj
+        out[s:s + 512] = (d2 <= r2).sum(1)
+    return out

@@ -263,6 +263,54 @@ def test_dbscan_degenerate_inputs(pkg):
     assert np.array_equal(lab.cpu().numpy().astype(np.int64), want)
 
 
+@pytest.mark.parametrize("r", [0.5, 0.05, 2.0])
+def test_local_point_density_matches_oracle(pkg, r):
+    """KDTree.query_radius(count_only=True) of the visualisation paths, 3-D and 2-D projection, bit-exact counts:
+    dense rings (cells entirely inside the ball are counted wholesale), clutter, and pairs exactly r apart."""
+    from lidar_ai_recommendation_software_b200.utils import visualization as viz
+    rng = np.random.default_rng(5)
+    th = np.linspace(0, 2 * np.pi, 4000, endpoint=False)
+    ring = np.stack([1.5 * np.cos(th), 1.5 * np.sin(th), rng.normal(0, 0.01, th.size)], 1)
+    pts = np.concatenate([ring, rng.uniform(-3, 3, (3000, 3)), rng.normal(0, 0.15, (3000, 3))])
+    pts[:30] = pts[30:60] + np.array([r, 0.0, 0.0])
+    got = viz.local_point_density(pts, r)
+    assert got.dtype == np.int64 and np.array_equal(got, nps.local_density_counts(pts, r))
+    got2 = viz.local_point_density(pts[:, :2], r)
+    assert np.array_equal(got2, nps.local_density_counts(pts[:, :2], r))
+    assert viz.local_point_density(np.zeros((0, 3)), r).shape == (0,)
+
+
+def test_projection_histogram_matches_numpy_semantics(pkg, processed_b, case_points):
+    from lidar_ai_recommendation_software_b200.utils import visualization as viz
+    pd = processed_b("crowd_20k")
+    for dims in (("x", "y"), ("x", "z"), ("y", "z")):
+        heat, xc, yc = viz.projection_histogram(pd, dims, 64)
+        want, ex, ey = ref_path.heatmap_counts(pd, bins=64, dims=tuple("xyz".index(d) for d in dims))
+        assert np.array_equal(heat, np.asarray(want, dtype=np.float64).T)
+        assert np.array_equal(xc, (ex[:-1] + ex[1:]) / 2) and np.array_equal(yc, (ey[:-1] + ey[1:]) / 2)
+
+
+def test_windows_core_run_analysis_socket(pkg, case_points):
+    """ProjectManager.run_analysis keys (project_manager.py:338-348), JSON-serialisable, consistent with the models."""
+    import json
+    from lidar_ai_recommendation_software_b200.windows_core import convert_numpy, run_analysis
+    pts = case_points("crowd_20k")
+    res = run_analysis(pts, {"grid_size": 1.0})
+    assert list(res) == ["total_people", "avg_density", "max_density", "density_map", "hotspots", "avg_speed",
+                         "dominant_direction", "bottlenecks", "timestamp"]
+    json.dumps(convert_numpy(res))
+    pd = pkg.apps.preprocess_point_cloud(pts)
+    dens = pkg.CDM(grid_size=1.0).analyze(pd)
+    flow = pkg.CFM().analyze(pd)
+    assert res["total_people"] == dens["total_people"] and np.array_equal(res["density_map"], dens["density_map"])
+    assert res["max_density"] == dens["max_density"] and res["dominant_direction"] == flow["dominant_direction"]
+    assert [b["severity"] for b in res["bottlenecks"]] == [b["severity"] for b in flow["bottlenecks"]]
+    res_a = run_analysis(pts, {"variant": "A"})
+    assert res_a["total_people"] == 1       # variant A merges the venue into one cluster, like the reference
+    with pytest.raises(ValueError):
+        run_analysis(pts, {"variant": "C"})
+
+
 def test_cluster_centroids_exact(pkg):
     rng = np.random.default_rng(1)
     pts = rng.uniform(-80, 80, (50000, 3))

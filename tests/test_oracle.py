@@ -99,6 +99,17 @@ def test_radius_count_matches_kdtree():
     assert np.array_equal(nps.radius_count(c, q, 2.0), want)
 
 
+def test_local_density_counts_match_kdtree():
+    """visualisation local density (utils/visualization.py:43-45, 164-168): 3-D and 2-D, points on the radius."""
+    KDTree = pytest.importorskip("sklearn.neighbors").KDTree
+    rng = np.random.default_rng(11)
+    p3 = np.concatenate([rng.uniform(-3, 3, (1500, 3)), rng.normal(0, 0.2, (1500, 3))])
+    p3[:20] = p3[20:40] + np.array([0.5, 0.0, 0.0])      # exactly r apart
+    assert np.array_equal(nps.local_density_counts(p3, 0.5), KDTree(p3).query_radius(p3, r=0.5, count_only=True))
+    p2 = p3[:, :2]
+    assert np.array_equal(nps.local_density_counts(p2, 0.5), KDTree(p2).query_radius(p2, r=0.5, count_only=True))
+
+
 # ---- REF rows vs golden vectors of the unmodified reference ------------------------------------
 @pytest.mark.parametrize("name", CASE_NAMES)
 def test_preprocess_variant_a(name, golden, case_points):
