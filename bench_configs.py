@@ -188,19 +188,46 @@ def run_seq(args, torch, dev, rank, world, dist):
     pd, res = one(0)
     fr = pipe.result()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
     people = 0
     matched = 0
-    for j, f in enumerate(mine):
-        pd, res = one(j + 1)
-        people += pd[preprocess.DEVICE_KEY].n_clusters
-        if "matches" in res:
-            matched += int((np.asarray(res["matches"]) >= 0).sum())
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    if args.dropin or args.workers <= 1:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for j, f in enumerate(mine):
+            pd, res = one(j + 1)
+            people += pd[preprocess.DEVICE_KEY].n_clusters
+            if "matches" in res:
+                matched += int((np.asarray(res["matches"]) >= 0).sum())
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    else:
+        from lidar_ai_recommendation_software_b200.sequence import SequenceRunner
+        runner = SequenceRunner(variant="B", workers=args.workers, dt=0.1)
+        runner.model = model                      # carries the halo frame's people positions
+        for _ in runner.run([pool64[1 % pool_n], pool64[2 % pool_n]]):     # warm the worker threads / streams
+            pass
+        model.prev_positions = None
+        list(runner.run([pool64[0]]))             # halo / first frame again, so the timed frames all match
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+
+        def feed():
+            for j in range(len(mine)):
+                k = (j + 1) % pool_n
+                pipe.enqueue(dpool[k])            # voxel downsample + density of the float4 frame (main stream)
+                yield pool64[k]
+
+        for pd, res in runner.run(feed()):
+            people += pd[preprocess.DEVICE_KEY].n_clusters
+            if "matches" in res:
+                matched += int((np.asarray(res["matches"]) >= 0).sum())
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        runner.close()
     # device-only share: the frame pipeline alone on the same frames
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -224,6 +251,7 @@ def run_seq(args, torch, dev, rank, world, dist):
                          ": 3 sigma, 30th-pct ground split, DBSCAN eps 0.3, labels) + extract_people_positions + "
                          "CrowdFlowModel.analyze_sequence_frame (NEW frame_flow after the first frame) + FramePipeline "
                          "voxel 0.05 m / density 0.5 m on the float4 frame",
+            "preprocess_workers": 1 if (args.dropin or args.workers <= 1) else args.workers,
             "mean_clusters_per_frame": people / max(1, len(mine)),
             "frame_pipeline_ms_per_frame_device": vox_ms,
             "frame_pipeline_Mpoints_per_s_device": pts_per_frame / (vox_ms * 1e-3) / 1e6,
@@ -312,7 +340,8 @@ def main():
     ap.add_argument("--rings", type=int, default=128)
     ap.add_argument("--azimuth", type=int, default=20480)
     ap.add_argument("--dropin", action="store_true", help="seq: time the numpy-in / numpy-out drop-in surface instead")
-    ap.add_argument("--profile", action="store_true", help="seq: print a per-stage host timeline of one frame")
+    ap.add_argument("--workers", type=int, default=2,
+                    help="seq: preprocess worker threads (one CUDA stream each); 1 = the serial loop")
     ap.add_argument("--points", type=int, default=50_000_000)
     ap.add_argument("--host-shards", type=int, default=8)
     args = ap.parse_args()

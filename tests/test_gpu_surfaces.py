@@ -364,6 +364,28 @@ def test_sequence_model_uses_previous_frame(pkg, processed_b):
     assert np.allclose(m[m > 0], 1.0, rtol=1e-3)
 
 
+def test_sequence_runner_equals_serial_loop(pkg):
+    """Worker threads / streams of SequenceRunner change nothing: same clusters, matches and flow vectors."""
+    from lidar_ai_recommendation_software_b200.sequence import SequenceRunner
+    frames = [np.ascontiguousarray(pkg.synth.ring_sequence_frame(i, rings=48, azimuth_steps=4096)[:, :3], dtype=np.float64)
+              for i in range(4)]
+    serial_model = pkg.CFM()
+    want = []
+    for f in frames:
+        pd = pkg.pre.run(f, variant="B", host_arrays=False)
+        want.append((pd[pkg.pre.DEVICE_KEY].n_clusters, serial_model.analyze_sequence_frame(pd, dt=0.1)))
+    runner = SequenceRunner(variant="B", workers=3, dt=0.1)
+    got = [(pd[pkg.pre.DEVICE_KEY].n_clusters, res) for pd, res in runner.run(iter(frames))]
+    runner.close()
+    assert len(got) == len(want)
+    for (nc_g, r_g), (nc_w, r_w) in zip(got, want):
+        assert nc_g == nc_w and r_g["dominant_direction"] == r_w["dominant_direction"]
+        assert np.array_equal(r_g["flow_vectors"]["vectors"], r_w["flow_vectors"]["vectors"])
+        assert ("matches" in r_g) == ("matches" in r_w)
+        if "matches" in r_w:
+            assert np.array_equal(r_g["matches"], r_w["matches"])
+
+
 def test_errors_are_python_exceptions(pkg):
     with pytest.raises(Exception):
         pkg.dp.preprocess_lidar_data(np.zeros((0, 3)))
