@@ -380,7 +380,8 @@ def main():
     e2e_val = n * e2e_steps * world / float(te.item()) / 1e6
     e2e = {"value": e2e_val, "unit": "Mpoints/s", "h2d_bytes_per_step": hp.h2d_bytes(n),
            "d2h_bytes_per_step": hp.d2h_bytes(n), "steps": e2e_steps,
-           "api": f"ops.HostFramePipeline.submit/collect (pinned numpy in, numpy out, {args.e2e_slots} slots in flight)"}
+           "api": f"ops.HostFramePipeline.submit/collect = one lidar_frame_voxel_density_host C-ABI call per frame "
+                  f"(pinned numpy in, numpy out, {args.e2e_slots} slots in flight)"}
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------
     cpu = None

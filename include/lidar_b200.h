@@ -356,6 +356,33 @@ int lidar_frame_voxel_density_timed(const void* d_points, int64_t n, double voxe
                                     lidar_frame_desc* d_desc, const lidar_frame_caps* caps, void* d_ws,
                                     size_t ws_bytes, void* stream, void** h_events6);
 
+/* ------------------------------------------------------------------------------------------- *
+ * The same frame from HOST buffers, in ONE call (the path a sensor driver or the numpy surface
+ * takes): copy-in, the frame kernel(s), the SoA repack and ONE copy-out are enqueued on `stream`.
+ *
+ *   h_points      (n,4) float32 in page-locked host memory
+ *   d_points      device staging for the frame, >= 16*n bytes
+ *   d_voxels      lidar_voxel[n] scratch (the records before the repack)
+ *   d_out, h_out  result block, device and page-locked host copy, >= lidar_frame_host_block_bytes()
+ *
+ * Result block layout for a frame of n points (np = n rounded up to a multiple of 8, every array
+ * 32-byte aligned); lidar_frame_host_block_layout() returns the byte offsets:
+ *   [0] voxel_key int32[np] | [1] inverse int32[np] | [2] centroids float[np*4] | [3] counts int32[np]
+ *   | [4] unique keys int32[np] | [5] grid int32[max_nx*max_ny] | [6] lidar_frame_desc
+ * Per-voxel arrays hold n_voxels (desc) valid rows.  The block is copied at the size of THIS frame,
+ * so a short frame costs proportionally fewer PCIe bytes.  flags: LIDAR_HOST_UNIQUE_KEYS adds array [4]
+ * (otherwise empty); LIDAR_HOST_NO_PER_POINT leaves voxel_key / inverse on the device (the copy starts at
+ * the centroids).  Nothing synchronises: wait on the stream (or an event recorded after the call) before
+ * reading h_out.
+ * ------------------------------------------------------------------------------------------- */
+enum { LIDAR_HOST_UNIQUE_KEYS = 1, LIDAR_HOST_NO_PER_POINT = 2 };
+size_t lidar_frame_host_block_bytes(int64_t n, const lidar_frame_caps* caps, int flags);
+int lidar_frame_host_block_layout(int64_t n, const lidar_frame_caps* caps, int flags, size_t* h_offsets7);
+int lidar_frame_voxel_density_host(const void* h_points, int64_t n, double voxel_size, double grid_size,
+                                   const double* h_origin3, const double* h_xy_range4, void* d_points,
+                                   lidar_voxel* d_voxels, void* d_out, void* h_out, int flags,
+                                   const lidar_frame_caps* caps, void* d_ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

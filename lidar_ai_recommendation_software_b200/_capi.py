@@ -70,6 +70,7 @@ class FrameCaps(C.Structure):
 
 
 _vp, _i32, _i64, _sz, _dbl = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
+HOST_UNIQUE_KEYS, HOST_NO_PER_POINT = 1, 2     # flags of lidar_frame_voxel_density_host
 
 # name -> (restype, argtypes).  tests/test_abi.py checks this table against include/lidar_b200.h.
 PROTOTYPES: dict[str, tuple] = {
@@ -122,6 +123,10 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_frame_trace_offset": (_sz, [C.POINTER(FrameCaps)]),
     "lidar_frame_workspace_bytes": (_sz, [C.POINTER(FrameCaps)]),
     "lidar_frame_pack_soa": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "lidar_frame_host_block_bytes": (_sz, [_i64, _vp, _i32]),
+    "lidar_frame_host_block_layout": (_i32, [_i64, _vp, _i32, C.POINTER(C.c_size_t)]),
+    "lidar_frame_voxel_density_host": (_i32, [_vp, _i64, _dbl, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp,
+                                              _vp, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
     "lidar_frame_workspace_init": (_i32, [_vp, _sz, C.POINTER(FrameCaps), _vp]),
     "lidar_frame_voxel_density": (_i32, [_vp, _i64, _dbl, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          _vp, _vp, _vp, _vp, _vp, C.POINTER(FrameCaps), _vp, _sz, _vp]),

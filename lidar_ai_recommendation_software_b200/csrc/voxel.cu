@@ -1582,6 +1582,71 @@ int lidar_frame_pack_soa(const lidar_voxel* d_voxels, const lidar_frame_desc* d_
     return LIDAR_OK;
 }
 
+// ---- host-buffer entry: one call = copy-in + frame + repack + ONE copy-out -------------------------
+static void host_block_offsets(int64_t n, const lidar_frame_caps& c, int flags, size_t off[8]) {
+    const size_t np = (size_t)((n + 7) & ~(int64_t)7);
+    const size_t grid_cells = (size_t)(c.max_nx > 0 ? c.max_nx : 0) * (size_t)(c.max_ny > 0 ? c.max_ny : 0);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t a = (o + 31) & ~(size_t)31; o = a + bytes; return a; };
+    off[0] = take(4 * np);          // voxel_key
+    off[1] = take(4 * np);          // inverse
+    off[2] = take(16 * np);         // centroids
+    off[3] = take(4 * np);          // counts
+    off[4] = take((flags & LIDAR_HOST_UNIQUE_KEYS) ? 4 * np : 0);   // unique keys
+    off[5] = take(4 * grid_cells);  // grid
+    off[6] = take(sizeof(lidar_frame_desc));
+    off[7] = (o + 31) & ~(size_t)31;
+}
+
+size_t lidar_frame_host_block_bytes(int64_t n, const lidar_frame_caps* caps, int flags) {
+    if (!caps || n < 0) return 0;
+    size_t off[8];
+    host_block_offsets(n, *caps, flags, off);
+    return off[7];
+}
+
+int lidar_frame_host_block_layout(int64_t n, const lidar_frame_caps* caps, int flags, size_t* h_offsets7) {
+    LIDAR_REQUIRE(caps && h_offsets7 && n >= 0, LIDAR_ERR_INVALID, "lidar_frame_host_block_layout: bad argument");
+    size_t off[8];
+    host_block_offsets(n, *caps, flags, off);
+    for (int i = 0; i < 7; ++i) h_offsets7[i] = off[i];
+    return LIDAR_OK;
+}
+
+int lidar_frame_voxel_density_host(const void* h_points, int64_t n, double voxel_size, double grid_size,
+                                   const double* h_origin3, const double* h_xy_range4, void* d_points,
+                                   lidar_voxel* d_voxels, void* d_out, void* h_out, int flags,
+                                   const lidar_frame_caps* caps, void* d_ws, size_t ws_bytes, void* stream) {
+    LIDAR_REQUIRE(caps != nullptr, LIDAR_ERR_INVALID, "lidar_frame_voxel_density_host: caps is NULL");
+    LIDAR_REQUIRE(n >= 0 && n <= caps->max_points, LIDAR_ERR_CAPACITY,
+                  "lidar_frame_voxel_density_host: n=%lld exceeds caps.max_points=%lld", (long long)n,
+                  (long long)caps->max_points);
+    LIDAR_REQUIRE(d_out && h_out && d_voxels && (n == 0 || (h_points && d_points)), LIDAR_ERR_INVALID,
+                  "lidar_frame_voxel_density_host: NULL buffer");
+    size_t off[8];
+    host_block_offsets(n, *caps, flags, off);
+    char* out = static_cast<char*>(d_out);
+    cudaStream_t st = as_stream(stream);
+    if (n > 0) LIDAR_CUDA_TRY(cudaMemcpyAsync(d_points, h_points, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    lidar_frame_desc* d_desc = reinterpret_cast<lidar_frame_desc*>(out + off[6]);
+    int32_t* d_grid = grid_size > 0.0 ? reinterpret_cast<int32_t*>(out + off[5]) : nullptr;
+    const int rc = frame_voxel_density_impl(d_points, n, voxel_size, grid_size, h_origin3, h_xy_range4,
+                                            reinterpret_cast<int32_t*>(out + off[0]), reinterpret_cast<int32_t*>(out + off[1]),
+                                            d_voxels, d_grid, d_desc, caps, d_ws, ws_bytes, stream, nullptr);
+    if (rc != LIDAR_OK) return rc;
+    if (n > 0) {
+        k_frame_pack<<<frame_grid(n, 4), kFrameThreads, 0, st>>>(d_voxels, d_desc, n, reinterpret_cast<float4*>(out + off[2]),
+                                                                 reinterpret_cast<int32_t*>(out + off[3]),
+                                                                 (flags & LIDAR_HOST_UNIQUE_KEYS) ? reinterpret_cast<int32_t*>(out + off[4]) : nullptr);
+        LIDAR_CHECK_LAUNCH();
+    }
+    // one copy-out: the grid is zero-filled to its capacity by the frame, the per-voxel tails are never read;
+    // without the per-point outputs the copy starts at the centroids
+    const size_t first = (flags & LIDAR_HOST_NO_PER_POINT) ? off[2] : 0;
+    LIDAR_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(h_out) + first, out + first, off[7] - first, cudaMemcpyDeviceToHost, st));
+    return LIDAR_OK;
+}
+
 int lidar_frame_voxel_density(const void* d_points, int64_t n, double voxel_size, double grid_size,
                               const double* h_origin3, const double* h_xy_range4, int32_t* d_voxel_key,
                               int32_t* d_inverse, lidar_voxel* d_voxels, int32_t* d_grid, lidar_frame_desc* d_desc,

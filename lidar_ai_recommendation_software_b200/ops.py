@@ -324,11 +324,12 @@ class FramePipeline:
 class HostFramePipeline:
     """The call a user of the numpy surface makes: HOST float4 frame in, HOST numpy results out.
 
-    Pinned staging buffers, one H2D copy of the frame, the frame kernel, a repack of the 32-byte voxel
-    records into the structure-of-arrays the numpy surface returns (16 B centroid + 4 B count per voxel:
-    fewer bytes over PCIe), one D2H copy per output.  Slots alternate on their own streams so the copies
-    of one frame overlap the kernels and copies of the next (`submit` / `collect`); `process` is the
-    synchronous single-frame form.
+    One C-ABI call per frame (`lidar_frame_voxel_density_host`): the copy-in of the frame from page-locked host
+    memory, the frame kernel, the repack of the 32-byte voxel records into the structure-of-arrays the numpy
+    surface returns (16 B centroid + 4 B count per voxel: fewer bytes over PCIe) and ONE copy-out of the whole
+    result block are enqueued on the slot's stream.  Slots alternate on their own streams so the copies of one
+    frame overlap the kernels and copies of the next (`submit` / `collect`); `process` is the synchronous
+    single-frame form.
     """
 
     def __init__(self, max_points: int, voxel_size: float, grid_size: float = 0.0, slots: int = 2,
@@ -336,55 +337,60 @@ class HostFramePipeline:
         self.device = require_cuda()
         self.per_point_outputs = per_point_outputs
         self.unique_keys = unique_keys
+        self.voxel_size, self.grid_size = float(voxel_size), float(grid_size)
+        self.flags = (_capi.HOST_UNIQUE_KEYS if unique_keys else 0) | (0 if per_point_outputs else _capi.HOST_NO_PER_POINT)
         self.slots = []
         n = int(max_points)
         dev = self.device
+        c = dict(max_key_space=1 << 28, max_nx=1024, max_ny=1024)
+        c.update(caps)
+        if self.grid_size <= 0:
+            c["max_nx"] = c["max_ny"] = 0
+        self.caps = FrameCaps(n, int(c["max_key_space"]), int(c["max_nx"]), int(c["max_ny"]))
+        ws_bytes = lib.lidar_frame_workspace_bytes(C.byref(self.caps))
+        block = lib.lidar_frame_host_block_bytes(n, C.byref(self.caps), self.flags)
+        if ws_bytes == 0 or block == 0:
+            raise ValueError("invalid frame capacities")
         for _ in range(slots):
-            pipe = FramePipeline(n, voxel_size, grid_size, device=dev, **caps)
             st = torch.cuda.Stream(device=dev)
             slot = {
-                "pipe": pipe, "stream": st, "n": 0,
+                "stream": st, "n": 0,
+                "ws": torch.empty(ws_bytes, dtype=torch.uint8, device=dev),
                 "h_in": torch.empty((n, 4), dtype=torch.float32).pin_memory(),
                 "d_in": torch.empty((n, 4), dtype=torch.float32, device=dev),
-                "d_cen": torch.empty((n, 4), dtype=torch.float32, device=dev),
-                "d_cnt": torch.empty(n, dtype=torch.int32, device=dev),
-                "d_ukey": torch.empty(n, dtype=torch.int32, device=dev) if unique_keys else None,
-                "h_cen": torch.empty((n, 4), dtype=torch.float32).pin_memory(),
-                "h_cnt": torch.empty(n, dtype=torch.int32).pin_memory(),
-                "h_ukey": torch.empty(n, dtype=torch.int32).pin_memory() if unique_keys else None,
-                "h_inv": torch.empty(n, dtype=torch.int32).pin_memory() if per_point_outputs else None,
-                "h_key": torch.empty(n, dtype=torch.int32).pin_memory() if per_point_outputs else None,
-                "h_grid": (torch.empty(pipe.grid.numel(), dtype=torch.int32).pin_memory()
-                           if pipe.grid is not None else None),
+                "d_vox": torch.empty((n, 8), dtype=torch.float32, device=dev),
+                "d_out": torch.empty(block, dtype=torch.uint8, device=dev),
+                "h_out": torch.empty(block, dtype=torch.uint8).pin_memory(),
             }
+            check(lib.lidar_frame_workspace_init(_ptr(slot["ws"]), ws_bytes, C.byref(self.caps), _stream_ptr()))
             self.slots.append(slot)
         self._next = 0
         self._pending: list[dict] = []
         torch.cuda.synchronize(self.device)   # workspace zeroing ran on the constructing stream
 
+    def _layout(self, n: int):
+        off = (C.c_size_t * 7)()
+        check(lib.lidar_frame_host_block_layout(n, C.byref(self.caps), self.flags, off))
+        return [int(v) for v in off]
+
     def h2d_bytes(self, n: int) -> int:
         return n * 16
 
     def d2h_bytes(self, n: int) -> int:
-        """Bytes copied device -> host per frame of n points (the voxel count is not known on the host
-        when the copies are enqueued, so the per-voxel arrays travel at their capacity n)."""
-        s = self.slots[0]
-        b = n * (16 + 4) + C.sizeof(FrameDesc)
-        if self.unique_keys:
-            b += n * 4
-        if self.per_point_outputs:
-            b += 2 * n * 4
-        if s["h_grid"] is not None:
-            b += s["h_grid"].numel() * 4
-        return b
+        """Bytes copied device -> host per frame of n points (the voxel count is not known on the host when the
+        copy is enqueued, so the per-voxel arrays travel at the size of the frame)."""
+        total = int(lib.lidar_frame_host_block_bytes(n, C.byref(self.caps), self.flags))
+        return total - (0 if self.per_point_outputs else self._layout(n)[2])
 
     def submit(self, points: np.ndarray | torch.Tensor, origin=None, xy_range=None) -> None:
-        """Stage one host frame and enqueue copy-in, kernels and copy-out on the slot's stream."""
+        """Stage one host frame and enqueue copy-in, kernels and copy-out on the slot's stream (one C call)."""
         slot = self.slots[self._next]
         self._next = (self._next + 1) % len(self.slots)
         if slot in self._pending:
             raise RuntimeError("all slots busy: call collect() first")
         src = torch.from_numpy(points) if isinstance(points, np.ndarray) else points
+        if src.dim() != 2 or src.shape[1] != 4 or src.dtype != torch.float32 or not src.is_contiguous():
+            raise ValueError("HostFramePipeline takes contiguous (n,4) float32 frames")
         n = src.shape[0]
         if src.is_pinned():
             h_in = src                      # caller already owns pinned memory: no staging copy
@@ -392,46 +398,51 @@ class HostFramePipeline:
             slot["h_in"][:n].copy_(src)
             h_in = slot["h_in"][:n]
         slot["n"] = n
-        pipe = slot["pipe"]
-        with torch.cuda.stream(slot["stream"]):
-            slot["d_in"][:n].copy_(h_in, non_blocking=True)
-            pipe.enqueue(slot["d_in"][:n], origin=origin, xy_range=xy_range)
-            check(lib.lidar_frame_pack_soa(_ptr(pipe.voxels), _ptr(pipe.desc_dev), n, _ptr(slot["d_cen"]),
-                                           _ptr(slot["d_cnt"]), _ptr(slot["d_ukey"]), _stream_ptr()))
-            pipe.desc_host.copy_(pipe.desc_dev, non_blocking=True)
-            slot["h_cen"][:n].copy_(slot["d_cen"][:n], non_blocking=True)
-            slot["h_cnt"][:n].copy_(slot["d_cnt"][:n], non_blocking=True)
-            if self.unique_keys:
-                slot["h_ukey"][:n].copy_(slot["d_ukey"][:n], non_blocking=True)
-            if self.per_point_outputs:
-                slot["h_inv"][:n].copy_(pipe.inverse[:n], non_blocking=True)
-                slot["h_key"][:n].copy_(pipe.voxel_key[:n], non_blocking=True)
-            if slot["h_grid"] is not None:
-                slot["h_grid"].copy_(pipe.grid, non_blocking=True)
+        slot["src"] = h_in                  # keep the source alive until the copy-in has run
+        o3 = (C.c_double * 3)(*[float(v) for v in origin]) if origin is not None else None
+        r4 = (C.c_double * 4)(*[float(v) for v in xy_range]) if xy_range is not None else None
+        try:
+            check(lib.lidar_frame_voxel_density_host(h_in.data_ptr(), n, self.voxel_size, self.grid_size, o3, r4,
+                                                     _ptr(slot["d_in"]), _ptr(slot["d_vox"]), _ptr(slot["d_out"]),
+                                                     slot["h_out"].data_ptr(), self.flags, C.byref(self.caps),
+                                                     _ptr(slot["ws"]), slot["ws"].numel(), slot["stream"].cuda_stream))
+        except Exception:
+            with torch.cuda.stream(slot["stream"]):
+                check(lib.lidar_frame_workspace_init(_ptr(slot["ws"]), slot["ws"].numel(), C.byref(self.caps), _stream_ptr()))
+            raise
         self._pending.append(slot)
 
     def collect(self, copy: bool = True) -> dict:
-        """Wait for the oldest submitted frame and return its results as numpy arrays."""
+        """Wait for the oldest submitted frame and return its results as numpy arrays (`copy=False`: views of the
+        slot's pinned block, valid until the slot is reused)."""
         slot = self._pending.pop(0)
         slot["stream"].synchronize()
-        pipe = slot["pipe"]
-        desc = FrameDesc.from_buffer_copy(pipe.desc_host.numpy().tobytes())
+        n = slot["n"]
+        off = self._layout(n)
+        raw = slot["h_out"].numpy()
+        desc = FrameDesc.from_buffer_copy(raw[off[6]: off[6] + C.sizeof(FrameDesc)].tobytes())
         if desc.status != 0:
-            pipe.reset()
+            with torch.cuda.stream(slot["stream"]):
+                check(lib.lidar_frame_workspace_init(_ptr(slot["ws"]), slot["ws"].numel(), C.byref(self.caps), _stream_ptr()))
+            slot["stream"].synchronize()
             raise _capi.LidarError(int(desc.status), "frame exceeded its capacities")
-        n, v = slot["n"], int(desc.n_voxels)
+        v = int(desc.n_voxels)
         cp = (lambda a: a.copy()) if copy else (lambda a: a)
+
+        def arr(k, dtype, count):
+            return np.frombuffer(raw, dtype=dtype, count=count, offset=off[k])
+
         out = {
-            "centroids": cp(slot["h_cen"].numpy()[:v]), "counts": cp(slot["h_cnt"].numpy()[:v]),
+            "centroids": cp(arr(2, np.float32, 4 * v).reshape(v, 4)), "counts": cp(arr(3, np.int32, v)),
             "n_voxels": v, "dims": tuple(desc.dims[:3]), "origin": tuple(desc.origin[:3]), "desc": desc,
         }
         if self.unique_keys:
-            out["unique_keys"] = cp(slot["h_ukey"].numpy()[:v])
+            out["unique_keys"] = cp(arr(4, np.int32, v))
         if self.per_point_outputs:
-            out["inverse"] = cp(slot["h_inv"].numpy()[:n])
-            out["voxel_key"] = cp(slot["h_key"].numpy()[:n])
-        if slot["h_grid"] is not None:
-            out["grid_counts"] = cp(slot["h_grid"].numpy()[: desc.nx * desc.ny].reshape(desc.nx, desc.ny))
+            out["inverse"] = cp(arr(1, np.int32, n))
+            out["voxel_key"] = cp(arr(0, np.int32, n))
+        if self.grid_size > 0:
+            out["grid_counts"] = cp(arr(5, np.int32, desc.nx * desc.ny).reshape(desc.nx, desc.ny))
         return out
 
     def process(self, points, origin=None, xy_range=None) -> dict:

@@ -158,3 +158,52 @@ def test_host_frame_pipeline_numpy_in_numpy_out(ops, synth, pinned):
         wc, _, _ = ref_path.grid_density_counts(xyz[:, :2], (xyz[:, 0].min(), xyz[:, 0].max()),
                                                 (xyz[:, 1].min(), xyz[:, 1].max()), 0.5)
         assert np.array_equal(out["grid_counts"], wc)
+
+
+def test_streaming_mode_back_to_back_frames_equal_cooperative(ops, synth):
+    """Streaming mode (ordinary launch + programmatic dependent launch: the next frame's load runs under the
+    current frame's tail) must leave every output untouched.  Different frames are enqueued back to back on one
+    stream without host synchronisation, alternating between two pipelines' outputs is NOT allowed in this mode,
+    so one pipeline is reused and each result is cloned on the stream right after its frame."""
+    frames = [torch.from_numpy(synth.crowd_frame(n, seed=s, extent=e)).cuda()
+              for s, (n, e) in enumerate([(200_000, 30.0), (1_000_000, 50.0), (50_000, 10.0), (1_000_000, 50.0), (7, 2.0)])]
+    pipe = ops.FramePipeline(max_points=1_000_000, voxel_size=0.05, grid_size=0.5, max_nx=256, max_ny=256)
+    ops.set_frame_mode(ops.FRAME_FUSED, 512, 1, 0)
+
+    def snapshot():
+        # device-side clones on the same stream: ordered after the frame, no host synchronisation
+        return dict(key=pipe.voxel_key.clone(), inv=pipe.inverse.clone(), vox=pipe.voxels.clone(),
+                    grid=pipe.grid.clone(), desc=pipe.desc_dev.clone())
+
+    want = []
+    for f in frames:
+        pipe.enqueue(f)
+        want.append(snapshot())
+    torch.cuda.synchronize()
+    try:
+        ops.set_frame_streaming(True)
+        got = []
+        for rep in range(3):                      # several rounds back to back: 15 dependent launches
+            for f in frames:
+                pipe.enqueue(f)
+                if rep == 2:
+                    got.append(snapshot())
+        torch.cuda.synchronize()
+    finally:
+        ops.set_frame_streaming(False)
+    for w, g, f in zip(want, got, frames):
+        n = f.shape[0]
+        assert torch.equal(w["key"][:n], g["key"][:n]) and torch.equal(w["inv"][:n], g["inv"][:n])
+        nv = int(pipe_desc_n_voxels(w["desc"]))
+        assert nv == int(pipe_desc_n_voxels(g["desc"]))
+        assert torch.equal(w["vox"][:nv], g["vox"][:nv])
+        assert torch.equal(w["grid"], g["grid"])
+
+
+def pipe_desc_n_voxels(desc_dev: torch.Tensor) -> int:
+    from lidar_ai_recommendation_software_b200 import _capi
+    import ctypes
+    raw = desc_dev.cpu().numpy().tobytes()
+    d = _capi.FrameDesc.from_buffer_copy(raw[:ctypes.sizeof(_capi.FrameDesc)])
+    assert d.status == 0
+    return d.n_voxels
