@@ -92,6 +92,22 @@ def test_hist2d_edge_cases(ops):
     assert int(got.sum()) == 0
 
 
+def test_hist2d_big_scan_equals_numpy(ops, synth):
+    """5 M points of the venue scan on a grid too large for shared memory (the GLOBAL path of config 5):
+    counts must equal numpy's, accumulate into a pre-filled output, and sum to n."""
+    pts = synth.venue_scan_shard(5_000_000, 7, 0, 1)
+    xy = pts[:, :2].astype(np.float64)
+    ex = ops.arange_edges(xy[:, 0].min(), xy[:, 0].max(), 0.5)
+    ey = ops.arange_edges(xy[:, 1].min(), xy[:, 1].max(), 0.5)
+    assert (len(ex) - 1) * (len(ey) - 1) * 4 > 227 * 1024
+    want = nps.histogram2d_counts(xy[:, 0], xy[:, 1], ex, ey)
+    d = dev(pts)
+    got = ops.hist2d_points_counts(d, ex, ey)
+    assert np.array_equal(got.cpu().numpy(), want) and int(got.sum()) == len(pts)
+    again = ops.hist2d_points_counts(d, ex, ey, out=got)       # accumulates on top
+    assert np.array_equal(again.cpu().numpy(), 2 * want)
+
+
 def test_heatmap_linspace_edges_float4(ops, synth):
     pts = synth.crowd_frame(300000, seed=9)
     xyz = pts[:, :3].astype(np.float64)
