@@ -89,6 +89,17 @@ def reference_sample() -> np.ndarray:
     return np.column_stack((x, y, z))
 
 
+def tiny_cloud() -> np.ndarray:
+    """14 points: both degenerate guards of the reference's preprocess fire (<= 10 ground, <= 10 non-ground)."""
+    return np.random.default_rng(4).uniform(-2, 2, (14, 3))
+
+
+def sparse_cloud() -> np.ndarray:
+    """300 scattered returns on a 60 m x 60 m x 3 m volume: no DBSCAN cluster at eps = 0.3 m."""
+    r = np.random.default_rng(9)
+    return np.column_stack([r.uniform(-30, 30, 300), r.uniform(-30, 30, 300), r.uniform(0, 3, 300)])
+
+
 def ring_sequence_frame(frame: int, rings: int = 128, azimuth_steps: int = 20480, seed: int = 0,
                         extent: float = 50.0, n_people: int = 600, dt: float = 0.1) -> np.ndarray:
     """C.3 128-beam frame (~2.6 M returns), scan ordered (ring-major, azimuth-minor).
@@ -122,20 +133,21 @@ def ring_sequence_frame(frame: int, rings: int = 128, azimuth_steps: int = 20480
         idx = np.arange(lo, hi + 1) % azimuth_steps
         nearest[idx] = np.minimum(nearest[idx], r)
     frng = np.random.default_rng(seed * 100003 + frame)
-    for e in elev:
-        ce, se = np.cos(e), np.sin(e)
-        ground_r = h / np.tan(-e) if e < -1e-6 else np.inf          # horizontal range of ground hit
-        hr = np.full(azimuth_steps, ground_r)
-        # person hit if the ray is between z=0 and z=1.7 at the person's range
-        z_at_person = h + nearest * np.tan(e)
-        hit = (nearest < hr) & (z_at_person >= 0.0) & (z_at_person <= 1.7)
-        hr = np.where(hit, nearest, hr)
-        ok = np.isfinite(hr) & (hr / max(ce, 1e-9) <= 120.0)
-        x = hr * np.cos(az)
-        y = hr * np.sin(az)
-        z = np.where(hit, z_at_person, 0.1 * np.sin(0.5 * x) * np.cos(0.5 * y))
-        x, y, z = x[ok], y[ok], z[ok]
-        noise = frng.normal(0.0, 0.01, (x.size, 3))
-        inten = frng.uniform(0.0, 1.0, x.size)
-        pts.append(np.column_stack([x + noise[:, 0], y + noise[:, 1], z + noise[:, 2], inten]))
+    with np.errstate(invalid="ignore"):   # rays that hit nothing carry inf ranges until they are masked out
+        for e in elev:
+            ce, se = np.cos(e), np.sin(e)
+            ground_r = h / np.tan(-e) if e < -1e-6 else np.inf          # horizontal range of ground hit
+            hr = np.full(azimuth_steps, ground_r)
+            # person hit if the ray is between z=0 and z=1.7 at the person's range
+            z_at_person = h + nearest * np.tan(e)
+            hit = (nearest < hr) & (z_at_person >= 0.0) & (z_at_person <= 1.7)
+            hr = np.where(hit, nearest, hr)
+            ok = np.isfinite(hr) & (hr / max(ce, 1e-9) <= 120.0)
+            x = hr * np.cos(az)
+            y = hr * np.sin(az)
+            z = np.where(hit, z_at_person, 0.1 * np.sin(0.5 * x) * np.cos(0.5 * y))
+            x, y, z = x[ok], y[ok], z[ok]
+            noise = frng.normal(0.0, 0.01, (x.size, 3))
+            inten = frng.uniform(0.0, 1.0, x.size)
+            pts.append(np.column_stack([x + noise[:, 0], y + noise[:, 1], z + noise[:, 2], inten]))
     return np.concatenate(pts, 0).astype(np.float32)

@@ -55,6 +55,8 @@ CASES = {
     "ref_sample_10k": lambda synth: synth.reference_sample(),
     "crowd_20k": lambda synth: synth.add_outliers(synth.crowd_frame(20000, seed=3, extent=15.0))[:, :3].astype(np.float64),
     "crowd_100k": lambda synth: synth.crowd_frame(100000, seed=0, extent=50.0)[:, :3].astype(np.float64),
+    "tiny_14": lambda synth: synth.tiny_cloud(),
+    "sparse_300": lambda synth: synth.sparse_cloud(),
 }
 
 

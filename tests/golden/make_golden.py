@@ -126,6 +126,12 @@ def main():
              dp, CDM, CFM, B)
     # case 3: BASELINE config 1 — 100 k-point crowd frame, 100 m x 100 m
     run_case("crowd_100k", synth.crowd_frame(100000, seed=0, extent=50.0)[:, :3].astype(np.float64), dp, CDM, CFM, B)
+    # case 4: degenerate guards — 14 points: <= 10 ground points (fallback plane, data_processing.py:181-183) and
+    #         <= 10 non-ground points (all-zero labels, :199-200)
+    run_case("tiny_14", synth.tiny_cloud(), dp, CDM, CFM, B)
+    # case 5: 300 scattered returns — several clusters in variant A (eps in sigma units), NO cluster in variant B
+    #         (the empty-people dicts of app_simplified.py:234-316 / 318-464)
+    run_case("sparse_300", synth.sparse_cloud(), dp, CDM, CFM, B)
 
 
 if __name__ == "__main__":

@@ -14,7 +14,7 @@ from oracle import new_ops, np_semantics as nps, ref_path
 
 pytestmark = pytest.mark.gpu
 
-CASE_NAMES = ["ref_sample_10k", "crowd_20k", "crowd_100k"]
+CASE_NAMES = ["ref_sample_10k", "crowd_20k", "crowd_100k", "tiny_14", "sparse_300"]
 
 
 def sha(a) -> str:

@@ -10,7 +10,7 @@ import pytest
 
 from oracle import new_ops, np_semantics as nps, ref_path
 
-CASE_NAMES = ["ref_sample_10k", "crowd_20k", "crowd_100k"]
+CASE_NAMES = ["ref_sample_10k", "crowd_20k", "crowd_100k", "tiny_14", "sparse_300"]
 
 
 def sha(a) -> str:
