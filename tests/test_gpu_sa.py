@@ -37,6 +37,25 @@ def test_fps_bit_exact(pn2, b, n, m):
     assert np.array_equal(got, want)
 
 
+def test_fps_many_clouds_waves_and_repeatability(pn2):
+    """More clusters than fit at once (40 clouds x 8 CTAs: several waves), every cluster size (1, 2, 4, 8 CTAs),
+    m == n (every point gets picked, the tail runs on all-zero distances), identical clouds in one batch, and the
+    same launch repeated: the mbarrier / st.async exchange must neither hang nor depend on scheduling."""
+    rng = np.random.default_rng(3)
+    big = rng.uniform(-1, 1, (40, 16384, 3)).astype(np.float32)
+    big[7] = big[3]
+    got = pn2.furthest_point_sample(dev(big), 96).cpu().numpy()
+    assert np.array_equal(got[7], got[3])
+    for b in (0, 3, 39):
+        assert np.array_equal(got[b], new_ops.furthest_point_sample(big[b:b + 1], 96)[0])
+    for _ in range(3):
+        assert np.array_equal(pn2.furthest_point_sample(dev(big), 96).cpu().numpy(), got)
+    for n in (7, 2048, 2100, 4096, 4100, 8192, 9000):          # 1, 1, 2, 2, 4, 4, 8 CTAs per cloud
+        xyz = rng.uniform(-1, 1, (3, n, 3)).astype(np.float32)
+        m = n if n <= 2100 else 200
+        assert np.array_equal(pn2.furthest_point_sample(dev(xyz), m).cpu().numpy(), new_ops.furthest_point_sample(xyz, m))
+
+
 def test_fps_large_cloud_fallback(pn2):
     xyz = np.random.default_rng(0).normal(size=(1, 20000, 3)).astype(np.float32)
     want = new_ops.furthest_point_sample(xyz, 64)
