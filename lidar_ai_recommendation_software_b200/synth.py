@@ -151,3 +151,4 @@ def ring_sequence_frame(frame: int, rings: int = 128, azimuth_steps: int = 20480
             inten = frng.uniform(0.0, 1.0, x.size)
             pts.append(np.column_stack([x + noise[:, 0], y + noise[:, 1], z + noise[:, 2], inten]))
     return np.concatenate(pts, 0).astype(np.float32)
+
