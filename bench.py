@@ -196,6 +196,8 @@ def main():
                     help="experiment: ordinary instead of cooperative launch (lets frames of different streams overlap)")
     ap.add_argument("--pdl", type=int, default=-1,
                     help="programmatic dependent launch of the fused kernel (1/0; default: library setting)")
+    ap.add_argument("--scan-order", type=int, default=0,
+                    help="1: the scan-order variant of the fused kernel (run-length aggregation, summary-bitmap scan)")
     ap.add_argument("--streaming", type=int, default=1,
                     help="fused back end, one stream: ordinary launch + programmatic dependent launch for the "
                          "device-resident leg (frames back to back on one stream); 0 = cooperative launches")
@@ -233,6 +235,8 @@ def main():
     if args.fused_plain_launch:
         from lidar_ai_recommendation_software_b200 import _capi
         _capi.check(_capi.lib.lidar_frame_set_fused_plain_launch(1))
+    if args.scan_order:
+        ops.set_frame_scan_order(True)
     if args.pdl >= 0:
         from lidar_ai_recommendation_software_b200 import _capi
         _capi.check(_capi.lib.lidar_frame_set_fused_pdl(args.pdl))

@@ -270,7 +270,7 @@ typedef struct lidar_frame_desc {
     /* fused kernel only — timeline of CTA 0 (ns between consecutive %globaltimer stamps):
      *  [0] load+zero+bbox  [1] barrier 1   [2] descriptor   [3] mark        [4] barrier 2
      *  [5] scan popcounts  [6] wait totals [7] prefixes     [8] barrier 3   [9] rank
-     *  [10] barrier 4      [11] clean+finalize              [15] = CTAs of the grid.
+     *  [10] barrier 4      [11] clean+finalize   [14] = 1 if the summary-bitmap scan ran   [15] = CTAs of the grid.
      * All zero when the five-kernel path ran.                                                 */
     uint32_t trace_ns[16];
 } lidar_frame_desc;
@@ -313,6 +313,17 @@ int lidar_frame_set_fused_plain_launch(int on);
  * pipeline's workspace or outputs waits (griddepcontrol.wait) until the previous kernel has completed.
  * Outputs are identical.  Process-wide setting. */
 int lidar_frame_set_fused_pdl(int on);
+/* The scan-order variant of k_frame_fused (off by default; process-wide): for frames as a sensor delivers them
+ * (adjacent points adjacent in space) and / or key spaces much larger than the data (a 240 m x 240 m ring scan).
+ *   - run-length aggregation across adjacent lanes: only the first lane of a run of equal voxel keys touches the
+ *     occupancy bitmap, only the first lane of a run of equal density cells issues the reduction (with the run
+ *     length), runs of later members of one voxel are summed with a segmented warp scan before they reach the
+ *     accumulators: most same-address L2 atomics of such a frame disappear;
+ *   - when there are more than 1.5 occupancy groups per point, scan and clean walk a summary bitmap of the occupied
+ *     groups instead of streaming all of them: the frame costs what its data costs, not what its bounding box costs.
+ * Outputs are identical to the default variant (integer sums, same order).  The default variant is the faster one
+ * on shuffled, dense frames (the benchmark): the kernel is instruction-cache bound and does not carry this code. */
+int lidar_frame_set_fused_scan_order(int on);
 /* diagnostics: byte offset inside the workspace of uint64 stamps[ctas][16] (%globaltimer, ns) that
  * every CTA of the last k_frame_fused launch wrote at its 13 trace points (see trace_ns). */
 size_t lidar_frame_trace_offset(const lidar_frame_caps* caps);

@@ -45,14 +45,15 @@ constexpr int kScanGroupsPerThread = 4;                               // each th
 constexpr int kScanTileGroups = kFrameThreads * kScanGroupsPerThread; // 1024 groups = 229 376 voxels per tile
 
 struct FrameWsLayout {
-    size_t off_partial, off_ctrl, off_groups, off_tile_desc, off_acc, off_cnt, off_cta_desc, off_trace, off_grid_rep, total;
-    int64_t groups, tiles;
+    size_t off_partial, off_ctrl, off_groups, off_tile_desc, off_acc, off_cnt, off_cta_desc, off_trace, off_grid_rep, off_l1, off_l1cnt, total;
+    int64_t groups, tiles, l1_words;
 };
 
 struct FrameCtrl {
     unsigned int bbox_ticket;
     unsigned int scan_ticket;
     unsigned int grid_bar;     // fused kernel: grid-barrier arrival counter (reset by the last CTA to exit)
+    unsigned int grid_bar_b;   // scan-order variant: the extra barrier of the sparse scan (same reset)
     unsigned int exit_ticket;  // fused kernel: CTAs that have passed the last barrier
     unsigned long long dirty_groups;  // occupancy groups the previous frame may have set
 };
@@ -84,6 +85,9 @@ static FrameWsLayout frame_layout(const lidar_frame_caps& c) {
     L.off_cta_desc = take(sizeof(unsigned long long) * kFusedMaxCtas);
     L.off_trace = take(sizeof(unsigned long long) * 16 * kFusedMaxCtas);
     L.off_grid_rep = take(sizeof(int32_t) * kGridRepCells);
+    L.l1_words = (L.groups + 31) / 32;             // summary: one bit per occupancy group (scan-order variant)
+    L.off_l1 = take(sizeof(uint32_t) * (size_t)L.l1_words);
+    L.off_l1cnt = take(sizeof(uint32_t) * (size_t)L.l1_words);   // occupied cells per summary word, then their prefix
     L.total = ws_align(o);
     return L;
 }
@@ -442,6 +446,9 @@ __device__ __forceinline__ uint32_t* occupancy_word(uint32_t* groups, int key, u
     const unsigned g = (unsigned)key / kGroupVoxels, b = (unsigned)key - g * kGroupVoxels;
     bit = 1u << (b & 31);
     return groups + (size_t)g * 8 + 1 + (b >> 5);
+}
+__device__ __forceinline__ void red_or_b32(unsigned* p, unsigned v) {
+    asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // 256-bit global accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256): a whole 32-byte occupancy group or
@@ -806,6 +813,8 @@ struct FusedArgs {
     unsigned long long* cta_desc;
     unsigned long long* trace_all;   // [G][16] %globaltimer stamps of every CTA (diagnostics)
     int32_t* grid_rep;               // kGridRepCells zeroed cells: private replicas of the density grid
+    uint32_t* l1;                    // scan-order variant: summary bitmap, bit g = occupancy group g is not empty
+    uint32_t* l1cnt;                 // scan-order variant: occupied cells per summary word, then their exclusive prefix
     int smem_points;      // resident points per CTA (shared-memory capacity)
     int smem_groups;      // capacity of the per-group popcount cache (bytes) per CTA
 };
@@ -882,6 +891,12 @@ __device__ __forceinline__ void fused_grid_barrier(unsigned* ctr, unsigned targe
 
 #define FUSED_TRACE(k) do { if (tid == 0) s_trace[k] = global_timer_ns(); } while (0)
 
+// kScan = the scan-order variant (lidar_frame_set_fused_scan_order): frames as a sensor delivers them, and / or key
+// spaces much larger than the data.  It adds (a) run-length aggregation across adjacent lanes in the mark and rank
+// phases and (b) a scan / clean that walks a summary bitmap of the occupied groups instead of streaming every group.
+// The default instantiation (kScan = false) contains none of that code: the kernel is instruction-cache bound, and
+// compiling both into one body cost the shuffled benchmark 5 %.
+template <bool kScan>
 __global__ void __launch_bounds__(kFusedMaxThreads, 1)
 k_frame_fused(const FusedArgs A) {
     extern __shared__ __align__(128) unsigned char fsm[];
@@ -1025,6 +1040,13 @@ k_frame_fused(const FusedArgs A) {
     FUSED_TRACE(3);
     const bool ok = D.status == 0;
     const int64_t ng = ok ? (D.key_space + kGroupVoxels - 1) / kGroupVoxels : 0;
+    // scan-order variant, sparse key space (a 240 m x 240 m ring scan: 2.8 M groups, 0.3 M of them occupied): scan and
+    // clean walk a summary bitmap (one bit per group, set by whoever touches an empty word) instead of streaming every
+    // group, so the frame costs what its DATA costs, not what its bounding box costs.  Same decision in every CTA.
+    const int64_t l1_used = (ng + 31) / 32;
+    const int64_t lpc = (l1_used + G - 1) / G;                 // summary words per CTA (prefix pass)
+    const bool sparse = kScan && ok && 2 * ng > 3 * n;
+    __shared__ unsigned s_cta_base[kScan ? kFusedMaxCtas : 1];
     // density grid replicas: R copies of nx*ny cells, CTA b adds into copy b % R
     const int ncell = D.nx * D.ny;
     int grid_reps = (ok && ncell > 0) ? kGridRepCells / ncell : 0;
@@ -1034,38 +1056,93 @@ k_frame_fused(const FusedArgs A) {
     // ---- phase 1: mark ----------------------------------------------------------------------------
     if (ok) {
         const MarkConst K = make_mark_const(D);
-        // resident points: kFusedBatch points per thread per trip, all their atomicOr in flight together
-        for (int j0 = tid; j0 < res; j0 += kFusedBatch * T) {
-            float4 q[kFusedBatch];
-            int key[kFusedBatch];
-            unsigned bit[kFusedBatch], old[kFusedBatch];
+        if constexpr (kScan) {
+            // Run-length aggregation across the warp: adjacent lanes hold adjacent points, and a sensor delivers them
+            // in scan order -- 25 consecutive returns of a ring share a 5 cm voxel near the sensor.  Only the first
+            // lane of a run of equal keys touches the bitmap (the others are later members by construction), and
+            // only the first lane of a run of equal density cells issues the reduction, with the run length: most of
+            // the L2 atomics of such a frame disappear, all of them same-address (serialised) ones.
+            for (int j0 = tid; j0 - (int)lane < res; j0 += kFusedBatch * T) {      // warp-uniform trip count
+                float4 q[kFusedBatch];
+                int key[kFusedBatch];
+                unsigned bit[kFusedBatch], old[kFusedBatch];
 #pragma unroll
-            for (int u = 0; u < kFusedBatch; ++u) {
-                const int j = j0 + u * T;
-                q[u] = s_pts[j < res ? j : j0];
-            }
+                for (int u = 0; u < kFusedBatch; ++u) {
+                    const int j = j0 + u * T;
+                    q[u] = s_pts[j < res ? j : 0];
+                }
 #pragma unroll
-            for (int u = 0; u < kFusedBatch; ++u) {
-                key[u] = voxel_key_of(q[u], D, K);
-                uint32_t* w = occupancy_word(A.groups, key[u], bit[u]);
-                old[u] = 0u;
-                if (j0 + u * T < res) old[u] = atomicOr(w, bit[u]);
-            }
+                for (int u = 0; u < kFusedBatch; ++u) {
+                    const bool live = j0 + u * T < res;
+                    key[u] = voxel_key_of(q[u], D, K);
+                    const int kk = live ? key[u] : -1 - (int)lane;             // dead lanes never join a run
+                    const int prev = __shfl_up_sync(0xffffffffu, kk, 1);
+                    const bool head = lane == 0 || kk != prev;
+                    uint32_t* w = occupancy_word(A.groups, key[u], bit[u]);
+                    old[u] = bit[u];               // later members of a run, and dead slots: "bit already set"
+                    if (live && head) old[u] = atomicOr(w, bit[u]);
+                }
+                if (sparse) {
 #pragma unroll
-            for (int u = 0; u < kFusedBatch; ++u) {
-                const int j = j0 + u * T;
-                if (j < res) {
-                    st_stream_s32(A.voxel_key + c0 + j, key[u]);
-                    if (K.do_grid) {
-                        const int cell = grid_cell_of(q[u], D, K);
-                        if (cell >= 0) red_add_s32(grid_acc + cell, 1);
+                    for (int u = 0; u < kFusedBatch; ++u) {
+                        if (old[u] == 0u) {                                    // first to touch this word
+                            const unsigned g = (unsigned)key[u] / kGroupVoxels;
+                            red_or_b32(A.l1 + (g >> 5), 1u << (g & 31));
+                        }
                     }
                 }
-            }
 #pragma unroll
-            for (int u = 0; u < kFusedBatch; ++u) {
-                const int j = j0 + u * T;
-                if (j < res) s_key[j] = (unsigned)key[u] | ((old[u] & bit[u]) ? kDupFlag : 0u);
+                for (int u = 0; u < kFusedBatch; ++u) {
+                    const int j = j0 + u * T;
+                    const bool live = j < res;
+                    if (live) st_stream_s32(A.voxel_key + c0 + j, key[u]);
+                    if (K.do_grid) {
+                        const int cell = live ? grid_cell_of(q[u], D, K) : -1;
+                        const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
+                        const bool chead = lane == 0 || cell != prev;
+                        const unsigned heads = __ballot_sync(0xffffffffu, chead);
+                        if (chead && cell >= 0) {
+                            const unsigned above = lane == 31 ? 0u : heads & (0xffffffffu << (lane + 1));
+                            red_add_s32(grid_acc + cell, (above ? __ffs(above) - 1 : 32) - (int)lane);
+                        }
+                    }
+                    if (live) s_key[j] = (unsigned)key[u] | ((old[u] & bit[u]) ? kDupFlag : 0u);
+                }
+            }
+        } else {
+            // resident points: kFusedBatch points per thread per trip, all their atomicOr in flight together
+            for (int j0 = tid; j0 < res; j0 += kFusedBatch * T) {
+                float4 q[kFusedBatch];
+                int key[kFusedBatch];
+                unsigned bit[kFusedBatch], old[kFusedBatch];
+#pragma unroll
+                for (int u = 0; u < kFusedBatch; ++u) {
+                    const int j = j0 + u * T;
+                    q[u] = s_pts[j < res ? j : j0];
+                }
+#pragma unroll
+                for (int u = 0; u < kFusedBatch; ++u) {
+                    key[u] = voxel_key_of(q[u], D, K);
+                    uint32_t* w = occupancy_word(A.groups, key[u], bit[u]);
+                    old[u] = 0u;
+                    if (j0 + u * T < res) old[u] = atomicOr(w, bit[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < kFusedBatch; ++u) {
+                    const int j = j0 + u * T;
+                    if (j < res) {
+                        st_stream_s32(A.voxel_key + c0 + j, key[u]);
+                        if (K.do_grid) {
+                            const int cell = grid_cell_of(q[u], D, K);
+                            if (cell >= 0) red_add_s32(grid_acc + cell, 1);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kFusedBatch; ++u) {
+                    const int j = j0 + u * T;
+                    if (j < res) s_key[j] = (unsigned)key[u] | ((old[u] & bit[u]) ? kDupFlag : 0u);
+                }
             }
         }
         // spill points: the flagged key goes to global memory, phase 3 strips the flag
@@ -1075,6 +1152,10 @@ k_frame_fused(const FusedArgs A) {
             unsigned bit;
             uint32_t* w = occupancy_word(A.groups, key, bit);
             const unsigned old = atomicOr(w, bit);
+            if (sparse && old == 0u) {
+                const unsigned g = (unsigned)key / kGroupVoxels;
+                red_or_b32(A.l1 + (g >> 5), 1u << (g & 31));
+            }
             if (K.do_grid) {
                 const int cell = grid_cell_of(q, D, K);
                 if (cell >= 0) red_add_s32(grid_acc + cell, 1);
@@ -1096,7 +1177,49 @@ k_frame_fused(const FusedArgs A) {
     const int64_t w0 = g0 + (int64_t)warp * wseg < g1 ? g0 + (int64_t)warp * wseg : g1;
     const int64_t w1 = w0 + wseg < g1 ? w0 + wseg : g1;
     unsigned long long n_voxels = 0ull;
-    if (ok) {
+    // sparse scan (scan-order variant).  Pass A, summary words dealt round-robin to the CTAs (occupied words cluster
+    // in key space -- near the sensor -- so contiguous ranges would leave most CTAs idle): occupied cells per word.  Pass B, contiguous range per CTA: exclusive prefix inside the range, total of the range.
+    const int64_t lw0 = (int64_t)b * lpc < l1_used ? (int64_t)b * lpc : l1_used;
+    const int64_t lw1 = lw0 + lpc < l1_used ? lw0 + lpc : l1_used;
+    if (sparse) {
+        for (int64_t lw = (int64_t)tid * G + b; lw < l1_used; lw += (int64_t)G * T) {   // word w -> CTA w % G
+            unsigned word = __ldcg(A.l1 + lw);
+            unsigned cnt = 0;
+            while (word) {
+                const int64_t g = lw * 32 + (__ffs(word) - 1);
+                word &= word - 1;
+                cnt += group_popc(ld_cg_256(A.groups + (size_t)g * 8));
+            }
+            A.l1cnt[lw] = cnt;
+        }
+        fused_grid_barrier(&A.ctrl->grid_bar_b, (unsigned)G);
+        const int64_t lchunk = (lpc + T - 1) / T;
+        const int64_t t0w = lw0 + (int64_t)tid * lchunk < lw1 ? lw0 + (int64_t)tid * lchunk : lw1;
+        const int64_t t1w = t0w + lchunk < lw1 ? t0w + lchunk : lw1;
+        unsigned mine = 0;
+        for (int64_t lw = t0w; lw < t1w; ++lw) mine += __ldcg(A.l1cnt + lw);
+        unsigned inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (unsigned)o) inc += t;
+        }
+        if (lane == 31) s_wsum[warp] = inc;
+        __syncthreads();
+        unsigned total = 0, warp_off = 0;
+        for (int w = 0; w < nwarp; ++w) {
+            if (w < warp) warp_off += s_wsum[w];
+            total += s_wsum[w];
+        }
+        unsigned run = warp_off + inc - mine;
+        for (int64_t lw = t0w; lw < t1w; ++lw) {
+            const unsigned c = __ldcg(A.l1cnt + lw);
+            A.l1cnt[lw] = run;                  // exclusive prefix inside this CTA's range
+            run += c;
+        }
+        if (tid == 0) A.cta_desc[b] = (unsigned long long)total;
+        FUSED_TRACE(6);
+    } else if (ok) {
         const bool cache = gpc <= (int64_t)A.smem_groups;
         unsigned mine = 0;
         for (int64_t row = w0; row < w1; row += 32 * kFusedBatch) {
@@ -1151,11 +1274,45 @@ k_frame_fused(const FusedArgs A) {
         }
         __syncthreads();
         FUSED_TRACE(7);
+        n_voxels = s_base_total[1];
+        if (sparse) {
+            // pass C, strided again: base of the owning range + prefix inside it, then the prefix of every occupied
+            // group of the word goes into word 0 of the group
+            {
+                unsigned long long acc = 0ull;          // exclusive scan of the G range totals (G <= 1024: one warp)
+                if (warp == 0) {
+                    for (int c0_ = 0; c0_ < G; c0_ += 32) {
+                        const int c = c0_ + (int)lane;
+                        unsigned v = c < G ? (unsigned)__ldcg(A.cta_desc + c) : 0u;
+                        unsigned inc = v;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                            if (lane >= (unsigned)o) inc += t;
+                        }
+                        if (c < G) s_cta_base[c] = (unsigned)acc + inc - v;
+                        acc += __shfl_sync(0xffffffffu, inc, 31);
+                    }
+                }
+                __syncthreads();
+            }
+            for (int64_t lw = (int64_t)tid * G + b; lw < l1_used; lw += (int64_t)G * T) {   // word w -> CTA w % G
+                unsigned word = __ldcg(A.l1 + lw);
+                if (!word) continue;
+                unsigned run = s_cta_base[(int)(lw / lpc)] + __ldcg(A.l1cnt + lw);
+                while (word) {
+                    const int64_t g = lw * 32 + (__ffs(word) - 1);
+                    word &= word - 1;
+                    const unsigned pc = group_popc(ld_cg_256(A.groups + (size_t)g * 8));
+                    A.groups[(size_t)g * 8] = run;
+                    run += pc;
+                }
+            }
+        }
         unsigned warp_off = 0;
         for (int w = 0; w < warp; ++w) warp_off += s_wsum[w];
-        n_voxels = s_base_total[1];
         unsigned run = (unsigned)s_base_total[0] + warp_off;
-        for (int64_t row = w0; row < w1; row += 32) {
+        for (int64_t row = w0; row < (sparse ? w0 : w1); row += 32) {
             const int64_t g = row + lane;
             unsigned pc = 0;
             if (g < w1) pc = cache ? (unsigned)s_gcnt[g - g0] : group_popc(ld_cg_256(A.groups + (size_t)g * 8));
@@ -1177,14 +1334,51 @@ k_frame_fused(const FusedArgs A) {
     if (ok) {
         uint2* ring = s_ring + (size_t)warp * kFusedRing;
         unsigned head = 0, count = 0;   // warp-uniform
-        auto drain = [&](unsigned slot) {
-            const uint2 e = ring[slot];
-            const int j = (int)e.x;
-            float4 q;
-            int key;
-            if (j < res) { q = s_pts[j]; key = (int)(s_key[j] & ~kDupFlag); }
-            else { q = __ldcg(gp + j); key = __ldcg(A.voxel_key + c0 + j); }   // flag already stripped
-            accumulate_dup(q, key, e.y, D, A.acc, A.cnt);
+        // Drains up to 32 parked later-members (all lanes enter; `active` is false in the tail of the last drain).
+        // Scan-order variant: consecutive entries of the ring are consecutive points, which in scan order belong to the
+        // same voxel; a segmented inclusive scan over runs of equal rank (5 shuffle steps) leaves the exact integer
+        // sum of every run in its last lane, which issues the five reductions for the whole run.
+        auto drain = [&](unsigned slot, bool active) {
+            if constexpr (kScan) {
+                const uint2 e = active ? ring[slot] : make_uint2(0u, 0xffffffffu - lane);   // inactive: a run of its own
+                Fixed4 f = {0, 0, 0, 0};
+                if (active) {
+                    const int j = (int)e.x;
+                    float4 q;
+                    int key;
+                    if (j < res) { q = s_pts[j]; key = (int)(s_key[j] & ~kDupFlag); }
+                    else { q = __ldcg(gp + j); key = __ldcg(A.voxel_key + c0 + j); }   // flag already stripped
+                    f = fixed_offsets(q, key, D);
+                }
+                const unsigned r = e.y;
+                const unsigned prev = __shfl_up_sync(0xffffffffu, r, 1);
+                const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || r != prev);
+                const int start = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));   // first lane of this run
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const long long x = __shfl_up_sync(0xffffffffu, f.x, o), y = __shfl_up_sync(0xffffffffu, f.y, o);
+                    const long long z = __shfl_up_sync(0xffffffffu, f.z, o), w = __shfl_up_sync(0xffffffffu, f.w, o);
+                    if ((int)lane - o >= start) { f.x += x; f.y += y; f.z += z; f.w += w; }
+                }
+                const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+                if (active && tail) {
+                    unsigned long long* Acc = reinterpret_cast<unsigned long long*>(A.acc + (size_t)r * 4);
+                    red_add_u64(Acc + 0, (unsigned long long)f.x);
+                    red_add_u64(Acc + 1, (unsigned long long)f.y);
+                    red_add_u64(Acc + 2, (unsigned long long)f.z);
+                    red_add_u64(Acc + 3, (unsigned long long)f.w);
+                    red_add_s32(A.cnt + r, (int)lane - start + 1);
+                }
+            } else {
+                if (!active) return;
+                const uint2 e = ring[slot];
+                const int j = (int)e.x;
+                float4 q;
+                int key;
+                if (j < res) { q = s_pts[j]; key = (int)(s_key[j] & ~kDupFlag); }
+                else { q = __ldcg(gp + j); key = __ldcg(A.voxel_key + c0 + j); }   // flag already stripped
+                accumulate_dup(q, key, e.y, D, A.acc, A.cnt);
+            }
         };
         const int m_round = (m + 31) & ~31;
         for (int j0 = tid; j0 < m_round; j0 += kFusedBatch * T) {
@@ -1221,7 +1415,7 @@ k_frame_fused(const FusedArgs A) {
                     count += __popc(mm);
                     __syncwarp();
                     if (count >= 32) {
-                        drain((head + lane) % kFusedRing);
+                        drain((head + lane) % kFusedRing, true);
                         head = (head + 32) % kFusedRing;
                         count -= 32;
                         __syncwarp();
@@ -1229,7 +1423,7 @@ k_frame_fused(const FusedArgs A) {
                 }
             }
         }
-        if (lane < count) drain((head + lane) % kFusedRing);
+        if (count) drain((head + lane) % kFusedRing, lane < count);
     }
     FUSED_TRACE(10);
     fused_grid_barrier(&A.ctrl->grid_bar, 5u * G);
@@ -1257,9 +1451,21 @@ k_frame_fused(const FusedArgs A) {
         Word8 z;
 #pragma unroll
         for (int k = 0; k < 8; ++k) z.w[k] = 0u;
-        for (int64_t row = w0; row < w1; row += 32) {
-            const int64_t g = row + lane;
-            if (g < w1) st_256(A.groups + (size_t)g * 8, z);
+        if (sparse) {
+            for (int64_t lw = (int64_t)tid * G + b; lw < l1_used; lw += (int64_t)G * T) {   // word w -> CTA w % G
+                unsigned word = __ldcg(A.l1 + lw);
+                if (word) A.l1[lw] = 0u;
+                while (word) {
+                    const int64_t g = lw * 32 + (__ffs(word) - 1);
+                    word &= word - 1;
+                    st_256(A.groups + (size_t)g * 8, z);
+                }
+            }
+        } else {
+            for (int64_t row = w0; row < w1; row += 32) {
+                const int64_t g = row + lane;
+                if (g < w1) st_256(A.groups + (size_t)g * 8, z);
+            }
         }
         unsigned* ring = reinterpret_cast<unsigned*>(s_ring + (size_t)warp * kFusedRing);
         unsigned head = 0, count = 0;
@@ -1303,12 +1509,14 @@ k_frame_fused(const FusedArgs A) {
         if (b == 0) {
 #pragma unroll
             for (int k = 0; k < 12; ++k) D.trace_ns[k] = (uint32_t)(s_trace[k + 1] - s_trace[k]);
+            D.trace_ns[14] = sparse ? 1u : 0u;
             D.trace_ns[15] = (uint32_t)G;
             *A.D = D;
         }
         __threadfence();
         if (atomicAdd(&A.ctrl->exit_ticket, 1u) == (unsigned)G - 1u) {
             A.ctrl->grid_bar = 0u;
+            A.ctrl->grid_bar_b = 0u;
             A.ctrl->exit_ticket = 0u;
             A.ctrl->dirty_groups = 0ull;     // phase 4 left the bitmap clean
         }
@@ -1343,6 +1551,7 @@ static int g_fused_ctas_per_sm = 1;
 static int g_fused_smem_kb = 0;          // 0 = as much as the chunk needs, up to the opt-in maximum
 static int g_fused_plain_launch = 0;     // experiment: ordinary launch instead of cooperative (see header)
 static int g_fused_pdl = 0;              // programmatic dependent launch: frame f+1 loads while frame f drains
+static int g_fused_scan_order = 0;       // 1: the scan-order variant of k_frame_fused (see the kernel's header)
 static bool g_fused_attr_set = false;
 static size_t g_fused_attr_bytes = 0;
 
@@ -1380,6 +1589,11 @@ size_t lidar_frame_trace_offset(const lidar_frame_caps* caps) {
 
 int lidar_frame_set_fused_plain_launch(int on) {
     g_fused_plain_launch = on ? 1 : 0;
+    return LIDAR_OK;
+}
+
+int lidar_frame_set_fused_scan_order(int on) {
+    g_fused_scan_order = on ? 1 : 0;
     return LIDAR_OK;
 }
 
@@ -1468,7 +1682,7 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
         const int G = sm_count() * g_fused_ctas_per_sm;
         LIDAR_REQUIRE(G <= kFusedMaxCtas, LIDAR_ERR_CAPACITY, "lidar_frame_voxel_density: fused grid too large");
         const size_t ring_bytes = (size_t)(T / 32) * kFusedRing * sizeof(uint2);
-        const size_t static_bytes = 4096;    // static __shared__ of k_frame_fused, rounded up
+        const size_t static_bytes = 8192;    // static __shared__ of k_frame_fused (scan-order variant: + 4 KB of range bases), rounded up
         size_t budget = g_fused_smem_kb ? (size_t)g_fused_smem_kb * 1024 : smem_optin();
         if (budget > smem_optin()) budget = smem_optin();
         LIDAR_REQUIRE(budget > static_bytes + ring_bytes + 4096, LIDAR_ERR_INVALID,
@@ -1485,7 +1699,9 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
         if (spts < 0) spts = 0;
         const size_t dyn = (size_t)spts * 20 + ring_bytes + gbytes;
         if (!g_fused_attr_set || dyn > g_fused_attr_bytes) {
-            LIDAR_CUDA_TRY(cudaFuncSetAttribute(k_frame_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            LIDAR_CUDA_TRY(cudaFuncSetAttribute(k_frame_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(smem_optin() - static_bytes)));
+            LIDAR_CUDA_TRY(cudaFuncSetAttribute(k_frame_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)(smem_optin() - static_bytes)));
             g_fused_attr_set = true;
             g_fused_attr_bytes = smem_optin() - static_bytes;
@@ -1509,6 +1725,8 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
         A.grid_rep = reinterpret_cast<int32_t*>(ws + L.off_grid_rep);
         A.smem_points = (int)spts;
         A.smem_groups = (int)gbytes;
+        A.l1 = reinterpret_cast<uint32_t*>(ws + L.off_l1);
+        A.l1cnt = reinterpret_cast<uint32_t*>(ws + L.off_l1cnt);
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(G);
         cfg.blockDim = dim3(T);
@@ -1528,7 +1746,8 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
         }
         cfg.attrs = attr;
         cfg.numAttrs = na;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, k_frame_fused, A);
+        cudaError_t le = g_fused_scan_order ? cudaLaunchKernelEx(&cfg, k_frame_fused<true>, A)
+                                            : cudaLaunchKernelEx(&cfg, k_frame_fused<false>, A);
         if (le == cudaSuccess) {
             for (int i = 1; i <= 5; ++i) LIDAR_CUDA_TRY(mark(i));
             return LIDAR_OK;

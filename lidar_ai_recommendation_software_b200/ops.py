@@ -17,7 +17,7 @@ from . import _capi
 from ._capi import FMT_F32X4, FMT_F64X3, HIST_AUTO, FrameCaps, FrameDesc, check, lib
 
 __all__ = [
-    "require_cuda", "point_format", "bbox", "moments", "hist2d_counts", "hist2d_points_counts", "roi_crop", "ball_count", "set_dbscan_dense", "set_frame_streaming",
+    "require_cuda", "point_format", "bbox", "moments", "hist2d_counts", "hist2d_points_counts", "roi_crop", "ball_count", "set_dbscan_dense", "set_frame_streaming", "set_frame_scan_order",
     "FramePipeline", "HostFramePipeline", "voxel_downsample", "arange_edges", "linspace_edges",
 ]
 
@@ -193,6 +193,14 @@ def set_frame_mode(mode: int = FRAME_AUTO, threads: int = 0, ctas_per_sm: int = 
     check(lib.lidar_frame_set_fused(int(mode), int(threads), int(ctas_per_sm), int(smem_kb)))
 
 
+def set_frame_scan_order(on: bool = True) -> None:
+    """Scan-order variant of the fused frame kernel (process-wide, off by default): for frames as a sensor delivers
+    them (adjacent points adjacent in space) and key spaces much larger than the data -- run-length aggregation of
+    the L2 atomics across adjacent lanes, and a scan / clean that walks a summary bitmap of the occupied groups.
+    Identical outputs; the default variant is the faster one on shuffled, dense frames."""
+    check(lib.lidar_frame_set_fused_scan_order(1 if on else 0))
+
+
 def set_frame_streaming(on: bool = True) -> None:
     """Streaming mode of the fused frame kernel (process-wide, off by default): ordinary launch + programmatic
     dependent launch, so that with frames enqueued back to back on ONE stream the launch gap disappears and the
@@ -244,7 +252,13 @@ class FramePipeline:
 
     def __init__(self, max_points: int, voxel_size: float, grid_size: float = 0.0,
                  max_key_space: int = 1 << 28, max_nx: int = 1024, max_ny: int = 1024,
-                 device: torch.device | None = None):
+                 device: torch.device | None = None, scan_order: bool | str = "auto"):
+        """`scan_order`: which variant of the fused kernel runs the frames (identical outputs) -- False: the default
+        (shuffled / dense frames), True: the scan-order variant (`set_frame_scan_order`), "auto": decided from the
+        last descriptor read back by `result()` (more than 1.5 occupancy groups per point, or fewer than one voxel
+        per two points, say the next frame is a sensor-ordered / sparse one too)."""
+        self.scan_order = scan_order
+        self._scan_hint = False
         self.device = device or require_cuda()
         self.voxel_size = float(voxel_size)
         self.grid_size = float(grid_size)
@@ -284,6 +298,9 @@ class FramePipeline:
         o3 = (C.c_double * 3)(*[float(v) for v in origin]) if origin is not None else None
         r4 = (C.c_double * 4)(*[float(v) for v in xy_range]) if xy_range is not None else None
         self._n = n
+        if self.scan_order is not None:
+            want = self._scan_hint if self.scan_order == "auto" else bool(self.scan_order)
+            check(lib.lidar_frame_set_fused_scan_order(1 if want else 0))
         args = (_ptr(points), n, self.voxel_size, self.grid_size, o3, r4, _ptr(self.voxel_key),
                 _ptr(self.inverse), _ptr(self.voxels), _ptr(self.grid), _ptr(self.desc_dev), C.byref(self.caps),
                 _ptr(self.ws), self.ws.numel(), _stream_ptr())
@@ -314,6 +331,7 @@ class FramePipeline:
                                    f"(max {self.caps.max_key_space}), grid {desc.nx}x{desc.ny} "
                                    f"(max {self.caps.max_nx}x{self.caps.max_ny})")
         n, v = self._n, int(desc.n_voxels)
+        self._scan_hint = n > 0 and (2 * ((int(desc.key_space) + 223) // 224) > 3 * n or 2 * v < n)
         grid = None
         if self.grid is not None:
             grid = self.grid[: desc.nx * desc.ny].view(desc.nx, desc.ny)

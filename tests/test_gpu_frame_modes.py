@@ -75,6 +75,51 @@ def test_fused_equals_multikernel_and_oracle(ops, synth, n, extent):
     same(base, run(ops, pipe, d, (1, 0, 0, 0)))
 
 
+def test_fused_scan_order_variant_equals_default_and_oracle(ops, synth):
+    """The scan-order variant of the fused kernel (run-length aggregation across adjacent lanes; summary-bitmap scan
+    when there are more than 1.5 occupancy groups per point) must equal the default variant, the five-kernel path and
+    the oracle -- on scan-ordered sparse frames, on dense shuffled ones, with heavy duplication, frame after frame on
+    ONE pipeline (the clean-up of one mode must leave the workspace valid for the other)."""
+    ring = synth.ring_sequence_frame(2, rings=64, azimuth_steps=4096)          # scan-ordered, 240 m x 240 m: sparse
+    dense = synth.crowd_frame(150_000, seed=8, extent=6.0)                     # 12 m x 12 m, shuffled: dense
+    runs = np.repeat(synth.crowd_frame(3000, seed=9, extent=4.0), 40, axis=0)  # 40 identical points in a row
+    cap = max(len(ring), len(dense), len(runs))
+    pipe = ops.FramePipeline(max_points=cap, voxel_size=0.05, grid_size=0.5, max_key_space=(1 << 31) - 1,
+                             max_nx=1024, max_ny=1024, scan_order=None)     # None: the test drives the global switch
+    try:
+        for pts, want_sparse in ((ring, 1), (dense, 0), (runs, 0), (ring, 1), (ring, 1), (dense, 0)):
+            d = torch.from_numpy(pts).cuda()
+            ops.set_frame_scan_order(True)
+            got = run(ops, pipe, d, (2, 512, 1, 0))
+            assert got["trace_ns"][15] > 0 and got["trace_ns"][14] == want_sparse
+            spill = run(ops, pipe, d, (2, 256, 1, 24))          # tiny shared-memory budget: the spill paths
+            ops.set_frame_scan_order(False)
+            default = run(ops, pipe, d, (2, 512, 1, 0))
+            assert default["trace_ns"][15] > 0 and default["trace_ns"][14] == 0
+            base = run(ops, pipe, d, (1, 0, 0, 0))
+            same(base, got)
+            same(base, spill)
+            same(base, default)
+            want = new_ops.voxel_downsample(pts, 0.05)
+            assert np.array_equal(got["inverse"].cpu().numpy(), want["inverse"])
+            assert np.array_equal(got["counts"].cpu().numpy(), want["counts"])
+            assert np.array_equal(got["voxel_key"].cpu().numpy(), want["voxel_key"])
+    finally:
+        ops.set_frame_scan_order(False)
+    # "auto" (the default): the descriptor of the last frame read back picks the variant of the next one
+    auto = ops.FramePipeline(max_points=cap, voxel_size=0.05, grid_size=0.5, max_key_space=(1 << 31) - 1,
+                             max_nx=1024, max_ny=1024)
+    ops.set_frame_mode(ops.FRAME_FUSED, 512, 1, 0)
+    seen = []
+    for pts in (ring, ring, dense, dense, ring):
+        auto.enqueue(torch.from_numpy(pts).cuda())
+        seen.append(int(auto.result().desc.trace_ns[14]))
+    # one frame of lag; [14] says whether the summary-bitmap scan ran: default variant, scan variant on the sparse
+    # ring frame, scan variant on dense data (no summary scan), default, default
+    assert seen == [0, 1, 0, 0, 0]
+    ops.set_frame_scan_order(False)
+
+
 def test_fused_origin_range_and_duplicates(ops, synth):
     pts = synth.crowd_frame(5000, seed=1, extent=3.0)
     pts = np.concatenate([pts, pts[:1000]])
