@@ -1182,15 +1182,34 @@ k_frame_fused(const FusedArgs A) {
     const int64_t lw0 = (int64_t)b * lpc < l1_used ? (int64_t)b * lpc : l1_used;
     const int64_t lw1 = lw0 + lpc < l1_used ? lw0 + lpc : l1_used;
     if (sparse) {
-        for (int64_t lw = (int64_t)tid * G + b; lw < l1_used; lw += (int64_t)G * T) {   // word w -> CTA w % G
-            unsigned word = __ldcg(A.l1 + lw);
-            unsigned cnt = 0;
-            while (word) {
-                const int64_t g = lw * 32 + (__ffs(word) - 1);
-                word &= word - 1;
-                cnt += group_popc(ld_cg_256(A.groups + (size_t)g * 8));
+        // warp gw of the grid takes the words gw, gw + W, ...; each lane fetches one of them, then the warp visits
+        // the non-empty ones two at a time with one LANE per occupancy group (64 group loads in flight per warp)
+        const int W = G * nwarp, gw = warp * G + b;
+        for (int64_t k0 = 0; gw + k0 * W < l1_used; k0 += 32) {
+            const int64_t mylw = gw + (k0 + lane) * (int64_t)W;
+            const unsigned myword = mylw < l1_used ? __ldcg(A.l1 + mylw) : 0u;
+            unsigned nz = __ballot_sync(0xffffffffu, myword != 0u);
+            unsigned mycnt = 0;
+            while (nz) {
+                const int s0 = __ffs(nz) - 1;
+                nz &= nz - 1;
+                const int s1 = nz ? __ffs(nz) - 1 : s0;
+                nz &= nz - 1;                                    // no-op when nz was already 0
+                const unsigned w0 = __shfl_sync(0xffffffffu, myword, s0);
+                const unsigned w1 = s1 != s0 ? __shfl_sync(0xffffffffu, myword, s1) : 0u;
+                const int64_t g0_ = (gw + (k0 + s0) * (int64_t)W) * 32 + lane, g1_ = (gw + (k0 + s1) * (int64_t)W) * 32 + lane;
+                unsigned pc0 = 0, pc1 = 0;
+                Word8 a, c;
+                if ((w0 >> lane) & 1u) a = ld_cg_256(A.groups + (size_t)g0_ * 8);
+                if ((w1 >> lane) & 1u) c = ld_cg_256(A.groups + (size_t)g1_ * 8);
+                if ((w0 >> lane) & 1u) pc0 = group_popc(a);
+                if ((w1 >> lane) & 1u) pc1 = group_popc(c);
+                pc0 = warp_sum_u32(pc0);
+                pc1 = warp_sum_u32(pc1);
+                if ((int)lane == s0) mycnt = pc0;
+                if ((int)lane == s1 && s1 != s0) mycnt = pc1;
             }
-            A.l1cnt[lw] = cnt;
+            if (mylw < l1_used) A.l1cnt[mylw] = mycnt;
         }
         fused_grid_barrier(&A.ctrl->grid_bar_b, (unsigned)G);
         const int64_t lchunk = (lpc + T - 1) / T;
@@ -1296,16 +1315,34 @@ k_frame_fused(const FusedArgs A) {
                 }
                 __syncthreads();
             }
-            for (int64_t lw = (int64_t)tid * G + b; lw < l1_used; lw += (int64_t)G * T) {   // word w -> CTA w % G
-                unsigned word = __ldcg(A.l1 + lw);
-                if (!word) continue;
-                unsigned run = s_cta_base[(int)(lw / lpc)] + __ldcg(A.l1cnt + lw);
-                while (word) {
-                    const int64_t g = lw * 32 + (__ffs(word) - 1);
-                    word &= word - 1;
-                    const unsigned pc = group_popc(ld_cg_256(A.groups + (size_t)g * 8));
-                    A.groups[(size_t)g * 8] = run;
-                    run += pc;
+            const int W = G * nwarp, gw = warp * G + b;
+            for (int64_t k0 = 0; gw + k0 * W < l1_used; k0 += 32) {
+                const int64_t mylw = gw + (k0 + lane) * (int64_t)W;
+                const unsigned myword = mylw < l1_used ? __ldcg(A.l1 + mylw) : 0u;
+                const unsigned mybase = myword ? s_cta_base[(int)(mylw / lpc)] + __ldcg(A.l1cnt + mylw) : 0u;
+                unsigned nz = __ballot_sync(0xffffffffu, myword != 0u);
+                while (nz) {
+                    const int s0 = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    const int s1 = nz ? __ffs(nz) - 1 : s0;
+                    nz &= nz - 1;
+                    const unsigned w0 = __shfl_sync(0xffffffffu, myword, s0);
+                    const unsigned w1 = s1 != s0 ? __shfl_sync(0xffffffffu, myword, s1) : 0u;
+                    const unsigned b0 = __shfl_sync(0xffffffffu, mybase, s0), b1 = __shfl_sync(0xffffffffu, mybase, s1);
+                    const int64_t g0_ = (gw + (k0 + s0) * (int64_t)W) * 32 + lane, g1_ = (gw + (k0 + s1) * (int64_t)W) * 32 + lane;
+                    const bool on0 = (w0 >> lane) & 1u, on1 = (w1 >> lane) & 1u;
+                    Word8 a, c;
+                    if (on0) a = ld_cg_256(A.groups + (size_t)g0_ * 8);
+                    if (on1) c = ld_cg_256(A.groups + (size_t)g1_ * 8);
+                    const unsigned pc0 = on0 ? group_popc(a) : 0u, pc1 = on1 ? group_popc(c) : 0u;
+                    unsigned i0 = pc0, i1 = pc1;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+                        if (lane >= (unsigned)o) { i0 += t0; i1 += t1; }
+                    }
+                    if (on0) A.groups[(size_t)g0_ * 8] = b0 + i0 - pc0;
+                    if (on1) A.groups[(size_t)g1_ * 8] = b1 + i1 - pc1;
                 }
             }
         }

@@ -351,8 +351,10 @@ class HostFramePipeline:
     """
 
     def __init__(self, max_points: int, voxel_size: float, grid_size: float = 0.0, slots: int = 2,
-                 per_point_outputs: bool = True, unique_keys: bool = False, **caps):
+                 per_point_outputs: bool = True, unique_keys: bool = False, scan_order: bool | str = "auto", **caps):
         self.device = require_cuda()
+        self.scan_order = scan_order          # as in FramePipeline: False / True / "auto" (from the last descriptor)
+        self._scan_hint = False
         self.per_point_outputs = per_point_outputs
         self.unique_keys = unique_keys
         self.voxel_size, self.grid_size = float(voxel_size), float(grid_size)
@@ -419,6 +421,9 @@ class HostFramePipeline:
         slot["src"] = h_in                  # keep the source alive until the copy-in has run
         o3 = (C.c_double * 3)(*[float(v) for v in origin]) if origin is not None else None
         r4 = (C.c_double * 4)(*[float(v) for v in xy_range]) if xy_range is not None else None
+        if self.scan_order is not None:
+            want = self._scan_hint if self.scan_order == "auto" else bool(self.scan_order)
+            check(lib.lidar_frame_set_fused_scan_order(1 if want else 0))
         try:
             check(lib.lidar_frame_voxel_density_host(h_in.data_ptr(), n, self.voxel_size, self.grid_size, o3, r4,
                                                      _ptr(slot["d_in"]), _ptr(slot["d_vox"]), _ptr(slot["d_out"]),
@@ -445,6 +450,7 @@ class HostFramePipeline:
             slot["stream"].synchronize()
             raise _capi.LidarError(int(desc.status), "frame exceeded its capacities")
         v = int(desc.n_voxels)
+        self._scan_hint = n > 0 and (2 * ((int(desc.key_space) + 223) // 224) > 3 * n or 2 * v < n)
         cp = (lambda a: a.copy()) if copy else (lambda a: a)
 
         def arr(k, dtype, count):
