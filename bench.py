@@ -181,7 +181,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=1_000_000)
-    ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--e2e-slots", type=int, default=3, help="frames in flight in the end-to-end leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="frame kernel grid cap (0 = library default)")
