@@ -26,13 +26,18 @@ bbox_kernel(Loader L, int64_t n, double* __restrict__ out8, ReduceWs* __restrict
     double mn[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
     double mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Pt p = L.load(i);
+    auto fold = [&](const Pt& p) {
         mn[0] = fmin(mn[0], p.x); mx[0] = fmax(mx[0], p.x);
         mn[1] = fmin(mn[1], p.y); mx[1] = fmax(mx[1], p.y);
         mn[2] = fmin(mn[2], p.z); mx[2] = fmax(mx[2], p.z);
         mn[3] = fmin(mn[3], p.w); mx[3] = fmax(mx[3], p.w);
+    };
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {      // four points (12 loads of the fp64 layout) in flight
+        const Pt a = L.load(i), b = L.load(i + stride), c = L.load(i + 2 * stride), d = L.load(i + 3 * stride);
+        fold(a); fold(b); fold(c); fold(d);
     }
+    for (; i < n; i += stride) fold(L.load(i));
     __shared__ double s_mn[kRedThreads / 32][4];
     __shared__ double s_mx[kRedThreads / 32][4];
     __shared__ bool s_last;
@@ -147,12 +152,18 @@ moments_kernel(Loader L, int64_t n, double cx, double cy, double cz, double* __r
                ReduceWs* __restrict__ ws) {
     double s[6] = {0, 0, 0, 0, 0, 0};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        Pt p = L.load(i);
+    auto fold = [&](const Pt& p) {
         const double dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
         s[0] += dx; s[1] += dy; s[2] += dz;
         s[3] += __dmul_rn(dx, dx); s[4] += __dmul_rn(dy, dy); s[5] += __dmul_rn(dz, dz);
+    };
+    // the loads of four points are issued together; the adds stay in index order (same sums as the plain loop)
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        const Pt a = L.load(i), b = L.load(i + stride), c = L.load(i + 2 * stride), d = L.load(i + 3 * stride);
+        fold(a); fold(b); fold(c); fold(d);
     }
+    for (; i < n; i += stride) fold(L.load(i));
     __shared__ double s_p[kRedThreads / 32][6];
     __shared__ bool s_last;
     const int warp = threadIdx.x >> 5;
