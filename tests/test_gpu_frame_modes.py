@@ -205,6 +205,31 @@ def test_host_frame_pipeline_numpy_in_numpy_out(ops, synth, pinned):
         assert np.array_equal(out["grid_counts"], wc)
 
 
+def test_host_frame_pipeline_sensor_frames_auto_variant(ops, synth):
+    """Scan-ordered 128-beam frames through the host-buffer surface: after the first descriptor comes back the
+    pipeline switches itself to the scan-order variant of the kernel; every integer output still equals the oracle's."""
+    ops.set_frame_mode(ops.FRAME_FUSED, 512, 1, 0)
+    frames = [synth.ring_sequence_frame(i, rings=48, azimuth_steps=4096) for i in range(3)]
+    cap = max(len(f) for f in frames)
+    hp = ops.HostFramePipeline(max_points=cap, voxel_size=0.05, grid_size=0.5, slots=2, unique_keys=True,
+                               max_key_space=(1 << 31) - 1, max_nx=1024, max_ny=1024)
+    seen = []
+    for f in frames:
+        out = hp.process(f)
+        seen.append(int(out["desc"].trace_ns[14]))
+        want = new_ops.voxel_downsample(f, 0.05)
+        assert out["n_voxels"] == len(want["unique_keys"])
+        assert np.array_equal(out["inverse"], want["inverse"]) and np.array_equal(out["voxel_key"], want["voxel_key"])
+        assert np.array_equal(out["counts"], want["counts"]) and np.array_equal(out["unique_keys"], want["unique_keys"])
+        assert np.allclose(out["centroids"], want["centroids"], rtol=1e-6, atol=1e-7)
+        xyz = f[:, :3].astype(np.float64)
+        wc, _, _ = ref_path.grid_density_counts(xyz[:, :2], (xyz[:, 0].min(), xyz[:, 0].max()),
+                                                (xyz[:, 1].min(), xyz[:, 1].max()), 0.5)
+        assert np.array_equal(out["grid_counts"], wc)
+    assert seen == [0, 1, 1]
+    ops.set_frame_scan_order(False)
+
+
 def test_streaming_mode_back_to_back_frames_equal_cooperative(ops, synth):
     """Streaming mode (ordinary launch + programmatic dependent launch: the next frame's load runs under the
     current frame's tail) must leave every output untouched.  Different frames are enqueued back to back on one
