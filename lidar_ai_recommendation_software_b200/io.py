@@ -14,13 +14,40 @@ import numpy as np
 import pandas as pd
 
 
+def _ascii_rows_exact(text: str, max_rows: int | None = None) -> np.ndarray:
+    """The reference's own loop (utils/data_processing.py:66-74, 96-105): the first three fields of every
+    non-empty line that has at least three; `max_rows` limits the LINES looked at, like its `range`."""
+    lines = text.splitlines()
+    if max_rows is not None:
+        lines = lines[:max_rows]
+    rows = []
+    for line in lines:
+        line = line.strip()
+        if line:
+            values = line.split()
+            if len(values) >= 3:
+                rows.append([float(v) for v in values[:3]])
+    return np.array(rows)
+
+
 def _ascii_rows(text: str, max_rows: int | None = None) -> np.ndarray:
-    """First three whitespace-separated numeric columns of every non-empty line with >= 3 fields."""
+    """First three whitespace-separated numeric columns of every non-empty line with >= 3 fields: a vectorised
+    tokenizer for the regular case, the reference's loop whenever a line is short, blank inside a counted range, or
+    holds something pandas would read as missing (so the result is the reference's in every case)."""
     if not text.strip():
         return np.empty((0, 3))
-    df = pd.read_csv(_io.StringIO(text), sep=r"\s+", header=None, usecols=[0, 1, 2], dtype=np.float64,
-                     engine="c", nrows=max_rows, on_bad_lines="skip", skip_blank_lines=True)
-    return df.to_numpy(dtype=np.float64)
+    body = text if max_rows is None else "\n".join(text.splitlines()[:max_rows])
+    regular = max_rows is None or "\n\n" not in body.strip("\n")
+    if regular:
+        try:
+            df = pd.read_csv(_io.StringIO(body), sep=r"\s+", header=None, usecols=[0, 1, 2], dtype=np.float64,
+                             engine="c", skip_blank_lines=True)
+            arr = df.to_numpy(dtype=np.float64)
+            if not np.isnan(arr).any():
+                return arr
+        except Exception:
+            pass
+    return _ascii_rows_exact(text, max_rows)
 
 
 def _load_pcd(path: str) -> np.ndarray:

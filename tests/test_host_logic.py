@@ -64,3 +64,27 @@ def test_loader_formats(tmp_path):
         load_lidar_data(str(tmp_path / "nope.xyz"))
     with pytest.raises(Exception, match="Unsupported file format"):
         load_lidar_data(str(tmp_path / "a.bin"))
+
+
+def test_loader_matches_reference_fixtures():
+    """Every format the reference's load_lidar_data reads (utils/data_processing.py:8-125): the arrays the UNMODIFIED
+    reference returned for the files under tests/golden/loader (made by tests/golden/make_golden_loader.py), bit for
+    bit; inputs the reference rejects must be rejected with the same wrapped message."""
+    from pathlib import Path
+    import warnings
+    from lidar_ai_recommendation_software_b200.io import load_lidar_data
+    d = Path(__file__).resolve().parent / "golden" / "loader"
+    exp = np.load(d / "expected.npz", allow_pickle=False)
+    assert len(exp.files) == 10
+    for key in exp.files:
+        if key.endswith(":error"):
+            name = key[: -len(":error")]
+            with pytest.raises(Exception) as ei, warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                load_lidar_data(str(d / name))
+            assert str(ei.value).startswith("Failed to load point cloud file:")
+            if name.endswith(".las"):
+                assert str(ei.value) == str(exp[key])
+        else:
+            got = np.asarray(load_lidar_data(str(d / key)), dtype=np.float64)
+            assert got.shape == exp[key].shape and np.array_equal(got, exp[key]), key
