@@ -332,6 +332,15 @@ def test_downsample_point_cloud_contract(pkg):
     assert all(tuple(r) in rows for r in out) and len({tuple(r) for r in out}) == 100
     assert pkg.dp.downsample_point_cloud(pts, 1.0) is pts
     assert pkg.dp.downsample_point_cloud(pts, 1e-9).shape == (1, 3)
+    # the draw is the reference's own expression on the GLOBAL legacy RNG (utils/data_processing.py:245-249): with
+    # the same seed the result is the reference's, row for row, and the RNG is left in the same state
+    big = np.random.default_rng(1).normal(size=(200_000, 3))
+    np.random.seed(123)
+    got = pkg.dp.downsample_point_cloud(big, 0.1)
+    after = np.random.random()
+    np.random.seed(123)
+    want = big[np.random.choice(len(big), max(1, int(len(big) * 0.1)), replace=False)]
+    assert np.array_equal(got, want) and after == np.random.random()
 
 
 def test_frame_flow_matches_oracle(pkg):
