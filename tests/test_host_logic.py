@@ -88,3 +88,36 @@ def test_loader_matches_reference_fixtures():
         else:
             got = np.asarray(load_lidar_data(str(d / key)), dtype=np.float64)
             assert got.shape == exp[key].shape and np.array_equal(got, exp[key]), key
+
+
+def test_windows_data_loader_matches_reference_fixtures():
+    """The desktop shell's DataLoader (windows_implementation/core/data_loader.py:30-447): points, metadata and
+    exceptions of the UNMODIFIED reference for every fixture file (tests/golden/make_golden_loader.py)."""
+    import json
+    import logging
+    import warnings
+    from pathlib import Path
+    from lidar_ai_recommendation_software_b200.windows_core.data_loader import DataLoader, Dataset
+    logging.disable(logging.CRITICAL)
+    try:
+        d = Path(__file__).resolve().parent / "golden" / "loader"
+        exp = np.load(d / "expected_dataloader.npz", allow_pickle=False)
+        names = sorted({k.split(":")[0] for k in exp.files})
+        assert len(names) == 20
+        for name in names:
+            if name + ":error" in exp.files:
+                with pytest.raises(Exception) as ei, warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    DataLoader().load_file(str(d / name))
+                got = type(ei.value).__name__ + ": " + str(ei.value).replace(str(d), "<dir>")
+                assert got == str(exp[name + ":error"]), name
+            else:
+                ds = DataLoader().load_file(str(d / name))
+                assert isinstance(ds, Dataset)
+                pts = np.asarray(ds.points, dtype=np.float64)
+                assert pts.shape == exp[name].shape and np.array_equal(pts, exp[name], equal_nan=True), name
+                assert ds.metadata["file_path"] == str(d / name)
+                meta = {k: v for k, v in ds.metadata.items() if k != "file_path"}
+                assert json.loads(json.dumps(meta, sort_keys=True)) == json.loads(str(exp[name + ":meta"])), name
+    finally:
+        logging.disable(logging.NOTSET)
