@@ -120,6 +120,34 @@ def test_fused_scan_order_variant_equals_default_and_oracle(ops, synth):
     ops.set_frame_scan_order(False)
 
 
+def test_back_ends_alternate_freely_on_one_pipeline(ops, synth):
+    """40 frames of different sizes and extents through ONE pipeline while the back end changes at random between the
+    default fused variant (which alternates two occupancy bitmaps and leaves the cleaning of one to the next frame), the
+    scan-order variant and the five-kernel path: whatever the order, every frame's outputs equal a fresh pipeline's."""
+    rng = np.random.default_rng(77)
+    shapes = [(60_000, 12.0), (200_000, 30.0), (5_000, 40.0), (120_000, 8.0), (1, 1.0), (33_000, 50.0)]
+    frames = [synth.crowd_frame(n, seed=100 + i, extent=e) for i, (n, e) in enumerate(shapes)]
+    dev_frames = [torch.from_numpy(f).cuda() for f in frames]
+    cap = max(n for n, _ in shapes)
+    kw = dict(max_points=cap, voxel_size=0.05, grid_size=0.5, max_key_space=1 << 28, max_nx=512, max_ny=512, scan_order=None)
+    ref_pipe = ops.FramePipeline(**kw)
+    want = []
+    ops.set_frame_scan_order(False)
+    for d in dev_frames:
+        want.append(run(ops, ref_pipe, d, (1, 0, 0, 0)))
+        ref_pipe.reset()
+    pipe = ops.FramePipeline(**kw)
+    try:
+        for step in range(40):
+            i = int(rng.integers(len(frames)))
+            mode = int(rng.integers(3))
+            ops.set_frame_scan_order(mode == 1)
+            got = run(ops, pipe, dev_frames[i], (1, 0, 0, 0) if mode == 2 else (2, 512, 1, 0))
+            same(want[i], got)
+    finally:
+        ops.set_frame_scan_order(False)
+
+
 def test_fused_origin_range_and_duplicates(ops, synth):
     pts = synth.crowd_frame(5000, seed=1, extent=3.0)
     pts = np.concatenate([pts, pts[:1000]])
