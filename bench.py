@@ -32,6 +32,14 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+# The contract is ONE JSON line on stdout, but libraries write there too (torch's NCCL process group announces
+# "NCCL version ..." on fd 1 at the first collective).  Everything that is not the result line goes to stderr.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: str) -> None:
+    os.write(_RESULT_FD, (line + "\n").encode())
 
 VOXEL = 0.05
 GRID = 0.5
@@ -171,7 +179,7 @@ def run_reference(args, rank: int):
         "e2e": {"value": val, "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def main():
@@ -414,7 +422,7 @@ def main():
             "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": (1 if fused else 5) * args.steps, "clocks": clk,
         }
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

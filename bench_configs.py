@@ -26,6 +26,14 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+# The contract is ONE JSON line on stdout, but libraries write there too (torch's NCCL process group announces
+# "NCCL version ..." on fd 1 at the first collective).  Everything that is not the result line goes to stderr.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: str) -> None:
+    os.write(_RESULT_FD, (line + "\n").encode())
 
 
 def peaks():
@@ -102,7 +110,7 @@ def run_surfaces(args, torch, dev):
                                           "calculate_grid_density_points_1000k": 166.0, "histogram2d_bins100_1000k": 152.0,
                                           "downsample_point_cloud_1000k": 38.0,
                                           "preprocess_lidar_data_1000k": "infeasible (sklearn neighbour lists ~50 GB)"}}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def run_sa(args, torch, dev, rank, world):
@@ -149,7 +157,7 @@ def run_sa(args, torch, dev, rank, world):
         "Mpoints_per_s_input": B * N / (t_all * 1e-3) / 1e6,
         "out_bytes": B * 128 * M * 4,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def run_seq(args, torch, dev, rank, world, dist):
@@ -260,7 +268,7 @@ def run_seq(args, torch, dev, rank, world, dist):
             "timing": "host wall clock around the per-frame drop-in calls (numpy in / numpy out, copies included), max over ranks",
             "synth_s_per_frame_host": gen_s / max(1, pool_n), "data": "synthetic (Appendix C.3)", "scaling": "strong",
         }
-        print(json.dumps(line))
+        emit(json.dumps(line))
 
 
 def run_scan(args, torch, dev, rank, world, dist):
@@ -328,7 +336,7 @@ def run_scan(args, torch, dev, rank, world, dist):
             "timing": "call = host wall clock around sharding.sharded_grid_density (median), kernels = CUDA events; max over ranks",
             "synth_s_host": gen_s, "data": "synthetic (Appendix C.4)", "scaling": "strong",
         }
-        print(json.dumps(line))
+        emit(json.dumps(line))
 
 
 def main():
