@@ -20,6 +20,27 @@ struct ReduceWs {
     unsigned int ticket;
 };
 
+// The last CTA folds the per-CTA partials.  All 256 threads take part -- thread t folds channel t % 8 of the CTAs
+// t / 8, t / 8 + 32, ... and the 32 partial results of a channel are then folded in a fixed order -- instead of
+// eight threads walking up to 592 partials one dependent L2 load at a time (that tail was most of the launch on
+// a 1 M-point cloud).  The order is fixed by the launch shape, so results stay deterministic.
+template <class Op>
+__device__ __forceinline__ void fold_partials(const ReduceWs* ws, int channels, double identity, Op op, double* out) {
+    __shared__ double s_fold[32][8];
+    const int ch = threadIdx.x & 7, row = threadIdx.x >> 3;       // kRedThreads == 256: 32 rows of 8 channels
+    double v = identity;
+    if (ch < channels)
+        for (unsigned b = row; b < gridDim.x; b += 32) v = op(v, __ldcg(&ws->partial[b][ch]), ch);
+    s_fold[row][ch] = v;
+    __syncthreads();
+    if (threadIdx.x < channels) {
+        double r = s_fold[0][threadIdx.x];
+        for (int k = 1; k < 32; ++k) r = op(r, s_fold[k][threadIdx.x], (int)threadIdx.x);
+        out[threadIdx.x] = r;
+    }
+}
+static_assert(kRedThreads == 256, "fold_partials assumes 32 rows of 8 channels");
+
 template <class Loader>
 __global__ void __launch_bounds__(kRedThreads)
 bbox_kernel(Loader L, int64_t n, double* __restrict__ out8, ReduceWs* __restrict__ ws) {
@@ -71,14 +92,9 @@ bbox_kernel(Loader L, int64_t n, double* __restrict__ out8, ReduceWs* __restrict
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (threadIdx.x < 8) {
-        const bool is_max = threadIdx.x >= 4;
-        double v = is_max ? -INFINITY : INFINITY;
-        for (unsigned b = 0; b < gridDim.x; ++b) {
-            double q = ((volatile double*)ws->partial[b])[threadIdx.x];
-            v = is_max ? fmax(v, q) : fmin(v, q);
-        }
-        out8[threadIdx.x] = v;
+    {
+        const double ident = (threadIdx.x & 7) >= 4 ? -INFINITY : INFINITY;
+        fold_partials(ws, 8, ident, [](double a, double q, int ch) { return ch >= 4 ? fmax(a, q) : fmin(a, q); }, out8);
     }
     if (threadIdx.x == 0) ws->ticket = 0u;
 }
@@ -132,14 +148,9 @@ bbox_f32x4_kernel(LoadF32x4 L, int64_t n, double* __restrict__ out8, ReduceWs* _
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (threadIdx.x < 8) {
-        const bool is_max = threadIdx.x >= 4;
-        double v = is_max ? -INFINITY : INFINITY;
-        for (unsigned b = 0; b < gridDim.x; ++b) {
-            const double q = ((volatile double*)ws->partial[b])[threadIdx.x];
-            v = is_max ? fmax(v, q) : fmin(v, q);
-        }
-        out8[threadIdx.x] = v;
+    {
+        const double ident = (threadIdx.x & 7) >= 4 ? -INFINITY : INFINITY;
+        fold_partials(ws, 8, ident, [](double a, double q, int ch) { return ch >= 4 ? fmax(a, q) : fmin(a, q); }, out8);
     }
     if (threadIdx.x == 0) ws->ticket = 0u;
 }
@@ -188,11 +199,7 @@ moments_kernel(Loader L, int64_t n, double cx, double cy, double cz, double* __r
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (threadIdx.x < 6) {
-        double v = 0;
-        for (unsigned b = 0; b < gridDim.x; ++b) v += ((volatile double*)ws->partial[b])[threadIdx.x];
-        out6[threadIdx.x] = v;
-    }
+    fold_partials(ws, 6, 0.0, [](double a, double q, int) { return a + q; }, out6);
     if (threadIdx.x == 0) ws->ticket = 0u;
 }
 
