@@ -164,7 +164,9 @@ ground_split_kernel(const double* __restrict__ pts, int64_t n, double thr, doubl
 }
 
 // ------------------------------------------------------------------------------------------------
-// radix select on fp64 keys (8 passes of 8 bits), state kept on the device
+// radix select on fp64 keys (8 passes of 8 bits), state kept on the device.  Passes 0 and 1 read the column; the keys
+// that carry the winning 16-bit prefix (a few per cent of a height column) are then compacted, and passes 2..7 run on
+// that buffer instead of re-reading the whole column six more times.
 // ------------------------------------------------------------------------------------------------
 struct SelectState {
     unsigned long long prefix;   // key bits fixed so far (high bits)
@@ -175,6 +177,7 @@ struct SelectState {
     // second order statistic
     unsigned long long count_le; // #elements <= kth
     unsigned long long min_gt;   // smallest key > kth (key space)
+    unsigned long long n_buf;    // keys that survived the first two passes (compacted, see select_compact_kernel)
 };
 
 __device__ __forceinline__ unsigned long long f64_key(double d) {
@@ -187,6 +190,31 @@ __device__ __forceinline__ double key_f64(unsigned long long k) {
 }
 
 constexpr int kSelThreads = 256;
+
+// Last CTA of a pass: the digit whose bucket holds rank k.  One thread per digit and a block-wide scan of the 256
+// counts (a single thread walking them with dependent loads took ~10 us per pass -- most of a pass on 1 M keys).
+__device__ __forceinline__ void select_pick_digit(SelectState* st, unsigned long long prefix) {
+    __shared__ unsigned s_w[kSelThreads / 32];
+    const unsigned c = ((volatile unsigned*)st->hist)[threadIdx.x];     // kSelThreads == 256 == digits
+    const long long k = st->k;
+    unsigned inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane_id() >= (unsigned)o) inc += t;
+    }
+    if (lane_id() == 31) s_w[threadIdx.x >> 5] = inc;
+    __syncthreads();                                  // also: every thread has read st->k before anyone writes it
+    unsigned off = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) off += s_w[w];
+    const long long hi = (long long)off + inc, lo = hi - c;
+    if ((k >= lo && k < hi) || (threadIdx.x == 255 && k >= hi)) {
+        st->k = k >= hi ? k - hi : k - lo;
+        st->prefix = (prefix << 8) | (unsigned long long)threadIdx.x;
+    }
+    st->hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) st->ticket = 0;
+}
 
 __global__ void __launch_bounds__(kSelThreads)
 select_pass_kernel(const double* __restrict__ col, int64_t stride_el, int64_t n, int pass, SelectState* st) {
@@ -210,20 +238,57 @@ select_pass_kernel(const double* __restrict__ col, int64_t stride_el, int64_t n,
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (threadIdx.x == 0) {
-        long long k = st->k;
-        int d = 0;
-        for (; d < 256; ++d) {
-            const long long c = (long long)((volatile unsigned*)st->hist)[d];
-            if (k < c) break;
-            k -= c;
+    select_pick_digit(st, prefix);
+}
+
+// keys whose top 16 bits equal the prefix fixed by passes 0 and 1 -> buf (order irrelevant: later passes only count)
+__global__ void __launch_bounds__(kSelThreads)
+select_compact_kernel(const double* __restrict__ col, int64_t stride_el, int64_t n, SelectState* st,
+                      unsigned long long* __restrict__ buf) {
+    const unsigned long long prefix = st->prefix;     // 16 bits
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_round = ((n + 31) / 32) * 32;     // whole warps stay in the loop for the ballot
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += step) {
+        unsigned long long key = 0ull;
+        bool keep = false;
+        if (i < n) {
+            key = f64_key(__ldg(col + i * stride_el));
+            keep = (key >> 48) == prefix;
         }
-        if (d > 255) d = 255;
-        st->k = k;
-        st->prefix = (prefix << 8) | (unsigned long long)d;
-        for (int j = 0; j < 256; ++j) st->hist[j] = 0;
-        st->ticket = 0;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+            unsigned long long base = 0ull;
+            if (lane_id() == 0) base = atomicAdd(&st->n_buf, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) buf[base + __popc(m & lanemask_lt())] = key;
+        }
     }
+}
+
+// passes 2..7 on the compacted keys
+__global__ void __launch_bounds__(kSelThreads)
+select_pass_buf_kernel(const unsigned long long* __restrict__ buf, int pass, SelectState* st) {
+    __shared__ unsigned s_hist[256];
+    __shared__ bool s_last;
+    s_hist[threadIdx.x] = 0;  // kSelThreads == 256
+    __syncthreads();
+    const unsigned long long prefix = st->prefix;
+    const int64_t n = (int64_t)st->n_buf;
+    const int shift = 56 - 8 * pass;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const unsigned long long key = __ldcg(buf + i);
+        if ((key >> (shift + 8)) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xff], 1u);
+    }
+    __syncthreads();
+    if (s_hist[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], s_hist[threadIdx.x]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    select_pick_digit(st, prefix);
 }
 
 __global__ void __launch_bounds__(kSelThreads)
@@ -268,7 +333,7 @@ select_next_kernel(const double* __restrict__ col, int64_t stride_el, int64_t n,
 __global__ void select_init_kernel(SelectState* st, int64_t k) {
     if (threadIdx.x < 256) st->hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
-        st->prefix = 0; st->k = k; st->ticket = 0; st->pad = 0; st->count_le = 0; st->min_gt = ~0ull;
+        st->prefix = 0; st->k = k; st->ticket = 0; st->pad = 0; st->count_le = 0; st->min_gt = ~0ull; st->n_buf = 0ull;
     }
 }
 
@@ -340,7 +405,7 @@ extern "C" {
 
 size_t lidar_preprocess_workspace_bytes(int64_t n) {
     size_t a = pre_layout(n < 0 ? 0 : n).total;
-    size_t b = ws_align(sizeof(SelectState));
+    size_t b = ws_align(sizeof(SelectState)) + ws_align(sizeof(unsigned long long) * (size_t)(n < 0 ? 0 : n));   // + compaction buffer
     return a > b ? a : b;
 }
 
@@ -414,9 +479,26 @@ int lidar_select_kth(const double* d_column, int64_t stride_elems, int64_t n, in
     int grid = (int)((n + kSelThreads * 8 - 1) / (kSelThreads * 8));
     const int cap = sm_count() * 8;
     grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
-    for (int pass = 0; pass < 8; ++pass) {
-        select_pass_kernel<<<grid, kSelThreads, 0, st>>>(d_column, stride_elems, n, pass, S);
+    const size_t buf_off = ws_align(sizeof(SelectState));
+    const bool buffered = ws_bytes >= buf_off + sizeof(unsigned long long) * (size_t)n && n >= 65536;
+    if (buffered) {
+        unsigned long long* buf = reinterpret_cast<unsigned long long*>(static_cast<char*>(d_ws) + buf_off);
+        for (int pass = 0; pass < 2; ++pass) {
+            select_pass_kernel<<<grid, kSelThreads, 0, st>>>(d_column, stride_elems, n, pass, S);
+            LIDAR_CHECK_LAUNCH();
+        }
+        select_compact_kernel<<<grid, kSelThreads, 0, st>>>(d_column, stride_elems, n, S, buf);
         LIDAR_CHECK_LAUNCH();
+        const int bgrid = grid < sm_count() ? grid : sm_count();      // the buffer is small: one CTA per SM at most
+        for (int pass = 2; pass < 8; ++pass) {
+            select_pass_buf_kernel<<<bgrid, kSelThreads, 0, st>>>(buf, pass, S);
+            LIDAR_CHECK_LAUNCH();
+        }
+    } else {
+        for (int pass = 0; pass < 8; ++pass) {
+            select_pass_kernel<<<grid, kSelThreads, 0, st>>>(d_column, stride_elems, n, pass, S);
+            LIDAR_CHECK_LAUNCH();
+        }
     }
     select_next_kernel<<<grid, kSelThreads, 0, st>>>(d_column, stride_elems, n, k, S, d_out2);
     LIDAR_CHECK_LAUNCH();

@@ -190,6 +190,15 @@ def test_select_kth_matches_sort(pkg):
             assert a == s[k] and b == s[min(k + 1, n - 1)]
         thr = pkg.pre.percentile_from_order_stats(*pkg.ops.select_kth(d[:, 2], int(np.floor((n - 1) * 0.3))), n, 30)
         assert thr == float(np.percentile(x[:, 2], 30))
+    # the buffered path (n >= 65536: keys with the winning 16-bit prefix are compacted after two passes) on degenerate
+    # columns: every value equal (the buffer holds all of them), two values, a height column with heavy ties
+    for col in (np.full(70_000, 1.25), np.repeat([0.5, -0.5], 40_000), np.round(rng.uniform(0, 2, 300_000), 2)):
+        d = torch.from_numpy(np.column_stack([col, col, col])).cuda()
+        s = np.sort(col)
+        n = len(col)
+        for k in sorted({0, n // 3, n // 2, n - 2, n - 1}):
+            a, b = pkg.ops.select_kth(d[:, 2], k)
+            assert a == s[k] and b == s[min(k + 1, n - 1)]
 
 
 @pytest.mark.parametrize("eps,seed", [(0.3, 0), (0.5, 1), (0.15, 2), (1.5, 3)])
