@@ -143,6 +143,43 @@ int lidar_gather_rows(const void* d_src, int64_t n_rows, int row_bytes, const in
 int lidar_scatter_labels(const int32_t* d_labels, const int32_t* d_index, int64_t m, int64_t* d_full, int64_t n,
                          void* stream);
 
+/* The stages above as ONE enqueue without host round trips (every scalar one stage hands to the next -- mean, std,
+ * thresholds, the inlier count, the percentile rank and its lerp, the scaler statistics, eps -- stays on the device,
+ * computed with the same float64 expressions the host path uses):
+ *   bbox + mean/std of the raw cloud (data_processing.py:143,151-152) -> 3-sigma filter + colours (:153-157) ->
+ *   30th-percentile of the inlier heights (:164) -> ground split + plane sums + bbox of the inliers and of the
+ *   non-ground points (:165-188, 207-208) -> with LIDAR_FRONT_SCALER: StandardScaler statistics, the scaled copy and
+ *   the adaptive eps (:190-196).
+ * Every output array has capacity n rows; the valid row counts are d_front->n_in / n_nonground.  The caller copies
+ * *d_front back once (sizeof(lidar_front_desc)) and checks n_in > 0.  key_in / key_ng are scratch. */
+typedef struct lidar_front_desc {
+    double bbox_raw[8];      /* lidar_bbox of the raw cloud: min x,y,z,(w) then max x,y,z,(w) */
+    double sum1[6];          /* lidar_moments about 0 */
+    double mean[3];
+    double sum2[6];          /* lidar_moments about mean */
+    double std[3], thr[3], tol[3];
+    double zmin, zden;
+    int64_t n_in;            /* inliers */
+    uint64_t guard_sigma;
+    double kth[2];           /* z_(lo), z_(lo+1) of the inliers */
+    double z_thr;            /* np.percentile(z, 30) */
+    int64_t n_nonground;
+    uint64_t guard_ground;
+    double plane[10];        /* lidar_ground_split sums about mean */
+    double bbox_in[6];       /* min xyz, max xyz of the inliers */
+    double bbox_ng[6];       /* ... of the non-ground points */
+    double t1[6], sc_mean[3], t2[6], scale[3];   /* StandardScaler.fit of the non-ground points */
+    double u1[6], xm[3], u2[6], xstd[3];         /* np.std of the scaled points */
+    double eps;
+    uint64_t key_in[6], key_ng[6];
+} lidar_front_desc;
+#define LIDAR_FRONT_COLORS 1
+#define LIDAR_FRONT_SCALER 2
+size_t lidar_preprocess_front_workspace_bytes(int64_t n);
+int lidar_preprocess_front(const double* d_points, int64_t n, int flags, double* d_inliers, double* d_colors,
+                           double* d_nonground, int32_t* d_ng_index, double* d_scaled, lidar_front_desc* d_front,
+                           void* d_ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------- *
  * K7  DBSCAN with scikit-learn-identical labels (sklearn 1.9.0 DBSCAN(eps, min_samples).fit(X).labels_;
  *     data_processing.py:197, app_simplified.py:107).  d_points (m,3) fp64; h_min3/h_max3 = bbox of

@@ -69,8 +69,27 @@ class FrameCaps(C.Structure):
     ]
 
 
+class FrontDesc(C.Structure):
+    """Mirror of `lidar_front_desc`: every scalar the chained preprocess leaves on the device."""
+
+    _fields_ = [
+        ("bbox_raw", C.c_double * 8), ("sum1", C.c_double * 6), ("mean", C.c_double * 3), ("sum2", C.c_double * 6),
+        ("std", C.c_double * 3), ("thr", C.c_double * 3), ("tol", C.c_double * 3),
+        ("zmin", C.c_double), ("zden", C.c_double),
+        ("n_in", C.c_int64), ("guard_sigma", C.c_uint64),
+        ("kth", C.c_double * 2), ("z_thr", C.c_double),
+        ("n_nonground", C.c_int64), ("guard_ground", C.c_uint64),
+        ("plane", C.c_double * 10), ("bbox_in", C.c_double * 6), ("bbox_ng", C.c_double * 6),
+        ("t1", C.c_double * 6), ("sc_mean", C.c_double * 3), ("t2", C.c_double * 6), ("scale", C.c_double * 3),
+        ("u1", C.c_double * 6), ("xm", C.c_double * 3), ("u2", C.c_double * 6), ("xstd", C.c_double * 3),
+        ("eps", C.c_double),
+        ("key_in", C.c_uint64 * 6), ("key_ng", C.c_uint64 * 6),
+    ]
+
+
 _vp, _i32, _i64, _sz, _dbl = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
 HOST_UNIQUE_KEYS, HOST_NO_PER_POINT = 1, 2     # flags of lidar_frame_voxel_density_host
+FRONT_COLORS, FRONT_SCALER = 1, 2              # flags of lidar_preprocess_front
 
 # name -> (restype, argtypes).  tests/test_abi.py checks this table against include/lidar_b200.h.
 PROTOTYPES: dict[str, tuple] = {
@@ -86,6 +105,8 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_roi_crop": (_i32, [_vp, _i32, _i64, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp, _vp,
                               _vp, _sz, _vp]),
     "lidar_preprocess_workspace_bytes": (_sz, [_i64]),
+    "lidar_preprocess_front_workspace_bytes": (_sz, [_i64]),
+    "lidar_preprocess_front": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "lidar_sigma_filter": (_i32, [_vp, _i64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                   _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "lidar_select_kth": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),

@@ -46,6 +46,11 @@ size_t smem_optin();     // max opt-in dynamic shared memory per block
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// reduce.cu: lidar_moments of an (n,3) fp64 cloud whose row count / centre live in device memory (either may be
+// NULL: then cap rows / centre 0).  The workspace's ticket must be zero (it is after every reduction).
+int moments_f64x3_dev(const double* d_points, int64_t cap, const long long* d_n, const double* d_center3,
+                      double* d_out6, void* d_reduce_ws, cudaStream_t st);
+
 // Bump allocator over the caller-provided workspace (no hidden cudaMalloc in the hot path).
 struct Workspace {
     char* base;

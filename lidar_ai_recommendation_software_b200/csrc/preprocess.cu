@@ -15,6 +15,16 @@
 
 namespace lidar {
 
+// order-preserving map fp64 -> u64 (radix select keys; bbox atomics of the chained preprocess)
+__device__ __forceinline__ unsigned long long f64_key(double d) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(unsigned long long k) {
+    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
 // ------------------------------------------------------------------------------------------------
 // 3-sigma filter
 // ------------------------------------------------------------------------------------------------
@@ -27,8 +37,13 @@ __global__ void __launch_bounds__(kCmpThreads)
 sigma_filter_kernel(const double* __restrict__ pts, int64_t n, SigmaParams P, uint8_t* __restrict__ mask,
                     double* __restrict__ out_pts, double* __restrict__ out_col, int64_t* __restrict__ count,
                     unsigned long long* __restrict__ guard, unsigned long long* tile_desc, CompactCtrl* ctrl,
-                    int n_tiles) {
+                    int n_tiles, const lidar_front_desc* __restrict__ F = nullptr) {
     __shared__ int s_tile;
+    if (F) {                                  // chained preprocess: the statistics were left on the device
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { P.mean[c] = F->mean[c]; P.thr[c] = F->thr[c]; P.tol[c] = F->tol[c]; }
+        P.zmin = F->zmin; P.zden = F->zden;
+    }
     unsigned guard_local = 0;
     while (true) {
         if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ctrl->ticket, 1u);
@@ -91,10 +106,17 @@ __global__ void __launch_bounds__(kCmpThreads)
 ground_split_kernel(const double* __restrict__ pts, int64_t n, double thr, double cx, double cy, double cz,
                     double* __restrict__ out_pts, int32_t* __restrict__ out_index, int64_t* __restrict__ count,
                     double* __restrict__ plane_out10, unsigned long long* __restrict__ guard, double tol,
-                    unsigned long long* tile_desc, CompactCtrl* ctrl, PlaneWs* pw, int n_tiles) {
+                    unsigned long long* tile_desc, CompactCtrl* ctrl, PlaneWs* pw, int n_tiles,
+                    lidar_front_desc* F = nullptr) {
     __shared__ int s_tile;
+    if (F) {                                  // chained preprocess: count, threshold and centre from the device
+        n = F->n_in; thr = F->z_thr; cx = F->mean[0]; cy = F->mean[1]; cz = F->mean[2];
+    }
     // {n, Sx, Sy, Sz, Sxx, Sxy, Syy, Sxz, Syz, unused} about the centre (cx,cy,cz)
     double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    // chained preprocess only: bbox of all rows [0..2] min, [3..5] max, and of the rows kept [6..11]
+    double bb[12] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY,
+                     INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
     unsigned guard_local = 0;
     while (true) {
         if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ctrl->ticket, 1u);
@@ -115,6 +137,14 @@ ground_split_kernel(const double* __restrict__ pts, int64_t n, double thr, doubl
                 const bool ground = z[j] <= thr;
                 keep[j] = !ground;
                 if (fabs(z[j] - thr) <= tol && z[j] != thr) ++guard_local;
+                if (F) {
+                    bb[0] = fmin(bb[0], x[j]); bb[1] = fmin(bb[1], y[j]); bb[2] = fmin(bb[2], z[j]);
+                    bb[3] = fmax(bb[3], x[j]); bb[4] = fmax(bb[4], y[j]); bb[5] = fmax(bb[5], z[j]);
+                    if (!ground) {
+                        bb[6] = fmin(bb[6], x[j]); bb[7] = fmin(bb[7], y[j]); bb[8] = fmin(bb[8], z[j]);
+                        bb[9] = fmax(bb[9], x[j]); bb[10] = fmax(bb[10], y[j]); bb[11] = fmax(bb[11], z[j]);
+                    }
+                }
                 if (ground) {
                     const double dx = x[j] - cx, dy = y[j] - cy, dz = z[j] - cz;
                     s[0] += 1.0; s[1] += dx; s[2] += dy; s[3] += dz;
@@ -133,6 +163,22 @@ ground_split_kernel(const double* __restrict__ pts, int64_t n, double thr, doubl
             }
     }
     if (guard_local) atomicAdd(guard, (unsigned long long)guard_local);
+    if (F) {                                  // min / max select, so ordered-key atomics are exact and order free
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {
+            const bool is_max = (c % 6) >= 3;
+            bb[c] = is_max ? warp_max(bb[c]) : warp_min(bb[c]);
+        }
+        if (lane_id() == 0) {
+#pragma unroll
+            for (int c = 0; c < 12; ++c) {
+                const bool is_max = (c % 6) >= 3;
+                if (bb[c] == (is_max ? -INFINITY : INFINITY)) continue;
+                unsigned long long* dst = reinterpret_cast<unsigned long long*>(c < 6 ? F->key_in : F->key_ng) + (c % 6);
+                if (is_max) atomicMax(dst, f64_key(bb[c])); else atomicMin(dst, f64_key(bb[c]));
+            }
+        }
+    }
     // deterministic fold of the plane moments: warp tree, CTA partial, last CTA folds in CTA order
     __shared__ double s_p[kCmpThreads / 32][9];
     __shared__ bool s_last;
@@ -161,6 +207,10 @@ ground_split_kernel(const double* __restrict__ pts, int64_t n, double thr, doubl
         plane_out10[threadIdx.x] = v;
     }
     if (threadIdx.x == 0) { plane_out10[9] = 0.0; pw->ticket = 0u; }
+    if (F && threadIdx.x < 12) {              // every CTA's atomics are visible: its ticket came after a fence
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(threadIdx.x < 6 ? F->key_in : F->key_ng) + (threadIdx.x % 6);
+        (threadIdx.x < 6 ? F->bbox_in : F->bbox_ng)[threadIdx.x % 6] = key_f64(*((volatile const unsigned long long*)src));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -178,16 +228,9 @@ struct SelectState {
     unsigned long long count_le; // #elements <= kth
     unsigned long long min_gt;   // smallest key > kth (key space)
     unsigned long long n_buf;    // keys that survived the first two passes (compacted, see select_compact_kernel)
+    long long k0;                // the rank asked for (st->k is consumed by the passes)
 };
 
-__device__ __forceinline__ unsigned long long f64_key(double d) {
-    unsigned long long b = (unsigned long long)__double_as_longlong(d);
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double key_f64(unsigned long long k) {
-    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
-    return __longlong_as_double((long long)b);
-}
 
 constexpr int kSelThreads = 256;
 
@@ -217,7 +260,9 @@ __device__ __forceinline__ void select_pick_digit(SelectState* st, unsigned long
 }
 
 __global__ void __launch_bounds__(kSelThreads)
-select_pass_kernel(const double* __restrict__ col, int64_t stride_el, int64_t n, int pass, SelectState* st) {
+select_pass_kernel(const double* __restrict__ col, int64_t stride_el, int64_t n, int pass, SelectState* st,
+                   const long long* __restrict__ d_n = nullptr) {
+    if (d_n) n = *d_n;
     __shared__ unsigned s_hist[256];
     __shared__ bool s_last;
     s_hist[threadIdx.x] = 0;  // kSelThreads == 256
@@ -244,7 +289,8 @@ select_pass_kernel(const double* __restrict__ col, int64_t stride_el, int64_t n,
 // keys whose top 16 bits equal the prefix fixed by passes 0 and 1 -> buf (order irrelevant: later passes only count)
 __global__ void __launch_bounds__(kSelThreads)
 select_compact_kernel(const double* __restrict__ col, int64_t stride_el, int64_t n, SelectState* st,
-                      unsigned long long* __restrict__ buf) {
+                      unsigned long long* __restrict__ buf, const long long* __restrict__ d_n = nullptr) {
+    if (d_n) n = *d_n;
     const unsigned long long prefix = st->prefix;     // 16 bits
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     const int64_t n_round = ((n + 31) / 32) * 32;     // whole warps stay in the loop for the ballot
@@ -292,8 +338,9 @@ select_pass_buf_kernel(const unsigned long long* __restrict__ buf, int pass, Sel
 }
 
 __global__ void __launch_bounds__(kSelThreads)
-select_next_kernel(const double* __restrict__ col, int64_t stride_el, int64_t n, int64_t k, SelectState* st,
-                   double* __restrict__ out2) {
+select_next_kernel(const double* __restrict__ col, int64_t stride_el, int64_t n, SelectState* st,
+                   double* __restrict__ out2, lidar_front_desc* F = nullptr) {
+    if (F) n = F->n_in;
     __shared__ unsigned long long s_cnt[kSelThreads / 32];
     __shared__ unsigned long long s_min[kSelThreads / 32];
     __shared__ bool s_last;
@@ -325,14 +372,30 @@ select_next_kernel(const double* __restrict__ col, int64_t stride_el, int64_t n,
     __threadfence();
     const unsigned long long cle = *((volatile unsigned long long*)&st->count_le);
     const unsigned long long mgt = *((volatile unsigned long long*)&st->min_gt);
-    out2[0] = key_f64(kth);
-    out2[1] = ((long long)cle >= k + 2 || mgt == ~0ull) ? key_f64(kth) : key_f64(mgt);
+    const long long k = st->k0;
+    const double a = key_f64(kth);
+    const double b = ((long long)cle >= k + 2 || mgt == ~0ull) ? key_f64(kth) : key_f64(mgt);
+    out2[0] = a;
+    out2[1] = b;
     st->ticket = 0;
+    if (F) {
+        // np.percentile(z, 30), method 'linear' (numpy/lib/_function_base_impl.py _quantile + _lerp): virtual index
+        // (n-1)*q, t = its fraction, a + (b-a)*t below one half and b - (b-a)*(1-t) from there on
+        const double virt = __dmul_rn((double)(n - 1), __ddiv_rn(30.0, 100.0));
+        const double t = __dsub_rn(virt, floor(virt));
+        const double d = __dsub_rn(b, a);
+        F->z_thr = t >= 0.5 ? __dsub_rn(b, __dmul_rn(d, __dsub_rn(1.0, t))) : __dadd_rn(a, __dmul_rn(d, t));
+    }
 }
 
-__global__ void select_init_kernel(SelectState* st, int64_t k) {
+__global__ void select_init_kernel(SelectState* st, int64_t k, const lidar_front_desc* F = nullptr) {
     if (threadIdx.x < 256) st->hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
+        if (F) {                              // lo = floor((n_in - 1) * 0.3), the lower rank of the 30th percentile
+            const long long n_in = F->n_in;
+            k = n_in > 0 ? (long long)floor(__dmul_rn((double)(n_in - 1), __ddiv_rn(30.0, 100.0))) : 0;
+        }
+        st->k0 = k;
         st->prefix = 0; st->k = k; st->ticket = 0; st->pad = 0; st->count_le = 0; st->min_gt = ~0ull; st->n_buf = 0ull;
     }
 }
@@ -374,6 +437,73 @@ __global__ void gather_rows_kernel(const uint32_t* __restrict__ in, int row_word
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// chained preprocess (lidar_preprocess_front): the scalar glue between the stages, one thread each.  The
+// expressions are the ones preprocess.py evaluates with numpy on the host path (same IEEE operations, same order).
+// ------------------------------------------------------------------------------------------------
+enum { kGlueInit = 0, kGlueMean, kGlueStd, kGlueScMean, kGlueScale, kGlueXMean, kGlueEps };
+
+__global__ void front_glue_kernel(lidar_front_desc* F, int stage, long long n) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double m = (double)F->n_nonground;
+    switch (stage) {
+    case kGlueInit:
+        for (int c = 0; c < 3; ++c) { F->key_in[c] = F->key_ng[c] = ~0ull; F->key_in[3 + c] = F->key_ng[3 + c] = 0ull; }
+        break;
+    case kGlueMean:                                        // np.mean(points, axis=0): sum / n
+        for (int c = 0; c < 3; ++c) F->mean[c] = __ddiv_rn(F->sum1[c], (double)n);
+        break;
+    case kGlueStd:                                         // np.std: sqrt(mean of squared deviations); 3 sigma
+        for (int c = 0; c < 3; ++c) {
+            const double sd = __dsqrt_rn(__ddiv_rn(F->sum2[3 + c], (double)n));
+            F->std[c] = sd;
+            F->thr[c] = __dmul_rn(3.0, sd);
+            F->tol[c] = __dmul_rn(1e-9, sd);
+        }
+        F->zmin = F->bbox_raw[2];
+        F->zden = __dadd_rn(__dsub_rn(F->bbox_raw[6], F->bbox_raw[2]), 1e-10);
+        break;
+    case kGlueScMean:                                      // StandardScaler.fit: mean_
+        for (int c = 0; c < 3; ++c) F->sc_mean[c] = __ddiv_rn(F->t1[c], m);
+        break;
+    case kGlueScale:                                       // sklearn _incremental_mean_and_var + _handle_zeros_in_scale
+        for (int c = 0; c < 3; ++c) {
+            const double corr = __ddiv_rn(__dmul_rn(F->t2[c], F->t2[c]), m);
+            const double var = __ddiv_rn(__dsub_rn(F->t2[3 + c], corr), m);
+            double sc = __dsqrt_rn(var);
+            if (fabs(sc) <= 10.0 * 2.220446049250313e-16) sc = 1.0;
+            F->scale[c] = sc;
+        }
+        break;
+    case kGlueXMean:
+        for (int c = 0; c < 3; ++c) F->xm[c] = __ddiv_rn(F->u1[c], m);
+        break;
+    case kGlueEps: {                                       // eps = max(0.2, min(0.5, np.mean(np.std(X, axis=0)) * 0.5))
+        for (int c = 0; c < 3; ++c) F->xstd[c] = __dsqrt_rn(__ddiv_rn(F->u2[3 + c], m));
+        const double avg = __dmul_rn(__ddiv_rn(__dadd_rn(__dadd_rn(F->xstd[0], F->xstd[1]), F->xstd[2]), 3.0), 0.5);
+        double e = avg < 0.5 ? avg : 0.5;
+        e = e > 0.2 ? e : 0.2;
+        F->eps = e;
+        break;
+    }
+    default: break;
+    }
+}
+
+__global__ void standardize_front_kernel(const double* __restrict__ in, const lidar_front_desc* __restrict__ F,
+                                         double* __restrict__ out) {
+    const int64_t n3 = 3 * F->n_nonground;
+    const double m0 = F->sc_mean[0], m1 = F->sc_mean[1], m2 = F->sc_mean[2];
+    const double s0 = F->scale[0], s1 = F->scale[1], s2 = F->scale[2];
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += step) {
+        const int c = (int)(i % 3);
+        const double m = c == 0 ? m0 : (c == 1 ? m1 : m2);
+        const double s = c == 0 ? s0 : (c == 1 ? s1 : s2);
+        out[i] = __ddiv_rn(__dsub_rn(in[i], m), s);
+    }
+}
+
 static int ew_grid(int64_t n) {
     int64_t want = (n + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 8;
@@ -397,11 +527,127 @@ static PreLayout pre_layout(int64_t n) {
     return L;
 }
 
+struct FrontLayout {
+    size_t off_reduce, off_pre, off_select, total;
+};
+static FrontLayout front_layout(int64_t n) {
+    FrontLayout L;
+    L.off_reduce = 0;
+    L.off_pre = ws_align(lidar_reduce_workspace_bytes());
+    L.off_select = ws_align(L.off_pre + pre_layout(n).total);
+    L.total = ws_align(L.off_select + ws_align(sizeof(SelectState)) + sizeof(unsigned long long) * (size_t)n);
+    return L;
+}
+
 }  // namespace lidar
 
 using namespace lidar;
 
 extern "C" {
+
+size_t lidar_preprocess_front_workspace_bytes(int64_t n) { return front_layout(n < 0 ? 0 : n).total; }
+
+int lidar_preprocess_front(const double* d_points, int64_t n, int flags, double* d_inliers, double* d_colors,
+                           double* d_nonground, int32_t* d_ng_index, double* d_scaled, lidar_front_desc* d_front,
+                           void* d_ws, size_t ws_bytes, void* stream) {
+    LIDAR_REQUIRE(n > 0 && n < (1ll << 31), LIDAR_ERR_INVALID, "lidar_preprocess_front: need 0 < n < 2^31");
+    LIDAR_REQUIRE(d_points && d_inliers && d_nonground && d_ng_index && d_front, LIDAR_ERR_INVALID,
+                  "lidar_preprocess_front: NULL argument");
+    LIDAR_REQUIRE(!(flags & LIDAR_FRONT_COLORS) || d_colors, LIDAR_ERR_INVALID, "lidar_preprocess_front: colours without a buffer");
+    LIDAR_REQUIRE(!(flags & LIDAR_FRONT_SCALER) || d_scaled, LIDAR_ERR_INVALID, "lidar_preprocess_front: scaler without a buffer");
+    const FrontLayout FL = front_layout(n);
+    LIDAR_REQUIRE(d_ws && ws_bytes >= FL.total, LIDAR_ERR_WORKSPACE, "lidar_preprocess_front: workspace too small (%zu < %zu)",
+                  ws_bytes, FL.total);
+    cudaStream_t st = as_stream(stream);
+    char* ws = static_cast<char*>(d_ws);
+    void* rws = ws + FL.off_reduce;
+    char* pws = ws + FL.off_pre;
+    const PreLayout L = pre_layout(n);
+    lidar_front_desc* F = d_front;
+    auto glue = [&](int stage) -> int {
+        front_glue_kernel<<<1, 32, 0, st>>>(F, stage, (long long)n);
+        LIDAR_CHECK_LAUNCH();
+        return LIDAR_OK;
+    };
+    auto reset_compaction = [&]() -> int {
+        LIDAR_CUDA_TRY(cudaMemsetAsync(pws, 0, ws_align(L.off_desc + sizeof(unsigned long long) * L.tiles), st));
+        return LIDAR_OK;
+    };
+    int rc;
+    LIDAR_CUDA_TRY(cudaMemsetAsync(F, 0, sizeof(lidar_front_desc), st));
+    LIDAR_CUDA_TRY(cudaMemsetAsync(rws, 0, lidar_reduce_workspace_bytes(), st));
+    if ((rc = glue(kGlueInit)) != LIDAR_OK) return rc;
+    // raw cloud: bbox, mean, population std
+    if ((rc = lidar_bbox(d_points, LIDAR_FMT_F64X3, n, F->bbox_raw, rws, lidar_reduce_workspace_bytes(), stream)) != LIDAR_OK) return rc;
+    if ((rc = moments_f64x3_dev(d_points, n, nullptr, nullptr, F->sum1, rws, st)) != LIDAR_OK) return rc;
+    if ((rc = glue(kGlueMean)) != LIDAR_OK) return rc;
+    if ((rc = moments_f64x3_dev(d_points, n, nullptr, F->mean, F->sum2, rws, st)) != LIDAR_OK) return rc;
+    if ((rc = glue(kGlueStd)) != LIDAR_OK) return rc;
+    // 3-sigma filter
+    int grid = sm_count() * 4;
+    if ((int64_t)grid > L.tiles) grid = (int)L.tiles;
+    if ((rc = reset_compaction()) != LIDAR_OK) return rc;
+    sigma_filter_kernel<<<grid, kCmpThreads, 0, st>>>(d_points, n, SigmaParams{}, nullptr, d_inliers,
+        (flags & LIDAR_FRONT_COLORS) ? d_colors : nullptr, &F->n_in, reinterpret_cast<unsigned long long*>(&F->guard_sigma),
+        reinterpret_cast<unsigned long long*>(pws + L.off_desc), reinterpret_cast<CompactCtrl*>(pws + L.off_ctrl),
+        (int)L.tiles, F);
+    LIDAR_CHECK_LAUNCH();
+    // 30th percentile of the inlier heights: radix select with the count and the rank read on the device
+    {
+        SelectState* S = reinterpret_cast<SelectState*>(ws + FL.off_select);
+        unsigned long long* buf = reinterpret_cast<unsigned long long*>(ws + FL.off_select + ws_align(sizeof(SelectState)));
+        const double* col = d_inliers + 2;
+        const long long* d_n = reinterpret_cast<const long long*>(&F->n_in);
+        select_init_kernel<<<1, 256, 0, st>>>(S, 0, F);
+        LIDAR_CHECK_LAUNCH();
+        int sgrid = (int)((n + kSelThreads * 8 - 1) / (kSelThreads * 8));
+        const int cap = sm_count() * 8;
+        sgrid = sgrid < 1 ? 1 : (sgrid > cap ? cap : sgrid);
+        if (n >= 65536) {
+            for (int pass = 0; pass < 2; ++pass) {
+                select_pass_kernel<<<sgrid, kSelThreads, 0, st>>>(col, 3, n, pass, S, d_n);
+                LIDAR_CHECK_LAUNCH();
+            }
+            select_compact_kernel<<<sgrid, kSelThreads, 0, st>>>(col, 3, n, S, buf, d_n);
+            LIDAR_CHECK_LAUNCH();
+            const int bgrid = sgrid < sm_count() ? sgrid : sm_count();
+            for (int pass = 2; pass < 8; ++pass) {
+                select_pass_buf_kernel<<<bgrid, kSelThreads, 0, st>>>(buf, pass, S);
+                LIDAR_CHECK_LAUNCH();
+            }
+        } else {
+            for (int pass = 0; pass < 8; ++pass) {
+                select_pass_kernel<<<sgrid, kSelThreads, 0, st>>>(col, 3, n, pass, S, d_n);
+                LIDAR_CHECK_LAUNCH();
+            }
+        }
+        select_next_kernel<<<sgrid, kSelThreads, 0, st>>>(col, 3, n, S, F->kth, F);
+        LIDAR_CHECK_LAUNCH();
+    }
+    // ground split + plane sums + both bboxes
+    if ((rc = reset_compaction()) != LIDAR_OK) return rc;
+    LIDAR_CUDA_TRY(cudaMemsetAsync(pws + L.off_plane + offsetof(PlaneWs, ticket), 0, sizeof(unsigned), st));
+    if (grid > kPlaneMaxBlocks) grid = kPlaneMaxBlocks;
+    ground_split_kernel<<<grid, kCmpThreads, 0, st>>>(d_inliers, n, 0.0, 0.0, 0.0, 0.0, d_nonground, d_ng_index,
+        &F->n_nonground, F->plane, reinterpret_cast<unsigned long long*>(&F->guard_ground), 0.0,
+        reinterpret_cast<unsigned long long*>(pws + L.off_desc), reinterpret_cast<CompactCtrl*>(pws + L.off_ctrl),
+        reinterpret_cast<PlaneWs*>(pws + L.off_plane), (int)L.tiles, F);
+    LIDAR_CHECK_LAUNCH();
+    if (flags & LIDAR_FRONT_SCALER) {
+        const long long* d_m = reinterpret_cast<const long long*>(&F->n_nonground);
+        if ((rc = moments_f64x3_dev(d_nonground, n, d_m, nullptr, F->t1, rws, st)) != LIDAR_OK) return rc;
+        if ((rc = glue(kGlueScMean)) != LIDAR_OK) return rc;
+        if ((rc = moments_f64x3_dev(d_nonground, n, d_m, F->sc_mean, F->t2, rws, st)) != LIDAR_OK) return rc;
+        if ((rc = glue(kGlueScale)) != LIDAR_OK) return rc;
+        standardize_front_kernel<<<ew_grid(n * 3), 256, 0, st>>>(d_nonground, F, d_scaled);
+        LIDAR_CHECK_LAUNCH();
+        if ((rc = moments_f64x3_dev(d_scaled, n, d_m, nullptr, F->u1, rws, st)) != LIDAR_OK) return rc;
+        if ((rc = glue(kGlueXMean)) != LIDAR_OK) return rc;
+        if ((rc = moments_f64x3_dev(d_scaled, n, d_m, F->xm, F->u2, rws, st)) != LIDAR_OK) return rc;
+        if ((rc = glue(kGlueEps)) != LIDAR_OK) return rc;
+    }
+    return LIDAR_OK;
+}
 
 size_t lidar_preprocess_workspace_bytes(int64_t n) {
     size_t a = pre_layout(n < 0 ? 0 : n).total;
@@ -500,7 +746,7 @@ int lidar_select_kth(const double* d_column, int64_t stride_elems, int64_t n, in
             LIDAR_CHECK_LAUNCH();
         }
     }
-    select_next_kernel<<<grid, kSelThreads, 0, st>>>(d_column, stride_elems, n, k, S, d_out2);
+    select_next_kernel<<<grid, kSelThreads, 0, st>>>(d_column, stride_elems, n, S, d_out2);
     LIDAR_CHECK_LAUNCH();
     return LIDAR_OK;
 }

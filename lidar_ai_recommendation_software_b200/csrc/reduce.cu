@@ -160,7 +160,10 @@ bbox_f32x4_kernel(LoadF32x4 L, int64_t n, double* __restrict__ out8, ReduceWs* _
 template <class Loader>
 __global__ void __launch_bounds__(kRedThreads)
 moments_kernel(Loader L, int64_t n, double cx, double cy, double cz, double* __restrict__ out6,
-               ReduceWs* __restrict__ ws) {
+               ReduceWs* __restrict__ ws, const long long* __restrict__ d_n = nullptr,
+               const double* __restrict__ d_center3 = nullptr) {
+    if (d_n) n = *d_n;                        // chained preprocess: count and centre come from the previous stage
+    if (d_center3) { cx = d_center3[0]; cy = d_center3[1]; cz = d_center3[2]; }
     double s[6] = {0, 0, 0, 0, 0, 0};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     auto fold = [&](const Pt& p) {
@@ -209,6 +212,17 @@ static int reduce_grid(int64_t n) {
     if (cap > kRedMaxBlocks) cap = kRedMaxBlocks;
     if (want < 1) want = 1;
     return (int)(want < cap ? want : cap);
+}
+
+// lidar_moments with the row count and the centre in device memory (lidar_preprocess_front); the grid is sized by
+// the capacity, so the fold order is fixed by `cap` alone
+int moments_f64x3_dev(const double* d_points, int64_t cap, const long long* d_n, const double* d_center3,
+                      double* d_out6, void* d_reduce_ws, cudaStream_t st) {
+    ReduceWs* ws = static_cast<ReduceWs*>(d_reduce_ws);
+    moments_kernel<<<reduce_grid(cap), kRedThreads, 0, st>>>(LoadF64x3{d_points}, cap, 0.0, 0.0, 0.0, d_out6, ws, d_n,
+                                                             d_center3);
+    LIDAR_CHECK_LAUNCH();
+    return LIDAR_OK;
 }
 
 }  // namespace lidar

@@ -17,7 +17,7 @@ from . import _capi
 from ._capi import FMT_F32X4, FMT_F64X3, HIST_AUTO, FrameCaps, FrameDesc, check, lib
 
 __all__ = [
-    "require_cuda", "point_format", "bbox", "moments", "hist2d_counts", "hist2d_points_counts", "roi_crop", "ball_count", "set_dbscan_dense", "set_frame_streaming", "set_frame_scan_order",
+    "require_cuda", "point_format", "bbox", "moments", "hist2d_counts", "hist2d_points_counts", "roi_crop", "ball_count", "set_dbscan_dense", "set_frame_streaming", "set_frame_scan_order", "preprocess_front",
     "FramePipeline", "HostFramePipeline", "voxel_downsample", "arange_edges", "linspace_edges",
 ]
 
@@ -537,6 +537,36 @@ def select_kth(column: torch.Tensor, k: int):
     return a, b
 
 
+def preprocess_front(points: torch.Tensor, want_colors: bool = True, scaler: bool = False):
+    """Everything of the preprocess functions before DBSCAN as ONE enqueue and ONE read-back
+    (`lidar_preprocess_front`): bbox / mean / std of the raw cloud, 3-sigma filter (+ colours), the 30th
+    percentile of the inlier heights, ground split with the plane sums and both bboxes, and for variant A the
+    StandardScaler statistics, the scaled copy and eps (utils/data_processing.py:143-196).
+
+    Returns (desc: _capi.FrontDesc (host copy), inliers, colors | None, non_ground, non_ground_index int32,
+    scaled | None); the arrays are views of capacity-n buffers cut to the counts in `desc`."""
+    _check_f64x3(points)
+    dev, n = points.device, points.shape[0]
+    inl = torch.empty_like(points)
+    col = torch.empty_like(points) if want_colors else None
+    ng = torch.empty_like(points)
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    X = torch.empty_like(points) if scaler else None
+    nb = C.sizeof(_capi.FrontDesc)
+    d_desc = torch.empty(nb, dtype=torch.uint8, device=dev)
+    h_desc = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+    ws = _scratch.get("front", lib.lidar_preprocess_front_workspace_bytes(n), dev)
+    flags = (_capi.FRONT_COLORS if want_colors else 0) | (_capi.FRONT_SCALER if scaler else 0)
+    check(lib.lidar_preprocess_front(_ptr(points), n, flags, _ptr(inl), _ptr(col), _ptr(ng), _ptr(idx), _ptr(X),
+                                     _ptr(d_desc), _ptr(ws), ws.numel(), _stream_ptr()))
+    h_desc.copy_(d_desc, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    desc = _capi.FrontDesc.from_buffer_copy(h_desc.numpy().tobytes())
+    n_in, m = int(desc.n_in), int(desc.n_nonground)
+    return (desc, inl[:n_in], (col[:n_in] if col is not None else None), ng[:m], idx[:m],
+            (X[:m] if X is not None else None))
+
+
 def ground_split(points: torch.Tensor, z_threshold: float, center, tol: float = 0.0):
     """z <= thr split (utils/data_processing.py:165-188).
 
@@ -575,8 +605,10 @@ def set_dbscan_dense(on: bool = True) -> None:
     check(lib.lidar_dbscan_set_dense(1 if on else 0))
 
 
-def dbscan(points: torch.Tensor, eps: float, min_samples: int = 5, tol: float = 0.0, bounds=None):
-    """sklearn-identical DBSCAN labels (int32 (m,)), number of clusters, knife-edge guard count."""
+def dbscan(points: torch.Tensor, eps: float, min_samples: int = 5, tol: float = 0.0, bounds=None, defer: bool = False):
+    """sklearn-identical DBSCAN labels (int32 (m,)), number of clusters, knife-edge guard count.
+    `defer=True` skips the read-back: returns (labels, info) with info a 2-element int64 device tensor
+    [n_clusters in the low 32 bits, guard] for the caller to fetch together with its other results."""
     _check_f64x3(points)
     dev, m = points.device, points.shape[0]
     labels = torch.empty(m, dtype=torch.int32, device=dev)
@@ -593,6 +625,8 @@ def dbscan(points: torch.Tensor, eps: float, min_samples: int = 5, tol: float = 
     info = torch.zeros(2, dtype=torch.int64, device=dev)   # [n_clusters (int32 in low word), guard]
     check(lib.lidar_dbscan(_ptr(points), m, float(eps), int(min_samples), float(tol), lo, hi, _ptr(labels),
                            _ptr(info), _ptr(info[1:]), _ptr(ws), ws.numel(), _stream_ptr()))
+    if defer:
+        return labels, info
     nc, guard = (int(v) for v in info.tolist())
     return labels, nc & 0xffffffff, guard
 

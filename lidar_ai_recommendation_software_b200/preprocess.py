@@ -4,9 +4,12 @@
     variant "B"  preprocess_point_cloud of the Streamlit apps   (app_simplified.py:76-137)
 
 Every per-point stage runs in the CUDA core (bbox, moments, 3-sigma filter + compaction + colours,
-radix select, ground split + plane moments, scaler, DBSCAN, label scatter).  The host only derives a
-handful of scalars between launches (mean/std from sums, the percentile lerp, the 3x3 plane solve,
-eps) with the same float64 expressions numpy uses.  There is no CPU path for the per-point work.
+radix select, ground split + plane moments, scaler, DBSCAN, label scatter).  The stages before DBSCAN are
+ONE enqueue (`lidar_preprocess_front`): the scalars one stage hands to the next (mean/std from sums, the
+percentile rank and lerp, the scaler statistics, eps) are derived on the device with the same float64
+expressions numpy uses, and come back in one read-back; a whole call waits on the device two or three
+times (front, DBSCAN's grid sizing needs the bbox on the host, results).  The host solves the 3x3 plane
+system.  There is no CPU path for the per-point work.
 """
 from __future__ import annotations
 
@@ -107,79 +110,65 @@ def run(points, variant: str = "A", host_arrays: bool = True) -> dict:
     if d_pts is None:
         d_pts = torch.from_numpy(host).to(dev, non_blocking=False)
 
-    # --- colours need z min/max of the RAW cloud (data_processing.py:143) ---------------------
-    bb = ops.bbox(d_pts).cpu().numpy()
-    zmin, zmax = bb[2], bb[6]
-    zden = (zmax - zmin) + 1e-10
-
-    # --- mean / population std per axis (np.mean, np.std; :151-152) ---------------------------
-    s1 = ops.moments(d_pts).cpu().numpy()
-    mean = s1[:3] / n
-    s2 = ops.moments(d_pts, center=mean).cpu().numpy()
-    std = np.sqrt(s2[3:] / n)
-    thr = 3 * std
-    tol = 1e-9 * std
-    inl, col, _, guard_sigma = ops.sigma_filter(d_pts, mean, thr, tol, zmin, zden, want_colors=host_arrays)
+    # --- everything before DBSCAN is one enqueue and one read-back (lidar_preprocess_front): z min/max of the RAW
+    #     cloud for the colours (data_processing.py:143), mean / population std (:151-152), the 3-sigma filter
+    #     (:153-157), np.percentile(z, 30) and the ground split (:164-166), the plane sums (:169-177), the bbox of the
+    #     inliers (:207-217) and, for variant A, StandardScaler + the adaptive eps (:190-196) ----------------------
+    desc, inl, col, ng, ng_index, X = ops.preprocess_front(d_pts, want_colors=host_arrays, scaler=(variant == "A"))
     n_in = inl.shape[0]
     if n_in == 0:
         raise IndexError("index -1 is out of bounds for axis 0 with size 0")   # np.percentile of an empty array
-
-    # --- ground split at the 30th percentile of z (:164-166) -----------------------------------
-    lo_idx = math.floor((n_in - 1) * (np.float64(30) / 100.0))
-    a, b = ops.select_kth(inl[:, 2], lo_idx)
-    z_thr = percentile_from_order_stats(a, b, n_in, 30)
-    ng, ng_index, plane_sums, _ = ops.ground_split(inl, z_thr, mean)
+    mean = np.array(desc.mean)
+    plane_sums = np.array(desc.plane)
     n_ground = int(round(plane_sums[0]))
     m = ng.shape[0]
+    lo3, hi3 = np.array(desc.bbox_in[:3]), np.array(desc.bbox_in[3:])
 
     out: dict = {}
-    guards = {"sigma": guard_sigma, "dbscan": 0}
+    guards = {"sigma": int(desc.guard_sigma), "dbscan": 0}
     if variant == "A":
         if n_ground > 10:
             plane = _plane_from_sums(plane_sums, mean)
         else:
-            bb_in = ops.bbox(inl).cpu().numpy()
-            plane = np.array([0, 0, 1, -bb_in[2]])
+            plane = np.array([0, 0, 1, -lo3[2]])
     # --- clustering of the non-ground points (:186-200 / app_simplified.py:102-110) -------------
+    info = None
     if m > 10:
+        b_lo, b_hi = np.array(desc.bbox_ng[:3]), np.array(desc.bbox_ng[3:])
         if variant == "A":
-            t1 = ops.moments(ng).cpu().numpy()
-            sc_mean = t1[:3] / m
-            t2 = ops.moments(ng, center=sc_mean).cpu().numpy()
-            var = (t2[3:] - t2[:3] ** 2 / m) / m          # sklearn _incremental_mean_and_var
-            scale = np.sqrt(var)
-            scale = np.where(np.isclose(scale, 0.0, atol=10 * np.finfo(np.float64).eps, rtol=0.0), 1.0, scale)
-            X = ops.standardize(ng, sc_mean, scale)
-            u1 = ops.moments(X).cpu().numpy()
-            xm = u1[:3] / m
-            u2 = ops.moments(X, center=xm).cpu().numpy()
-            xstd = np.sqrt(u2[3:] / m)
-            avg_distance = np.mean(xstd) * 0.5
-            eps = max(0.2, min(0.5, avg_distance))
-            tol_db = 1e-12
+            sc_mean, scale = np.array(desc.sc_mean), np.array(desc.scale)
+            b_lo, b_hi = (b_lo - sc_mean) / scale, (b_hi - sc_mean) / scale   # the scaler is monotone per axis
+            Xd, eps, tol_db = X, float(desc.eps), 1e-12
         else:
-            X, eps, tol_db = ng, 0.3, 0.0
-        labels, n_clusters, guards["dbscan"] = ops.dbscan(X, eps, 5, tol=tol_db)
+            Xd, eps, tol_db = ng, 0.3, 0.0
+        labels, info = ops.dbscan(Xd, eps, 5, tol=tol_db, bounds=(b_lo, b_hi), defer=True)
+        n_clusters = None
     else:
         labels = torch.zeros(m, dtype=torch.int32, device=dev)
         n_clusters = 1 if m > 0 else 0
     full = ops.scatter_labels(labels, ng_index, n_in)
 
-    # --- bbox of the inliers (:207-217) ---------------------------------------------------------
-    bb_in = ops.bbox(inl).cpu().numpy()
-    lo3, hi3 = bb_in[:3], bb_in[4:7]
     dims = {
         "x_range": (lo3[0], hi3[0]), "y_range": (lo3[1], hi3[1]), "z_range": (lo3[2], hi3[2]),
         "width": hi3[0] - lo3[0], "length": hi3[1] - lo3[1], "height": hi3[2] - lo3[2],
     }
 
+    def _info(h):
+        nc, guard = (int(v) for v in h.tolist())
+        guards["dbscan"] = guard
+        return nc & 0xffffffff
+
     if not host_arrays:
+        if info is not None:
+            n_clusters = _info(_to_host(info)[0])
         if variant == "A":
             out["ground_plane"] = plane
         out["dimensions"] = dims
         out[DEVICE_KEY] = DeviceCache(inl, full, None, n_clusters, guards)
         return out
-    h_points, h_clusters, h_colors = _to_host(inl, full, col)
+    h_points, h_clusters, h_colors, h_info = _to_host(inl, full, col, info)
+    if info is not None:
+        n_clusters = _info(h_info)
     out["points"] = h_points
     out["colors"] = h_colors
     if variant == "A":
@@ -212,9 +201,13 @@ def people_positions(processed: dict) -> np.ndarray:
     pts, lab = device_view(processed)
     if lab.numel() == 0:
         return np.array([])
-    mx = int(lab.max().item())
-    if mx < 0:
+    cache = processed.get(DEVICE_KEY)
+    if isinstance(cache, DeviceCache) and cache.matches(processed) and cache.n_clusters is not None:
+        n_ids = cache.n_clusters             # labels of our own DBSCAN: 0..n_clusters-1, known without a read-back
+    else:
+        n_ids = int(lab.max().item()) + 1
+    if n_ids <= 0:
         return np.array([])
-    cent, counts = ops.cluster_centroids(pts, lab, mx + 1)
-    keep = (counts > 0).cpu().numpy()
-    return np.ascontiguousarray(cent.cpu().numpy()[keep][:, :2])
+    cent, counts = ops.cluster_centroids(pts, lab, n_ids)
+    h_cent, h_counts = _to_host(cent, counts)
+    return np.ascontiguousarray(h_cent[h_counts > 0][:, :2])

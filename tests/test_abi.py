@@ -50,6 +50,9 @@ def test_struct_mirrors_match_c_layout():
       printf("%zu %zu %zu %zu %zu %zu\n", sizeof(lidar_frame_desc), offsetof(lidar_frame_desc, dims),
              offsetof(lidar_frame_desc, key_space), offsetof(lidar_frame_desc, nx),
              offsetof(lidar_frame_desc, n_voxels), sizeof(lidar_frame_caps));
+      printf("%zu %zu %zu %zu %zu %zu\n", sizeof(lidar_front_desc), offsetof(lidar_front_desc, n_in),
+             offsetof(lidar_front_desc, z_thr), offsetof(lidar_front_desc, plane),
+             offsetof(lidar_front_desc, eps), offsetof(lidar_front_desc, key_ng));
       return 0; }'''
     import tempfile
     with tempfile.TemporaryDirectory() as td:
@@ -59,8 +62,10 @@ def test_struct_mirrors_match_c_layout():
         subprocess.run(["gcc", "-I", str(ROOT / "include"), str(c), "-o", str(exe)], check=True)
         out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     D = _capi.FrameDesc
+    F = _capi.FrontDesc
     want = [ctypes.sizeof(D), D.dims.offset, D.key_space.offset, D.nx.offset, D.n_voxels.offset,
-            ctypes.sizeof(_capi.FrameCaps)]
+            ctypes.sizeof(_capi.FrameCaps),
+            ctypes.sizeof(F), F.n_in.offset, F.z_thr.offset, F.plane.offset, F.eps.offset, F.key_ng.offset]
     assert [int(x) for x in out] == want
 
 
