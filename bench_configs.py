@@ -214,7 +214,9 @@ def run_seq(args, torch, dev, rank, world, dist):
         from lidar_ai_recommendation_software_b200.sequence import SequenceRunner
         runner = SequenceRunner(variant="B", workers=args.workers, dt=0.1)
         runner.model = model                      # carries the halo frame's people positions
-        for _ in runner.run([pool64[1 % pool_n], pool64[2 % pool_n]]):     # warm the worker threads / streams
+        # warm the worker threads: every (stream, frame size) pair once, so that the caching allocator of each
+        # stream already owns its blocks (a cudaMalloc inside the timed region costs a device synchronisation)
+        for _ in runner.run([pool64[i % pool_n] for i in range(pool_n * args.workers)]):
             pass
         model.prev_positions = None
         list(runner.run([pool64[0]]))             # halo / first frame again, so the timed frames all match

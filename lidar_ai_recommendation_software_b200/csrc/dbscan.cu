@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kDbThreads)
 db_core(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* __restrict__ scell,
         const int* __restrict__ sidx, const double* __restrict__ sx, const double* __restrict__ sy,
         const double* __restrict__ sz, double eps2, double tol, int min_samples, uint8_t* __restrict__ core_s,
-        uint8_t* __restrict__ core_o, unsigned long long* __restrict__ guard) {
+        uint8_t* __restrict__ core_o, unsigned long long* __restrict__ guard, int* __restrict__ crep) {
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= m) return;
     if (G.dense) {
@@ -186,7 +186,11 @@ db_core(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* _
             if (((cnt - band_in) >= min_samples) != ((cnt + band_out) >= min_samples)) atomicAdd(guard, 1ull);
         }
         core_s[pos] = core;
-        core_o[sidx[pos]] = core;
+        const int oi = sidx[pos];
+        core_o[oi] = core;
+        // representative of the cell = its core point with the lowest original index (kNoRep: no core point).
+        // The core points of a dense cell are mutual neighbours, so one of them stands for all in the set tests.
+        if (core) atomicMin(&crep[c], oi);
         return;
     }
     int cnt = 0, band_in = 0, band_out = 0;
@@ -201,6 +205,8 @@ db_core(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* _
     core_s[pos] = core;
     core_o[sidx[pos]] = core;
 }
+
+constexpr int kNoRep = 0x7f7f7f7f;   // crep[] after cudaMemset(0x7f): the cell has no core point
 
 __device__ __forceinline__ int uf_find(int* parent, int x) {
     int p = ((volatile int*)parent)[x];
@@ -247,21 +253,32 @@ db_union(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* 
 }
 
 // ---- dense grid ------------------------------------------------------------------------------------
+// The common case of a (point, neighbour cell) visit is "that cell has no core point" or "it is already in my
+// set": both are decided from ONE load of the cell's representative (crep, filled by db_core) plus a find, without
+// touching the cell's start offsets, its core flags or its index list.
 __global__ void __launch_bounds__(kDbThreads)
 db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* __restrict__ scell,
                const int* __restrict__ sidx, const double* __restrict__ sx, const double* __restrict__ sy,
                const double* __restrict__ sz, double eps2, double tol, const uint8_t* __restrict__ core_s,
-               int* __restrict__ parent, unsigned long long* __restrict__ guard) {
+               int* __restrict__ parent, unsigned long long* __restrict__ guard, const int* __restrict__ crep,
+               int phase) {
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= m || !core_s[pos]) return;
     const int oi = sidx[pos];
     const int c = scell[pos];
     unsigned band = 0;   // decisions of this point that rest on a pair inside the tol band (certificate)
-    // (a) the core points of one cell are mutual neighbours: link to the first of them
+    // Two launches.  Phase 0: only the representatives walk their neighbour cells -- one thread per cell instead of
+    // one per point, and it already merges most cell pairs that touch.  Phase 1: everybody else; by now the set
+    // test skips nearly every neighbour cell, so the distance loop runs only for pairs of cells that the
+    // representatives could not join (when all points start together, every one of them tests every neighbour
+    // cell before any merge has spread: 3/4 of the kernel was that distance loop).
+    // (a) the core points of one cell are mutual neighbours: link to the cell's representative
     {
-        const int jf = first_core(core_s, (int)cell_start[c], (int)cell_start[c + 1]);
-        if (jf != pos) uf_union(parent, oi, sidx[jf]);
+        const int rep = crep[c];
+        if ((rep == oi) != (phase == 0)) return;
+        if (rep != oi) uf_union(parent, oi, rep);
     }
+    int myroot = uf_find(parent, oi);
     // (b) neighbour cells with a larger id (the pair is examined from the smaller side): one core pair within
     //     eps merges the two cells; cells already in this point's set are skipped without a distance test
     const double x = sx[pos], y = sy[pos], z = sz[pos];
@@ -276,15 +293,15 @@ db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const
         for (int ay = (cy - R > 0 ? cy - R : 0); ay <= (cy + R < G.g[1] - 1 ? cy + R : G.g[1] - 1); ++ay) {
             const int col = cell_id(G, ax, ay, 0);
             if (col + z1 <= c) continue;
-            unsigned b1 = cell_start[col + z0];
             for (int az = z0; az <= z1; ++az) {
-                const unsigned b0 = b1;
-                b1 = cell_start[col + az + 1];
-                if (col + az <= c || b0 == b1) continue;
+                if (col + az <= c) continue;
+                const int rep = crep[col + az];
+                if (rep >= kNoRep) continue;
                 if (cell_box_dist2(G, ax, ay, az, x, y, z) > eps2 + tol) continue;
-                const int jf = first_core(core_s, (int)b0, (int)b1);
-                if (jf < 0) continue;
-                if (uf_find(parent, sidx[jf]) == uf_find(parent, oi)) continue;
+                myroot = uf_find(parent, myroot);
+                if (uf_find(parent, rep) == myroot) continue;
+                const int jf = (int)cell_start[col + az];
+                const unsigned b1 = cell_start[col + az + 1];
                 // merge on a pair that is certainly within eps; pairs inside the band are used only if no certain
                 // pair exists, and then count against the certificate (as do near misses)
                 int hit = -1, maybe = -1;
@@ -310,7 +327,8 @@ __global__ void __launch_bounds__(kDbThreads)
 db_border_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* __restrict__ scell,
                 const int* __restrict__ sidx, const double* __restrict__ sx, const double* __restrict__ sy,
                 const double* __restrict__ sz, double eps2, double tol, const uint8_t* __restrict__ core_s,
-                const int* __restrict__ label_s, int* __restrict__ labels, unsigned long long* __restrict__ guard) {
+                const int* __restrict__ label_s, int* __restrict__ labels, unsigned long long* __restrict__ guard,
+                const int* __restrict__ crep) {
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= m || core_s[pos]) return;
     unsigned band = 0;
@@ -327,16 +345,14 @@ db_border_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, cons
     for (int ax = (cx - R > 0 ? cx - R : 0); ax <= (cx + R < G.g[0] - 1 ? cx + R : G.g[0] - 1); ++ax)
         for (int ay = (cy - R > 0 ? cy - R : 0); ay <= (cy + R < G.g[1] - 1 ? cy + R : G.g[1] - 1); ++ay) {
             const int col = cell_id(G, ax, ay, 0);
-            unsigned b1 = cell_start[col + z0];
             for (int az = z0; az <= z1; ++az) {
-                const unsigned b0 = b1;
-                b1 = cell_start[col + az + 1];
-                if (b0 == b1) continue;
-                const int jf = first_core(core_s, (int)b0, (int)b1);
-                if (jf < 0) continue;
-                const int lab = label_s[jf];          // every core point of a cell carries the same label
-                if (lab >= best) continue;
+                const int rep = crep[col + az];
+                if (rep >= kNoRep) continue;          // no core point in that cell
+                const int lab = labels[rep];          // every core point of a cell carries the same label (written
+                if (lab >= best) continue;            // by db_label_core; this kernel only writes non-core entries)
                 if (cell_box_dist2(G, ax, ay, az, x, y, z) > eps2 + tol) continue;
+                const int jf = (int)cell_start[col + az];
+                const unsigned b1 = cell_start[col + az + 1];
                 bool hit = false, maybe = false;
                 unsigned miss = 0;
                 for (int j = jf; j < (int)b1; ++j) {
@@ -581,14 +597,20 @@ centroid_accumulate(const double* __restrict__ pts, const long long* __restrict_
         const unsigned act = __activemask();
         const unsigned peers = __match_any_sync(act, lab);
         const int leader = __ffs(peers) - 1;
-        // reduce inside each peer group by walking its members
-        unsigned rem = peers;
         long long sum[6] = {0, 0, 0, 0, 0, 0};
-        while (rem) {
-            const int src = __ffs(rem) - 1;
-            rem &= rem - 1;
+        if (lab >= 0) {
+            // Sum inside each peer group with REDUX, which takes an arbitrary member mask: the 64-bit addends are
+            // cut into 22 + 22 + 20 bit pieces (32 of them cannot overflow 32 bits) and the piece sums are put
+            // back together modulo 2^64, i.e. exactly the two's-complement sum.  (A member-by-member shuffle walk
+            // cost 32 x 12 SHFL per warp on clouds in scan order, where a whole warp shares one cluster.)
 #pragma unroll
-            for (int c = 0; c < 6; ++c) sum[c] += __shfl_sync(peers, v[c], src);
+            for (int c = 0; c < 6; ++c) {
+                const unsigned long long u = (unsigned long long)v[c];
+                const unsigned long long s0 = __reduce_add_sync(peers, (unsigned)(u & 0x3fffffull));
+                const unsigned long long s1 = __reduce_add_sync(peers, (unsigned)((u >> 22) & 0x3fffffull));
+                const unsigned long long s2 = __reduce_add_sync(peers, (unsigned)(u >> 44));
+                sum[c] = (long long)(s0 + (s1 << 22) + (s2 << 44));
+            }
         }
         if (lab >= 0 && (int)lane_id() == leader) {
             unsigned long long* A = reinterpret_cast<unsigned long long*>(acc + (size_t)lab * 6);
@@ -647,7 +669,7 @@ int lidar_dbscan(const double* d_points, int64_t m, double eps, int min_samples,
     LIDAR_REQUIRE(d_points && d_labels && h_min3 && h_max3, LIDAR_ERR_INVALID, "lidar_dbscan: NULL argument");
     CellGrid G;
     // dense grid unless the tol band could reach same-cell pairs (they sit >= 2e-6 * eps^2 below the threshold)
-    LIDAR_REQUIRE(make_grid(h_min3, h_max3, eps, tol <= 1e-7 * eps * eps && g_db_dense, &G), LIDAR_ERR_INVALID,
+    LIDAR_REQUIRE(make_grid(h_min3, h_max3, eps, tol <= 1e-7 * eps * eps && g_db_dense && m < (int64_t)kNoRep, &G), LIDAR_ERR_INVALID,
                   "lidar_dbscan: cannot build a cell grid for this bbox");
     const DbLayout L = db_layout(m, G.ncell);
     LIDAR_REQUIRE(d_ws && ws_bytes >= L.total, LIDAR_ERR_WORKSPACE, "lidar_dbscan: workspace too small (%zu < %zu)",
@@ -681,10 +703,18 @@ int lidar_dbscan(const double* d_points, int64_t m, double eps, int min_samples,
     LIDAR_CUDA_TRY(launch_exclusive_scan(cell_count, cell_start, (int64_t)G.ncell, nullptr, scan_ws, st));
     db_scatter<<<g256, 256, 0, st>>>(d_points, mi, cell, slot, cell_start, sidx, scell, sx, sy, sz, parent);
     LIDAR_CHECK_LAUNCH();
+    // the per-cell counters are dead after the scan: the same array now holds the cells' representatives
+    int* crep = reinterpret_cast<int*>(cell_count);
+    if (G.dense) LIDAR_CUDA_TRY(cudaMemsetAsync(crep, 0x7f, sizeof(int) * G.ncell, st));
     db_core<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, min_samples, core_s,
-                                         core_o, guard);
+                                         core_o, guard, crep);
     LIDAR_CHECK_LAUNCH();
-    if (G.dense) db_union_dense<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard);
+    if (G.dense) {
+        for (int phase = 0; phase < 2; ++phase) {
+            db_union_dense<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard, crep, phase);
+            LIDAR_CHECK_LAUNCH();
+        }
+    }
     else db_union<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard);
     LIDAR_CHECK_LAUNCH();
     db_roots<<<g256, 256, 0, st>>>(mi, core_o, parent, is_root);
@@ -693,7 +723,7 @@ int lidar_dbscan(const double* d_points, int64_t m, double eps, int min_samples,
     LIDAR_CUDA_TRY(cudaMemcpyAsync(d_n_clusters, root_rank + mi, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     db_label_core<<<g256, 256, 0, st>>>(mi, sidx, core_s, parent, root_rank, label_s, d_labels);
     LIDAR_CHECK_LAUNCH();
-    if (G.dense) db_border_dense<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, label_s, d_labels, guard);
+    if (G.dense) db_border_dense<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, label_s, d_labels, guard, crep);
     else db_border<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, label_s,
                                                 d_labels, guard);
     LIDAR_CHECK_LAUNCH();

@@ -164,6 +164,7 @@ ground_split_kernel(const double* __restrict__ pts, int64_t n, double thr, doubl
     }
     if (guard_local) atomicAdd(guard, (unsigned long long)guard_local);
     if (F) {                                  // min / max select, so ordered-key atomics are exact and order free
+        __shared__ double s_bb[kCmpThreads / 32][12];
 #pragma unroll
         for (int c = 0; c < 12; ++c) {
             const bool is_max = (c % 6) >= 3;
@@ -171,11 +172,17 @@ ground_split_kernel(const double* __restrict__ pts, int64_t n, double thr, doubl
         }
         if (lane_id() == 0) {
 #pragma unroll
-            for (int c = 0; c < 12; ++c) {
-                const bool is_max = (c % 6) >= 3;
-                if (bb[c] == (is_max ? -INFINITY : INFINITY)) continue;
+            for (int c = 0; c < 12; ++c) s_bb[threadIdx.x >> 5][c] = bb[c];
+        }
+        __syncthreads();
+        if (threadIdx.x < 12) {               // one atomic per CTA and channel
+            const int c = threadIdx.x;
+            const bool is_max = (c % 6) >= 3;
+            double v = s_bb[0][c];
+            for (int w = 1; w < kCmpThreads / 32; ++w) v = is_max ? fmax(v, s_bb[w][c]) : fmin(v, s_bb[w][c]);
+            if (v != (is_max ? -INFINITY : INFINITY)) {
                 unsigned long long* dst = reinterpret_cast<unsigned long long*>(c < 6 ? F->key_in : F->key_ng) + (c % 6);
-                if (is_max) atomicMax(dst, f64_key(bb[c])); else atomicMin(dst, f64_key(bb[c]));
+                if (is_max) atomicMax(dst, f64_key(v)); else atomicMin(dst, f64_key(v));
             }
         }
     }

@@ -54,6 +54,44 @@ class _Scratch(threading.local):
 _scratch = _Scratch()
 
 
+class _PinnedScratch(threading.local):
+    """Per-thread page-locked staging for small read-backs (descriptors, counters, centroids).  A fresh
+    `torch.empty(pin_memory=True)` per call can fall through torch's caching host allocator to cudaHostAlloc,
+    which costs about a millisecond and synchronises the device."""
+
+    def __init__(self):
+        self.bufs: dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, nbytes: int) -> torch.Tensor:
+        buf = self.bufs.get(name)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, pin_memory=True)
+            self.bufs[name] = buf
+        return buf
+
+
+_pinned = _PinnedScratch()
+
+
+def fetch(name: str, *tensors: torch.Tensor):
+    """Small device tensors -> numpy through this thread's pinned staging buffer `name`: the copies are enqueued,
+    then ONE wait on the current stream.  The arrays are views of the staging buffer: valid until the next
+    `fetch` with the same name on this thread (copy them to keep them)."""
+    sizes = [t.numel() * t.element_size() for t in tensors]
+    offs, o = [], 0
+    for b in sizes:
+        offs.append(o)
+        o += (b + 63) & ~63
+    buf = _pinned.get(name, o)
+    views = []
+    for t, off, b in zip(tensors, offs, sizes):
+        v = buf[off:off + b].view(t.dtype).view(t.shape)
+        v.copy_(t, non_blocking=True)
+        views.append(v)
+    torch.cuda.current_stream().synchronize()
+    return [v.numpy() for v in views]
+
+
 def point_format(points: torch.Tensor) -> int:
     """F32X4 for (n,4) float32, F64X3 for (n,3) float64 — contiguous CUDA tensors only."""
     if not points.is_cuda or not points.is_contiguous():
@@ -553,15 +591,12 @@ def preprocess_front(points: torch.Tensor, want_colors: bool = True, scaler: boo
     idx = torch.empty(n, dtype=torch.int32, device=dev)
     X = torch.empty_like(points) if scaler else None
     nb = C.sizeof(_capi.FrontDesc)
-    d_desc = torch.empty(nb, dtype=torch.uint8, device=dev)
-    h_desc = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+    d_desc = _scratch.get("front_desc", nb, dev)
     ws = _scratch.get("front", lib.lidar_preprocess_front_workspace_bytes(n), dev)
     flags = (_capi.FRONT_COLORS if want_colors else 0) | (_capi.FRONT_SCALER if scaler else 0)
     check(lib.lidar_preprocess_front(_ptr(points), n, flags, _ptr(inl), _ptr(col), _ptr(ng), _ptr(idx), _ptr(X),
                                      _ptr(d_desc), _ptr(ws), ws.numel(), _stream_ptr()))
-    h_desc.copy_(d_desc, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    desc = _capi.FrontDesc.from_buffer_copy(h_desc.numpy().tobytes())
+    desc = _capi.FrontDesc.from_buffer_copy(fetch("front_desc", d_desc[:nb])[0].tobytes())
     n_in, m = int(desc.n_in), int(desc.n_nonground)
     return (desc, inl[:n_in], (col[:n_in] if col is not None else None), ng[:m], idx[:m],
             (X[:m] if X is not None else None))

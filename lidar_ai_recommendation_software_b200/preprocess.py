@@ -160,7 +160,7 @@ def run(points, variant: str = "A", host_arrays: bool = True) -> dict:
 
     if not host_arrays:
         if info is not None:
-            n_clusters = _info(_to_host(info)[0])
+            n_clusters = _info(ops.fetch("dbscan_info", info)[0])
         if variant == "A":
             out["ground_plane"] = plane
         out["dimensions"] = dims
@@ -209,5 +209,5 @@ def people_positions(processed: dict) -> np.ndarray:
     if n_ids <= 0:
         return np.array([])
     cent, counts = ops.cluster_centroids(pts, lab, n_ids)
-    h_cent, h_counts = _to_host(cent, counts)
-    return np.ascontiguousarray(h_cent[h_counts > 0][:, :2])
+    h_cent, h_counts = ops.fetch("centroids", cent, counts)
+    return np.ascontiguousarray(h_cent[h_counts > 0][:, :2])      # fancy index: a fresh array, not the staging view
