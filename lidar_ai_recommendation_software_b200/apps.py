@@ -70,11 +70,10 @@ def analyze_crowd_density(processed_data):
             density_grid = np.zeros((len(y_grid) - 1, len(x_grid) - 1))
         max_density = np.max(density_grid)
         threshold = max(0.5, avg_density * 1.5)
-        hot = []
         jj, ii = np.nonzero(density_grid >= threshold)          # row-major: j outer, i inner — upstream's loop order
-        for j, i in zip(jj, ii):
-            hot.append({"x": cx[i], "y": cy[j], "density": density_grid[j, i]})
-        hot = sorted(hot, key=lambda h: h["density"], reverse=True)[:5]
+        # upstream's stable descending sort of one dict per hot cell, cut to five = a stable argsort of the negated values
+        top = np.argsort(-density_grid[jj, ii], kind="stable")[:5]
+        hot = [{"x": cx[ii[t]], "y": cy[jj[t]], "density": density_grid[jj[t], ii[t]]} for t in top]
     else:
         density_grid, max_density, hot = np.zeros((1, 1)), 0, []
     return {"total_people": num_people, "avg_density": avg_density, "max_density": max_density,

@@ -260,22 +260,15 @@ __global__ void __launch_bounds__(kDbThreads)
 db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* __restrict__ scell,
                const int* __restrict__ sidx, const double* __restrict__ sx, const double* __restrict__ sy,
                const double* __restrict__ sz, double eps2, double tol, const uint8_t* __restrict__ core_s,
-               int* __restrict__ parent, unsigned long long* __restrict__ guard, const int* __restrict__ crep,
-               int phase) {
+               int* __restrict__ parent, unsigned long long* __restrict__ guard, const int* __restrict__ crep) {
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= m || !core_s[pos]) return;
     const int oi = sidx[pos];
     const int c = scell[pos];
     unsigned band = 0;   // decisions of this point that rest on a pair inside the tol band (certificate)
-    // Two launches.  Phase 0: only the representatives walk their neighbour cells -- one thread per cell instead of
-    // one per point, and it already merges most cell pairs that touch.  Phase 1: everybody else; by now the set
-    // test skips nearly every neighbour cell, so the distance loop runs only for pairs of cells that the
-    // representatives could not join (when all points start together, every one of them tests every neighbour
-    // cell before any merge has spread: 3/4 of the kernel was that distance loop).
     // (a) the core points of one cell are mutual neighbours: link to the cell's representative
     {
         const int rep = crep[c];
-        if ((rep == oi) != (phase == 0)) return;
         if (rep != oi) uf_union(parent, oi, rep);
     }
     int myroot = uf_find(parent, oi);
@@ -709,12 +702,7 @@ int lidar_dbscan(const double* d_points, int64_t m, double eps, int min_samples,
     db_core<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, min_samples, core_s,
                                          core_o, guard, crep);
     LIDAR_CHECK_LAUNCH();
-    if (G.dense) {
-        for (int phase = 0; phase < 2; ++phase) {
-            db_union_dense<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard, crep, phase);
-            LIDAR_CHECK_LAUNCH();
-        }
-    }
+    if (G.dense) db_union_dense<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard, crep);
     else db_union<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard);
     LIDAR_CHECK_LAUNCH();
     db_roots<<<g256, 256, 0, st>>>(mi, core_o, parent, is_root);

@@ -39,9 +39,11 @@ class CrowdDensityModel:
         avg_density = np.mean(flat_density[occupied]) if np.any(occupied) else 0
 
         threshold = max(0.5, avg_density * 1.5)
-        hotspots = [{"x": flat_x[i], "y": flat_y[i], "density": flat_density[i]}
-                    for i in np.where(flat_density >= threshold)[0]]
-        hotspots = sorted(hotspots, key=lambda h: h["density"], reverse=True)[:5]   # stable, like upstream
+        # upstream builds a dict per cell over the threshold and keeps the first five of a stable descending sort;
+        # a stable argsort of the negated densities picks the same five without the per-cell Python objects
+        cand = np.where(flat_density >= threshold)[0]
+        top = cand[np.argsort(-flat_density[cand], kind="stable")[:5]]
+        hotspots = [{"x": flat_x[i], "y": flat_y[i], "density": flat_density[i]} for i in top]
         return {
             "total_people": total_people, "avg_density": avg_density, "max_density": max_density,
             "density_map": density_grid, "grid_coordinates": (flat_x, flat_y), "density_values": flat_density,
