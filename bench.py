@@ -204,6 +204,8 @@ def main():
                     help="experiment: ordinary instead of cooperative launch (lets frames of different streams overlap)")
     ap.add_argument("--pdl", type=int, default=-1,
                     help="programmatic dependent launch of the fused kernel (1/0; default: library setting)")
+    ap.add_argument("--l2-persist-mb", type=int, default=24,
+                    help="pin this many MB of the occupancy groups in L2 (access policy window); 0 = off")
     ap.add_argument("--scan-order", type=int, default=0,
                     help="1: the scan-order variant of the fused kernel (run-length aggregation, summary-bitmap scan)")
     ap.add_argument("--streaming", type=int, default=1,
@@ -248,6 +250,9 @@ def main():
     if args.pdl >= 0:
         from lidar_ai_recommendation_software_b200 import _capi
         _capi.check(_capi.lib.lidar_frame_set_fused_pdl(args.pdl))
+    if args.l2_persist_mb > 0:
+        from lidar_ai_recommendation_software_b200 import _capi
+        _capi.check(_capi.lib.lidar_frame_set_fused_l2_persist(args.l2_persist_mb << 20))
     ops.set_frame_mode(ops.FRAME_FUSED if fused else ops.FRAME_MULTIKERNEL, args.fused_threads,
                        args.fused_ctas_per_sm, args.fused_smem_kb)
     # the fused kernel fills the device by itself (frames of other streams would only queue behind it);

@@ -350,6 +350,10 @@ int lidar_frame_set_fused_plain_launch(int on);
  * pipeline's workspace or outputs waits (griddepcontrol.wait) until the previous kernel has completed.
  * Outputs are identical.  Process-wide setting. */
 int lidar_frame_set_fused_pdl(int on);
+/* Keep up to `bytes` of the occupancy groups resident in L2 (access policy window on every k_frame_fused launch,
+ * persisting hits / streaming misses; cudaLimitPersistingL2CacheSize is raised to match; clamped to what the
+ * device allows).  0 = off (default).  Process-wide. */
+int lidar_frame_set_fused_l2_persist(size_t bytes);
 /* The scan-order variant of k_frame_fused (off by default; process-wide): for frames as a sensor delivers them
  * (adjacent points adjacent in space) and / or key spaces much larger than the data (a 240 m x 240 m ring scan).
  *   - run-length aggregation across adjacent lanes: only the first lane of a run of equal voxel keys touches the

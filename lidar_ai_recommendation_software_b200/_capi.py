@@ -141,6 +141,7 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_frame_set_fused": (_i32, [_i32, _i32, _i32, _i32]),
     "lidar_frame_set_fused_plain_launch": (_i32, [_i32]),
     "lidar_frame_set_fused_pdl": (_i32, [_i32]),
+    "lidar_frame_set_fused_l2_persist": (_i32, [_sz]),
     "lidar_frame_set_fused_scan_order": (_i32, [_i32]),
     "lidar_frame_trace_offset": (_sz, [C.POINTER(FrameCaps)]),
     "lidar_frame_workspace_bytes": (_sz, [C.POINTER(FrameCaps)]),

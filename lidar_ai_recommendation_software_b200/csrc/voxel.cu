@@ -1589,6 +1589,7 @@ static int g_fused_smem_kb = 0;          // 0 = as much as the chunk needs, up t
 static int g_fused_plain_launch = 0;     // experiment: ordinary launch instead of cooperative (see header)
 static int g_fused_pdl = 0;              // programmatic dependent launch: frame f+1 loads while frame f drains
 static int g_fused_scan_order = 0;       // 1: the scan-order variant of k_frame_fused (see the kernel's header)
+static size_t g_fused_l2_persist = 0;     // bytes of the occupancy groups pinned in L2 (access policy window), 0 = off
 static bool g_fused_attr_set = false;
 static size_t g_fused_attr_bytes = 0;
 
@@ -1631,6 +1632,21 @@ int lidar_frame_set_fused_plain_launch(int on) {
 
 int lidar_frame_set_fused_scan_order(int on) {
     g_fused_scan_order = on ? 1 : 0;
+    return LIDAR_OK;
+}
+
+int lidar_frame_set_fused_l2_persist(size_t bytes) {
+    if (bytes) {
+        int dev = 0, max_persist = 0, max_window = 0;
+        LIDAR_CUDA_TRY(cudaGetDevice(&dev));
+        LIDAR_CUDA_TRY(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+        LIDAR_CUDA_TRY(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+        if (bytes > (size_t)max_persist) bytes = (size_t)max_persist;
+        if (bytes > (size_t)max_window) bytes = (size_t)max_window;
+        LIDAR_REQUIRE(bytes > 0, LIDAR_ERR_INVALID, "lidar_frame_set_fused_l2_persist: the device has no persisting L2");
+        LIDAR_CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
+    }
+    g_fused_l2_persist = bytes;
     return LIDAR_OK;
 }
 
@@ -1769,8 +1785,21 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
         cfg.blockDim = dim3(T);
         cfg.dynamicSmemBytes = dyn;
         cfg.stream = st;
-        cudaLaunchAttribute attr[2];
+        cudaLaunchAttribute attr[3];
         int na = 0;
+        if (g_fused_l2_persist) {
+            // the occupancy groups are the one structure every point hits twice at random: keep them resident in L2
+            // while the frames (read once) and the outputs (written once) stream past
+            size_t bytes = (size_t)L.groups * 32;
+            if (bytes > g_fused_l2_persist) bytes = g_fused_l2_persist;
+            attr[na].id = cudaLaunchAttributeAccessPolicyWindow;
+            attr[na].val.accessPolicyWindow.base_ptr = groups;
+            attr[na].val.accessPolicyWindow.num_bytes = bytes;
+            attr[na].val.accessPolicyWindow.hitRatio = 1.0f;
+            attr[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            ++na;
+        }
         if (!g_fused_plain_launch) {
             attr[na].id = cudaLaunchAttributeCooperative;      // gang scheduling: the grid barriers cannot deadlock
             attr[na].val.cooperative = 1;
