@@ -423,6 +423,7 @@ def main():
                        "streams": S, "backend": args.mode,
                        "launch": ("ordinary launch + programmatic dependent launch (one pipeline, one stream)"
                                   if streaming else "cooperative launch" if fused else "five ordinary launches"),
+                       "l2_persist_mb": args.l2_persist_mb,
                        "sharding": "independent frames per rank, no collective"},
             "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": (1 if fused else 5) * args.steps, "clocks": clk,
