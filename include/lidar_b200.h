@@ -354,7 +354,8 @@ int lidar_frame_set_fused_pdl(int on);
  * persisting hits / streaming misses; cudaLimitPersistingL2CacheSize is raised to match; clamped to what the
  * device allows).  0 = off (default).  Process-wide. */
 int lidar_frame_set_fused_l2_persist(size_t bytes);
-/* The scan-order variant of k_frame_fused (off by default; process-wide): for frames as a sensor delivers them
+/* The scan-order variant of k_frame_fused (off by default; a per-host-thread setting, so that pipelines driven from
+ * different threads choose independently): for frames as a sensor delivers them
  * (adjacent points adjacent in space) and / or key spaces much larger than the data (a 240 m x 240 m ring scan).
  *   - run-length aggregation across adjacent lanes: only the first lane of a run of equal voxel keys touches the
  *     occupancy bitmap, only the first lane of a run of equal density cells issues the reduction (with the run

@@ -1588,7 +1588,8 @@ static int g_fused_ctas_per_sm = 1;
 static int g_fused_smem_kb = 0;          // 0 = as much as the chunk needs, up to the opt-in maximum
 static int g_fused_plain_launch = 0;     // experiment: ordinary launch instead of cooperative (see header)
 static int g_fused_pdl = 0;              // programmatic dependent launch: frame f+1 loads while frame f drains
-static int g_fused_scan_order = 0;       // 1: the scan-order variant of k_frame_fused (see the kernel's header)
+static thread_local int g_fused_scan_order = 0;   // 1: the scan-order variant of k_frame_fused (see the kernel's header).
+                                                  // Per host thread: pipelines of different threads pick their variant independently
 static size_t g_fused_l2_persist = 0;     // bytes of the occupancy groups pinned in L2 (access policy window), 0 = off
 static bool g_fused_attr_set = false;
 static size_t g_fused_attr_bytes = 0;

@@ -232,7 +232,7 @@ def set_frame_mode(mode: int = FRAME_AUTO, threads: int = 0, ctas_per_sm: int = 
 
 
 def set_frame_scan_order(on: bool = True) -> None:
-    """Scan-order variant of the fused frame kernel (process-wide, off by default): for frames as a sensor delivers
+    """Scan-order variant of the fused frame kernel (per host thread, off by default): for frames as a sensor delivers
     them (adjacent points adjacent in space) and key spaces much larger than the data -- run-length aggregation of
     the L2 atomics across adjacent lanes, and a scan / clean that walks a summary bitmap of the occupied groups.
     Identical outputs; the default variant is the faster one on shuffled, dense frames."""
