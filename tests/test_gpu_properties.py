@@ -186,3 +186,25 @@ def test_chained_preprocess_front_is_numpy(p):
     np.testing.assert_array_equal(np.array(desc.bbox_in), np.concatenate([kept.min(axis=0), kept.max(axis=0)]))
     h = (kept[:, 2] - p[:, 2].min()) / (p[:, 2].max() - p[:, 2].min() + 1e-10)
     np.testing.assert_array_equal(col.cpu().numpy(), np.stack([h, 0.5 * (1 - h), np.full_like(h, 0.5)], 1))
+
+
+@pytest.mark.parametrize("rings,azimuth", [(24, 6000), (40, 4096)])
+def test_dbscan_on_a_ring_scan_is_sklearns(rings, azimuth):
+    """Scan-ordered sensor frame: cells of hundreds of returns and neighbouring ground rings that never merge — the
+    case the heavy-cell separation certificate of db_union_dense exists for."""
+    from sklearn.cluster import DBSCAN
+    from lidar_ai_recommendation_software_b200 import ops, synth
+    f = synth.ring_sequence_frame(1, rings=rings, azimuth_steps=azimuth, n_people=150)[:, :3].astype(np.float64)
+    f = f[f[:, 2] > np.percentile(f[:, 2], 30)]
+    f = np.ascontiguousarray(f[np.linalg.norm(f[:, :2], axis=1) < 40.0])
+    assert 20_000 < f.shape[0] < 200_000
+    want = DBSCAN(eps=0.3, min_samples=5).fit(f).labels_
+    d = torch.from_numpy(f).cuda()
+    for dense in (True, False):
+        ops.set_dbscan_dense(dense)
+        try:
+            labels, nc, guard = ops.dbscan(d, 0.3, 5, tol=0.0)
+        finally:
+            ops.set_dbscan_dense(True)
+        np.testing.assert_array_equal(labels.cpu().numpy(), want)
+        assert nc == want.max() + 1 and guard == 0
