@@ -121,3 +121,18 @@ def test_windows_data_loader_matches_reference_fixtures():
                 assert json.loads(json.dumps(meta, sort_keys=True)) == json.loads(str(exp[name + ":meta"])), name
     finally:
         logging.disable(logging.NOTSET)
+
+
+def test_hotspot_selection_is_upstreams_stable_sort():
+    """The top-5 hotspot rule of both density surfaces (models/crowd_density_model.py:93-105,
+    app_simplified.py:289-305): one dict per cell over the threshold, stable sort by density descending, first
+    five.  The package picks them with a stable argsort of the negated densities: same cells, same order, ties
+    included."""
+    rng = np.random.default_rng(7)
+    for _ in range(500):
+        v = rng.integers(0, 6, size=int(rng.integers(0, 60))).astype(np.float64) / 4
+        thr = max(0.5, float(rng.uniform(0, 1.5)))
+        cand = np.where(v >= thr)[0]
+        ref = sorted([{"i": int(i), "d": v[i]} for i in cand], key=lambda h: h["d"], reverse=True)[:5]
+        top = cand[np.argsort(-v[cand], kind="stable")[:5]]
+        assert [h["i"] for h in ref] == [int(i) for i in top]
