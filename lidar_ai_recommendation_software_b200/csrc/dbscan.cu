@@ -256,6 +256,7 @@ db_union(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* 
 // The common case of a (point, neighbour cell) visit is "that cell has no core point" or "it is already in my
 // set": both are decided from ONE load of the cell's representative (crep, filled by db_core) plus a find, without
 // touching the cell's start offsets, its core flags or its index list.
+template <int kAhead>
 __global__ void __launch_bounds__(kDbThreads)
 db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* __restrict__ scell,
                const int* __restrict__ sidx, const double* __restrict__ sx, const double* __restrict__ sy,
@@ -299,12 +300,27 @@ db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const
                 // pair exists, and then count against the certificate (as do near misses)
                 int hit = -1, maybe = -1;
                 unsigned miss = 0;
-                for (int j = jf; j < (int)b1; ++j) {
-                    if (!core_s[j]) continue;
-                    const double r = rdist_of(x, y, z, sx[j], sy[j], sz[j]);
-                    if (tol > 0.0 && fabs(r - eps2) <= tol) {
-                        if (r <= eps2) maybe = j; else ++miss;
-                    } else if (r <= eps2) { hit = j; break; }
+                // kAhead (four) candidates are loaded before the first is judged: the scan is one dependent L2 round trip per
+                // iteration otherwise (measured per thread: ~1000 clocks per candidate, and threads that scan one or
+                // two thousand candidates of heavy cells are the kernel's 0.5 ms tail).  Judged in index order, so
+                // the decisions are the ones of the plain loop.
+                for (int j0 = jf; j0 < (int)b1 && hit < 0; j0 += kAhead) {
+                    uint8_t cf[kAhead];
+                    double qx[kAhead], qy[kAhead], qz[kAhead];
+#pragma unroll
+                    for (int k = 0; k < kAhead; ++k) {
+                        const int j = j0 + k < (int)b1 ? j0 + k : (int)b1 - 1;
+                        cf[k] = core_s[j];
+                        qx[k] = sx[j]; qy[k] = sy[j]; qz[k] = sz[j];
+                    }
+#pragma unroll
+                    for (int k = 0; k < kAhead; ++k) {
+                        if (j0 + k >= (int)b1 || !cf[k] || hit >= 0) continue;
+                        const double r = rdist_of(x, y, z, qx[k], qy[k], qz[k]);
+                        if (tol > 0.0 && fabs(r - eps2) <= tol) {
+                            if (r <= eps2) maybe = j0 + k; else ++miss;
+                        } else if (r <= eps2) hit = j0 + k;
+                    }
                 }
                 if (hit >= 0) uf_union(parent, oi, sidx[hit]);
                 else {
@@ -702,7 +718,8 @@ int lidar_dbscan(const double* d_points, int64_t m, double eps, int min_samples,
     db_core<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, min_samples, core_s,
                                          core_o, guard, crep);
     LIDAR_CHECK_LAUNCH();
-    if (G.dense) db_union_dense<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard, crep);
+    // look-ahead of 4 candidates (56 registers): whole DBSCAN of a 128-beam frame 0.95 -> 0.79 ms; 2: 0.80 ms, 8: 1.02 ms (92 registers)
+    if (G.dense) db_union_dense<4><<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard, crep);
     else db_union<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard);
     LIDAR_CHECK_LAUNCH();
     db_roots<<<g256, 256, 0, st>>>(mi, core_o, parent, is_root);
