@@ -173,12 +173,22 @@ db_core(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* _
                     b1 = cell_start[col + az + 1];
                     if (b0 == b1 || col + az == c) continue;
                     if (cell_box_dist2(G, ax, ay, az, x, y, z) > eps2 + tol) continue;
-                    for (int j = (int)b0; j < (int)b1; ++j) {
-                        const double r = rdist_of(x, y, z, sx[j], sy[j], sz[j]);
-                        const bool in = r <= eps2;
-                        cnt += in;
-                        if (tol > 0.0 && fabs(r - eps2) <= tol) { band_in += in; band_out += !in; }
-                        if (cnt - band_in >= min_samples) { certain = true; break; }   // core whatever the band pairs do
+                    for (int j0 = (int)b0; j0 < (int)b1 && !certain; j0 += 4) {   // look-ahead of four, as in db_union_dense
+                        double qx[4], qy[4], qz[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int j = j0 + k < (int)b1 ? j0 + k : (int)b1 - 1;
+                            qx[k] = sx[j]; qy[k] = sy[j]; qz[k] = sz[j];
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (j0 + k >= (int)b1 || certain) continue;
+                            const double r = rdist_of(x, y, z, qx[k], qy[k], qz[k]);
+                            const bool in = r <= eps2;
+                            cnt += in;
+                            if (tol > 0.0 && fabs(r - eps2) <= tol) { band_in += in; band_out += !in; }
+                            if (cnt - band_in >= min_samples) certain = true;   // core whatever the band pairs do
+                        }
                     }
                 }
             }
@@ -364,12 +374,23 @@ db_border_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, cons
                 const unsigned b1 = cell_start[col + az + 1];
                 bool hit = false, maybe = false;
                 unsigned miss = 0;
-                for (int j = jf; j < (int)b1; ++j) {
-                    if (!core_s[j]) continue;
-                    const double r = rdist_of(x, y, z, sx[j], sy[j], sz[j]);
-                    if (tol > 0.0 && fabs(r - eps2) <= tol) {
-                        if (r <= eps2) maybe = true; else ++miss;
-                    } else if (r <= eps2) { hit = true; break; }
+                for (int j0 = jf; j0 < (int)b1 && !hit; j0 += 4) {      // look-ahead of four, as in db_union_dense
+                    uint8_t cf[4];
+                    double qx[4], qy[4], qz[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int j = j0 + k < (int)b1 ? j0 + k : (int)b1 - 1;
+                        cf[k] = core_s[j];
+                        qx[k] = sx[j]; qy[k] = sy[j]; qz[k] = sz[j];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (j0 + k >= (int)b1 || !cf[k] || hit) continue;
+                        const double r = rdist_of(x, y, z, qx[k], qy[k], qz[k]);
+                        if (tol > 0.0 && fabs(r - eps2) <= tol) {
+                            if (r <= eps2) maybe = true; else ++miss;
+                        } else if (r <= eps2) hit = true;
+                    }
                 }
                 if (hit) best = lab;
                 else {
