@@ -102,7 +102,7 @@ struct PlaneWs {
     unsigned int ticket;
 };
 
-__global__ void __launch_bounds__(kCmpThreads)
+__global__ void __launch_bounds__(kCmpThreads, 2)
 ground_split_kernel(const double* __restrict__ pts, int64_t n, double thr, double cx, double cy, double cz,
                     double* __restrict__ out_pts, int32_t* __restrict__ out_index, int64_t* __restrict__ count,
                     double* __restrict__ plane_out10, unsigned long long* __restrict__ guard, double tol,
