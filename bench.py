@@ -252,7 +252,11 @@ def main():
         _capi.check(_capi.lib.lidar_frame_set_fused_pdl(args.pdl))
     if args.l2_persist_mb > 0:
         from lidar_ai_recommendation_software_b200 import _capi
-        _capi.check(_capi.lib.lidar_frame_set_fused_l2_persist(args.l2_persist_mb << 20))
+        try:        # an optimisation, not a requirement: a device that refuses the carve-out runs without it
+            _capi.check(_capi.lib.lidar_frame_set_fused_l2_persist(args.l2_persist_mb << 20))
+        except _capi.LidarError as e:
+            print(f"bench: L2 persistence not available ({e}); continuing without it", file=sys.stderr)
+            args.l2_persist_mb = 0
     ops.set_frame_mode(ops.FRAME_FUSED if fused else ops.FRAME_MULTIKERNEL, args.fused_threads,
                        args.fused_ctas_per_sm, args.fused_smem_kb)
     # the fused kernel fills the device by itself (frames of other streams would only queue behind it);
