@@ -2,10 +2,11 @@
 
 One frame = variant-A/B preprocess (device-resident mode of `preprocess.run`) followed by
 `CrowdFlowModel.analyze_sequence_frame`, which needs the frames IN ORDER (it matches people against the
-previous frame, NEW op B.3).  The preprocess of different frames is independent, and a good part of its wall
-time is host latency between launches (a dozen scalar read-backs: counts, order statistics, the eps bbox), so
+previous frame, NEW op B.3).  The preprocess of different frames is independent; a call still waits on the
+device twice (the descriptor of the chained front, DBSCAN's counters) and copies 37 MB in, so
 `SequenceRunner` runs it on a few worker threads, each with its own CUDA stream (ctypes and torch release the
-GIL while they wait), and feeds the results to the flow model in frame order on the caller's thread.
+GIL while they wait): the copy-in of one frame, the kernels of another and the host-side steps of a third
+overlap, and the results are fed to the flow model in frame order on the caller's thread.
 Results are identical to the serial loop.
 """
 from __future__ import annotations
