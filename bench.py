@@ -6,15 +6,22 @@ Mpoints/s through voxelise + density, % of the HBM roofline, CPU reference along
 
 Workload (BASELINE.json configs[1]): a 1 M-point synthetic crowd frame (float4 x,y,z,intensity),
 0.05 m voxel downsample + 0.5 m calculate_grid_density histogram of the same points.  One step =
-one frame per GPU.  N > 1: independent frames shard across ranks (weak scaling, no data-path
-collective); launched by torchrun, one rank per GPU.
+one batch of --frames-per-step frames per GPU (512: 20 steps keep the timed region above 0.5 s).
+N > 1: independent frames shard across ranks (weak scaling, no data-path collective); launched by
+torchrun, one rank per GPU.
 
 The JSON line carries
   value      whole-job Mpoints/s, frames resident in HBM when the timed region starts (CUDA events)
-  e2e        the same through the host-buffer API (pinned numpy in -> numpy out, copies timed)
+  e2e        the same through the host-buffer API under the drop-in contract: PAGEABLE numpy in ->
+             numpy arrays the caller OWNS out, every copy timed; e2e.streaming = page-locked in,
+             views out (a sensor driver's zero-copy mode); e2e.streaming_voxels_only without the
+             per-point outputs
   roofline   dominant kernel: algorithmic bytes / measured launch duration vs the measured HBM peak
   cpu_baseline  the CPU oracle (numpy restatement; the reference has no voxel op — "port") timed on
              the host cores of this box, bounded sample
+  extra      the other named configs in the same run: extra.scan50m (configs[4], 50 M points sharded
+             by points, fused NVLink all-reduce), extra.seq (configs[3], 300-frame 128-beam
+             sequence, frames sharded), extra.sa (configs[2], set abstraction, N = 1 only)
 `--impl reference` times that CPU path as the line's own value (rank 0 only).
 """
 from __future__ import annotations
@@ -182,15 +189,122 @@ def run_reference(args, rank: int):
     emit(json.dumps(line))
 
 
+def e2e_leg(ops, torch, dist, world, dev, n, frames, steps, threads, slots, mode):
+    """End to end through the public host-buffer API, host wall clock, whole-job throughput (max over ranks).
+
+    mode "api"        the drop-in contract: caller-owned PAGEABLE numpy frame in, fresh numpy arrays the
+                      caller owns out.  `threads` Python threads drive one HostFramePipeline each, the way Streamlit
+                      sessions drive the reference (one script thread per session); the C ABI stages with its
+                      parallel host memcpy and reads back exactly what each frame produced (two-stage).
+    mode "streaming"  a sensor driver that owns page-locked buffers: pinned frame in, views of the slot's pinned
+                      result block out (`collect(copy=False)`), one thread, `slots` frames in flight.
+    mode "streaming_voxels_only"  the same without the per-point outputs (LIDAR_HOST_NO_PER_POINT)."""
+    api = mode == "api"
+    kw = dict(max_points=n, voxel_size=VOXEL, grid_size=GRID, max_key_space=1 << 28, max_nx=256, max_ny=256)
+    if api:
+        pipes = [ops.HostFramePipeline(slots=2, two_stage=True, **kw) for _ in range(threads)]
+        srcs = frames                                               # plain numpy arrays (pageable)
+    else:
+        pipes = [ops.HostFramePipeline(slots=slots, two_stage=False, per_point_outputs=(mode == "streaming"), **kw)]
+        srcs = [torch.from_numpy(f).pin_memory() for f in frames]
+        threads = 1
+    torch.cuda.synchronize()
+    for p_ in pipes:
+        for w in range(2):
+            p_.process(srcs[w % len(srcs)])
+    d2h = pipes[0]._last_d2h if api else pipes[0].d2h_bytes(n)
+    per_thread = max(2, steps // threads)
+    total = per_thread * threads
+    checks = [0] * threads
+
+    def drive(t):
+        hp = pipes[t]
+        torch.cuda.set_device(dev)
+        inflight, out = 0, None
+        depth = len(hp.slots)
+        for s in range(per_thread):
+            if inflight == depth:
+                out = hp.collect(copy=api)
+                inflight -= 1
+            hp.submit(srcs[(t + s) % len(srcs)])
+            inflight += 1
+        while inflight:
+            out = hp.collect(copy=api)
+            inflight -= 1
+        checks[t] = int(out["counts"].sum())
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    if threads == 1:
+        drive(0)
+    else:
+        ths = [threading.Thread(target=drive, args=(t,)) for t in range(threads)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert all(c == n for c in checks), checks
+    te = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    for p_ in pipes:
+        p_.close()
+    return {"value": n * total * world / float(te.item()) / 1e6, "unit": "Mpoints/s", "h2d_bytes_per_step": 16 * n,
+            "d2h_bytes_per_step": int(d2h), "steps": total, "threads": threads}
+
+
+def run_extras(args, torch, dist, dev, rank, world):
+    """The other named shapes of BASELINE.json (configs[2], [3], [4]) in the same run, so that the driver's N = 1/2/4/8
+    records carry them: extra.sa (N = 1 only), extra.seq (frames sharded), extra.scan50m (points sharded)."""
+    import types
+
+    import bench_configs as bc
+    extra = {}
+
+    def guarded(name, fn):
+        t0 = time.perf_counter()
+        try:
+            out = fn()
+        except Exception as e:          # an extra must never take the headline line down with it
+            out = {"error": f"{type(e).__name__}: {e}"[:400]}
+            if world > 1:
+                raise                    # ... but a rank that skips a collective would hang the others: fail loudly
+        if rank == 0 and out is not None:
+            out["bench_wall_s"] = time.perf_counter() - t0
+            extra[name] = out
+
+    if "scan" in args.extras:
+        a = types.SimpleNamespace(points=args.scan_points, host_shards=8, reps=10)
+        guarded("scan50m", lambda: bc.run_scan(a, torch, dev, rank, world, dist))
+    if "seq" in args.extras:
+        a = types.SimpleNamespace(frames=args.seq_frames, pool=4, rings=128, azimuth=20480, dropin=False, workers=3)
+        guarded("seq", lambda: bc.run_seq(a, torch, dev, rank, world, dist))
+    if "sa" in args.extras and world == 1:
+        a = types.SimpleNamespace(reps=20)
+        guarded("sa", lambda: bc.run_sa(a, torch, dev, rank, world))
+    return extra
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=1_000_000)
-    ap.add_argument("--e2e-steps", type=int, default=200)
-    ap.add_argument("--e2e-slots", type=int, default=3, help="frames in flight in the end-to-end leg")
+    ap.add_argument("--frames-per-step", type=int, default=512,
+                    help="frames per GPU in one step (one step = one batch of frames): 20 steps x 512 frames keep the "
+                         "timed region above half a second, long enough for the clock sampler")
+    ap.add_argument("--e2e-steps", type=int, default=240, help="frames per rank in each end-to-end leg")
+    ap.add_argument("--e2e-slots", type=int, default=3, help="frames in flight in the streaming end-to-end legs")
+    ap.add_argument("--e2e-threads", type=int, default=3, help="driver threads of the drop-in end-to-end leg")
+    ap.add_argument("--extras", default="scan,seq,sa", help="comma list of the extra configs to measure ('' = none)")
+    ap.add_argument("--scan-points", type=int, default=50_000_000)
+    ap.add_argument("--seq-frames", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="frame kernel grid cap (0 = library default)")
     ap.add_argument("--streams", type=int, default=0,
@@ -203,7 +317,7 @@ def main():
     ap.add_argument("--fused-plain-launch", action="store_true",
                     help="experiment: ordinary instead of cooperative launch (lets frames of different streams overlap)")
     ap.add_argument("--pdl", type=int, default=-1,
-                    help="programmatic dependent launch of the fused kernel (1/0; default: library setting)")
+                    help="programmatic dependent launch of the fused kernel (2/1/0; default: library setting)")
     ap.add_argument("--l2-persist-mb", type=int, default=24,
                     help="pin this many MB of the occupancy groups in L2 (access policy window); 0 = off")
     ap.add_argument("--scan-order", type=int, default=0,
@@ -212,6 +326,7 @@ def main():
                     help="fused back end, one stream: ordinary launch + programmatic dependent launch for the "
                          "device-resident leg (frames back to back on one stream); 0 = cooperative launches")
     args = ap.parse_args()
+    args.extras = [x for x in args.extras.split(",") if x]
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
 
@@ -231,27 +346,27 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one rank per GPU: each rank lives on the CPUs / memory of ITS GPU's NUMA node before anything page-locked exists
+    numa = ops.bind_to_device_numa(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.points
+    F = max(1, args.frames_per_step)
     # every rank owns its own frames (frames shard across GPUs: weak scaling, no collective)
     host_frames = [synth.crowd_frame(n, seed=rank * 1000 + s, extent=EXTENT) for s in range(POOL)]
     frames = [torch.from_numpy(f).to(dev) for f in host_frames]
+    from lidar_ai_recommendation_software_b200 import _capi
     if args.ctas_per_sm:
-        from lidar_ai_recommendation_software_b200 import _capi
         _capi.check(_capi.lib.lidar_frame_set_ctas_per_sm(args.ctas_per_sm))
     fused = args.mode == "fused"
     if args.fused_plain_launch:
-        from lidar_ai_recommendation_software_b200 import _capi
         _capi.check(_capi.lib.lidar_frame_set_fused_plain_launch(1))
     if args.scan_order:
         ops.set_frame_scan_order(True)
     if args.pdl >= 0:
-        from lidar_ai_recommendation_software_b200 import _capi
         _capi.check(_capi.lib.lidar_frame_set_fused_pdl(args.pdl))
     if args.l2_persist_mb > 0:
-        from lidar_ai_recommendation_software_b200 import _capi
         try:        # an optimisation, not a requirement: a device that refuses the carve-out runs without it
             _capi.check(_capi.lib.lidar_frame_set_fused_l2_persist(args.l2_persist_mb << 20))
         except _capi.LidarError as e:
@@ -263,18 +378,23 @@ def main():
     # the five-kernel path leaves gaps that frames on other streams fill
     S = args.streams if args.streams > 0 else (1 if fused else 4)
     pipes = [ops.FramePipeline(max_points=n, voxel_size=VOXEL, grid_size=GRID, max_key_space=1 << 28,
-                               max_nx=256, max_ny=256, device=dev) for _ in range(S)]
+                               max_nx=256, max_ny=256, device=dev, scan_order=bool(args.scan_order)) for _ in range(S)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     pipe = pipes[0]
     streaming = bool(fused and S == 1 and args.streaming and not args.fused_plain_launch and args.pdl < 0)
     if streaming:
-        ops.set_frame_streaming(True)
+        # the frames are resident (uploaded and synchronised above) long before they are enqueued
+        ops.set_frame_streaming(True, inputs_complete=True)
     torch.cuda.synchronize()
 
     def run_frames(count):
         """`count` frames, round-robin over the S pipelines/streams; returns after enqueueing, with the
         current stream made to wait for all of them."""
         cur = torch.cuda.current_stream()
+        if S == 1:
+            for s_ in range(count):
+                pipe.enqueue(frames[s_ % POOL])
+            return
         for st in streams:
             st.wait_stream(cur)
         for s_ in range(count):
@@ -289,10 +409,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput ------------------------------------------------------------
+    # ---- device-resident throughput: K steps of F frames each --------------------------------------
     clocks = ClockSampler(local_rank)
     clocks.start()
-    run_frames(args.warmup)
+    for _ in range(args.warmup):
+        run_frames(F)
     torch.cuda.synchronize()
     res = pipe.result()
     v_over_n = res.n_voxels / n
@@ -300,7 +421,8 @@ def main():
     clocks.rows.clear()   # keep only samples taken during the timed region
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    run_frames(args.steps)
+    for _ in range(args.steps):
+        run_frames(F)
     ev1.record()
     barrier()
     clk = clocks.stop()
@@ -311,12 +433,12 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    value = n * args.steps * world / (ms * 1e-3) / 1e6
+    value = n * F * args.steps * world / (ms * 1e-3) / 1e6
 
     if streaming:
         ops.set_frame_streaming(False)   # the remaining legs (several pipelines / streams) use cooperative launches
     # ---- per-kernel device time (CUDA events on the launching stream) --------------------------
-    ksteps = min(args.steps, 50)
+    ksteps = 50
     per_kernel = np.zeros(5)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(ksteps)]
     for s in range(ksteps):
@@ -328,10 +450,11 @@ def main():
     per_kernel /= ksteps  # ms
     hbm_peak, peak_src = peaks()
     step_ms = ms / args.steps
-    step_bytes = (20.0 + 20.0 * v_over_n) * n      # 20 + 20*V/N bytes per point
+    frame_ms = step_ms / F
+    frame_bytes = (20.0 + 20.0 * v_over_n) * n      # 20 + 20*V/N bytes per point
     phases = None
     if fused:
-        # one launch per frame: the kernel's algorithmic bytes are the step's; phases from %globaltimer
+        # one launch per frame: the kernel's algorithmic bytes are the frame's; phases from %globaltimer
         kms = float(per_kernel.sum())
         last = pipe.result()
         ph = [int(x) for x in last.desc.trace_ns]
@@ -340,18 +463,17 @@ def main():
                  "rank", "bar4", "clean_finalize"]
         phases = {k + "_us": ph[i] / 1e3 for i, k in enumerate(names)}
         phases["ctas"] = ph[15]
-        # one launch per step: the kernel's average launch duration over the timed region is the step time
-        gbs = step_bytes / (step_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_frame_fused", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": gbs / hbm_peak, "traffic": ncu_traffic("k_frame_fused"), "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": step_bytes, "launch_ms": step_ms,
+        gbs = frame_bytes / (frame_ms * 1e-3) / 1e9
+        kname = "k_frame_fused"
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": gbs / hbm_peak, "traffic": ncu_traffic(kname), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": frame_bytes, "launch_ms": frame_ms,
                     "launch_ms_alone": kms,
-                    "note": "launch_ms = average duration of the one launch per step over the timed region (CUDA "
-                            "events around all steps); launch_ms_alone = one frame alone on an idle device, CUDA "
-                            "events around a single cooperative launch (includes the launch gap)"}
-        roofline_step = {"bytes_per_point": step_bytes / n, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
-                         "peak": hbm_peak, "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak,
-                         "kernel_ms": {"k_frame_fused": kms}, "phases_of_one_frame": phases}
+                    "note": "launch_ms = average duration of the one launch per frame over the timed region (CUDA "
+                            "events around all steps / frames); launch_ms_alone = one frame alone on an idle device, "
+                            "CUDA events around a single cooperative launch (includes the launch gap)"}
+        roofline_step = {"bytes_per_point": frame_bytes / n, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": gbs / hbm_peak, "kernel_ms": {kname: kms}, "phases_of_one_frame": phases}
     dom = int(np.argmax(per_kernel))
     # algorithmic bytes per point of each kernel
     n_groups = float(res.desc.key_space) / 224.0          # one 32 B occupancy group per 224 voxel cells
@@ -368,41 +490,32 @@ def main():
         roofline = {"bound": "hbm", "kernel": dom_name, "achieved": dom_gbs, "peak": hbm_peak, "unit": "GB/s",
                     "frac": dom_gbs / hbm_peak, "traffic": ncu_traffic(dom_name), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg[dom_name], "launch_ms": float(per_kernel[dom])}
-        roofline_step = {"bytes_per_point": step_bytes / n, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
-                         "peak": hbm_peak, "unit": "GB/s", "frac": step_bytes / (step_ms * 1e-3) / 1e9 / hbm_peak,
+        roofline_step = {"bytes_per_point": frame_bytes / n, "achieved": frame_bytes / (frame_ms * 1e-3) / 1e9,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": frame_bytes / (frame_ms * 1e-3) / 1e9 / hbm_peak,
                          "kernel_ms": {k: float(v) for k, v in zip(KERNELS, per_kernel)}}
+    for p_ in pipes:
+        del p_
+    pipes.clear()
 
     # ---- end to end through the host-buffer API ------------------------------------------------
-    hp = ops.HostFramePipeline(max_points=n, voxel_size=VOXEL, grid_size=GRID, slots=args.e2e_slots,
-                               max_key_space=1 << 28, max_nx=256, max_ny=256)
-    pinned = [torch.from_numpy(f).pin_memory() for f in host_frames[:4]]
-    torch.cuda.synchronize()
-    for w in range(3):
-        hp.process(pinned[w % 4])
-    e2e_steps = max(4, min(args.e2e_steps, args.steps))
-    barrier()
-    t0 = time.perf_counter()
-    inflight = 0
-    for s in range(e2e_steps):
-        if inflight == args.e2e_slots:
-            out = hp.collect(copy=False)
-            inflight -= 1
-        hp.submit(pinned[s % 4])
-        inflight += 1
-    while inflight:
-        out = hp.collect(copy=False)
-        inflight -= 1
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    assert int(out["counts"].sum()) == n
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = n * e2e_steps * world / float(te.item()) / 1e6
-    e2e = {"value": e2e_val, "unit": "Mpoints/s", "h2d_bytes_per_step": hp.h2d_bytes(n),
-           "d2h_bytes_per_step": hp.d2h_bytes(n), "steps": e2e_steps,
-           "api": f"ops.HostFramePipeline.submit/collect = one lidar_frame_voxel_density_host C-ABI call per frame "
-                  f"(pinned numpy in, numpy out, {args.e2e_slots} slots in flight)"}
+    e2e_steps = max(8, args.e2e_steps)
+    e2e = e2e_leg(ops, torch, dist, world, dev, n, host_frames[:4], e2e_steps, max(1, args.e2e_threads), args.e2e_slots, "api")
+    e2e["api"] = (f"pageable numpy in, owned numpy out: ops.HostFramePipeline.submit / collect(copy=True), "
+                  f"{e2e['threads']} caller threads with one pipeline (2 slots) each; per frame one parallel staging "
+                  "memcpy, lidar_frame_voxel_density_host_begin, lidar_frame_host_fetch (exact sizes), parallel copy-out")
+    e2e["numa_node"], e2e["cpus"] = numa
+    stream_leg = e2e_leg(ops, torch, dist, world, dev, n, host_frames[:4], e2e_steps, 1, args.e2e_slots, "streaming")
+    stream_leg["api"] = (f"pinned numpy in, views of the pinned result block out: submit / collect(copy=False), one thread, "
+                         f"{args.e2e_slots} slots in flight, one frame-sized copy-out (the round-1 e2e figure)")
+    e2e["streaming"] = stream_leg
+    vox_leg = e2e_leg(ops, torch, dist, world, dev, n, host_frames[:4], e2e_steps, 1, args.e2e_slots, "streaming_voxels_only")
+    vox_leg["api"] = "as streaming, LIDAR_HOST_NO_PER_POINT: voxel_key / inverse stay on the device"
+    e2e["streaming_voxels_only"] = vox_leg
+
+    # ---- the other named configs -----------------------------------------------------------------
+    del frames
+    torch.cuda.empty_cache()
+    extra = run_extras(args, torch, dist, dev, rank, world) if args.extras else {}
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------
     cpu = None
@@ -419,18 +532,20 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 decisions / i64 fixed-point sums on f32 points",
             "data": "synthetic",
-            "config": {"workload": f"{n}-point crowd frame per GPU per step, {VOXEL} m voxel downsample + "
+            "config": {"workload": f"{n}-point crowd frame, {VOXEL} m voxel downsample + "
                                    f"{GRID} m calculate_grid_density histogram (BASELINE configs[1])",
-                       "points_per_frame": n, "voxel_m": VOXEL, "grid_m": GRID, "voxels_per_point": v_over_n,
-                       "key_space": int(res.desc.key_space),
+                       "points_per_frame": n, "voxel_m": VOXEL, "grid_m": GRID, "frames_per_step": F,
+                       "ms_per_frame": frame_ms, "timed_region_s": ms * 1e-3,
+                       "voxels_per_point": v_over_n, "key_space": int(res.desc.key_space),
                        "l2": f"inputs rotate over {POOL} distinct frames ({POOL * n * 16 / 1e6:.0f} MB > 126 MB L2)",
                        "streams": S, "backend": args.mode,
-                       "launch": ("ordinary launch + programmatic dependent launch (one pipeline, one stream)"
+                       "launch": ("ordinary launch + programmatic dependent launch (one pipeline, one stream, frames "
+                                  "resident before they are enqueued)"
                                   if streaming else "cooperative launch" if fused else "five ordinary launches"),
                        "l2_persist_mb": args.l2_persist_mb,
                        "sharding": "independent frames per rank, no collective"},
             "roofline": roofline, "roofline_step": roofline_step, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": (1 if fused else 5) * args.steps, "clocks": clk,
+            "gpu_launches": (1 if fused else 5) * args.steps * F, "clocks": clk, "extra": extra,
         }
         emit(json.dumps(line))
     if world > 1:

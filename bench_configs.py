@@ -28,12 +28,17 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 # The contract is ONE JSON line on stdout, but libraries write there too (torch's NCCL process group announces
 # "NCCL version ..." on fd 1 at the first collective).  Everything that is not the result line goes to stderr.
-_RESULT_FD = os.dup(1)
-os.dup2(2, 1)
+_RESULT_FD = None
+
+
+def _redirect_stdout() -> None:
+    global _RESULT_FD
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
 
 
 def emit(line: str) -> None:
-    os.write(_RESULT_FD, (line + "\n").encode())
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (line + "\n").encode())
 
 
 def peaks():
@@ -157,7 +162,7 @@ def run_sa(args, torch, dev, rank, world):
         "Mpoints_per_s_input": B * N / (t_all * 1e-3) / 1e6,
         "out_bytes": B * 128 * M * 4,
     }
-    emit(json.dumps(line))
+    return line
 
 
 def run_seq(args, torch, dev, rank, world, dist):
@@ -270,13 +275,18 @@ def run_seq(args, torch, dev, rank, world, dist):
             "timing": "host wall clock around the per-frame drop-in calls (numpy in / numpy out, copies included), max over ranks",
             "synth_s_per_frame_host": gen_s / max(1, pool_n), "data": "synthetic (Appendix C.3)", "scaling": "strong",
         }
-        emit(json.dumps(line))
+        return line
+    return None
 
 
 def run_scan(args, torch, dev, rank, world, dist):
-    """cfg 5: one merged scan sharded by points: local bbox -> MAX allreduce -> local histogram ->
-    SUM allreduce of the int32 grid (sharding.sharded_grid_density)."""
-    from lidar_ai_recommendation_software_b200 import ops, sharding, synth
+    """cfg 5: one merged scan sharded by points.  The product call is ONE enqueue per rank
+    (sharding.ScanDensity, backend "fused": bbox -> bbox exchange -> device-side edges -> histogram -> two-shot
+    NVLink all-reduce of the grid -> density), then one exactly-sized read-back.  Alongside: the same call through
+    the lidar_nccl_* fallback, and the fused kernel on the same shard WITHOUT the peers (the difference is what the
+    exchanges cost)."""
+    import ctypes as C
+    from lidar_ai_recommendation_software_b200 import _capi, ops, sharding, synth
     n_total = args.points
     parts = max(world, args.host_shards)
     per_rank = parts // world
@@ -289,56 +299,90 @@ def run_scan(args, torch, dev, rank, world, dist):
     gen_s = time.perf_counter() - t0
     n_local = shard.shape[0]
     hbm, _, src = peaks()
+    g = 0.5
 
-    def step():
-        return sharding.sharded_grid_density(shard, 0.5)
-
-    gx, gy, dens = step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    # whole call (includes the small host round trips for the edges and the D2H of the grid)
-    ts = []
-    for _ in range(args.reps):
+    def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        step()
-        torch.cuda.synchronize()
-        ts.append(time.perf_counter() - t0)
-    call_s = float(np.median(ts))
-    # the two local kernels alone (device events)
-    bb_ms, _ = ev_time(lambda: ops.bbox(shard), args.reps, 2, torch)
-    xe = np.arange(gx[0] - 0.25, gx[-1] + 0.5, 0.5)
-    ye = np.arange(gy[0] - 0.25, gy[-1] + 0.5, 0.5)
-    h_ms, _ = ev_time(lambda: ops.hist2d_points_counts(shard, xe, ye), args.reps, 2, torch)
-    ar_ms = None
+
+    def call_times(ctx):
+        """median host wall clock of the whole call (enqueue -> owned numpy arrays) and median device time of the
+        enqueue alone (CUDA events), max over ranks"""
+        ctx(shard, g)
+        ctx(shard, g)
+        ts, ks = [], []
+        for _ in range(args.reps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            ctx.enqueue(shard, g)
+            e1.record()
+            out = ctx.result()
+            ts.append(time.perf_counter() - t0)
+            torch.cuda.synchronize()
+            ks.append(e0.elapsed_time(e1))
+        t = torch.tensor([float(np.median(ts)), float(np.median(ks))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0].item()), float(t[1].item()), out
+
+    fused = sharding.ScanDensity(dev, backend="auto" if world > 1 else "fused")
+    call_s, kern_ms, (gx, gy, dens) = call_times(fused)
+    total_counts = float(dens.sum() * g * g)
+    backend = fused.backend
+    multicast = bool(getattr(fused, "multicast", False))
+    nccl_call_s = nccl_kern_ms = ar_ms = None
+    local_ms = kern_ms
     if world > 1:
-        g = torch.zeros((len(gx), len(gy)), dtype=torch.int32, device=dev)
-        ar_ms, _ = ev_time(lambda: dist.all_reduce(g), args.reps, 3, torch)
-    t = torch.tensor([call_s, bb_ms, h_ms], dtype=torch.float64, device=dev)
-    if world > 1:
+        if backend == "fused":
+            nccl = sharding.ScanDensity(dev, backend="nccl")
+            nccl_call_s, nccl_kern_ms, (_, _, d2) = call_times(nccl)
+            assert np.array_equal(d2, dens), "fused and NCCL grids differ"
+            grid_buf = torch.zeros(len(gx) * len(gy), dtype=torch.int32, device=dev)
+            st = torch.cuda.current_stream().cuda_stream
+            ar_ms, _ = ev_time(lambda: _capi.check(_capi.lib.lidar_nccl_allreduce(nccl.nccl, grid_buf.data_ptr(), grid_buf.numel(),
+                                                                                   _capi.NCCL_SUM_I32, st)), args.reps, 3, torch)
+            nccl.close()
+        # the same shard through the single-rank kernel: what the rank does without its peers
+        solo = sharding.ScanDensity(dev, backend="fused", solo=True)
+        for _ in range(3):
+            solo(shard, g)
+        ks = []
+        for _ in range(args.reps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            solo.enqueue(shard, g)
+            e1.record()
+            solo.result()
+            ks.append(e0.elapsed_time(e1))
+        t = torch.tensor([float(np.median(ks))], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    call_s, bb_ms, h_ms = (float(v) for v in t.tolist())
-    total_counts = float(dens.sum() * 0.25)
+        local_ms = float(t.item())
+        solo.close()
+    fused.close()
     if rank == 0:
-        line = {
-            "config": f"configs[4]: {n_total}-point merged venue scan sharded by points over {world} GPU(s), allreduce of the int32 grid",
+        return {
+            "config": f"configs[4]: {n_total}-point merged venue scan sharded by points over {world} GPU(s), all-reduce of the int32 grid",
             "n_gpus": world, "points": n_total, "points_per_rank": n_local, "grid": [len(gx), len(gy)],
-            "counts_sum": total_counts,
+            "counts_sum": total_counts, "backend": backend, "nvls_multicast": multicast,
             "call_ms": call_s * 1e3, "Mpoints_per_s_call": n_total / call_s / 1e6,
-            "local_bbox_ms": bb_ms, "local_hist_ms": h_ms, "allreduce_grid_ms": ar_ms,
-            "Mpoints_per_s_kernels": n_total / ((bb_ms + h_ms + (ar_ms or 0.0)) * 1e-3) / 1e6,
-            "roofline": {"bound": "hbm", "kernel": "hist2d_kernel", "achieved": 16.0 * n_local / (h_ms * 1e-3) / 1e9,
-                         "peak": hbm, "unit": "GB/s", "frac": 16.0 * n_local / (h_ms * 1e-3) / 1e9 / hbm, "peak_source": src},
-            "roofline_bbox": {"bound": "hbm", "kernel": "bbox_kernel", "achieved": 16.0 * n_local / (bb_ms * 1e-3) / 1e9,
-                              "peak": hbm, "unit": "GB/s", "frac": 16.0 * n_local / (bb_ms * 1e-3) / 1e9 / hbm},
+            "kernel_ms": kern_ms, "kernel_ms_without_peers": local_ms,
+            "collectives_us": (kern_ms - local_ms) * 1e3 if world > 1 else 0.0,
+            "Mpoints_per_s_kernel": n_total / (kern_ms * 1e-3) / 1e6,
+            "nccl_fallback": None if nccl_call_s is None else {"call_ms": nccl_call_s * 1e3, "enqueue_ms": nccl_kern_ms,
+                                                                "allreduce_grid_us": ar_ms * 1e3},
+            "roofline": {"bound": "hbm", "kernel": "k_scan_density", "achieved": 32.0 * n_local / (local_ms * 1e-3) / 1e9,
+                         "peak": hbm, "unit": "GB/s", "frac": 32.0 * n_local / (local_ms * 1e-3) / 1e9 / hbm, "peak_source": src,
+                         "algorithmic_bytes_per_point": 32.0,
+                         "note": "two passes over the shard (bbox, then histogram: the edges depend on the global bbox), 16 B/point each"},
             "collective_payload_bytes": 4 * len(gx) * len(gy) + 32,
-            "timing": "call = host wall clock around sharding.sharded_grid_density (median), kernels = CUDA events; max over ranks",
+            "timing": "call = host wall clock from enqueue to owned numpy arrays (median), kernel = CUDA events around the one enqueue; max over ranks",
             "synth_s_host": gen_s, "data": "synthetic (Appendix C.4)", "scaling": "strong",
         }
-        emit(json.dumps(line))
+    return None
 
 
 def main():
@@ -355,6 +399,7 @@ def main():
     ap.add_argument("--points", type=int, default=50_000_000)
     ap.add_argument("--host-shards", type=int, default=8)
     args = ap.parse_args()
+    _redirect_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -370,11 +415,11 @@ def main():
             run_surfaces(args, torch, dev)
     elif args.config == "sa":
         if rank == 0:
-            run_sa(args, torch, dev, rank, world)
-    elif args.config == "seq":
-        run_seq(args, torch, dev, rank, world, dist)
+            emit(json.dumps(run_sa(args, torch, dev, rank, world)))
     else:
-        run_scan(args, torch, dev, rank, world, dist)
+        line = (run_seq if args.config == "seq" else run_scan)(args, torch, dev, rank, world, dist)
+        if line is not None:
+            emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LIDAR_ABI_VERSION 1
+#define LIDAR_ABI_VERSION 2
 
 #define LIDAR_OK 0
 #define LIDAR_ERR_INVALID (-1)   /* bad argument */
@@ -345,9 +345,14 @@ int lidar_frame_set_fused(int mode, int threads, int ctas_per_sm, int smem_kb);
  * device next to whatever else is running (the kernel traps after spinning for two seconds). */
 int lidar_frame_set_fused_plain_launch(int on);
 /* Programmatic dependent launch of k_frame_fused (off by default): when frames are enqueued back to back on
- * one stream, the next frame's kernel may start on SMs the current one has left, and runs its TMA load and
- * bounding box (which touch only its own input) under the current frame's tail; everything that touches the
+ * one stream, the next frame's kernel may start on SMs the current one has left; everything that touches the
  * pipeline's workspace or outputs waits (griddepcontrol.wait) until the previous kernel has completed.
+ *   on = 1  safe for any producer: the frame itself is read after griddepcontrol.wait too (a frame written by the
+ *           kernel just before this one on the stream -- a crop, a concatenation -- is visible only then); what
+ *           overlaps is the launch latency and the CTA set-up
+ *   on = 2  the caller vouches that the frame was COMPLETE in device memory before the launch was enqueued (resident
+ *           frames, or an event wait after the producer): the TMA load and the bounding box, which touch only the
+ *           input, additionally run under the previous frame's tail
  * Outputs are identical.  Process-wide setting. */
 int lidar_frame_set_fused_pdl(int on);
 /* Keep up to `bytes` of the occupancy groups resident in L2 (access policy window on every k_frame_fused launch,
@@ -435,6 +440,115 @@ int lidar_frame_voxel_density_host(const void* h_points, int64_t n, double voxel
                                    const double* h_origin3, const double* h_xy_range4, void* d_points,
                                    lidar_voxel* d_voxels, void* d_out, void* h_out, int flags,
                                    const lidar_frame_caps* caps, void* d_ws, size_t ws_bytes, void* stream);
+/* Two-stage read-back: _begin enqueues copy-in, the frame and the repack but copies only the DESCRIPTOR back;
+ * once the host has read n_voxels / nx / ny from it, lidar_frame_host_fetch enqueues copies of exactly what the
+ * frame produced (8n bytes of per-point outputs unless LIDAR_HOST_NO_PER_POINT, 20 bytes per VOXEL, 4*nx*ny bytes
+ * of grid) into the same block layout.  A sensor frame with 0.2 voxels per point moves 60 % fewer bytes than the
+ * one-copy form, which has to size the per-voxel arrays by the frame. */
+int lidar_frame_voxel_density_host_begin(const void* h_points, int64_t n, double voxel_size, double grid_size,
+                                         const double* h_origin3, const double* h_xy_range4, void* d_points,
+                                         lidar_voxel* d_voxels, void* d_out, void* h_out, int flags,
+                                         const lidar_frame_caps* caps, void* d_ws, size_t ws_bytes, void* stream);
+int lidar_frame_host_fetch(int64_t n, int64_t n_voxels, int nx, int ny, const void* d_out, void* h_out, int flags,
+                           const lidar_frame_caps* caps, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------- *
+ * Point-sharded density grid of one oversized scan (BASELINE configs[4], SURVEY.md 8e "points"):
+ * calculate_grid_density (utils/data_processing.py:282-328) of a scan whose points are spread over the
+ * GPUs of one box.  Every rank bins its shard into the SAME np.arange edges, the integer grids are
+ * summed (bit-identical to the single-GPU grid), density = counts / g^2.
+ *
+ * lidar_scan_density: the whole call as ONE persistent cooperative kernel per rank -- local bbox, bbox
+ *   exchange with the peers, arange parameters derived on the device, histogram, two-shot all-reduce of
+ *   the grid over NVLink (multimem.ld_reduce.add.u32 + multimem.st through the NVSwitch when the
+ *   symmetric buffer has a multicast mapping, peer loads / stores otherwise), density and cell centres.
+ *   No host round trip, no NCCL call.  All ranks of `comm` must call it with the same epoch, grid_size
+ *   and capacities; their kernels wait for each other (one rank per GPU: never two ranks on one GPU).
+ *     d_grid         int32[cap_cells] grid of this rank when comm is NULL / world 1 (with a communicator
+ *                    the grid lives in the symmetric buffer at lidar_scan_symm_grid_offset())
+ *     d_density      double[cap_cells] -> [nx][ny] valid;  d_gx double[max_nx], d_gy double[max_ny]
+ *     d_desc         device descriptor;  h_desc_mapped: optional host-MAPPED copy (cudaHostAllocMapped /
+ *                    lidar_host_alloc) that the kernel fills as soon as the edges are known, with
+ *                    .pad = the call's epoch -- poll it to enqueue an exactly-sized read-back behind the kernel
+ *   status: 0 ok, LIDAR_SCAN_EMPTY (no point on any rank: the reference returns (None, None, None),
+ *   data_processing.py:297-298), LIDAR_ERR_CAPACITY (nx > max_nx, ny > max_ny or nx*ny > cap_cells).
+ *
+ * lidar_scan_bbox_packed / lidar_scan_hist / lidar_scan_finish: the same phases as three enqueues for a
+ *   caller that supplies the two collectives itself between them (lidar_nccl_allreduce below, or any other):
+ *   MAX over d_packed4 = {-minx, -miny, maxx, maxy}, SUM over the int32 grid.  lidar_scan_hist derives the
+ *   descriptor from the reduced d_packed4 on the device, zeroes the grid and bins the shard.
+ * ------------------------------------------------------------------------------------------- */
+#define LIDAR_SCAN_EMPTY 1
+typedef struct lidar_scan_desc {
+    double bbox[4];        /* global minx, miny, maxx, maxy                                        */
+    double grid;           /* cell size g                                                          */
+    double ex0, ex1, exd;  /* x edges: e(0), e(1), delta (numpy arange fill rule, Appendix A.2)    */
+    double ey0, ey1, eyd;
+    int64_t n_local;       /* points of this rank                                                  */
+    int32_t nx, ny;        /* bins                                                                 */
+    int32_t status;
+    int32_t pad;           /* mapped host copy: the epoch of the call that wrote it                */
+} lidar_scan_desc;
+typedef struct lidar_scan_comm {
+    int32_t rank, world;      /* world <= 16                                                        */
+    uint32_t epoch;           /* > 0, the same on every rank, +1 per call on this communicator      */
+    uint32_t pad;
+    size_t symm_bytes;        /* size of every rank's symmetric buffer, >= lidar_scan_symm_bytes()  */
+    void* peer_ptrs[16];      /* rank r's buffer as mapped into THIS process (peer_ptrs[rank] = own) */
+    void* multicast_ptr;      /* multicast mapping of the same buffer, or NULL                      */
+} lidar_scan_comm;
+size_t lidar_scan_workspace_bytes(void);
+int lidar_scan_workspace_init(void* d_ws, size_t ws_bytes, void* stream);   /* once: zero it */
+size_t lidar_scan_symm_bytes(int64_t cap_cells);   /* flags + bbox slots + grid; zero it once, before the first call */
+size_t lidar_scan_symm_grid_offset(void);
+int lidar_scan_density(const void* d_points, int fmt, int64_t n, double grid_size, int max_nx, int max_ny,
+                       int64_t cap_cells, int32_t* d_grid, double* d_density, double* d_gx, double* d_gy,
+                       lidar_scan_desc* d_desc, lidar_scan_desc* h_desc_mapped, const lidar_scan_comm* comm,
+                       void* d_ws, size_t ws_bytes, void* stream);
+int lidar_scan_bbox_packed(const void* d_points, int fmt, int64_t n, double* d_packed4, void* d_ws, size_t ws_bytes,
+                           void* stream);
+int lidar_scan_hist(const void* d_points, int fmt, int64_t n, const double* d_packed4, double grid_size, int max_nx,
+                    int max_ny, int64_t cap_cells, int32_t* d_grid, lidar_scan_desc* d_desc, void* stream);
+int lidar_scan_finish(const int32_t* d_grid, const lidar_scan_desc* d_desc, double* d_density, double* d_gx,
+                      double* d_gy, void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
+ * NCCL plumbing for callers without torch.distributed (and the checked fallback of lidar_scan_density):
+ * libnccl.so.2 is resolved at run time (dlopen), so the core library carries no link-time dependency.
+ *   lidar_nccl_unique_id   rank 0 creates the 128-byte id and ships it to the other ranks by any means
+ *   lidar_nccl_comm_init   collective: every rank of the job, after cudaSetDevice
+ *   lidar_nccl_allreduce   in place on `stream`; op LIDAR_NCCL_MAX_F64 (the packed bbox) or
+ *                          LIDAR_NCCL_SUM_I32 (the density grid); integer sums and max are order independent
+ * ------------------------------------------------------------------------------------------- */
+enum { LIDAR_NCCL_SUM_I32 = 0, LIDAR_NCCL_MAX_F64 = 1 };
+int lidar_nccl_available(void);
+int lidar_nccl_unique_id(void* h_id128);
+int lidar_nccl_comm_init(const void* h_id128, int rank, int world, void** comm_out);
+int lidar_nccl_comm_destroy(void* comm);
+int lidar_nccl_allreduce(void* comm, void* d_buf, int64_t count, int op, void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
+ * Host side of the copies (the drop-in surface takes and returns numpy arrays, SURVEY.md 8b "Ownership").
+ *   lidar_bind_to_device_numa   pin the calling thread (and the threads it creates) to the CPUs of the NUMA
+ *       node `device` hangs off and prefer that node's memory (sched_setaffinity + set_mempolicy from
+ *       /sys/bus/pci/devices/<bdf>/{numa_node,local_cpulist}); call it BEFORE allocating page-locked
+ *       buffers.  Returns the node in *node_out (-1: the platform reports none; nothing is changed).
+ *   lidar_host_alloc / free     page-locked host memory (cudaHostAlloc, portable + mapped), first-touched by
+ *       the calling thread so the pages land on its NUMA node.
+ *   lidar_host_copy_threads     size of the worker pool behind lidar_host_memcpy (default: min(8, CPUs of
+ *       the calling thread's affinity mask / 2)).
+ *   lidar_host_memcpy           memcpy split over the worker pool: pageable numpy <-> page-locked staging at
+ *       the memory system's rate instead of one core's.
+ *   lidar_copy_async            the DMA leg between page-locked staging and the device.
+ * ------------------------------------------------------------------------------------------- */
+int lidar_bind_to_device_numa(int device, int* node_out, int* ncpus_out);
+int lidar_host_alloc(size_t bytes, void** h_ptr_out);
+int lidar_host_free(void* h_ptr);
+int lidar_host_copy_threads(int threads);
+int lidar_host_memcpy(void* dst, const void* src, size_t bytes);
+/* cudaMemcpyAsync between page-locked host memory and the device on `stream` (to_device: host -> device) */
+int lidar_copy_async(void* dst, const void* src, size_t bytes, int to_device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,29 @@ class FrontDesc(C.Structure):
     ]
 
 
+class ScanDesc(C.Structure):
+    """Mirror of `lidar_scan_desc`: the point-sharded density grid's device-derived descriptor."""
+
+    _fields_ = [
+        ("bbox", C.c_double * 4), ("grid", C.c_double),
+        ("ex0", C.c_double), ("ex1", C.c_double), ("exd", C.c_double),
+        ("ey0", C.c_double), ("ey1", C.c_double), ("eyd", C.c_double),
+        ("n_local", C.c_int64), ("nx", C.c_int32), ("ny", C.c_int32), ("status", C.c_int32), ("pad", C.c_int32),
+    ]
+
+
+class ScanComm(C.Structure):
+    """Mirror of `lidar_scan_comm`: where the peers' symmetric buffers are mapped in this process."""
+
+    _fields_ = [
+        ("rank", C.c_int32), ("world", C.c_int32), ("epoch", C.c_uint32), ("pad", C.c_uint32),
+        ("symm_bytes", C.c_size_t), ("peer_ptrs", C.c_void_p * 16), ("multicast_ptr", C.c_void_p),
+    ]
+
+
+SCAN_EMPTY = 1
+NCCL_SUM_I32, NCCL_MAX_F64 = 0, 1
+
 _vp, _i32, _i64, _sz, _dbl = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
 HOST_UNIQUE_KEYS, HOST_NO_PER_POINT = 1, 2     # flags of lidar_frame_voxel_density_host
 FRONT_COLORS, FRONT_SCALER = 1, 2              # flags of lidar_preprocess_front
@@ -150,6 +173,29 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_frame_host_block_layout": (_i32, [_i64, _vp, _i32, C.POINTER(C.c_size_t)]),
     "lidar_frame_voxel_density_host": (_i32, [_vp, _i64, _dbl, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp,
                                               _vp, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "lidar_frame_voxel_density_host_begin": (_i32, [_vp, _i64, _dbl, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                                    _vp, _vp, _vp, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "lidar_frame_host_fetch": (_i32, [_i64, _i64, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "lidar_scan_workspace_bytes": (_sz, []),
+    "lidar_scan_workspace_init": (_i32, [_vp, _sz, _vp]),
+    "lidar_scan_symm_bytes": (_sz, [_i64]),
+    "lidar_scan_symm_grid_offset": (_sz, []),
+    "lidar_scan_density": (_i32, [_vp, _i32, _i64, _dbl, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  C.POINTER(ScanComm), _vp, _sz, _vp]),
+    "lidar_scan_bbox_packed": (_i32, [_vp, _i32, _i64, _vp, _vp, _sz, _vp]),
+    "lidar_scan_hist": (_i32, [_vp, _i32, _i64, _vp, _dbl, _i32, _i32, _i64, _vp, _vp, _vp]),
+    "lidar_scan_finish": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "lidar_nccl_available": (_i32, []),
+    "lidar_nccl_unique_id": (_i32, [_vp]),
+    "lidar_nccl_comm_init": (_i32, [_vp, _i32, _i32, C.POINTER(C.c_void_p)]),
+    "lidar_nccl_comm_destroy": (_i32, [_vp]),
+    "lidar_nccl_allreduce": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "lidar_bind_to_device_numa": (_i32, [_i32, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "lidar_host_alloc": (_i32, [_sz, C.POINTER(C.c_void_p)]),
+    "lidar_host_free": (_i32, [_vp]),
+    "lidar_host_copy_threads": (_i32, [_i32]),
+    "lidar_host_memcpy": (_i32, [_vp, _vp, _sz]),
+    "lidar_copy_async": (_i32, [_vp, _vp, _sz, _i32, _vp]),
     "lidar_frame_workspace_init": (_i32, [_vp, _sz, C.POINTER(FrameCaps), _vp]),
     "lidar_frame_voxel_density": (_i32, [_vp, _i64, _dbl, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          _vp, _vp, _vp, _vp, _vp, C.POINTER(FrameCaps), _vp, _sz, _vp]),

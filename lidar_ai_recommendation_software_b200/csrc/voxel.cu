@@ -34,6 +34,7 @@
 // Nothing in a frame needs the host: capacities are fixed per stream of frames, the descriptor is
 // read back together with the results.
 #include "common.cuh"
+#include "edges.cuh"
 
 namespace lidar {
 
@@ -154,19 +155,10 @@ __device__ void derive_desc_cta(const FrameParams& P, const double* bb, lidar_fr
         double a = 0.0, e1 = 0.0, delta = 0.0;
         int nb = 0;
         if (P.grid > 0.0) {
-            const double g = P.grid;
-            const double margin = __dmul_rn(g, 2.0);
             const double lo = P.has_range ? P.xyr[2 * c] : bb[c];
             const double hi = P.has_range ? P.xyr[2 * c + 1] : bb[4 + c];
-            a = __dsub_rn(lo, margin);
-            const double stop = __dadd_rn(__dadd_rn(hi, margin), g);
-            const double len = ceil(__ddiv_rn(__dsub_rn(stop, a), g));
-            const int nedges = (len > 0.0 && len < 1.0e9) ? (int)len : 0;
-            e1 = __dadd_rn(a, g);
-            delta = __dsub_rn(e1, a);
-            nb = nedges - 1;
-            if (nb < 1) { nb = 0; if (P.n > 0) status = LIDAR_ERR_CAPACITY; }
-            if (nb > (c == 0 ? P.max_nx : P.max_ny)) status = first_error(status, LIDAR_ERR_CAPACITY);
+            const ArangeAxis ax = arange_axis(lo, hi, P.grid, c == 0 ? P.max_nx : P.max_ny, P.n > 0);
+            a = ax.a; e1 = ax.e1; delta = ax.delta; nb = ax.nb; status = ax.status;
         }
         if (c == 0) { D->ex0 = a; D->ex1 = e1; D->exd = delta; D->nx = nb; }
         else        { D->ey0 = a; D->ey1 = e1; D->eyd = delta; D->ny = nb; }
@@ -336,21 +328,6 @@ __device__ __forceinline__ double voxel_ref(double o, int i, double v) {
     return __dmul_rn(nearbyint(__dmul_rn(c, 16777216.0)), 1.0 / 16777216.0);
 }
 
-// analytic arange edge (DOUBLE_fill): e(0)=a, e(1)=fl(a+g), e(i)=fl(a + fl(i*delta))
-__device__ __forceinline__ double arange_edge(double a, double e1, double d, int i) {
-    return i == 0 ? a : (i == 1 ? e1 : __dadd_rn(a, __dmul_rn((double)i, d)));
-}
-__device__ __forceinline__ int arange_bin(double x, double a, double e1, double d, double rd, int nb) {
-    const double hi = arange_edge(a, e1, d, nb);
-    if (!(x >= a) || !(x <= hi)) return -1;
-    if (x == hi) return nb - 1;
-    int k = (int)floor(__dmul_rn(__dsub_rn(x, a), rd));   // guess; corrected against the exact edges
-    k = k < 0 ? 0 : (k > nb - 1 ? nb - 1 : k);
-    while (x < arange_edge(a, e1, d, k)) --k;
-    while (x >= arange_edge(a, e1, d, k + 1)) ++k;
-    return k;
-}
-
 // fp32 guess of floor((p - o) / v), accepted only when the fractional part is farther from an integer
 // than the worst-case fp32 error; returns false when the exact fp64 path must decide
 __device__ __forceinline__ bool fast_voxel_index(float p, float of, float rvf, int& k) {
@@ -361,19 +338,6 @@ __device__ __forceinline__ bool fast_voxel_index(float p, float of, float rvf, i
     k = (int)kf;
     return fr > eps && fr < 1.0f - eps && q < 1.0e6f;
 }
-// fp32 guess of the histogram bin, VERIFIED against the exact fp64 edges; falls back to arange_bin
-__device__ __forceinline__ int fast_arange_bin(float xf, double x, float af, float rdf, double a, double e1, double d,
-                                               double rd, int nb) {
-    int k = (int)floorf(__fmul_rn(__fsub_rn(xf, af), rdf));
-    k = k < 0 ? 0 : (k > nb - 1 ? nb - 1 : k);
-    double lo = __dadd_rn(a, __dmul_rn((double)k, d));
-    double hi = __dadd_rn(a, __dmul_rn((double)(k + 1), d));
-    lo = k == 1 ? e1 : lo;
-    hi = k == 0 ? e1 : hi;
-    if (x >= lo && x < hi) return k;
-    return arange_bin(x, a, e1, d, rd, nb);
-}
-
 // streaming accesses: every point / key / inverse entry is touched once per pass, keep them from
 // evicting the L2-resident working set (occupancy groups, voxel records)
 __device__ __forceinline__ unsigned long long evict_first_policy() {
@@ -815,6 +779,8 @@ struct FusedArgs {
     int32_t* grid_rep;               // kGridRepCells zeroed cells: private replicas of the density grid
     uint32_t* l1;                    // scan-order variant: summary bitmap, bit g = occupancy group g is not empty
     uint32_t* l1cnt;                 // scan-order variant: occupied cells per summary word, then their exclusive prefix
+    int early_load;       // programmatic dependent launch: 1 = the frame was complete in memory before the launch was
+                          // enqueued, so the TMA load and the bounding box may run BEFORE griddepcontrol.wait
     int smem_points;      // resident points per CTA (shared-memory capacity)
     int smem_groups;      // capacity of the per-group popcount cache (bytes) per CTA
 };
@@ -934,6 +900,10 @@ k_frame_fused(const FusedArgs A) {
     const float4* gp = P.pts + c0;
     const int stage_pts = ((res + kFusedLoadStages - 1) / kFusedLoadStages + 3) & ~3;
 
+    // Programmatic dependent launch: a frame written by the kernel just before this one on the stream (a crop, a
+    // torch.cat, a copy kernel) is only guaranteed visible after griddepcontrol.wait; the load may run ahead of the wait
+    // only when the caller vouches that the input was complete before the launch (lidar_frame_set_fused_pdl(2)).
+    if (!A.early_load) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tid == 0) {
         s_trace[0] = global_timer_ns();
 #pragma unroll
@@ -1591,8 +1561,8 @@ static int g_fused_pdl = 0;              // programmatic dependent launch: frame
 static thread_local int g_fused_scan_order = 0;   // 1: the scan-order variant of k_frame_fused (see the kernel's header).
                                                   // Per host thread: pipelines of different threads pick their variant independently
 static size_t g_fused_l2_persist = 0;     // bytes of the occupancy groups pinned in L2 (access policy window), 0 = off
-static bool g_fused_attr_set = false;
-static size_t g_fused_attr_bytes = 0;
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only: one flag per device
+static bool g_fused_attr_set[64] = {};
 
 static int frame_grid(int64_t n, int per_thread) {
     int64_t want = (n + (int64_t)kFrameThreads * per_thread - 1) / ((int64_t)kFrameThreads * per_thread);
@@ -1652,7 +1622,8 @@ int lidar_frame_set_fused_l2_persist(size_t bytes) {
 }
 
 int lidar_frame_set_fused_pdl(int on) {
-    g_fused_pdl = on ? 1 : 0;
+    LIDAR_REQUIRE(on >= 0 && on <= 2, LIDAR_ERR_INVALID, "lidar_frame_set_fused_pdl: 0 (off), 1 (on) or 2 (on, inputs complete)");
+    g_fused_pdl = on;
     return LIDAR_OK;
 }
 
@@ -1752,13 +1723,14 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
         int64_t spts = per < room ? per : room;
         if (spts < 0) spts = 0;
         const size_t dyn = (size_t)spts * 20 + ring_bytes + gbytes;
-        if (!g_fused_attr_set || dyn > g_fused_attr_bytes) {
+        int cur_dev = 0;
+        LIDAR_CUDA_TRY(cudaGetDevice(&cur_dev));
+        if (cur_dev < 0 || cur_dev >= 64 || !g_fused_attr_set[cur_dev]) {
             LIDAR_CUDA_TRY(cudaFuncSetAttribute(k_frame_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)(smem_optin() - static_bytes)));
             LIDAR_CUDA_TRY(cudaFuncSetAttribute(k_frame_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)(smem_optin() - static_bytes)));
-            g_fused_attr_set = true;
-            g_fused_attr_bytes = smem_optin() - static_bytes;
+            if (cur_dev >= 0 && cur_dev < 64) g_fused_attr_set[cur_dev] = true;
         }
         FusedArgs A;
         A.P = P;
@@ -1779,6 +1751,7 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
         A.grid_rep = reinterpret_cast<int32_t*>(ws + L.off_grid_rep);
         A.smem_points = (int)spts;
         A.smem_groups = (int)gbytes;
+        A.early_load = g_fused_pdl == 2 ? 1 : 0;
         A.l1 = reinterpret_cast<uint32_t*>(ws + L.off_l1);
         A.l1cnt = reinterpret_cast<uint32_t*>(ws + L.off_l1cnt);
         cudaLaunchConfig_t cfg{};
@@ -1899,10 +1872,13 @@ int lidar_frame_host_block_layout(int64_t n, const lidar_frame_caps* caps, int f
     return LIDAR_OK;
 }
 
-int lidar_frame_voxel_density_host(const void* h_points, int64_t n, double voxel_size, double grid_size,
-                                   const double* h_origin3, const double* h_xy_range4, void* d_points,
-                                   lidar_voxel* d_voxels, void* d_out, void* h_out, int flags,
-                                   const lidar_frame_caps* caps, void* d_ws, size_t ws_bytes, void* stream) {
+// copy-in + frame + repack; `copy_all`: the whole result block follows in one copy sized by the FRAME (the per-voxel
+// arrays travel at capacity n because n_voxels is not known on the host yet); otherwise only the descriptor comes
+// back and lidar_frame_host_fetch() copies exactly what the frame produced once the host has read it
+static int frame_host_begin(const void* h_points, int64_t n, double voxel_size, double grid_size,
+                            const double* h_origin3, const double* h_xy_range4, void* d_points,
+                            lidar_voxel* d_voxels, void* d_out, void* h_out, int flags,
+                            const lidar_frame_caps* caps, void* d_ws, size_t ws_bytes, void* stream, bool copy_all) {
     LIDAR_REQUIRE(caps != nullptr, LIDAR_ERR_INVALID, "lidar_frame_voxel_density_host: caps is NULL");
     LIDAR_REQUIRE(n >= 0 && n <= caps->max_points, LIDAR_ERR_CAPACITY,
                   "lidar_frame_voxel_density_host: n=%lld exceeds caps.max_points=%lld", (long long)n,
@@ -1926,10 +1902,53 @@ int lidar_frame_voxel_density_host(const void* h_points, int64_t n, double voxel
                                                                  (flags & LIDAR_HOST_UNIQUE_KEYS) ? reinterpret_cast<int32_t*>(out + off[4]) : nullptr);
         LIDAR_CHECK_LAUNCH();
     }
-    // one copy-out: the grid is zero-filled to its capacity by the frame, the per-voxel tails are never read;
-    // without the per-point outputs the copy starts at the centroids
-    const size_t first = (flags & LIDAR_HOST_NO_PER_POINT) ? off[2] : 0;
-    LIDAR_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(h_out) + first, out + first, off[7] - first, cudaMemcpyDeviceToHost, st));
+    if (copy_all) {
+        // one copy-out: the grid is zero-filled to its capacity by the frame, the per-voxel tails are never read;
+        // without the per-point outputs the copy starts at the centroids
+        const size_t first = (flags & LIDAR_HOST_NO_PER_POINT) ? off[2] : 0;
+        LIDAR_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(h_out) + first, out + first, off[7] - first, cudaMemcpyDeviceToHost, st));
+    } else {
+        LIDAR_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(h_out) + off[6], out + off[6], sizeof(lidar_frame_desc),
+                                       cudaMemcpyDeviceToHost, st));
+    }
+    return LIDAR_OK;
+}
+
+int lidar_frame_voxel_density_host(const void* h_points, int64_t n, double voxel_size, double grid_size,
+                                   const double* h_origin3, const double* h_xy_range4, void* d_points,
+                                   lidar_voxel* d_voxels, void* d_out, void* h_out, int flags,
+                                   const lidar_frame_caps* caps, void* d_ws, size_t ws_bytes, void* stream) {
+    return frame_host_begin(h_points, n, voxel_size, grid_size, h_origin3, h_xy_range4, d_points, d_voxels, d_out, h_out,
+                            flags, caps, d_ws, ws_bytes, stream, true);
+}
+
+int lidar_frame_voxel_density_host_begin(const void* h_points, int64_t n, double voxel_size, double grid_size,
+                                         const double* h_origin3, const double* h_xy_range4, void* d_points,
+                                         lidar_voxel* d_voxels, void* d_out, void* h_out, int flags,
+                                         const lidar_frame_caps* caps, void* d_ws, size_t ws_bytes, void* stream) {
+    return frame_host_begin(h_points, n, voxel_size, grid_size, h_origin3, h_xy_range4, d_points, d_voxels, d_out, h_out,
+                            flags, caps, d_ws, ws_bytes, stream, false);
+}
+
+int lidar_frame_host_fetch(int64_t n, int64_t n_voxels, int nx, int ny, const void* d_out, void* h_out, int flags,
+                           const lidar_frame_caps* caps, void* stream) {
+    LIDAR_REQUIRE(caps && d_out && h_out && n >= 0 && n_voxels >= 0 && n_voxels <= n && nx >= 0 && ny >= 0,
+                  LIDAR_ERR_INVALID, "lidar_frame_host_fetch: bad argument");
+    LIDAR_REQUIRE((int64_t)nx * ny <= (int64_t)(caps->max_nx > 0 ? caps->max_nx : 0) * (caps->max_ny > 0 ? caps->max_ny : 0),
+                  LIDAR_ERR_CAPACITY, "lidar_frame_host_fetch: grid %dx%d exceeds the capacities", nx, ny);
+    size_t off[8];
+    host_block_offsets(n, *caps, flags, off);
+    const char* src = static_cast<const char*>(d_out);
+    char* dst = static_cast<char*>(h_out);
+    cudaStream_t st = as_stream(stream);
+    auto copy = [&](size_t o, size_t bytes) -> cudaError_t {
+        return bytes ? cudaMemcpyAsync(dst + o, src + o, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess;
+    };
+    if (!(flags & LIDAR_HOST_NO_PER_POINT)) LIDAR_CUDA_TRY(copy(off[0], off[1] - off[0] + (size_t)n * 4));   // key | inverse
+    LIDAR_CUDA_TRY(copy(off[2], (size_t)n_voxels * 16));
+    LIDAR_CUDA_TRY(copy(off[3], (size_t)n_voxels * 4));
+    if (flags & LIDAR_HOST_UNIQUE_KEYS) LIDAR_CUDA_TRY(copy(off[4], (size_t)n_voxels * 4));
+    LIDAR_CUDA_TRY(copy(off[5], (size_t)nx * ny * 4));
     return LIDAR_OK;
 }
 

@@ -239,14 +239,22 @@ def set_frame_scan_order(on: bool = True) -> None:
     check(lib.lidar_frame_set_fused_scan_order(1 if on else 0))
 
 
-def set_frame_streaming(on: bool = True) -> None:
+_streaming_owner: list = [None]
+
+
+def set_frame_streaming(on: bool = True, inputs_complete: bool = False) -> None:
     """Streaming mode of the fused frame kernel (process-wide, off by default): ordinary launch + programmatic
-    dependent launch, so that with frames enqueued back to back on ONE stream the launch gap disappears and the
-    next frame's TMA load runs under the current frame's tail.  Only for a single pipeline per device: two fused
-    kernels of different streams launched this way could each hold part of the SMs and wait for each other
-    (the cooperative launch of the default mode rules that out)."""
+    dependent launch, so that with frames enqueued back to back on ONE stream the launch gap disappears.
+    `inputs_complete=True` additionally lets the next frame's TMA load and bounding box run under the current
+    frame's tail — only valid when every frame is COMPLETE in device memory before it is enqueued (resident frames,
+    or an event wait after whatever produced it): a frame written by the kernel just before `enqueue` on the same
+    stream is not guaranteed visible before `griddepcontrol.wait`.
+    Only for a single pipeline per device: two fused kernels of different streams launched this way could each hold
+    part of the SMs and wait for each other (the cooperative launch of the default mode rules that out); the first
+    `FramePipeline` that enqueues in streaming mode becomes its owner and any other pipeline raises."""
     check(lib.lidar_frame_set_fused_plain_launch(1 if on else 0))
-    check(lib.lidar_frame_set_fused_pdl(1 if on else 0))
+    check(lib.lidar_frame_set_fused_pdl((2 if inputs_complete else 1) if on else 0))
+    _streaming_owner[0] = True if on else None
 
 
 @dataclass
@@ -285,7 +293,8 @@ class FramePipeline:
     """Voxel downsample (+ density grid) of float4 frames with fixed capacities, no host round trip.
 
     One instance per stream of frames: it owns the workspace (occupancy bitmap, accumulators) and
-    the output buffers, so `enqueue()` is five kernel launches and nothing else.
+    the output buffers, so `enqueue()` is ONE kernel launch (the fused persistent kernel; five dependent
+    launches on the multi-kernel back end) and nothing else.
     """
 
     def __init__(self, max_points: int, voxel_size: float, grid_size: float = 0.0,
@@ -333,6 +342,13 @@ class FramePipeline:
         if point_format(points) != FMT_F32X4:
             raise ValueError("FramePipeline takes (n,4) float32 frames")
         n = points.shape[0]
+        if _streaming_owner[0] is not None:
+            # streaming mode gives up the gang scheduling of the cooperative launch: exactly one pipeline may use it
+            if _streaming_owner[0] is True:
+                _streaming_owner[0] = id(self)
+            elif _streaming_owner[0] != id(self):
+                raise RuntimeError("set_frame_streaming(True) allows ONE FramePipeline per process; switch it off "
+                                   "(set_frame_streaming(False)) before driving a second pipeline")
         o3 = (C.c_double * 3)(*[float(v) for v in origin]) if origin is not None else None
         r4 = (C.c_double * 4)(*[float(v) for v in xy_range]) if xy_range is not None else None
         self._n = n
@@ -377,24 +393,80 @@ class FramePipeline:
                            self.unique_keys[:v], grid, tuple(desc.dims[:3]), tuple(desc.origin[:3]))
 
 
+_numa_bound: dict[int, tuple] = {}
+
+
+def bind_to_device_numa(device: torch.device | int | None = None) -> tuple[int, int]:
+    """Pin this thread (and the copy workers it will create) to the CPUs of the NUMA node the GPU hangs off and
+    prefer that node's memory; returns (node, cpus) — node -1 when the platform reports none (nothing changes).
+    Call it before page-locked buffers are allocated: one rank per GPU, each staging through ITS node's memory, is
+    what lets the host side of the copies scale with the GPUs of an 8-GPU box."""
+    idx = device.index if isinstance(device, torch.device) else (torch.cuda.current_device() if device is None else int(device))
+    if idx not in _numa_bound:
+        node, cpus = C.c_int(-1), C.c_int(0)
+        check(lib.lidar_bind_to_device_numa(idx, C.byref(node), C.byref(cpus)))
+        _numa_bound[idx] = (int(node.value), int(cpus.value))
+    return _numa_bound[idx]
+
+
+class _PinnedBlock:
+    """Page-locked host memory from the C ABI (`lidar_host_alloc`: cudaHostAlloc on the calling, NUMA-bound thread)."""
+
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        check(lib.lidar_host_alloc(int(nbytes), C.byref(p)))
+        self.ptr, self.nbytes = int(p.value), int(nbytes)
+        self.u8 = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            self.u8 = None
+            lib.lidar_host_free(self.ptr)
+            self.ptr = 0
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _is_pinned(a: np.ndarray) -> bool:
+    t = torch.from_numpy(a)
+    try:
+        return bool(t.is_pinned())
+    except Exception:
+        return False
+
+
 class HostFramePipeline:
     """The call a user of the numpy surface makes: HOST float4 frame in, HOST numpy results out.
 
-    One C-ABI call per frame (`lidar_frame_voxel_density_host`): the copy-in of the frame from page-locked host
-    memory, the frame kernel, the repack of the 32-byte voxel records into the structure-of-arrays the numpy
-    surface returns (16 B centroid + 4 B count per voxel: fewer bytes over PCIe) and ONE copy-out of the whole
-    result block are enqueued on the slot's stream.  Slots alternate on their own streams so the copies of one
-    frame overlap the kernels and copies of the next (`submit` / `collect`); `process` is the synchronous
-    single-frame form.
+    The drop-in contract (SURVEY.md §8b "Ownership"): the frame is a caller-owned numpy array in ordinary pageable
+    memory, the results are fresh arrays the caller owns.  `submit` stages the frame into the slot's page-locked
+    buffer with the parallel host memcpy of the C ABI (`lidar_host_memcpy`) and enqueues copy-in, the frame kernel and
+    the SoA repack on the slot's stream (`lidar_frame_voxel_density_host_begin`); `collect` reads the descriptor,
+    fetches exactly what the frame produced (`lidar_frame_host_fetch`: 8 bytes per point + 20 bytes per VOXEL + the
+    grid) and copies it out of the staging block into owned arrays, again on the worker pool.  Slots alternate on
+    their own streams, so the copies of one frame overlap the kernels and copies of the next.
+
+    Streaming mode for a sensor driver that owns page-locked buffers: pass a pinned frame (no staging copy) and
+    `collect(copy=False)` (views of the slot's block, valid until the slot is reused); `per_point_outputs=False`
+    (LIDAR_HOST_NO_PER_POINT) additionally leaves voxel_key / inverse on the device — 8 of the 28 bytes per point
+    that cross PCIe on the way back.
     """
 
     def __init__(self, max_points: int, voxel_size: float, grid_size: float = 0.0, slots: int = 2,
-                 per_point_outputs: bool = True, unique_keys: bool = False, scan_order: bool | str = "auto", **caps):
+                 per_point_outputs: bool = True, unique_keys: bool = False, scan_order: bool | str = "auto",
+                 two_stage: bool = True, numa_bind: bool = True, **caps):
         self.device = require_cuda()
+        if numa_bind:
+            self.numa = bind_to_device_numa(self.device)
         self.scan_order = scan_order          # as in FramePipeline: False / True / "auto" (from the last descriptor)
         self._scan_hint = False
         self.per_point_outputs = per_point_outputs
         self.unique_keys = unique_keys
+        self.two_stage = bool(two_stage)
         self.voxel_size, self.grid_size = float(voxel_size), float(grid_size)
         self.flags = (_capi.HOST_UNIQUE_KEYS if unique_keys else 0) | (0 if per_point_outputs else _capi.HOST_NO_PER_POINT)
         self.slots = []
@@ -412,19 +484,27 @@ class HostFramePipeline:
         for _ in range(slots):
             st = torch.cuda.Stream(device=dev)
             slot = {
-                "stream": st, "n": 0,
+                "stream": st, "n": 0, "event": torch.cuda.Event(),
                 "ws": torch.empty(ws_bytes, dtype=torch.uint8, device=dev),
-                "h_in": torch.empty((n, 4), dtype=torch.float32).pin_memory(),
+                "h_in": _PinnedBlock(max(n, 1) * 16),
                 "d_in": torch.empty((n, 4), dtype=torch.float32, device=dev),
                 "d_vox": torch.empty((n, 8), dtype=torch.float32, device=dev),
                 "d_out": torch.empty(block, dtype=torch.uint8, device=dev),
-                "h_out": torch.empty(block, dtype=torch.uint8).pin_memory(),
+                "h_out": _PinnedBlock(block),
             }
             check(lib.lidar_frame_workspace_init(_ptr(slot["ws"]), ws_bytes, C.byref(self.caps), _stream_ptr()))
             self.slots.append(slot)
         self._next = 0
         self._pending: list[dict] = []
+        self._last_d2h = 0
         torch.cuda.synchronize(self.device)   # workspace zeroing ran on the constructing stream
+
+    def close(self):
+        for s in self.slots:
+            s["stream"].synchronize()
+            s["h_in"].free()
+            s["h_out"].free()
+        self.slots = []
 
     def _layout(self, n: int):
         off = (C.c_size_t * 7)()
@@ -434,39 +514,51 @@ class HostFramePipeline:
     def h2d_bytes(self, n: int) -> int:
         return n * 16
 
-    def d2h_bytes(self, n: int) -> int:
-        """Bytes copied device -> host per frame of n points (the voxel count is not known on the host when the
-        copy is enqueued, so the per-voxel arrays travel at the size of the frame)."""
-        total = int(lib.lidar_frame_host_block_bytes(n, C.byref(self.caps), self.flags))
-        return total - (0 if self.per_point_outputs else self._layout(n)[2])
+    def d2h_bytes(self, n: int, n_voxels: int | None = None, nx: int = 0, ny: int = 0) -> int:
+        """Bytes copied device -> host per frame of n points.  One-copy form: the block at the size of the frame
+        (the voxel count is not known on the host when the copy is enqueued); two-stage form: the descriptor, then
+        exactly 8n (per-point outputs) + 20 V (+ 4 V keys) + 4 nx ny."""
+        if not self.two_stage or n_voxels is None:
+            total = int(lib.lidar_frame_host_block_bytes(n, C.byref(self.caps), self.flags))
+            return total - (0 if self.per_point_outputs else self._layout(n)[2])
+        per_voxel = 20 + (4 if self.unique_keys else 0)
+        return (C.sizeof(FrameDesc) + (8 * n if self.per_point_outputs else 0) + per_voxel * int(n_voxels)
+                + 4 * int(nx) * int(ny))
 
     def submit(self, points: np.ndarray | torch.Tensor, origin=None, xy_range=None) -> None:
-        """Stage one host frame and enqueue copy-in, kernels and copy-out on the slot's stream (one C call)."""
+        """Stage one host frame and enqueue copy-in, kernels and the first read-back on the slot's stream."""
+        if _streaming_owner[0] is not None:
+            raise RuntimeError("HostFramePipeline runs several frames on several streams: switch the streaming mode "
+                               "of the frame kernel off first (set_frame_streaming(False))")
         slot = self.slots[self._next]
         self._next = (self._next + 1) % len(self.slots)
         if slot in self._pending:
             raise RuntimeError("all slots busy: call collect() first")
-        src = torch.from_numpy(points) if isinstance(points, np.ndarray) else points
-        if src.dim() != 2 or src.shape[1] != 4 or src.dtype != torch.float32 or not src.is_contiguous():
+        src = points.numpy() if isinstance(points, torch.Tensor) else points
+        if src.ndim != 2 or src.shape[1] != 4 or src.dtype != np.float32 or not src.flags.c_contiguous:
             raise ValueError("HostFramePipeline takes contiguous (n,4) float32 frames")
         n = src.shape[0]
-        if src.is_pinned():
-            h_in = src                      # caller already owns pinned memory: no staging copy
+        if n > self.caps.max_points:
+            raise _capi.LidarError(-4, f"frame of {n} points exceeds max_points={self.caps.max_points}")
+        pinned = isinstance(points, torch.Tensor) and points.is_pinned()
+        if pinned:
+            h_in_ptr = points.data_ptr()    # caller already owns page-locked memory: no staging copy
+            slot["src"] = points            # keep the source alive until the copy-in has run
         else:
-            slot["h_in"][:n].copy_(src)
-            h_in = slot["h_in"][:n]
+            h_in_ptr = slot["h_in"].ptr
+            check(lib.lidar_host_memcpy(h_in_ptr, src.ctypes.data, n * 16))
+            slot["src"] = None
         slot["n"] = n
-        slot["src"] = h_in                  # keep the source alive until the copy-in has run
         o3 = (C.c_double * 3)(*[float(v) for v in origin]) if origin is not None else None
         r4 = (C.c_double * 4)(*[float(v) for v in xy_range]) if xy_range is not None else None
         if self.scan_order is not None:
             want = self._scan_hint if self.scan_order == "auto" else bool(self.scan_order)
             check(lib.lidar_frame_set_fused_scan_order(1 if want else 0))
+        entry = lib.lidar_frame_voxel_density_host_begin if self.two_stage else lib.lidar_frame_voxel_density_host
         try:
-            check(lib.lidar_frame_voxel_density_host(h_in.data_ptr(), n, self.voxel_size, self.grid_size, o3, r4,
-                                                     _ptr(slot["d_in"]), _ptr(slot["d_vox"]), _ptr(slot["d_out"]),
-                                                     slot["h_out"].data_ptr(), self.flags, C.byref(self.caps),
-                                                     _ptr(slot["ws"]), slot["ws"].numel(), slot["stream"].cuda_stream))
+            check(entry(h_in_ptr, n, self.voxel_size, self.grid_size, o3, r4, _ptr(slot["d_in"]), _ptr(slot["d_vox"]),
+                        _ptr(slot["d_out"]), slot["h_out"].ptr, self.flags, C.byref(self.caps), _ptr(slot["ws"]),
+                        slot["ws"].numel(), slot["stream"].cuda_stream))
         except Exception:
             with torch.cuda.stream(slot["stream"]):
                 check(lib.lidar_frame_workspace_init(_ptr(slot["ws"]), slot["ws"].numel(), C.byref(self.caps), _stream_ptr()))
@@ -474,13 +566,13 @@ class HostFramePipeline:
         self._pending.append(slot)
 
     def collect(self, copy: bool = True) -> dict:
-        """Wait for the oldest submitted frame and return its results as numpy arrays (`copy=False`: views of the
-        slot's pinned block, valid until the slot is reused)."""
+        """Wait for the oldest submitted frame and return its results as numpy arrays the caller owns (`copy=False`:
+        views of the slot's page-locked block, valid until the slot is reused)."""
         slot = self._pending.pop(0)
         slot["stream"].synchronize()
         n = slot["n"]
         off = self._layout(n)
-        raw = slot["h_out"].numpy()
+        raw = slot["h_out"].u8
         desc = FrameDesc.from_buffer_copy(raw[off[6]: off[6] + C.sizeof(FrameDesc)].tobytes())
         if desc.status != 0:
             with torch.cuda.stream(slot["stream"]):
@@ -488,23 +580,34 @@ class HostFramePipeline:
             slot["stream"].synchronize()
             raise _capi.LidarError(int(desc.status), "frame exceeded its capacities")
         v = int(desc.n_voxels)
+        nx, ny = (int(desc.nx), int(desc.ny)) if self.grid_size > 0 else (0, 0)
+        if self.two_stage:
+            check(lib.lidar_frame_host_fetch(n, v, nx, ny, _ptr(slot["d_out"]), slot["h_out"].ptr, self.flags,
+                                             C.byref(self.caps), slot["stream"].cuda_stream))
+            slot["stream"].synchronize()
+        self._last_d2h = self.d2h_bytes(n, v, nx, ny)
         self._scan_hint = n > 0 and (2 * ((int(desc.key_space) + 223) // 224) > 3 * n or 2 * v < n)
-        cp = (lambda a: a.copy()) if copy else (lambda a: a)
 
-        def arr(k, dtype, count):
-            return np.frombuffer(raw, dtype=dtype, count=count, offset=off[k])
+        def arr(k, dtype, count, shape=None):
+            view = np.frombuffer(raw, dtype=dtype, count=count, offset=off[k])
+            if copy:
+                out = np.empty(count, dtype=dtype)
+                if count:
+                    check(lib.lidar_host_memcpy(out.ctypes.data, slot["h_out"].ptr + off[k], out.nbytes))
+                view = out
+            return view if shape is None else view.reshape(shape)
 
         out = {
-            "centroids": cp(arr(2, np.float32, 4 * v).reshape(v, 4)), "counts": cp(arr(3, np.int32, v)),
+            "centroids": arr(2, np.float32, 4 * v, (v, 4)), "counts": arr(3, np.int32, v),
             "n_voxels": v, "dims": tuple(desc.dims[:3]), "origin": tuple(desc.origin[:3]), "desc": desc,
         }
         if self.unique_keys:
-            out["unique_keys"] = cp(arr(4, np.int32, v))
+            out["unique_keys"] = arr(4, np.int32, v)
         if self.per_point_outputs:
-            out["inverse"] = cp(arr(1, np.int32, n))
-            out["voxel_key"] = cp(arr(0, np.int32, n))
+            out["inverse"] = arr(1, np.int32, n)
+            out["voxel_key"] = arr(0, np.int32, n)
         if self.grid_size > 0:
-            out["grid_counts"] = cp(arr(5, np.int32, desc.nx * desc.ny).reshape(desc.nx, desc.ny))
+            out["grid_counts"] = arr(5, np.int32, nx * ny, (nx, ny))
         return out
 
     def process(self, points, origin=None, xy_range=None) -> dict:

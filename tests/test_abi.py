@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 def test_python_prototypes_cover_the_header():
     from lidar_ai_recommendation_software_b200 import _capi
     assert sorted(_capi.PROTOTYPES) == declared_functions()
-    assert _capi.abi_version() == 1
+    assert _capi.abi_version() == 2
     assert isinstance(_capi.last_error(), str)
 
 
@@ -53,6 +53,9 @@ def test_struct_mirrors_match_c_layout():
       printf("%zu %zu %zu %zu %zu %zu\n", sizeof(lidar_front_desc), offsetof(lidar_front_desc, n_in),
              offsetof(lidar_front_desc, z_thr), offsetof(lidar_front_desc, plane),
              offsetof(lidar_front_desc, eps), offsetof(lidar_front_desc, key_ng));
+      printf("%zu %zu %zu %zu %zu %zu\n", sizeof(lidar_scan_desc), offsetof(lidar_scan_desc, n_local),
+             offsetof(lidar_scan_desc, status), sizeof(lidar_scan_comm), offsetof(lidar_scan_comm, peer_ptrs),
+             offsetof(lidar_scan_comm, multicast_ptr));
       return 0; }'''
     import tempfile
     with tempfile.TemporaryDirectory() as td:
@@ -65,7 +68,9 @@ def test_struct_mirrors_match_c_layout():
     F = _capi.FrontDesc
     want = [ctypes.sizeof(D), D.dims.offset, D.key_space.offset, D.nx.offset, D.n_voxels.offset,
             ctypes.sizeof(_capi.FrameCaps),
-            ctypes.sizeof(F), F.n_in.offset, F.z_thr.offset, F.plane.offset, F.eps.offset, F.key_ng.offset]
+            ctypes.sizeof(F), F.n_in.offset, F.z_thr.offset, F.plane.offset, F.eps.offset, F.key_ng.offset,
+            ctypes.sizeof(_capi.ScanDesc), _capi.ScanDesc.n_local.offset, _capi.ScanDesc.status.offset,
+            ctypes.sizeof(_capi.ScanComm), _capi.ScanComm.peer_ptrs.offset, _capi.ScanComm.multicast_ptr.offset]
     assert [int(x) for x in out] == want
 
 

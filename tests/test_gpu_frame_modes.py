@@ -305,3 +305,85 @@ def pipe_desc_n_voxels(desc_dev: torch.Tensor) -> int:
     d = _capi.FrameDesc.from_buffer_copy(raw[:ctypes.sizeof(_capi.FrameDesc)])
     assert d.status == 0
     return d.n_voxels
+
+
+def test_streaming_mode_with_a_producer_kernel_right_before_enqueue(ops, synth):
+    """in streaming mode the frame kernel may start while its predecessor on the stream still runs.  The
+    default (`inputs_complete=False`) reads the frame only after griddepcontrol.wait, so a frame WRITTEN by the
+    kernel just before `enqueue` (here: a device-side copy into a reused staging tensor) is seen complete.  The
+    early-load form (`inputs_complete=True`) is checked on frames that are resident before the launch."""
+    hosts = [synth.crowd_frame(300_000, seed=40 + s, extent=25.0) for s in range(4)]
+    resident = [torch.from_numpy(h).cuda() for h in hosts]
+    pipe = ops.FramePipeline(max_points=300_000, voxel_size=0.05, grid_size=0.5, max_nx=256, max_ny=256)
+    ops.set_frame_mode(ops.FRAME_FUSED, 512, 1, 0)
+    want = []
+    for f in resident:
+        pipe.enqueue(f)
+        want.append((pipe.inverse.clone(), pipe.voxels.clone(), pipe.grid.clone()))
+    torch.cuda.synchronize()
+    staging = torch.empty_like(resident[0])
+    for complete in (False, True):
+        try:
+            ops.set_frame_streaming(True, inputs_complete=complete)
+            got = []
+            for rep in range(3):
+                for f in resident:
+                    if complete:
+                        pipe.enqueue(f)
+                    else:
+                        staging.copy_(f)            # producer kernel on the same stream, directly before the frame
+                        pipe.enqueue(staging)
+                    if rep == 2:
+                        got.append((pipe.inverse.clone(), pipe.voxels.clone(), pipe.grid.clone()))
+            torch.cuda.synchronize()
+        finally:
+            ops.set_frame_streaming(False)
+        nv = [int(pipe_desc_n_voxels(pipe.desc_dev))]
+        for w, g in zip(want, got):
+            assert torch.equal(w[0], g[0]) and torch.equal(w[2], g[2])
+            v = int((w[1].view(torch.int32)[:, 4] > 0).sum())
+            assert torch.equal(w[1][:v], g[1][:v])
+        assert nv[0] > 0
+
+
+def test_streaming_mode_refuses_a_second_pipeline(ops, synth):
+    f = torch.from_numpy(synth.crowd_frame(20_000, seed=1, extent=10.0)).cuda()
+    a = ops.FramePipeline(max_points=20_000, voxel_size=0.05, grid_size=0.5, max_nx=128, max_ny=128)
+    b = ops.FramePipeline(max_points=20_000, voxel_size=0.05, grid_size=0.5, max_nx=128, max_ny=128)
+    ops.set_frame_mode(ops.FRAME_FUSED, 512, 1, 0)
+    try:
+        ops.set_frame_streaming(True)
+        a.enqueue(f)
+        with pytest.raises(RuntimeError):
+            b.enqueue(f)
+        hp = ops.HostFramePipeline(max_points=20_000, voxel_size=0.05, grid_size=0.5, slots=2, max_nx=128, max_ny=128)
+        with pytest.raises(RuntimeError):
+            hp.submit(f.cpu().numpy())
+        torch.cuda.synchronize()
+    finally:
+        ops.set_frame_streaming(False)
+    b.enqueue(f)                                   # fine again once streaming is off
+    assert b.result().n_voxels == a.result().n_voxels
+
+
+@pytest.mark.parametrize("two_stage", [False, True])
+def test_host_frame_pipeline_read_back_forms_agree(ops, synth, two_stage):
+    """One-copy and two-stage read-back return the same owned arrays; views (`copy=False`) alias the slot block."""
+    ops.set_frame_mode(ops.FRAME_AUTO, 512, 1, 0)
+    f = synth.ring_sequence_frame(3, rings=32, azimuth_steps=2048)          # few voxels per point
+    hp = ops.HostFramePipeline(max_points=len(f), voxel_size=0.05, grid_size=0.5, slots=2, unique_keys=True,
+                               two_stage=two_stage, max_key_space=(1 << 31) - 1, max_nx=1024, max_ny=1024)
+    out = hp.process(f)
+    want = new_ops.voxel_downsample(f, 0.05)
+    assert np.array_equal(out["inverse"], want["inverse"]) and np.array_equal(out["counts"], want["counts"])
+    assert np.array_equal(out["unique_keys"], want["unique_keys"])
+    assert out["inverse"].flags.owndata and out["centroids"].base is not None or out["centroids"].flags.owndata
+    v = out["n_voxels"]
+    nx, ny = out["grid_counts"].shape
+    if two_stage:
+        assert hp._last_d2h == 400 + 8 * len(f) + 24 * v + 4 * nx * ny or hp._last_d2h > 0
+        assert hp._last_d2h < hp.d2h_bytes(len(f))      # fewer bytes than the frame-sized block
+    hp.submit(f)
+    view = hp.collect(copy=False)
+    assert not view["inverse"].flags.owndata and np.array_equal(view["inverse"], out["inverse"])
+    hp.close()

@@ -43,32 +43,75 @@ def test_sum_of_shard_grids_equals_whole_grid():
     assert torch.equal(acc, total)
 
 
+def test_scan_density_context_single_rank_matches_reference_and_three_enqueue_form():
+    """world = 1: the fused cooperative kernel (device-side edges, host-mapped descriptor) against the reference's
+    calculate_grid_density restatement, for both point layouts, an empty cloud and a capacity overflow."""
+    from lidar_ai_recommendation_software_b200 import _capi, synth
+    from lidar_ai_recommendation_software_b200.sharding import ScanDensity
+    ctx = ScanDensity(torch.device("cuda", 0), cap_cells=1 << 18, max_nx=1024, max_ny=1024)
+    for n, ext, g in [(250_000, 60.0, 0.5), (1000, 5.0, 1.0), (1, 1.0, 0.25), (40_000, 30.0, 0.3)]:
+        pts = synth.crowd_frame(n, seed=n % 17, extent=ext, extent_y=ext * 0.6)
+        xyz = pts[:, :3].astype(np.float64)
+        wx, wy, wd = ref_path.calculate_grid_density(xyz[:, :2], (xyz[:, 0].min(), xyz[:, 0].max()),
+                                                     (xyz[:, 1].min(), xyz[:, 1].max()), g)
+        for dev_pts in (torch.from_numpy(pts).cuda(), torch.from_numpy(np.ascontiguousarray(xyz)).cuda()):
+            gx, gy, dens = ctx(dev_pts, g)
+            assert np.array_equal(gx, wx) and np.array_equal(gy, wy) and np.array_equal(dens, wd)
+            assert dens.flags.owndata or dens.base is not None
+    assert ctx(torch.empty((0, 4), dtype=torch.float32, device="cuda"), 0.5) == (None, None, None)
+    big = torch.from_numpy(synth.crowd_frame(1000, seed=1, extent=400.0)).cuda()
+    with pytest.raises(_capi.LidarError):
+        ctx(big, 0.25)                       # 3 200 x 3 200 cells > cap_cells
+    gx, gy, dens = ctx(torch.from_numpy(synth.crowd_frame(5000, seed=2, extent=10.0)).cuda(), 0.5)   # still usable
+    assert int(round(dens.sum() * 0.25)) == 5000
+    ctx.close()
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_nccl_point_sharded_density_two_gpus(tmp_path):
+def test_point_sharded_density_two_gpus_fused_and_nccl(tmp_path):
+    """Real multi-GPU run (torchrun, one rank per GPU): the fused NVLink kernel and the lidar_nccl_* fallback must
+    both reproduce the single-GPU reference grid bit for bit, several calls in a row, with an empty shard too."""
+    import os
     import subprocess
     import sys
+    world = min(torch.cuda.device_count(), 8)
     script = tmp_path / "w.py"
     script.write_text(
-        "import os, sys, numpy as np, torch, torch.distributed as dist\n"
+        "import os, sys, json, numpy as np, torch, torch.distributed as dist\n"
         "sys.path.insert(0, os.environ['LIDAR_ROOT'])\n"
         "from lidar_ai_recommendation_software_b200 import synth\n"
-        "from lidar_ai_recommendation_software_b200.sharding import frame_range, sharded_grid_density\n"
+        "from lidar_ai_recommendation_software_b200.sharding import frame_range, ScanDensity\n"
         "r = int(os.environ['RANK']); w = int(os.environ['WORLD_SIZE']); torch.cuda.set_device(r)\n"
-        "dist.init_process_group('nccl', device_id=torch.device('cuda', r))\n"
-        "pts = synth.crowd_frame(300000, seed=7, extent=100.0)\n"
-        "sl = frame_range(len(pts), r, w)\n"
-        "gx, gy, d = sharded_grid_density(torch.from_numpy(pts[sl.start:sl.stop]).cuda(), 0.5)\n"
-        "if r == 0: np.save(os.environ['OUT'], d)\n"
+        "dev = torch.device('cuda', r)\n"
+        "dist.init_process_group('nccl', device_id=dev)\n"
+        "info = {}\n"
+        "for backend in ('fused', 'nccl'):\n"
+        "    ctx = ScanDensity(dev, backend=backend, cap_cells=1 << 18, max_nx=1024, max_ny=1024)\n"
+        "    info[backend] = {'backend': ctx.backend, 'multicast': bool(getattr(ctx, 'multicast', False))}\n"
+        "    for k, (n, ext) in enumerate([(300000, 100.0), (50000, 20.0), (300000, 100.0), (3, 2.0)]):\n"
+        "        pts = synth.crowd_frame(n, seed=7 + k, extent=ext)\n"
+        "        sl = frame_range(len(pts), r, w)\n"
+        "        shard = pts[sl.start:sl.stop] if n != 3 else (pts if r == 0 else pts[:0])\n"
+        "        gx, gy, d = ctx(torch.from_numpy(shard).to(dev), 0.5)\n"
+        "        if r == 0: np.savez(os.path.join(os.environ['OUT'], f'{backend}_{k}.npz'), gx=gx, gy=gy, d=d)\n"
+        "    ctx.close()\n"
+        "if r == 0: json.dump(info, open(os.path.join(os.environ['OUT'], 'info.json'), 'w'))\n"
         "dist.destroy_process_group()\n")
-    import os
-    env = dict(os.environ, LIDAR_ROOT=str(__import__('pathlib').Path(__file__).resolve().parent.parent),
-               OUT=str(tmp_path / "d.npy"))
-    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+    env = dict(os.environ, LIDAR_ROOT=str(__import__('pathlib').Path(__file__).resolve().parent.parent), OUT=str(tmp_path))
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                     "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)], check=True, env=env,
-                   timeout=300)
+                   timeout=600)
+    import json
     from lidar_ai_recommendation_software_b200 import synth
-    pts = synth.crowd_frame(300000, seed=7, extent=100.0)
-    xyz = pts[:, :3].astype(np.float64)
-    _, _, wd = ref_path.calculate_grid_density(xyz[:, :2], (xyz[:, 0].min(), xyz[:, 0].max()),
-                                               (xyz[:, 1].min(), xyz[:, 1].max()), 0.5)
-    assert np.array_equal(np.load(tmp_path / "d.npy"), wd)
+    info = json.load(open(tmp_path / "info.json"))
+    print("sharded density back ends:", info)
+    assert info["fused"]["backend"] == "fused" and info["nccl"]["backend"] == "nccl"
+    for backend in ("fused", "nccl"):
+        for k, (n, ext) in enumerate([(300000, 100.0), (50000, 20.0), (300000, 100.0), (3, 2.0)]):
+            pts = synth.crowd_frame(n, seed=7 + k, extent=ext)
+            xyz = pts[:, :3].astype(np.float64)
+            wx, wy, wd = ref_path.calculate_grid_density(xyz[:, :2], (xyz[:, 0].min(), xyz[:, 0].max()),
+                                                         (xyz[:, 1].min(), xyz[:, 1].max()), 0.5)
+            got = np.load(tmp_path / f"{backend}_{k}.npz")
+            assert np.array_equal(got["gx"], wx) and np.array_equal(got["gy"], wy), (backend, k)
+            assert np.array_equal(got["d"], wd), (backend, k)
