@@ -70,6 +70,11 @@ int lidar_bbox(const void* d_points, int fmt, int64_t n, double* d_out8, void* d
 int lidar_moments(const void* d_points, int fmt, int64_t n, const double* h_center3, double* d_out6,
                   void* d_ws, size_t ws_bytes, void* stream);
 
+/* distance of every point from the centroid (utils/visualization.py:50-54: np.mean(points, axis=0), then
+ *     np.sqrt(np.sum((points - centroid)**2, axis=1))): d_points (n,3) fp64 -> d_out double[n].  The centroid is the
+ *     device moments' sum / n (a parallel sum: within 1 ulp-scale of numpy's sequential mean, rtol 1e-12). */
+int lidar_centroid_distances(const double* d_points, int64_t n, double* d_out, void* d_ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------- *
  * K6  2-D histogram with numpy.histogramdd semantics: bin k <=> e[k] <= x < e[k+1], last bin
  *     closed, everything else (and NaN) dropped; edges and compares in fp64.
@@ -463,8 +468,10 @@ int lidar_frame_host_fetch(int64_t n, int64_t n_voxels, int nx, int ny, const vo
  *   exchange with the peers, arange parameters derived on the device, histogram, two-shot all-reduce of
  *   the grid over NVLink (multimem.ld_reduce.add.u32 + multimem.st through the NVSwitch when the
  *   symmetric buffer has a multicast mapping, peer loads / stores otherwise), density and cell centres.
- *   No host round trip, no NCCL call.  All ranks of `comm` must call it with the same epoch, grid_size
- *   and capacities; their kernels wait for each other (one rank per GPU: never two ranks on one GPU).
+ *   No host round trip, no NCCL call.  `epoch` > 0 numbers the calls made with this workspace / communicator
+ *   (+1 per call; the peers' flags and the host-mapped descriptor carry it).  All ranks of `comm` must call it
+ *   with the same epoch, grid_size and capacities; their kernels wait for each other (one rank per GPU: never
+ *   two ranks on one GPU).
  *     d_grid         int32[cap_cells] grid of this rank when comm is NULL / world 1 (with a communicator
  *                    the grid lives in the symmetric buffer at lidar_scan_symm_grid_offset())
  *     d_density      double[cap_cells] -> [nx][ny] valid;  d_gx double[max_nx], d_gy double[max_ny]
@@ -492,8 +499,6 @@ typedef struct lidar_scan_desc {
 } lidar_scan_desc;
 typedef struct lidar_scan_comm {
     int32_t rank, world;      /* world <= 16                                                        */
-    uint32_t epoch;           /* > 0, the same on every rank, +1 per call on this communicator      */
-    uint32_t pad;
     size_t symm_bytes;        /* size of every rank's symmetric buffer, >= lidar_scan_symm_bytes()  */
     void* peer_ptrs[16];      /* rank r's buffer as mapped into THIS process (peer_ptrs[rank] = own) */
     void* multicast_ptr;      /* multicast mapping of the same buffer, or NULL                      */
@@ -505,7 +510,7 @@ size_t lidar_scan_symm_grid_offset(void);
 int lidar_scan_density(const void* d_points, int fmt, int64_t n, double grid_size, int max_nx, int max_ny,
                        int64_t cap_cells, int32_t* d_grid, double* d_density, double* d_gx, double* d_gy,
                        lidar_scan_desc* d_desc, lidar_scan_desc* h_desc_mapped, const lidar_scan_comm* comm,
-                       void* d_ws, size_t ws_bytes, void* stream);
+                       uint32_t epoch, void* d_ws, size_t ws_bytes, void* stream);
 int lidar_scan_bbox_packed(const void* d_points, int fmt, int64_t n, double* d_packed4, void* d_ws, size_t ws_bytes,
                            void* stream);
 int lidar_scan_hist(const void* d_points, int fmt, int64_t n, const double* d_packed4, double grid_size, int max_nx,

@@ -102,7 +102,7 @@ class ScanComm(C.Structure):
     """Mirror of `lidar_scan_comm`: where the peers' symmetric buffers are mapped in this process."""
 
     _fields_ = [
-        ("rank", C.c_int32), ("world", C.c_int32), ("epoch", C.c_uint32), ("pad", C.c_uint32),
+        ("rank", C.c_int32), ("world", C.c_int32),
         ("symm_bytes", C.c_size_t), ("peer_ptrs", C.c_void_p * 16), ("multicast_ptr", C.c_void_p),
     ]
 
@@ -122,6 +122,7 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_reduce_workspace_bytes": (_sz, []),
     "lidar_bbox": (_i32, [_vp, _i32, _i64, _vp, _vp, _sz, _vp]),
     "lidar_moments": (_i32, [_vp, _i32, _i64, C.POINTER(C.c_double), _vp, _vp, _sz, _vp]),
+    "lidar_centroid_distances": (_i32, [_vp, _i64, _vp, _vp, _sz, _vp]),
     "lidar_hist2d_f64": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
     "lidar_hist2d_points": (_i32, [_vp, _i32, _i64, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
     "lidar_compact_workspace_bytes": (_sz, [_i64]),
@@ -181,7 +182,7 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_scan_symm_bytes": (_sz, [_i64]),
     "lidar_scan_symm_grid_offset": (_sz, []),
     "lidar_scan_density": (_i32, [_vp, _i32, _i64, _dbl, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
-                                  C.POINTER(ScanComm), _vp, _sz, _vp]),
+                                  C.POINTER(ScanComm), C.c_uint32, _vp, _sz, _vp]),
     "lidar_scan_bbox_packed": (_i32, [_vp, _i32, _i64, _vp, _vp, _sz, _vp]),
     "lidar_scan_hist": (_i32, [_vp, _i32, _i64, _vp, _dbl, _i32, _i32, _i64, _vp, _vp, _vp]),
     "lidar_scan_finish": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),

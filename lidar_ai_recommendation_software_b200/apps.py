@@ -4,8 +4,11 @@
 Swap-in: add one line after the inline definitions of the app file (before its UI section,
 app_simplified.py:942):
 
-    from lidar_ai_recommendation_software_b200.apps import (preprocess_point_cloud, density_heatmap_counts,
+    from lidar_ai_recommendation_software_b200.apps import (preprocess_point_cloud, create_density_heatmap,
                                                             analyze_crowd_density, analyze_crowd_flow)
+
+All four names the apps call (app_simplified.py:1028, 1074, 1159/1184, 1220) are shadowed by that one line; nothing
+inside the app files is edited.
 """
 from __future__ import annotations
 
@@ -34,6 +37,31 @@ def density_heatmap_counts(processed_data, bins=100, projection=(0, 1)):
     y_edges = np.linspace(r1[0], r1[1], bins + 1)
     counts = ops.hist2d_counts(pts[:, projection[0]], pts[:, projection[1]], x_edges, y_edges)
     return counts.cpu().numpy().astype(np.float64), x_edges, y_edges
+
+
+def density_heatmap_spec(processed_data, bins=100):
+    """Everything create_density_heatmap (app_simplified.py:198-232) puts into its figure, as plain arrays:
+    z = hist.T (rows = y), x / y = bin centres, and the layout strings.  The histogram runs on the device."""
+    hist, x_edges, y_edges = density_heatmap_counts(processed_data, bins=bins)
+    return {
+        "z": hist.T, "x": (x_edges[:-1] + x_edges[1:]) / 2, "y": (y_edges[:-1] + y_edges[1:]) / 2,
+        "colorscale": "Viridis", "colorbar": dict(title="Point Density"),
+        "layout": dict(xaxis_title="X (m)", yaxis_title="Y (m)", title="Point Density Heatmap", height=500),
+    }
+
+
+def create_density_heatmap(processed_data):
+    """app_simplified.py:198-232 under its own name and return contract: a plotly `go.Figure` holding one
+    `go.Heatmap(z=hist.T, x=x_centers, y=y_centers, colorscale='Viridis', colorbar=dict(title='Point Density'))`
+    with the reference's layout.  np.histogram2d(bins=100, range=[x_range, y_range]) of the raw points is the device
+    histogram (`density_heatmap_counts`); plotly is imported here, as the apps themselves import it
+    (app_simplified.py:6) — a host without plotly gets the same ImportError the app would raise."""
+    import plotly.graph_objects as go
+    spec = density_heatmap_spec(processed_data)
+    fig = go.Figure(data=go.Heatmap(z=spec["z"], x=spec["x"], y=spec["y"], colorscale=spec["colorscale"],
+                                    colorbar=spec["colorbar"]))
+    fig.update_layout(**spec["layout"])
+    return fig
 
 
 def _people(processed_data):

@@ -476,9 +476,16 @@ __global__ void front_glue_kernel(lidar_front_desc* F, int stage, long long n) {
     case kGlueScale:                                       // sklearn _incremental_mean_and_var + _handle_zeros_in_scale
         for (int c = 0; c < 3; ++c) {
             const double corr = __ddiv_rn(__dmul_rn(F->t2[c], F->t2[c]), m);
-            const double var = __ddiv_rn(__dsub_rn(F->t2[3 + c], corr), m);
+            double var = __ddiv_rn(__dsub_rn(F->t2[3 + c], corr), m);
+            if (!(var > 0.0)) var = 0.0;                   // rounding can leave a tiny negative variance: sqrt would be NaN
+            // StandardScaler.fit: constant_mask = _is_constant_feature(var_, mean_, n_samples_seen_), i.e.
+            //   var <= n*eps*var + (n*mean*eps)^2  (a near-constant column with a large mean, e.g. UTM x of one scan
+            // line, counts as constant), then scale_ = _handle_zeros_in_scale(sqrt(var_), constant_mask=constant_mask)
+            const double eps = 2.220446049250313e-16;
+            const double nme = __dmul_rn(__dmul_rn(m, F->sc_mean[c]), eps);
+            const double bound = __dadd_rn(__dmul_rn(__dmul_rn(m, eps), var), __dmul_rn(nme, nme));
             double sc = __dsqrt_rn(var);
-            if (fabs(sc) <= 10.0 * 2.220446049250313e-16) sc = 1.0;
+            if (var <= bound) sc = 1.0;
             F->scale[c] = sc;
         }
         break;

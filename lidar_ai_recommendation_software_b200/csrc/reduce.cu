@@ -225,13 +225,43 @@ int moments_f64x3_dev(const double* d_points, int64_t cap, const long long* d_n,
     return LIDAR_OK;
 }
 
+// utils/visualization.py:50-54: centroid = np.mean(points, axis=0); distances = sqrt(sum((p - centroid)^2, axis=1)).
+// The centroid comes from the device moments (sum / n, evaluated on the device from d_sum6 / n); the per-point part
+// follows numpy's expression: three squared differences added left to right, one correctly rounded sqrt.
+__global__ void __launch_bounds__(kRedThreads)
+centroid_distance_kernel(const double* __restrict__ pts, int64_t n, const double* __restrict__ sum6, double* __restrict__ out) {
+    const double inv_n = (double)n;
+    const double cx = __ddiv_rn(sum6[0], inv_n), cy = __ddiv_rn(sum6[1], inv_n), cz = __ddiv_rn(sum6[2], inv_n);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double dx = __dsub_rn(__ldg(pts + 3 * i), cx), dy = __dsub_rn(__ldg(pts + 3 * i + 1), cy);
+        const double dz = __dsub_rn(__ldg(pts + 3 * i + 2), cz);
+        out[i] = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+    }
+}
+
 }  // namespace lidar
 
 using namespace lidar;
 
 extern "C" {
 
-size_t lidar_reduce_workspace_bytes(void) { return ws_align(sizeof(ReduceWs)); }
+int lidar_centroid_distances(const double* d_points, int64_t n, double* d_out, void* d_ws, size_t ws_bytes, void* stream) {
+    LIDAR_REQUIRE(n >= 0 && (n == 0 || (d_points && d_out)), LIDAR_ERR_INVALID, "lidar_centroid_distances: bad argument");
+    LIDAR_REQUIRE(d_ws && ws_bytes >= ws_align(sizeof(ReduceWs)) + 64, LIDAR_ERR_WORKSPACE,
+                  "lidar_centroid_distances: workspace too small");
+    if (n == 0) return LIDAR_OK;
+    cudaStream_t st = as_stream(stream);
+    double* sum6 = reinterpret_cast<double*>(static_cast<char*>(d_ws) + ws_align(sizeof(ReduceWs)));
+    const double zero[3] = {0.0, 0.0, 0.0};
+    const int rc = lidar_moments(d_points, LIDAR_FMT_F64X3, n, zero, sum6, d_ws, ws_align(sizeof(ReduceWs)), stream);
+    if (rc != LIDAR_OK) return rc;
+    centroid_distance_kernel<<<reduce_grid(n), kRedThreads, 0, st>>>(d_points, n, sum6, d_out);
+    LIDAR_CHECK_LAUNCH();
+    return LIDAR_OK;
+}
+
+size_t lidar_reduce_workspace_bytes(void) { return ws_align(sizeof(ReduceWs)) + 256; }
 
 int lidar_bbox(const void* d_points, int fmt, int64_t n, double* d_out8, void* d_ws, size_t ws_bytes,
                void* stream) {

@@ -507,7 +507,7 @@ int lidar_scan_workspace_init(void* d_ws, size_t ws_bytes, void* stream) {
 int lidar_scan_density(const void* d_points, int fmt, int64_t n, double grid_size, int max_nx, int max_ny,
                        int64_t cap_cells, int32_t* d_grid, double* d_density, double* d_gx, double* d_gy,
                        lidar_scan_desc* d_desc, lidar_scan_desc* h_desc_mapped, const lidar_scan_comm* comm,
-                       void* d_ws, size_t ws_bytes, void* stream) {
+                       uint32_t epoch, void* d_ws, size_t ws_bytes, void* stream) {
     LIDAR_REQUIRE(n >= 0 && (n == 0 || d_points), LIDAR_ERR_INVALID, "lidar_scan_density: bad points");
     LIDAR_REQUIRE(fmt == LIDAR_FMT_F32X4 || fmt == LIDAR_FMT_F64X3, LIDAR_ERR_INVALID, "lidar_scan_density: unknown point format %d", fmt);
     LIDAR_REQUIRE(grid_size > 0.0, LIDAR_ERR_INVALID, "lidar_scan_density: grid_size must be > 0");
@@ -519,14 +519,14 @@ int lidar_scan_density(const void* d_points, int fmt, int64_t n, double grid_siz
     A.pts = d_points; A.fmt = fmt; A.n = n; A.g = grid_size; A.max_nx = max_nx; A.max_ny = max_ny; A.cap_cells = cap_cells;
     A.ws = static_cast<ScanWs*>(d_ws);
     A.density = d_density; A.gx = d_gx; A.gy = d_gy; A.desc_out = d_desc; A.desc_host = h_desc_mapped;
-    A.rank = 0; A.world = 1; A.epoch = 1u;
+    LIDAR_REQUIRE(epoch > 0, LIDAR_ERR_INVALID, "lidar_scan_density: epoch must be > 0 and increase by one per call");
+    A.rank = 0; A.world = 1; A.epoch = epoch;
     if (comm && comm->world > 1) {
         LIDAR_REQUIRE(comm->world <= kScanMaxWorld && comm->rank >= 0 && comm->rank < comm->world, LIDAR_ERR_INVALID,
                       "lidar_scan_density: bad communicator (rank %d of %d)", comm->rank, comm->world);
-        LIDAR_REQUIRE(comm->epoch > 0, LIDAR_ERR_INVALID, "lidar_scan_density: comm.epoch must be > 0 and increase by one per call");
         LIDAR_REQUIRE(comm->symm_bytes >= lidar_scan_symm_bytes(cap_cells), LIDAR_ERR_WORKSPACE,
                       "lidar_scan_density: symmetric buffer too small for cap_cells");
-        A.rank = comm->rank; A.world = comm->world; A.epoch = comm->epoch;
+        A.rank = comm->rank; A.world = comm->world;
         for (int r = 0; r < comm->world; ++r) {
             LIDAR_REQUIRE(comm->peer_ptrs[r] != nullptr, LIDAR_ERR_INVALID, "lidar_scan_density: peer %d has no mapping", r);
             A.peers[r] = static_cast<ScanSymmHeader*>(comm->peer_ptrs[r]);
@@ -538,7 +538,6 @@ int lidar_scan_density(const void* d_points, int fmt, int64_t n, double grid_siz
         LIDAR_REQUIRE(d_grid != nullptr, LIDAR_ERR_INVALID, "lidar_scan_density: d_grid is NULL");
         A.grid = d_grid;
     }
-    if (comm && comm->epoch > 0) A.epoch = comm->epoch;
     // co-resident persistent grid: as many CTAs per SM as the occupancy calculator allows, capped at 4
     int per_sm = 0;
     const void* fn = fmt == LIDAR_FMT_F32X4 ? (const void*)k_scan_density<LoadF32x4> : (const void*)k_scan_density<LoadF64x3>;

@@ -131,6 +131,17 @@ def moments(points: torch.Tensor, center=(0.0, 0.0, 0.0)) -> torch.Tensor:
     return out
 
 
+def centroid_distances(points: torch.Tensor) -> torch.Tensor:
+    """sqrt(sum((p - mean)^2)) per point of an (n,3) float64 CUDA tensor (utils/visualization.py:50-54)."""
+    if point_format(points) != FMT_F64X3:
+        raise ValueError("expected an (n,3) float64 CUDA tensor")
+    dev, n = points.device, points.shape[0]
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    ws = _scratch.get("reduce", lib.lidar_reduce_workspace_bytes(), dev)
+    check(lib.lidar_centroid_distances(_ptr(points), n, _ptr(out), _ptr(ws), ws.numel(), _stream_ptr()))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # edges (host-side parameter derivation — a few scalars, exactly the reference's numpy calls)
 # ------------------------------------------------------------------------------------------------
@@ -751,7 +762,7 @@ def dbscan(points: torch.Tensor, eps: float, min_samples: int = 5, tol: float = 
     dev, m = points.device, points.shape[0]
     labels = torch.empty(m, dtype=torch.int32, device=dev)
     if m == 0:
-        return labels, 0, 0
+        return (labels, torch.zeros(2, dtype=torch.int64, device=dev)) if defer else (labels, 0, 0)
     if bounds is None:
         bb = bbox(points).cpu().numpy()
         bounds = (bb[:3], bb[4:7])

@@ -14,6 +14,7 @@ system.  There is no CPU path for the per-point work.
 from __future__ import annotations
 
 import math
+import warnings
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -91,7 +92,16 @@ def run(points, variant: str = "A", host_arrays: bool = True) -> dict:
     """Full preprocess on the GPU; returns the reference's processed_data dict (numpy arrays) plus a
     DeviceCache under DEVICE_KEY.
 
-    `points` is the reference's (n,3) array, or an (n,3) float64 CUDA tensor that is already resident.
+    `points` is the reference's (n,3) array, or an (n,3) float64 CUDA tensor that is already resident.  Any other
+    dtype (float32, integers) is widened to float64 first: the reference computes in float64 on float64 loader
+    output (utils/data_processing.py:34-41), and the widening of a float32 cloud is exact — note that the REFERENCE
+    itself, fed float32, would compute its means and thresholds in float32 under NumPy 2 (SURVEY.md Appendix A.7);
+    results here are those of the widened cloud.
+
+    Knife edges: a point within 1e-9 sigma of the 3-sigma threshold, or (variant A) a pair within 1e-12 of eps^2, could
+    be decided differently by numpy's strictly sequential mean / the scaler's rounding.  The counts of such cases are
+    returned under `out["_lidar_b200"].guards`; when one is non-zero a `RuntimeWarning` says so (zero proves the mask
+    and labels equal the reference's for this input).
     `host_arrays=False` is the sequence mode (BASELINE configs[3]): the per-point outputs (points, colors,
     normals, clusters) stay on the device under DEVICE_KEY and are NOT copied back; the dict carries only
     `dimensions` (+ `ground_plane`).  extract_people_positions / the density and flow models accept it."""
@@ -158,6 +168,13 @@ def run(points, variant: str = "A", host_arrays: bool = True) -> dict:
         guards["dbscan"] = guard
         return nc & 0xffffffff
 
+    def _report_guards():
+        if guards["sigma"] or guards["dbscan"]:
+            warnings.warn(f"lidar_b200 preprocess: {guards['sigma']} point(s) within 1e-9 sigma of the 3-sigma "
+                          f"threshold and {guards['dbscan']} neighbour pair(s) within 1e-12 of eps^2 — the inlier mask / "
+                          "cluster labels may differ from numpy / scikit-learn for exactly those cases", RuntimeWarning,
+                          stacklevel=3)
+
     if not host_arrays:
         if info is not None:
             n_clusters = _info(ops.fetch("dbscan_info", info)[0])
@@ -165,6 +182,7 @@ def run(points, variant: str = "A", host_arrays: bool = True) -> dict:
             out["ground_plane"] = plane
         out["dimensions"] = dims
         out[DEVICE_KEY] = DeviceCache(inl, full, None, n_clusters, guards)
+        _report_guards()
         return out
     h_points, h_clusters, h_colors, h_info = _to_host(inl, full, col, info)
     if info is not None:
@@ -180,6 +198,7 @@ def run(points, variant: str = "A", host_arrays: bool = True) -> dict:
         out["ground_plane"] = plane
     out["dimensions"] = dims
     out[DEVICE_KEY] = DeviceCache(inl, full, (id(h_points), id(h_clusters)), n_clusters, guards)
+    _report_guards()
     return out
 
 
@@ -197,7 +216,9 @@ def device_view(processed: dict):
 
 def people_positions(processed: dict) -> np.ndarray:
     """extract_people_positions (utils/data_processing.py:251-280): centroid xy of every cluster id >= 0,
-    ascending id.  Cluster ids may be sparse (any int64 >= 0): they are ranked on the device first."""
+    ascending id.  Labels of our own DBSCAN are 0..C-1 and go straight to the device accumulators; a
+    caller-built dict may carry ANY int64 ids (the reference's np.unique accepts them): sparse or huge ids are ranked
+    with np.unique on the host first, so the accumulators are sized by the number of clusters, never by the largest id."""
     pts, lab = device_view(processed)
     if lab.numel() == 0:
         return np.array([])
@@ -206,6 +227,13 @@ def people_positions(processed: dict) -> np.ndarray:
         n_ids = cache.n_clusters             # labels of our own DBSCAN: 0..n_clusters-1, known without a read-back
     else:
         n_ids = int(lab.max().item()) + 1
+        if n_ids > lab.numel() + 1024:
+            # sparse ids: dense ranks (ascending id order is preserved, which is the output order of the reference)
+            host = lab.cpu().numpy()
+            ids = np.unique(host[host >= 0])
+            rank = np.where(host >= 0, np.searchsorted(ids, host), -1).astype(np.int64)
+            lab = torch.from_numpy(rank).to(lab.device)
+            n_ids = len(ids)
     if n_ids <= 0:
         return np.array([])
     cent, counts = ops.cluster_centroids(pts, lab, n_ids)

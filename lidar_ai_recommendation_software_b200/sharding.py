@@ -161,7 +161,7 @@ class ScanDensity:
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)          # every rank's buffer is zero before anybody's first kernel runs
         comm = _capi.ScanComm()
-        comm.rank, comm.world, comm.epoch, comm.symm_bytes = self.rank, self.world, 0, nbytes
+        comm.rank, comm.world, comm.symm_bytes = self.rank, self.world, nbytes
         ptrs = list(hdl.buffer_ptrs)
         for r in range(self.world):
             comm.peer_ptrs[r] = int(ptrs[r])
@@ -214,14 +214,11 @@ class ScanDensity:
         self._g = float(grid_size)
         n = points.shape[0]
         if self.backend == "fused":
-            comm_ref = None
-            if self.comm is not None:
-                self.comm.epoch = self.epoch
-                comm_ref = C.byref(self.comm)
+            comm_ref = C.byref(self.comm) if self.comm is not None else None
             _capi.check(lib.lidar_scan_density(
                 ops._ptr(points), fmt, n, self._g, self.max_nx, self.max_ny, self.cap_cells, ops._ptr(self.grid),
                 ops._ptr(self.density), ops._ptr(self.gx), ops._ptr(self.gy), ops._ptr(self.desc_dev), self._h_ptr,
-                comm_ref, ops._ptr(self.ws), self.ws.numel(), st))
+                comm_ref, self.epoch, ops._ptr(self.ws), self.ws.numel(), st))
         else:
             _capi.check(lib.lidar_scan_bbox_packed(ops._ptr(points), fmt, n, ops._ptr(self.packed), ops._ptr(self.ws),
                                                    self.ws.numel(), st))

@@ -45,10 +45,12 @@ def local_point_density(points, r=0.5):
 
 
 def distance_from_center(points):
-    """utils/visualization.py:50-54: Euclidean distance of every point from the centroid (np.mean)."""
-    pts = np.asarray(points, dtype=np.float64)
-    centroid = np.mean(pts, axis=0)
-    return np.sqrt(np.sum((pts - centroid) ** 2, axis=1))
+    """utils/visualization.py:50-54: Euclidean distance of every point from the centroid (np.mean), float64 (n,).
+    Device path: the moments kernel gives the centroid, one per-point kernel the distances (`lidar_centroid_distances`)."""
+    d = _device_points(points)
+    if d.shape[1] != 3:
+        raise ValueError("distance_from_center expects (n,3) points")
+    return ops.centroid_distances(d).cpu().numpy()
 
 
 def projection_histogram(processed_data, projection_dims=("x", "y"), resolution=100):

@@ -79,3 +79,35 @@ def test_front_degenerate_clouds():
     d = torch.tensor([[1.0, 2.0, 3.0]], dtype=torch.float64, device="cuda")
     desc, inl, *_ = ops.preprocess_front(d, want_colors=False)
     assert int(desc.n_in) == 0
+
+
+def test_scaler_treats_near_constant_columns_like_sklearn():
+    """StandardScaler.fit marks a column constant when var <= n*eps*var + (n*mean*eps)^2
+    (`_is_constant_feature`) — a scan line at UTM-sized x with sub-nanometre jitter gets scale 1, not 1/1e-10."""
+    from sklearn.preprocessing import StandardScaler
+    from lidar_ai_recommendation_software_b200 import ops
+    rng = np.random.default_rng(11)
+    n = 6000
+    pts = np.column_stack([4.0e5 + rng.normal(0, 2e-11, n) * 0 + rng.integers(0, 2, n) * 5.8e-11,   # two adjacent doubles
+                           rng.uniform(-20, 20, n), rng.uniform(0.0, 2.0, n)])
+    d = torch.from_numpy(np.ascontiguousarray(pts)).cuda()
+    desc, inl, col, ng, idx, X = ops.preprocess_front(d, want_colors=False, scaler=True)
+    hng = ng.cpu().numpy()
+    sk = StandardScaler().fit(hng)
+    assert sk.scale_[0] == 1.0                                   # sklearn calls the column constant
+    np.testing.assert_allclose(np.array(desc.scale), sk.scale_, rtol=1e-9)
+    np.testing.assert_allclose(X.cpu().numpy(), sk.transform(hng), rtol=1e-9, atol=1e-9)
+
+
+def test_people_positions_accepts_sparse_and_huge_cluster_ids():
+    """a caller-built processed_data may carry any int64 cluster ids (np.unique in the reference,
+    utils/data_processing.py:262-275): they are ranked first, not used to size the accumulators."""
+    from lidar_ai_recommendation_software_b200.utils import data_processing as dp
+    rng = np.random.default_rng(2)
+    pts = rng.uniform(-5, 5, (4000, 3))
+    ids = np.array([3, 17, 2**31 + 5, 2**40, 10**15], dtype=np.int64)
+    lab = np.where(rng.uniform(size=4000) < 0.2, -1, ids[rng.integers(0, len(ids), 4000)]).astype(np.int64)
+    got = dp.extract_people_positions({"points": pts, "clusters": lab})
+    want = np.array([pts[lab == c].mean(axis=0)[:2] for c in np.unique(lab[lab >= 0])])
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)

@@ -107,6 +107,38 @@ def test_people_positions_and_grid_density(name, pkg, golden, processed_a):
     assert np.array_equal(ex, g["heat_ex"]) and np.array_equal(ey, g["heat_ey"])
 
 
+def test_create_density_heatmap_under_its_own_name(pkg, golden, processed_a, monkeypatch):
+    """Surface B swaps `create_density_heatmap` in by name (app_simplified.py:198-232, called at :1074): same
+    go.Figure(go.Heatmap(z=hist.T, x=centres, y=centres, ...)) + layout.  plotly is not in this image, so a recording
+    stand-in of plotly.graph_objects shows what the figure is built from."""
+    import sys
+    import types
+
+    class _Rec:
+        def __init__(self, *a, **k):
+            self.args, self.kwargs, self.layout = a, k, {}
+
+        def update_layout(self, **k):
+            self.layout.update(k)
+
+    go = types.ModuleType("plotly.graph_objects")
+    go.Figure = type("Figure", (_Rec,), {})
+    go.Heatmap = type("Heatmap", (_Rec,), {})
+    plotly = types.ModuleType("plotly")
+    plotly.graph_objects = go
+    monkeypatch.setitem(sys.modules, "plotly", plotly)
+    monkeypatch.setitem(sys.modules, "plotly.graph_objects", go)
+    g, pa = golden("crowd_20k"), processed_a("crowd_20k")
+    fig = pkg.apps.create_density_heatmap(pa)
+    hm = fig.kwargs["data"]
+    assert isinstance(fig, go.Figure) and isinstance(hm, go.Heatmap)
+    assert np.array_equal(hm.kwargs["z"], g["heat_counts"].T.astype(np.float64)) and hm.kwargs["z"].dtype == np.float64
+    ex, ey = g["heat_ex"], g["heat_ey"]
+    assert np.array_equal(hm.kwargs["x"], (ex[:-1] + ex[1:]) / 2) and np.array_equal(hm.kwargs["y"], (ey[:-1] + ey[1:]) / 2)
+    assert hm.kwargs["colorscale"] == "Viridis" and hm.kwargs["colorbar"] == dict(title="Point Density")
+    assert fig.layout == dict(xaxis_title="X (m)", yaxis_title="Y (m)", title="Point Density Heatmap", height=500)
+
+
 @pytest.mark.parametrize("name", CASE_NAMES)
 def test_crowd_density_model(name, pkg, golden, processed_a):
     g = golden(name)
@@ -287,6 +319,19 @@ def test_local_point_density_matches_oracle(pkg, r):
     got2 = viz.local_point_density(pts[:, :2], r)
     assert np.array_equal(got2, nps.local_density_counts(pts[:, :2], r))
     assert viz.local_point_density(np.zeros((0, 3)), r).shape == (0,)
+
+
+def test_distance_from_center_on_the_device(pkg, case_points):
+    """utils/visualization.py:50-54 (np.mean + np.sqrt(np.sum((p - c)**2, axis=1))) through the device kernels."""
+    from lidar_ai_recommendation_software_b200.utils import visualization as viz
+    pts = case_points("crowd_20k")
+    want = np.sqrt(np.sum((pts - np.mean(pts, axis=0)) ** 2, axis=1))
+    got = viz.distance_from_center(pts)
+    assert got.dtype == np.float64 and got.shape == want.shape
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
+    far = pts + np.array([4.0e5, 5.0e6, 0.0])        # UTM-sized offsets: the centroid must not lose the small scale
+    assert np.allclose(viz.distance_from_center(far), np.sqrt(np.sum((far - np.mean(far, axis=0)) ** 2, axis=1)),
+                       rtol=1e-9, atol=1e-7)
 
 
 def test_projection_histogram_matches_numpy_semantics(pkg, processed_b, case_points):
