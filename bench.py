@@ -309,8 +309,9 @@ def main():
     ap.add_argument("--ctas-per-sm", type=int, default=0, help="frame kernel grid cap (0 = library default)")
     ap.add_argument("--streams", type=int, default=0,
                     help="independent frame pipelines in flight (frames round-robin over CUDA streams)")
-    ap.add_argument("--mode", default="fused", choices=["fused", "multikernel"],
-                    help="frame back end: one persistent cooperative kernel, or five dependent kernels")
+    ap.add_argument("--mode", default="fused", choices=["fused", "partitioned", "multikernel"],
+                    help="frame back end: the persistent fused kernel (occupancy bitmap in L2), the persistent partitioned "
+                         "kernel (MSD radix partition by voxel key, occupancy bits in shared memory), or five dependent kernels")
     ap.add_argument("--fused-threads", type=int, default=0)
     ap.add_argument("--fused-ctas-per-sm", type=int, default=0)
     ap.add_argument("--fused-smem-kb", type=int, default=0)
@@ -359,7 +360,7 @@ def main():
     from lidar_ai_recommendation_software_b200 import _capi
     if args.ctas_per_sm:
         _capi.check(_capi.lib.lidar_frame_set_ctas_per_sm(args.ctas_per_sm))
-    fused = args.mode == "fused"
+    fused = args.mode in ("fused", "partitioned")
     if args.fused_plain_launch:
         _capi.check(_capi.lib.lidar_frame_set_fused_plain_launch(1))
     if args.scan_order:
@@ -372,8 +373,8 @@ def main():
         except _capi.LidarError as e:
             print(f"bench: L2 persistence not available ({e}); continuing without it", file=sys.stderr)
             args.l2_persist_mb = 0
-    ops.set_frame_mode(ops.FRAME_FUSED if fused else ops.FRAME_MULTIKERNEL, args.fused_threads,
-                       args.fused_ctas_per_sm, args.fused_smem_kb)
+    frame_mode = {"fused": ops.FRAME_FUSED, "partitioned": ops.FRAME_PARTITIONED, "multikernel": ops.FRAME_MULTIKERNEL}[args.mode]
+    ops.set_frame_mode(frame_mode, args.fused_threads, args.fused_ctas_per_sm, args.fused_smem_kb)
     # the fused kernel fills the device by itself (frames of other streams would only queue behind it);
     # the five-kernel path leaves gaps that frames on other streams fill
     S = args.streams if args.streams > 0 else (1 if fused else 4)
@@ -459,12 +460,14 @@ def main():
         last = pipe.result()
         ph = [int(x) for x in last.desc.trace_ns]
         assert ph[15] > 0, "the fused kernel did not run"
-        names = ["load_bbox", "bar1", "desc", "mark", "bar2", "scan_popc", "scan_wait", "scan_prefix", "bar3",
-                 "rank", "bar4", "clean_finalize"]
+        names = (["load_bbox", "bar1", "desc", "keys_slots_claim", "bar2", "sort_scatter", "bar3", "owner_pass", "bar4",
+                  "ranks_records", "bar5", "finalize"] if args.mode == "partitioned" else
+                 ["load_bbox", "bar1", "desc", "mark", "bar2", "scan_popc", "scan_wait", "scan_prefix", "bar3",
+                  "rank", "bar4", "clean_finalize"])
         phases = {k + "_us": ph[i] / 1e3 for i, k in enumerate(names)}
         phases["ctas"] = ph[15]
         gbs = frame_bytes / (frame_ms * 1e-3) / 1e9
-        kname = "k_frame_fused"
+        kname = "k_frame_part" if args.mode == "partitioned" else "k_frame_fused"
         roofline = {"bound": "hbm", "kernel": kname, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                     "frac": gbs / hbm_peak, "traffic": ncu_traffic(kname), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": frame_bytes, "launch_ms": frame_ms,

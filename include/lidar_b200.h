@@ -342,8 +342,17 @@ size_t lidar_frame_workspace_bytes(const lidar_frame_caps* caps);
  *                            refused
  * threads / ctas_per_sm / smem_kb tune the fused kernel (0 keeps the current value; smem_kb 0 =
  * as much as the frame needs).  Both paths produce identical outputs.  Process-wide setting. */
-enum { LIDAR_FRAME_AUTO = 0, LIDAR_FRAME_MULTIKERNEL = 1, LIDAR_FRAME_FUSED = 2 };
+enum { LIDAR_FRAME_AUTO = 0, LIDAR_FRAME_MULTIKERNEL = 1, LIDAR_FRAME_FUSED = 2, LIDAR_FRAME_PARTITIONED = 3 };
 int lidar_frame_set_fused(int mode, int threads, int ctas_per_sm, int smem_kb);
+/*   LIDAR_FRAME_PARTITIONED  one persistent kernel (k_frame_part) built around an MSD radix partition by voxel-key
+ *                            range: points are binned into <= 2048 partitions of 2^18 voxel cells, 8-byte {key, cell}
+ *                            entries travel to the partition's owner CTA in run-coalesced writes, and the occupancy bits,
+ *                            their popcount prefix and the density cells of the owner's slab live in shared memory: no
+ *                            occupancy bitmap in global memory.  Needs caps.max_key_space <= 2^29 and the frame resident
+ *                            in shared memory (<= ~1.3 M points on 148 SMs), else LIDAR_ERR_CAPACITY.
+ * lidar_frame_set_partition_auto(1): LIDAR_FRAME_AUTO takes the partitioned back end whenever a frame is eligible (and the
+ * scan-order variant is not selected), the fused one otherwise. */
+int lidar_frame_set_partition_auto(int on);
 /* EXPERIMENT knob, off by default: launch k_frame_fused with an ordinary launch instead of a
  * cooperative one.  Cooperative launches of different streams do not overlap on the device; ordinary
  * ones do, but then co-residency of the grid is the caller's responsibility: the grid must fit the

@@ -163,6 +163,7 @@ PROTOTYPES: dict[str, tuple] = {
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "lidar_frame_set_ctas_per_sm": (_i32, [_i32]),
     "lidar_frame_set_fused": (_i32, [_i32, _i32, _i32, _i32]),
+    "lidar_frame_set_partition_auto": (_i32, [_i32]),
     "lidar_frame_set_fused_plain_launch": (_i32, [_i32]),
     "lidar_frame_set_fused_pdl": (_i32, [_i32]),
     "lidar_frame_set_fused_l2_persist": (_i32, [_sz]),

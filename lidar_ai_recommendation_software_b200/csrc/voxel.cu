@@ -46,7 +46,8 @@ constexpr int kScanGroupsPerThread = 4;                               // each th
 constexpr int kScanTileGroups = kFrameThreads * kScanGroupsPerThread; // 1024 groups = 229 376 voxels per tile
 
 struct FrameWsLayout {
-    size_t off_partial, off_ctrl, off_groups, off_tile_desc, off_acc, off_cnt, off_cta_desc, off_trace, off_grid_rep, off_l1, off_l1cnt, total;
+    size_t off_partial, off_ctrl, off_groups, off_tile_desc, off_acc, off_cnt, off_cta_desc, off_trace, off_grid_rep, off_l1, off_l1cnt,
+           off_ptotal, off_pvox, off_bucket, off_prank, total;
     int64_t groups, tiles, l1_words;
 };
 
@@ -89,6 +90,12 @@ static FrameWsLayout frame_layout(const lidar_frame_caps& c) {
     L.l1_words = (L.groups + 31) / 32;             // summary: one bit per occupancy group (scan-order variant)
     L.off_l1 = take(sizeof(uint32_t) * (size_t)L.l1_words);
     L.off_l1cnt = take(sizeof(uint32_t) * (size_t)L.l1_words);   // occupied cells per summary word, then their prefix
+    // partitioned back end (k_frame_part): claim counters and voxel counts per partition, the bucket of {key, cell}
+    // entries grouped by partition and the owners' answers (2048 = kPartMax partitions of 2^18 cells)
+    L.off_ptotal = take(sizeof(uint32_t) * 2048);
+    L.off_pvox = take(sizeof(uint32_t) * 2048);
+    L.off_bucket = take(sizeof(uint2) * (size_t)c.max_points);
+    L.off_prank = take(sizeof(uint32_t) * (size_t)c.max_points);
     L.total = ws_align(o);
     return L;
 }
@@ -1530,6 +1537,546 @@ k_frame_fused(const FusedArgs A) {
     }
 }
 
+// ================================================================================================
+// k_frame_part — the frame as ONE persistent kernel around an MSD radix PARTITION by voxel-key range
+// (the north star's "radix-sort-by-voxel-key", done as a single most-significant-digit pass).
+//
+// k_frame_fused pays four scattered 32-byte L2 operations per point on shuffled input (occupancy atomic,
+// density reduction, group load, record store) plus a 22 MB bitmap that is streamed twice.  Here the only
+// per-point traffic that is scattered by nature remains: each point's 32-byte record has to land at its
+// voxel's rank.  Everything else becomes shared-memory work or run-coalesced traffic:
+//
+//   phase 0  as k_frame_fused: TMA load of the CTA's chunk into shared memory, bounding box, descriptor
+//   phase 1  per point: voxel key, density cell, partition = key >> 18 (2^18 cells = 32 KB of occupancy
+//            bits); a shared-memory histogram hands every point its slot inside the CTA's run for that
+//            partition; ONE global atomicAdd per (CTA, partition) claims the run's place in the bucket
+//   phase 2  exclusive scan of the partition totals (every CTA, redundantly: <= 2048 values), CTA-local
+//            counting sort by partition (16-bit permutation in shared memory), then the 8-byte entries
+//            {key, cell} go to the bucket in SORTED order: adjacent threads write adjacent addresses
+//   phase 3  owner pass: CTA b owns a contiguous range of partitions, one at a time with all threads: occupancy
+//            bits + popcount prefix live in shared memory (atomicOr returns "first member or later one"), the
+//            density cells of the slab are counted in shared memory and flushed once; per entry the owner
+//            returns {rank inside the partition, later-member flag}; per partition its voxel count
+//   phase 4  exclusive scan of the partition voxel counts; every CTA reads the answers for ITS points back
+//            (sorted order: coalesced runs), inverse goes out coalesced, first members store their record,
+//            later members accumulate exact fixed-point sums (same device functions as k_frame_fused)
+//   phase 5  finalize the multi-member voxels (sweep of the member counters)
+//
+// No occupancy bitmap in global memory (nothing to stream, nothing to clean), no density replicas.
+// Outputs are identical to the other back ends (tests/test_gpu_frame_modes.py).  Eligible when the whole chunk of
+// every CTA is resident in shared memory and caps.max_key_space <= 2^29 (<= 2048 partitions).
+// ================================================================================================
+constexpr int kPartShift = 18;
+constexpr int kPartCells = 1 << kPartShift;
+constexpr int kPartWords64 = kPartCells / 64;        // 4096 prefix slots: one per 64 occupancy bits (two 32-bit words)
+constexpr int kPartMax = 2048;                       // partitions per frame
+constexpr int kPartDensCap = 1024;                   // density cells of a CTA's slab counted in shared memory
+constexpr unsigned kPartDup = 0x80000000u;
+constexpr int kPartRegs = 8;                        // bucket entries a thread of the owner keeps in registers per partition
+
+struct PartArgs {
+    FusedArgs F;
+    unsigned* ptotal;     // [kPartMax] entries claimed per partition (all-zero between frames)
+    unsigned* pvox;       // [kPartMax] voxels per partition
+    uint2* bucket;        // [max_points] {key, density cell} grouped by partition
+    unsigned* prank;      // [max_points] owner's answer per bucket slot: rank inside the partition | later-member flag
+    int pcap;             // capacity of the per-partition shared-memory arrays (>= partitions of any frame)
+    int union_bytes;      // shared-memory region shared by {key, cell, slot} (phases 1-2), the owner structures (3), inverse (4)
+};
+
+__device__ __forceinline__ unsigned cta_exclusive_scan_u32(unsigned* a, int n, unsigned* s_wsum /* [nwarp] */, int T) {
+    // in-place exclusive scan of a[0..n) by the whole CTA; returns the total.  Each thread owns a contiguous slice.
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+    const int per = (n + T - 1) / T;
+    const int i0 = tid * per < n ? tid * per : n, i1 = i0 + per < n ? i0 + per : n;
+    unsigned mine = 0;
+    for (int i = i0; i < i1; ++i) mine += a[i];
+    unsigned inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    unsigned woff = 0, total = 0;
+    for (int w = 0; w < nwarp; ++w) {
+        const unsigned v = s_wsum[w];
+        if (w < warp) woff += v;
+        total += v;
+    }
+    unsigned run = woff + inc - mine;
+    for (int i = i0; i < i1; ++i) {
+        const unsigned v = a[i];
+        a[i] = run;
+        run += v;
+    }
+    __syncthreads();
+    return total;
+}
+
+__global__ void __launch_bounds__(kFusedMaxThreads, 1)
+k_frame_part(const PartArgs PA) {
+    extern __shared__ __align__(128) unsigned char fsm[];
+    __shared__ lidar_frame_desc D;
+    __shared__ __align__(8) unsigned long long s_bar[kFusedLoadStages];
+    __shared__ double s_red[kFusedMaxThreads / 32][8];
+    __shared__ double s_bb[8];
+    __shared__ unsigned s_wsum[kFusedMaxThreads / 32];
+    __shared__ unsigned long long s_trace[16];
+    __shared__ int s_stat[8];
+
+    const FusedArgs& A = PA.F;
+    const int T = blockDim.x, tid = threadIdx.x, nwarp = T >> 5, warp = tid >> 5;
+    const unsigned lane = lane_id();
+    const int G = gridDim.x, b = blockIdx.x;
+    const FrameParams& P = A.P;
+    const int64_t n = P.n;
+
+    // shared-memory carve-up
+    const int spts = A.smem_points;
+    float4* s_pts = reinterpret_cast<float4*>(fsm);
+    unsigned short* s_perm = reinterpret_cast<unsigned short*>(fsm + (size_t)spts * 16);
+    unsigned* s_key = reinterpret_cast<unsigned*>(fsm + (size_t)spts * 18);           // spts is a multiple of 32
+    unsigned* s_hist = s_key + spts;
+    unsigned* s_delta = s_hist + PA.pcap;
+    uint2* s_ring = reinterpret_cast<uint2*>(s_delta + PA.pcap);
+    const size_t ring_bytes = (size_t)nwarp * kFusedRing * 8 > 8192 ? (size_t)nwarp * kFusedRing * 8 : 8192;   // doubles as s_pbase[2048]
+    unsigned char* s_union = reinterpret_cast<unsigned char*>(s_ring) + ring_bytes;
+    // phases 1-2 view of the union
+    unsigned short* s_cell = reinterpret_cast<unsigned short*>(s_union);
+    unsigned short* s_slot = reinterpret_cast<unsigned short*>(s_union + (size_t)spts * 2);
+    // phase 3 view: 2^18 occupancy bits as 32-bit words (native shared-memory atomicOr), a popcount prefix per 64 bits,
+    // the density cells of the slab
+    unsigned* s_bits = reinterpret_cast<unsigned*>(s_union);                           // 2 * kPartWords64 x 4 B = 32 KB
+    unsigned* s_pref = s_bits + 2 * kPartWords64;                                      // 16 KB
+    unsigned* s_dens = s_pref + kPartWords64;                                          // kPartDensCap x 4 B
+    // phase 4 view
+    unsigned* s_inv = reinterpret_cast<unsigned*>(s_union);
+
+    const int64_t per = ((n + G - 1) / G + 31) & ~(int64_t)31;
+    const int64_t c0 = (int64_t)b * per < n ? (int64_t)b * per : n;
+    const int m = (int)((c0 + per <= n ? c0 + per : n) - c0);       // host guarantees m <= spts
+    const float4* gp = P.pts + c0;
+    const int stage_pts = ((m + kFusedLoadStages - 1) / kFusedLoadStages + 3) & ~3;
+
+    if (!A.early_load) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tid == 0) {
+        s_trace[0] = global_timer_ns();
+#pragma unroll
+        for (int s = 0; s < kFusedLoadStages; ++s) fused_mbar_init(&s_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int s = 0; s < kFusedLoadStages; ++s) {
+            const int p0 = s * stage_pts;
+            int cnt = m - p0;
+            cnt = cnt < 0 ? 0 : (cnt > stage_pts ? stage_pts : cnt);
+            if (cnt > 0) {
+                fused_mbar_expect_tx(&s_bar[s], (unsigned)cnt * 16u);
+                fused_bulk_g2s(s_pts + p0, gp + p0, (unsigned)cnt * 16u, &s_bar[s]);
+            }
+        }
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    for (int p = tid; p < PA.pcap; p += T) s_hist[p] = 0u;
+    __syncthreads();
+    // ---- phase 0: bounding box of the chunk ----------------------------------------------------------
+    {
+        float mn[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int s = 0; s < kFusedLoadStages; ++s) {
+            const int p0 = s * stage_pts;
+            int p1 = p0 + stage_pts;
+            p1 = p1 > m ? m : p1;
+            if (p0 < p1) {
+                fused_mbar_wait(&s_bar[s], 0);
+                for (int j = p0 + tid; j < p1; j += T) {
+                    const float4 v = s_pts[j];
+                    mn[0] = fminf(mn[0], v.x); mx[0] = fmaxf(mx[0], v.x);
+                    mn[1] = fminf(mn[1], v.y); mx[1] = fmaxf(mx[1], v.y);
+                    mn[2] = fminf(mn[2], v.z); mx[2] = fmaxf(mx[2], v.z);
+                    mn[3] = fminf(mn[3], v.w); mx[3] = fmaxf(mx[3], v.w);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+                mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { s_red[warp][c] = (double)mn[c]; s_red[warp][4 + c] = (double)mx[c]; }
+        }
+        __syncthreads();
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    {
+        // the occupancy bitmap of the other back ends may be dirty if the previous frame of this workspace ran on the
+        // five-kernel path: clean it here so that the workspace invariants hold whichever back end comes next
+        const int64_t gt0 = (int64_t)b * T + tid, gstride = (int64_t)G * T;
+        int64_t dirty = (int64_t)A.ctrl->dirty_groups;
+        if (dirty > A.groups_cap) dirty = A.groups_cap;
+        uint4* b4 = reinterpret_cast<uint4*>(A.groups);
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int64_t k = gt0; k < dirty * 2; k += gstride) b4[k] = z;
+        for (int64_t k = gt0; k < A.grid_cap; k += gstride) A.grid_out[k] = 0;
+    }
+    if (tid < 8) {
+        const bool is_max = tid >= 4;
+        double v = is_max ? -INFINITY : INFINITY;
+        for (int w = 0; w < nwarp; ++w) v = is_max ? fmax(v, s_red[w][tid]) : fmin(v, s_red[w][tid]);
+        A.partial[(size_t)b * 8 + tid] = v;
+    }
+    FUSED_TRACE(1);
+    fused_grid_barrier(&A.ctrl->grid_bar, 1u * G);
+    FUSED_TRACE(2);
+    {
+        const int ch = tid & 7;
+        const bool is_max = ch >= 4;
+        double v = is_max ? -INFINITY : INFINITY;
+        for (int q = tid >> 3; q < G; q += T / 8) {
+            const double x = __ldcg(A.partial + (size_t)q * 8 + ch);
+            v = is_max ? fmax(v, x) : fmin(v, x);
+        }
+        for (int o = 8; o < 32; o <<= 1) {
+            const double x = __shfl_xor_sync(0xffffffffu, v, o);
+            v = is_max ? fmax(v, x) : fmin(v, x);
+        }
+        if (lane < 8) s_red[warp][lane] = v;
+        __syncthreads();
+        if (tid < 8) {
+            double r = s_red[0][tid];
+            for (int w = 1; w < nwarp; ++w) r = (tid >= 4) ? fmax(r, s_red[w][tid]) : fmin(r, s_red[w][tid]);
+            s_bb[tid] = r;
+        }
+        __syncthreads();
+        derive_desc_cta(P, s_bb, &D, s_stat);
+    }
+    FUSED_TRACE(3);
+    const bool ok = D.status == 0;
+    const int nparts = ok ? (int)((D.key_space + kPartCells - 1) >> kPartShift) : 0;     // <= pcap (host checked the capacity)
+    const int ncell = D.nx * D.ny;
+    const bool cell16 = ncell <= 0xffff;           // density cells travel as 16 bits in shared memory; else recomputed
+    const MarkConst K = make_mark_const(D);
+
+    // ---- phase 1: keys, cells, slots inside the CTA's per-partition runs ---------------------------------
+    if (ok) {
+        for (int j0 = tid; j0 < m; j0 += kFusedBatch * T) {
+            float4 q[kFusedBatch];
+            int key[kFusedBatch], cell[kFusedBatch];
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                const int j = j0 + u * T;
+                q[u] = s_pts[j < m ? j : j0];
+            }
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                key[u] = voxel_key_of(q[u], D, K);
+                cell[u] = (K.do_grid && cell16) ? grid_cell_of(q[u], D, K) + 1 : 0;          // 0 = outside
+            }
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                const int j = j0 + u * T;
+                if (j < m) {
+                    const unsigned slot = atomicAdd(&s_hist[key[u] >> kPartShift], 1u);
+                    s_key[j] = (unsigned)key[u];
+                    s_slot[j] = (unsigned short)slot;
+                    s_cell[j] = (unsigned short)cell[u];
+                    st_stream_s32(A.voxel_key + c0 + j, key[u]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // claim the place of every non-empty run in its partition's bucket: delta = offset inside the partition
+    if (ok) {
+        for (int p = tid; p < nparts; p += T) {
+            const unsigned c = s_hist[p];
+            s_delta[p] = c ? atomicAdd(PA.ptotal + p, c) : 0u;
+        }
+    }
+    FUSED_TRACE(4);
+    fused_grid_barrier(&A.ctrl->grid_bar, 2u * G);
+    FUSED_TRACE(5);
+
+    // ---- phase 2: partition bases, local counting sort, sorted scatter ------------------------------------
+    // owner of partition p: CTA floor(p * G / nparts), i.e. CTA b owns [ceil(b*nparts/G), ceil((b+1)*nparts/G)) -- sizes
+    // differ by at most one, every CTA gets work when nparts >= G
+    const int p0 = (int)(((long long)b * nparts + G - 1) / G);
+    const int p1 = (int)(((long long)(b + 1) * nparts + G - 1) / G);
+    unsigned* s_pbase = reinterpret_cast<unsigned*>(s_ring);     // [nparts <= 2048] bucket start of every partition: the
+                                                                  // ring area (8 B x 64 x warps >= 8 KB) is idle until phase 4
+    unsigned bucket_total = 0;
+    if (ok) {
+        for (int p = tid; p < nparts; p += T) s_pbase[p] = __ldcg(PA.ptotal + p);
+        __syncthreads();
+        bucket_total = cta_exclusive_scan_u32(s_pbase, nparts, s_wsum, T);        // == n
+        (void)cta_exclusive_scan_u32(s_hist, nparts, s_wsum, T);                   // local sorted position of every run
+        for (int p = tid; p < nparts; p += T) s_delta[p] += s_pbase[p];            // bucket position of this CTA's run
+        // permutation: sorted position -> point
+        for (int j = tid; j < m; j += T) s_perm[s_hist[s_key[j] >> kPartShift] + s_slot[j]] = (unsigned short)j;
+        __syncthreads();
+        // sorted scatter: thread t writes the entry of sorted position t; a run of one partition is contiguous in the bucket
+        // (every CTA starts at a different sorted position: without the rotation all 148 CTAs would write partition 0's
+        // window of the bucket at the same time, then partition 1's, ... one hot L2 region after the other)
+        const int rot = m ? (int)(((long long)b * m / G) & ~31ll) : 0;
+        for (int i = tid; i < m; i += T) {
+            const int t = i + rot < m ? i + rot : i + rot - m;
+            const int j = s_perm[t];
+            const unsigned key = s_key[j];
+            const unsigned p = key >> kPartShift;
+            const unsigned dest = s_delta[p] + ((unsigned)t - s_hist[p]);
+            PA.bucket[dest] = make_uint2(key, (unsigned)s_cell[j]);
+        }
+        __syncthreads();
+        // from here on: bucket slot of sorted position t = s_delta[p] + t
+        for (int p = tid; p < nparts; p += T) s_delta[p] -= s_hist[p];
+    }
+    FUSED_TRACE(6);
+    fused_grid_barrier(&A.ctrl->grid_bar, 3u * G);
+    FUSED_TRACE(7);
+
+    // ---- phase 3: owner pass over partitions [p0, p1) ------------------------------------------------------
+    if (ok) {
+        // density cells this CTA's slab can touch: [cell_lo, cell_lo + kPartDensCap); anything else goes straight to
+        // global memory (correct whatever the estimate: it only decides where the count is accumulated)
+        int cell_lo = 0;
+        if (K.do_grid && p0 < p1) {
+            const long long cells_per_ix = (long long)D.dims[1] * D.dims[2];
+            const int ix0 = (int)(((long long)p0 << kPartShift) / cells_per_ix);
+            const double x0 = __dadd_rn(D.origin[0], __dmul_rn((double)ix0, D.voxel));
+            int bx = arange_bin(x0, D.ex0, D.ex1, D.exd, K.rdx, D.nx);
+            bx = bx < 1 ? 0 : bx - 1;
+            cell_lo = bx * D.ny;
+        }
+        if (K.do_grid) {
+            for (int k = tid; k < kPartDensCap; k += T) s_dens[k] = 0u;
+        }
+        for (int p = p0; p < p1; ++p) {
+            const unsigned e0 = s_pbase[p], e1 = p + 1 < nparts ? s_pbase[p + 1] : bucket_total;
+            const unsigned kbase = (unsigned)p << kPartShift;
+            // the thread's entries stay in registers from the first pass to the second (all loads in flight at once);
+            // a partition with more than kPartRegs * T entries takes the streaming loops below for the remainder
+            uint2 en[kPartRegs];
+            unsigned ans[kPartRegs];
+#pragma unroll
+            for (int r = 0; r < kPartRegs; ++r) {
+                const unsigned e = e0 + tid + r * T;
+                en[r] = make_uint2(0u, 0u);
+                if (e < e1) en[r] = __ldcg(PA.bucket + e);
+            }
+            for (int w = tid; w < kPartWords64; w += T) reinterpret_cast<uint2*>(s_bits)[w] = make_uint2(0u, 0u);
+            __syncthreads();
+            auto mark_one = [&](const uint2& e_) -> unsigned {
+                const unsigned local = e_.x - kbase;
+                const unsigned bit = 1u << (local & 31);
+                const unsigned old = atomicOr(&s_bits[local >> 5], bit);
+                if (K.do_grid && cell16) {
+                    const int cell = (int)e_.y - 1;
+                    if (cell >= 0) {
+                        const int rel = cell - cell_lo;
+                        if (rel >= 0 && rel < kPartDensCap) atomicAdd(&s_dens[rel], 1u);
+                        else red_add_s32(A.grid_out + cell, 1);
+                    }
+                }
+                return (old & bit) ? kPartDup : 0u;
+            };
+            // pass A: occupancy bits; the old word says whether this entry is the first member of its voxel
+#pragma unroll
+            for (int r = 0; r < kPartRegs; ++r)
+                if (e0 + tid + r * T < e1) ans[r] = mark_one(en[r]);
+            for (unsigned e = e0 + tid + kPartRegs * T; e < e1; e += T) PA.prank[e] = mark_one(__ldcg(PA.bucket + e));
+            __syncthreads();
+            // popcount prefix per 64 bits.  Warp w owns the contiguous words [w*wpw, (w+1)*wpw); in round k its lanes read
+            // word base + 32k + lane (consecutive addresses: no bank conflicts) and a warp scan orders them
+            {
+                const unsigned long long* bits64 = reinterpret_cast<const unsigned long long*>(s_bits);
+                const int wpw = kPartWords64 / nwarp;                    // nwarp is a power of two <= 16: 256.. words
+                const int base = warp * wpw;
+                unsigned wsum = 0;
+                for (int k = 0; k < wpw; k += 32) wsum += __popcll(bits64[base + k + lane]);
+                wsum = warp_sum_u32(wsum);
+                if (lane == 0) s_wsum[warp] = wsum;
+                __syncthreads();
+                unsigned run = 0, total = 0;
+                for (int w = 0; w < nwarp; ++w) { const unsigned v = s_wsum[w]; if (w < warp) run += v; total += v; }
+                for (int k = 0; k < wpw; k += 32) {
+                    const unsigned pc = __popcll(bits64[base + k + lane]);
+                    unsigned inc = pc;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                        if ((int)lane >= o) inc += t;
+                    }
+                    s_pref[base + k + lane] = run + inc - pc;
+                    run += __shfl_sync(0xffffffffu, inc, 31);
+                }
+                if (tid == 0) PA.pvox[p] = total;
+                __syncthreads();
+            }
+            // pass B: rank inside the partition
+            auto rank_one = [&](unsigned key_) -> unsigned {
+                const unsigned local = key_ - kbase;
+                const unsigned long long w64 = reinterpret_cast<const unsigned long long*>(s_bits)[local >> 6];
+                return s_pref[local >> 6] + __popcll(w64 & ((1ull << (local & 63)) - 1ull));
+            };
+#pragma unroll
+            for (int r = 0; r < kPartRegs; ++r) {
+                const unsigned e = e0 + tid + r * T;
+                if (e < e1) PA.prank[e] = ans[r] | rank_one(en[r].x);
+            }
+            for (unsigned e = e0 + tid + kPartRegs * T; e < e1; e += T) PA.prank[e] |= rank_one(__ldcg(&PA.bucket[e].x));
+            __syncthreads();
+        }
+        if (K.do_grid) {
+            for (int k = tid; k < kPartDensCap; k += T) {
+                const unsigned c = s_dens[k];
+                if (c) red_add_s32(A.grid_out + cell_lo + k, (int)c);
+            }
+        }
+        // the claim counters go back to zero for the next frame (every CTA read them before barrier 3)
+        for (int p = p0 + tid; p < p1; p += T) PA.ptotal[p] = 0u;
+    }
+    FUSED_TRACE(8);
+    fused_grid_barrier(&A.ctrl->grid_bar, 4u * G);
+    FUSED_TRACE(9);
+
+    // ---- phase 4: global ranks, inverse, records -----------------------------------------------------------
+    unsigned long long n_voxels = 0ull;
+    if (ok) {
+        // s_hist <- exclusive scan of the partition voxel counts
+        for (int p = tid; p < nparts; p += T) s_hist[p] = __ldcg(PA.pvox + p);
+        __syncthreads();
+        n_voxels = cta_exclusive_scan_u32(s_hist, nparts, s_wsum, T);
+        if (tid == 0) D.n_voxels = (int64_t)n_voxels;
+        uint2* ring = s_ring + (size_t)warp * kFusedRing;
+        unsigned head = 0, count = 0;
+        auto drain = [&](unsigned slot, bool active) {
+            if (!active) return;
+            const uint2 e = ring[slot];
+            const float4 q = s_pts[e.x];
+            accumulate_dup(q, (int)s_key[e.x], e.y, D, A.acc, A.cnt);
+        };
+        const int m_round = (m + 31) & ~31;
+        const int rot = m ? (int)(((long long)b * m / G) & ~31ll) : 0;      // as in the scatter: CTAs start at different partitions
+        for (int t0 = tid; t0 < m_round; t0 += kFusedBatch * T) {
+            int j[kFusedBatch], tt[kFusedBatch];
+            unsigned ans[kFusedBatch], part[kFusedBatch];
+            int key[kFusedBatch];
+            float4 q[kFusedBatch];
+            bool live[kFusedBatch];
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                const int i = t0 + u * T;
+                live[u] = i < m;
+                tt[u] = i + rot < m ? i + rot : i + rot - m;             // sorted position handled by this lane
+                j[u] = live[u] ? (int)s_perm[tt[u]] : 0;
+                q[u] = s_pts[j[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                key[u] = (int)s_key[j[u]];
+                part[u] = (unsigned)key[u] >> kPartShift;
+                ans[u] = 0u;
+                if (live[u]) ans[u] = __ldcg(PA.prank + s_delta[part[u]] + (unsigned)tt[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                const unsigned r = s_hist[part[u]] + (ans[u] & ~kPartDup);
+                const bool dup = live[u] && (ans[u] & kPartDup) != 0u;
+                if (live[u]) {
+                    s_inv[j[u]] = r;
+                    if (!dup) store_first_member(A.voxels, r, q[u], key[u]);
+                    if (K.do_grid && !cell16) {
+                        const int cell = grid_cell_of(q[u], D, K);
+                        if (cell >= 0) red_add_s32(A.grid_out + cell, 1);
+                    }
+                }
+                const unsigned mm = __ballot_sync(0xffffffffu, dup);
+                if (mm) {
+                    if (dup) ring[(head + count + __popc(mm & lanemask_lt())) % kFusedRing] = make_uint2((unsigned)j[u], r);
+                    count += __popc(mm);
+                    __syncwarp();
+                    if (count >= 32) {
+                        drain((head + lane) % kFusedRing, true);
+                        head = (head + 32) % kFusedRing;
+                        count -= 32;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        if (count) drain((head + lane) % kFusedRing, lane < count);
+        __syncthreads();
+        for (int jj = tid; jj < m; jj += T) st_stream_s32(A.inverse + c0 + jj, (int)s_inv[jj]);
+    }
+    FUSED_TRACE(10);
+    fused_grid_barrier(&A.ctrl->grid_bar, 5u * G);
+    FUSED_TRACE(11);
+
+    // ---- phase 5: finalize the multi-member voxels ----------------------------------------------------------
+    if (ok) {
+        unsigned* ring = reinterpret_cast<unsigned*>(s_ring + (size_t)warp * kFusedRing);
+        unsigned head = 0, count = 0;
+        const double isx = 1.0 / D.fix_scale_xyz, isw = 1.0 / D.fix_scale_w;
+        const int64_t V = (int64_t)n_voxels;
+        const int64_t vper = ((V + G - 1) / G + 31) & ~(int64_t)31;
+        const int64_t v0 = (int64_t)b * vper;
+        const int64_t v1 = v0 + vper;
+        for (int64_t r0 = v0 + tid; r0 < v1; r0 += (int64_t)kFusedBatch * T) {
+            int c[kFusedBatch];
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                const int64_t r = r0 + (int64_t)u * T;
+                c[u] = (r < v1 && r < V) ? __ldcg(A.cnt + r) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < kFusedBatch; ++u) {
+                const int64_t r = r0 + (int64_t)u * T;
+                const bool hit = c[u] != 0;
+                const unsigned mm = __ballot_sync(0xffffffffu, hit);
+                if (mm) {
+                    if (hit) ring[(head + count + __popc(mm & lanemask_lt())) % kFusedRing] = (unsigned)r;
+                    count += __popc(mm);
+                    __syncwarp();
+                    if (count >= 32) {
+                        finalize_voxel(ring[(head + lane) % kFusedRing], D, isx, isw, A.acc, A.cnt, A.voxels);
+                        head = (head + 32) % kFusedRing;
+                        count -= 32;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        if (lane < count) finalize_voxel(ring[(head + lane) % kFusedRing], D, isx, isw, A.acc, A.cnt, A.voxels);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        s_trace[12] = global_timer_ns();
+        for (int k = 0; k < 13; ++k) A.trace_all[(size_t)b * 16 + k] = s_trace[k];
+        if (b == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) D.trace_ns[k] = (uint32_t)(s_trace[k + 1] - s_trace[k]);
+            D.trace_ns[13] = 1u;                    // partitioned back end
+            D.trace_ns[14] = 0u;
+            D.trace_ns[15] = (uint32_t)G;
+            *A.D = D;
+        }
+        __threadfence();
+        if (atomicAdd(&A.ctrl->exit_ticket, 1u) == (unsigned)G - 1u) {
+            A.ctrl->grid_bar = 0u;
+            A.ctrl->grid_bar_b = 0u;
+            A.ctrl->exit_ticket = 0u;
+            A.ctrl->dirty_groups = 0ull;
+        }
+    }
+}
+
 // ---- k_frame_pack -----------------------------------------------------------------------------
 // Host-bound results leave the device as structure-of-arrays: 16 B centroid + 4 B count (+ 4 B key) per
 // voxel instead of the 32-byte record, i.e. 37 % fewer bytes over PCIe for the same information.
@@ -1563,6 +2110,8 @@ static thread_local int g_fused_scan_order = 0;   // 1: the scan-order variant o
 static size_t g_fused_l2_persist = 0;     // bytes of the occupancy groups pinned in L2 (access policy window), 0 = off
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only: one flag per device
 static bool g_fused_attr_set[64] = {};
+static bool g_part_attr_set[64] = {};
+static int g_part_auto = 0;              // LIDAR_FRAME_AUTO prefers the partitioned back end when a frame is eligible
 
 static int frame_grid(int64_t n, int per_thread) {
     int64_t want = (n + (int64_t)kFrameThreads * per_thread - 1) / ((int64_t)kFrameThreads * per_thread);
@@ -1578,7 +2127,8 @@ using namespace lidar;
 extern "C" {
 
 int lidar_frame_set_fused(int mode, int threads, int ctas_per_sm, int smem_kb) {
-    LIDAR_REQUIRE(mode == LIDAR_FRAME_AUTO || mode == LIDAR_FRAME_MULTIKERNEL || mode == LIDAR_FRAME_FUSED,
+    LIDAR_REQUIRE(mode == LIDAR_FRAME_AUTO || mode == LIDAR_FRAME_MULTIKERNEL || mode == LIDAR_FRAME_FUSED ||
+                      mode == LIDAR_FRAME_PARTITIONED,
                   LIDAR_ERR_INVALID, "lidar_frame_set_fused: unknown mode %d", mode);
     LIDAR_REQUIRE(threads == 0 || (threads >= 128 && threads <= kFusedMaxThreads && threads % 32 == 0),
                   LIDAR_ERR_INVALID, "lidar_frame_set_fused: threads must be a multiple of 32 in [128, 512]");
@@ -1618,6 +2168,11 @@ int lidar_frame_set_fused_l2_persist(size_t bytes) {
         LIDAR_CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
     }
     g_fused_l2_persist = bytes;
+    return LIDAR_OK;
+}
+
+int lidar_frame_set_partition_auto(int on) {
+    g_part_auto = on ? 1 : 0;
     return LIDAR_OK;
 }
 
@@ -1754,10 +2309,43 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
         A.early_load = g_fused_pdl == 2 ? 1 : 0;
         A.l1 = reinterpret_cast<uint32_t*>(ws + L.off_l1);
         A.l1cnt = reinterpret_cast<uint32_t*>(ws + L.off_l1cnt);
+        // ---- partitioned back end: eligible when every CTA's chunk is resident and the key space fits 2048 partitions
+        bool use_part = false;
+        PartArgs PA{};
+        size_t dyn_part = 0;
+        if (g_fused_mode == LIDAR_FRAME_PARTITIONED || (g_fused_mode == LIDAR_FRAME_AUTO && g_part_auto && !g_fused_scan_order)) {
+            const int64_t pcap = ((((caps->max_key_space + kPartCells - 1) >> kPartShift) + 31) & ~(int64_t)31);
+            const size_t ring_part = ring_bytes > 8192 ? ring_bytes : 8192;          // doubles as the partition-base array
+            const size_t owner_bytes = (size_t)kPartWords64 * 12 + (size_t)kPartDensCap * 4;
+            size_t union_bytes = (size_t)per * 4 > owner_bytes ? (size_t)per * 4 : owner_bytes;   // {cell, slot} | owner | inverse
+            union_bytes = (union_bytes + 127) & ~(size_t)127;
+            dyn_part = (size_t)per * 22 + (size_t)pcap * 8 + ring_part + union_bytes;
+            const bool fits = pcap <= kPartMax && dyn_part + static_bytes <= smem_optin() && per < 65536 && (T & (T - 1)) == 0;
+            LIDAR_REQUIRE(fits || g_fused_mode != LIDAR_FRAME_PARTITIONED, LIDAR_ERR_CAPACITY,
+                          "lidar_frame_voxel_density: the partitioned back end needs caps.max_key_space <= 2^29 and the frame "
+                          "resident in shared memory (%lld points per CTA, %zu B of %zu B)", (long long)per,
+                          dyn_part + static_bytes, smem_optin());
+            if (fits) {
+                use_part = true;
+                PA.F = A;
+                PA.F.smem_points = (int)per;
+                PA.ptotal = reinterpret_cast<unsigned*>(ws + L.off_ptotal);
+                PA.pvox = reinterpret_cast<unsigned*>(ws + L.off_pvox);
+                PA.bucket = reinterpret_cast<uint2*>(ws + L.off_bucket);
+                PA.prank = reinterpret_cast<unsigned*>(ws + L.off_prank);
+                PA.pcap = (int)pcap;
+                PA.union_bytes = (int)union_bytes;
+                if (cur_dev < 0 || cur_dev >= 64 || !g_part_attr_set[cur_dev]) {
+                    LIDAR_CUDA_TRY(cudaFuncSetAttribute(k_frame_part, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                        (int)(smem_optin() - static_bytes)));
+                    if (cur_dev >= 0 && cur_dev < 64) g_part_attr_set[cur_dev] = true;
+                }
+            }
+        }
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(G);
         cfg.blockDim = dim3(T);
-        cfg.dynamicSmemBytes = dyn;
+        cfg.dynamicSmemBytes = use_part ? dyn_part : dyn;
         cfg.stream = st;
         cudaLaunchAttribute attr[3];
         int na = 0;
@@ -1786,8 +2374,9 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
         }
         cfg.attrs = attr;
         cfg.numAttrs = na;
-        cudaError_t le = g_fused_scan_order ? cudaLaunchKernelEx(&cfg, k_frame_fused<true>, A)
-                                            : cudaLaunchKernelEx(&cfg, k_frame_fused<false>, A);
+        cudaError_t le = use_part ? cudaLaunchKernelEx(&cfg, k_frame_part, PA)
+                         : g_fused_scan_order ? cudaLaunchKernelEx(&cfg, k_frame_fused<true>, A)
+                                              : cudaLaunchKernelEx(&cfg, k_frame_fused<false>, A);
         if (le == cudaSuccess) {
             for (int i = 1; i <= 5; ++i) LIDAR_CUDA_TRY(mark(i));
             return LIDAR_OK;

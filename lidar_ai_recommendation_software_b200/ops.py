@@ -231,7 +231,7 @@ def roi_crop(points: torch.Tensor, lo, hi, return_mask: bool = True):
 # ------------------------------------------------------------------------------------------------
 # K5 (+K6) frame pipeline
 # ------------------------------------------------------------------------------------------------
-FRAME_AUTO, FRAME_MULTIKERNEL, FRAME_FUSED = 0, 1, 2
+FRAME_AUTO, FRAME_MULTIKERNEL, FRAME_FUSED, FRAME_PARTITIONED = 0, 1, 2, 3
 
 
 def set_frame_mode(mode: int = FRAME_AUTO, threads: int = 0, ctas_per_sm: int = 0, smem_kb: int = 0) -> None:

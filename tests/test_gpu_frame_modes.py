@@ -387,3 +387,63 @@ def test_host_frame_pipeline_read_back_forms_agree(ops, synth, two_stage):
     view = hp.collect(copy=False)
     assert not view["inverse"].flags.owndata and np.array_equal(view["inverse"], out["inverse"])
     hp.close()
+
+
+PART_CONFIGS = [(3, 512, 1, 0), (3, 256, 1, 0), (3, 128, 1, 0)]
+
+
+@pytest.mark.parametrize("n,extent,key_space", [(1, 5.0, 1 << 28), (31, 5.0, 1 << 28), (777, 5.0, 1 << 22),
+                                                 (4736, 10.0, 1 << 28), (100003, 50.0, 1 << 28),
+                                                 (1_000_000, 50.0, 1 << 28), (300_000, 80.0, 1 << 29)])
+def test_partitioned_backend_equals_multikernel_and_oracle(ops, synth, n, extent, key_space):
+    """k_frame_part (MSD radix partition by voxel-key range, occupancy bits in shared memory) against the five-kernel
+    path, the fused kernel and the oracle, frame after frame on ONE pipeline (the back ends share the workspace)."""
+    pts = synth.crowd_frame(n, seed=5, extent=extent)
+    d = torch.from_numpy(pts).cuda()
+    pipe = ops.FramePipeline(max_points=n, voxel_size=0.05, grid_size=0.5, max_key_space=key_space, max_nx=512, max_ny=512)
+    base = run(ops, pipe, d, (1, 0, 0, 0))
+    want = new_ops.voxel_downsample(pts, 0.05)
+    assert np.array_equal(base["inverse"].cpu().numpy(), want["inverse"])
+    for cfg in PART_CONFIGS:
+        got = run(ops, pipe, d, cfg)
+        assert got["trace_ns"][15] > 0 and got["trace_ns"][13] == 1, "the partitioned kernel did not run"
+        same(base, got)
+        same(base, run(ops, pipe, d, (2, 512, 1, 0)))      # fused right after partitioned, same workspace
+    same(base, run(ops, pipe, d, (3, 512, 1, 0)))
+    same(base, run(ops, pipe, d, (1, 0, 0, 0)))
+
+
+def test_partitioned_backend_skewed_duplicated_and_gridless_frames(ops, synth):
+    """Everything in ONE voxel, heavy duplication, a partition holding most of the frame, no density grid, a density
+    grid with more than 65535 cells (cells are then recomputed by the point's own CTA), an explicit origin / range."""
+    rng = np.random.default_rng(3)
+    one = np.tile(np.array([[1.0, 2.0, 0.5, 0.25]], dtype=np.float32), (5000, 1))
+    runs = np.repeat(synth.crowd_frame(3000, seed=9, extent=4.0), 40, axis=0)
+    skew = synth.crowd_frame(200_000, seed=2, extent=3.0)                      # 6 m x 6 m: 2-3 partitions hold everything
+    skew[:50] = synth.crowd_frame(50, seed=3, extent=60.0)                      # ... inside a 120 m bounding box
+    wide = synth.crowd_frame(50_000, seed=4, extent=150.0)                      # 0.5 m grid: 604 x 604 cells > 65535
+    for pts, grid, kw in ((one, 0.5, {}), (runs, 0.5, {}), (skew, 0.5, {}), (skew, 0.0, {}), (wide, 0.5, {}),
+                          (skew, 0.5, dict(origin=(-70.0, -70.0, -1.0), xy_range=(-64.0, 64.0, -64.0, 64.0)))):
+        d = torch.from_numpy(np.ascontiguousarray(pts)).cuda()
+        pipe = ops.FramePipeline(max_points=len(pts), voxel_size=0.1, grid_size=grid, max_key_space=1 << 29,
+                                 max_nx=1024, max_ny=1024)
+        base = run(ops, pipe, d, (1, 0, 0, 0), **kw)
+        got = run(ops, pipe, d, (3, 512, 1, 0), **kw)
+        assert got["trace_ns"][13] == 1
+        same(base, got)
+        same(base, run(ops, pipe, d, (3, 512, 1, 0), **kw))                    # twice: the claim counters were reset
+        want = new_ops.voxel_downsample(pts, 0.1, origin=kw.get("origin"))
+        assert np.array_equal(got["inverse"].cpu().numpy(), want["inverse"])
+        assert np.array_equal(got["counts"].cpu().numpy(), want["counts"])
+
+
+def test_partitioned_backend_refuses_frames_it_cannot_hold(ops, synth):
+    from lidar_ai_recommendation_software_b200 import _capi
+    d = torch.from_numpy(synth.crowd_frame(1000, seed=1, extent=5.0)).cuda()
+    pipe = ops.FramePipeline(max_points=1000, voxel_size=0.05, grid_size=0.5, max_key_space=(1 << 31) - 1, max_nx=256, max_ny=256)
+    ops.set_frame_mode(ops.FRAME_PARTITIONED, 512, 1, 0)
+    with pytest.raises(_capi.LidarError):
+        pipe.enqueue(d)                                  # key-space capacity above 2^29: more than 2048 partitions
+    ops.set_frame_mode(ops.FRAME_AUTO, 512, 1, 0)
+    pipe.enqueue(d)
+    assert pipe.result().n_voxels > 0
