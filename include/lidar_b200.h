@@ -561,6 +561,12 @@ int lidar_host_alloc(size_t bytes, void** h_ptr_out);
 int lidar_host_free(void* h_ptr);
 int lidar_host_copy_threads(int threads);
 int lidar_host_memcpy(void* dst, const void* src, size_t bytes);
+/* several copies as ONE job for the pool (the arrays of a frame's result): the segments are treated as one byte range
+ * and cut into equal slices, so the workers are woken once.  count <= 64. */
+int lidar_host_memcpy_batch(int count, void* const* dst, const void* const* src, const size_t* bytes);
+/* wake the copy workers now: they spin (up to ~1 ms) for the next job instead of being woken through the futex when it
+ * arrives.  Call it right after enqueuing the DMA whose completion the copy waits for. */
+int lidar_host_copy_wake(void);
 /* cudaMemcpyAsync between page-locked host memory and the device on `stream` (to_device: host -> device) */
 int lidar_copy_async(void* dst, const void* src, size_t bytes, int to_device, void* stream);
 

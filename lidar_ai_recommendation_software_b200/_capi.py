@@ -197,6 +197,8 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_host_free": (_i32, [_vp]),
     "lidar_host_copy_threads": (_i32, [_i32]),
     "lidar_host_memcpy": (_i32, [_vp, _vp, _sz]),
+    "lidar_host_memcpy_batch": (_i32, [_i32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "lidar_host_copy_wake": (_i32, []),
     "lidar_copy_async": (_i32, [_vp, _vp, _sz, _i32, _vp]),
     "lidar_frame_workspace_init": (_i32, [_vp, _sz, C.POINTER(FrameCaps), _vp]),
     "lidar_frame_voxel_density": (_i32, [_vp, _i64, _dbl, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double),

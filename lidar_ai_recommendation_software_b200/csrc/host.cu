@@ -13,6 +13,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -23,6 +24,17 @@
 namespace lidar {
 
 // ---- worker pool ---------------------------------------------------------------------------------
+// A job is a list of (dst, src, bytes) segments treated as ONE byte range and cut into equal slices, one per worker
+// plus one for the caller.  Workers spin on the job counter for a short while after each job before they go to sleep
+// on the condition variable: the copies of a frame arrive in bursts (stage in, a DMA later copy out), and waking seven
+// sleeping threads through the futex costs more than a 4 MB copy takes (measured on the 16-vCPU host: ~0.25 ms per
+// wake-up against 0.22 ms for 28 MB at 126 GB/s).
+struct CopySeg {
+    char* dst;
+    const char* src;
+    size_t bytes;
+};
+
 class CopyPool {
   public:
     ~CopyPool() { stop(); }
@@ -30,77 +42,122 @@ class CopyPool {
         std::lock_guard<std::mutex> g(api_);
         if (n == (int)workers_.size()) return;
         stop();
-        quit_ = false;
-        gen_ = 0;
+        quit_.store(false);
+        gen_.store(0);
         for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { run(i); });
     }
     int size() {
         std::lock_guard<std::mutex> g(api_);
         return (int)workers_.size();
     }
-    // copy [src, src + bytes) -> dst with the pool + the calling thread
-    void copy(char* dst, const char* src, size_t bytes) {
+    // wake the workers without giving them work: they spin for the next job instead of sleeping through a DMA
+    void wake() {
         std::lock_guard<std::mutex> g(api_);
-        const size_t parts = workers_.size() + 1;
-        if (workers_.empty() || bytes < (size_t)(1 << 20)) {
-            memcpy(dst, src, bytes);
-            return;
-        }
-        // 64-byte aligned slices
-        const size_t per = ((bytes + parts - 1) / parts + 63) & ~(size_t)63;
+        if (workers_.empty()) return;
+        while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();      // every generation is acknowledged before the next
+        nseg_ = 0;
+        total_ = 0;
+        per_ = 64;
+        pending_.store((int)workers_.size(), std::memory_order_relaxed);
         {
             std::lock_guard<std::mutex> l(m_);
-            dst_ = dst; src_ = src; bytes_ = bytes; per_ = per;
-            pending_ = (int)workers_.size();
-            ++gen_;
+            gen_.fetch_add(1, std::memory_order_release);
         }
-        cv_.notify_all();
-        slice((int)workers_.size());            // the caller takes the last slice
-        std::unique_lock<std::mutex> l(m_);
-        done_.wait(l, [this] { return pending_ == 0; });
+        if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
+        // no wait: the next job's pending_ store must not race with late decrements, so copy() waits for them first
+    }
+    void set_spin_us(int us) { spin_us_.store(us); }
+    void copy(const CopySeg* segs, int nseg) {
+        std::lock_guard<std::mutex> g(api_);
+        while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();      // a wake() still being acknowledged
+        size_t total = 0;
+        for (int k = 0; k < nseg; ++k) total += segs[k].bytes;
+        if (workers_.empty() || total < (size_t)(1 << 20)) {
+            for (int k = 0; k < nseg; ++k)
+                if (segs[k].bytes) memcpy(segs[k].dst, segs[k].src, segs[k].bytes);
+            return;
+        }
+        const size_t parts = workers_.size() + 1;
+        segs_ = segs;
+        nseg_ = nseg;
+        total_ = total;
+        per_ = ((total + parts - 1) / parts + 63) & ~(size_t)63;
+        pending_.store((int)workers_.size(), std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> l(m_);          // a worker about to sleep re-checks gen_ under this lock
+            gen_.fetch_add(1, std::memory_order_release);
+        }
+        if (sleepers_.load(std::memory_order_acquire) > 0) cv_.notify_all();
+        slice((int)workers_.size());                    // the caller takes the last slice
+        while (pending_.load(std::memory_order_acquire) != 0) cpu_relax();
     }
 
   private:
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+    // bytes [a, a + len) of the concatenated segments
     void slice(int i) {
-        const size_t a = (size_t)i * per_;
-        if (a >= bytes_) return;
-        const size_t len = a + per_ <= bytes_ ? per_ : bytes_ - a;
-        memcpy(dst_ + a, src_ + a, len);
+        size_t a = (size_t)i * per_;
+        if (a >= total_) return;
+        size_t len = a + per_ <= total_ ? per_ : total_ - a;
+        for (int k = 0; k < nseg_ && len; ++k) {
+            const size_t sb = segs_[k].bytes;
+            if (a >= sb) { a -= sb; continue; }
+            const size_t take = sb - a < len ? sb - a : len;
+            memcpy(segs_[k].dst + a, segs_[k].src + a, take);
+            len -= take;
+            a = 0;
+        }
     }
     void run(int i) {
         unsigned long long seen = 0;
         for (;;) {
-            {
+            // spin first (up to ~1 ms: longer than the DMA that usually separates a wake-up call from the copy), then sleep
+            bool got = false;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int spin = 0;; ++spin) {
+                if (quit_.load(std::memory_order_relaxed)) return;
+                if (gen_.load(std::memory_order_acquire) != seen) { got = true; break; }
+                cpu_relax();
+                if ((spin & 255) == 255 &&
+                    std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_us_.load(std::memory_order_relaxed)))
+                    break;
+            }
+            if (!got) {
                 std::unique_lock<std::mutex> l(m_);
-                cv_.wait(l, [&] { return quit_ || gen_ != seen; });
-                if (quit_) return;
-                seen = gen_;
+                sleepers_.fetch_add(1, std::memory_order_release);
+                cv_.wait(l, [&] { return quit_.load() || gen_.load(std::memory_order_acquire) != seen; });
+                sleepers_.fetch_sub(1, std::memory_order_release);
+                if (quit_.load()) return;
             }
+            seen = gen_.load(std::memory_order_acquire);
             slice(i);
-            {
-                std::lock_guard<std::mutex> l(m_);
-                if (--pending_ == 0) done_.notify_one();
-            }
+            pending_.fetch_sub(1, std::memory_order_release);
         }
     }
     void stop() {
         {
             std::lock_guard<std::mutex> l(m_);
-            quit_ = true;
+            quit_.store(true);
         }
         cv_.notify_all();
         for (auto& t : workers_) t.join();
         workers_.clear();
     }
     std::mutex api_, m_;
-    std::condition_variable cv_, done_;
+    std::condition_variable cv_;
     std::vector<std::thread> workers_;
-    char* dst_ = nullptr;
-    const char* src_ = nullptr;
-    size_t bytes_ = 0, per_ = 0;
-    int pending_ = 0;
-    unsigned long long gen_ = 0;
-    bool quit_ = false;
+    const CopySeg* segs_ = nullptr;
+    int nseg_ = 0;
+    size_t total_ = 0, per_ = 0;
+    std::atomic<int> pending_{0}, sleepers_{0}, spin_us_{1000};
+    std::atomic<unsigned long long> gen_{0};
+    std::atomic<bool> quit_{false};
 };
 
 static CopyPool& pool() {
@@ -233,7 +290,28 @@ int lidar_host_memcpy(void* dst, const void* src, size_t bytes) {
     LIDAR_REQUIRE(bytes == 0 || (dst && src), LIDAR_ERR_INVALID, "lidar_host_memcpy: NULL buffer");
     if (bytes == 0) return LIDAR_OK;
     ensure_pool();
-    pool().copy(static_cast<char*>(dst), static_cast<const char*>(src), bytes);
+    const CopySeg seg{static_cast<char*>(dst), static_cast<const char*>(src), bytes};
+    pool().copy(&seg, 1);
+    return LIDAR_OK;
+}
+
+int lidar_host_copy_wake(void) {
+    ensure_pool();
+    pool().wake();
+    return LIDAR_OK;
+}
+
+int lidar_host_memcpy_batch(int count, void* const* dst, const void* const* src, const size_t* bytes) {
+    LIDAR_REQUIRE(count >= 0 && count <= 64 && (count == 0 || (dst && src && bytes)), LIDAR_ERR_INVALID,
+                  "lidar_host_memcpy_batch: bad argument (at most 64 segments)");
+    CopySeg segs[64];
+    for (int k = 0; k < count; ++k) {
+        LIDAR_REQUIRE(bytes[k] == 0 || (dst[k] && src[k]), LIDAR_ERR_INVALID, "lidar_host_memcpy_batch: NULL segment %d", k);
+        segs[k] = CopySeg{static_cast<char*>(dst[k]), static_cast<const char*>(src[k]), bytes[k]};
+    }
+    if (count == 0) return LIDAR_OK;
+    ensure_pool();
+    pool().copy(segs, count);
     return LIDAR_OK;
 }
 

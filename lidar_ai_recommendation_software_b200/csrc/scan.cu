@@ -93,6 +93,17 @@ __device__ __forceinline__ unsigned multimem_ld_reduce_add_u32(const void* mc) {
 __device__ __forceinline__ void multimem_st_u32(void* mc, unsigned v) {
     asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory");
 }
+// Two adjacent 32-bit counters as ONE 64-bit add: the sum of (hi << 32 | lo) over the ranks is (sum hi) << 32 | (sum lo)
+// as long as sum lo < 2^32 -- a density cell counts points, and a scan has fewer than 2^31 of them -- so the low word
+// never carries into the high one and a single switch operation reduces two cells.
+__device__ __forceinline__ unsigned long long multimem_ld_reduce_add_u64(const void* mc) {
+    unsigned long long v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u64 %0, [%1];" : "=l"(v) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st_u64(void* mc, unsigned long long v) {
+    asm volatile("multimem.st.relaxed.sys.global.u64 [%0], %1;" ::"l"(mc), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long scan_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -370,24 +381,25 @@ k_scan_density(const ScanArgs A) {
         if (b == 0) scan_rank_barrier(A, 1);             // every rank's grid is complete
         scan_grid_barrier(&A.ws->bar, ++bar_no * G);
         if (ok) {
-            const int64_t cells = (int64_t)D.nx * D.ny;
-            const int64_t per = (cells + A.world - 1) / A.world;
-            const int64_t s0 = (int64_t)A.rank * per < cells ? (int64_t)A.rank * per : cells;
-            const int64_t s1 = s0 + per < cells ? s0 + per : cells;
+            // slices in PAIRS of cells (8-byte units); the grid is padded to a multiple of 4 cells and zero beyond nx*ny
+            const int64_t pairs = ((int64_t)D.nx * D.ny + 1) / 2;
+            const int64_t per = (pairs + A.world - 1) / A.world;
+            const int64_t s0 = (int64_t)A.rank * per < pairs ? (int64_t)A.rank * per : pairs;
+            const int64_t s1 = s0 + per < pairs ? s0 + per : pairs;
             if (A.mc) {
                 // NVLS: the switch adds the replicas of a word and hands back the sum; the sum goes to every replica
                 char* mcg = A.mc + kSymmGridOffset;
                 for (int64_t k = s0 + t0; k < s1; k += stride) {
-                    const unsigned v = multimem_ld_reduce_add_u32(mcg + 4 * k);
-                    multimem_st_u32(mcg + 4 * k, v);
+                    const unsigned long long v = multimem_ld_reduce_add_u64(mcg + 8 * k);
+                    multimem_st_u64(mcg + 8 * k, v);
                 }
             } else {
                 for (int64_t k = s0 + t0; k < s1; k += stride) {
-                    int v = 0;
+                    unsigned long long v = 0ull;
                     for (int r = 0; r < A.world; ++r)
-                        v += __ldcg(reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(A.peers[r]) + kSymmGridOffset) + k);
+                        v += __ldcg(reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(A.peers[r]) + kSymmGridOffset) + k);
                     for (int r = 0; r < A.world; ++r)
-                        reinterpret_cast<int32_t*>(reinterpret_cast<char*>(A.peers[r]) + kSymmGridOffset)[k] = v;
+                        reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(A.peers[r]) + kSymmGridOffset)[k] = v;
                 }
             }
         }

@@ -7,6 +7,7 @@ Nothing here falls back to the CPU: without a CUDA device the functions raise.
 from __future__ import annotations
 
 import ctypes as C
+import sys
 import threading
 from dataclasses import dataclass
 
@@ -442,6 +443,38 @@ class _PinnedBlock:
             pass
 
 
+class ResultPool:
+    """Host memory for results the caller owns, without a page fault per page per call.
+
+    The drop-in surfaces return arrays the caller may keep for as long as it likes (SURVEY.md §8b "Ownership"), so a
+    result can never be a view of a staging buffer the library rewrites.  But a FRESH 28 MB numpy allocation per frame
+    costs more than the copy into it: glibc serves it with mmap, and every 4 KB page faults on first touch.  The pool
+    keeps a few ordinary (pageable) byte buffers and hands one out only when NO array referencing it is alive — numpy
+    makes every view, and every view of a view, hold a reference to the buffer object that owns the memory, so
+    `sys.getrefcount` of the buffer tells exactly that.  A caller that keeps its results simply makes the pool allocate
+    new buffers; nothing it holds is ever overwritten."""
+
+    def __init__(self, max_buffers: int = 6):
+        self.bufs: list[np.ndarray] = []
+        self.max_buffers = int(max_buffers)
+
+    def take(self, nbytes: int) -> np.ndarray:
+        nbytes = max(int(nbytes), 64)
+        for k in range(len(self.bufs)):
+            # references: the list, and the temporary inside getrefcount()
+            if self.bufs[k].nbytes >= nbytes and sys.getrefcount(self.bufs[k]) == 2:
+                return self.bufs[k]
+        buf = np.empty((nbytes + 4095) & ~4095, dtype=np.uint8)
+        if len(self.bufs) >= self.max_buffers:
+            for k in range(len(self.bufs)):                       # drop a buffer nobody uses (too small), else keep none
+                if sys.getrefcount(self.bufs[k]) == 2:
+                    del self.bufs[k]
+                    break
+        if len(self.bufs) < self.max_buffers:
+            self.bufs.append(buf)
+        return buf
+
+
 def _is_pinned(a: np.ndarray) -> bool:
     t = torch.from_numpy(a)
     try:
@@ -508,6 +541,7 @@ class HostFramePipeline:
         self._next = 0
         self._pending: list[dict] = []
         self._last_d2h = 0
+        self._pool = ResultPool()
         torch.cuda.synchronize(self.device)   # workspace zeroing ran on the constructing stream
 
     def close(self):
@@ -595,17 +629,24 @@ class HostFramePipeline:
         if self.two_stage:
             check(lib.lidar_frame_host_fetch(n, v, nx, ny, _ptr(slot["d_out"]), slot["h_out"].ptr, self.flags,
                                              C.byref(self.caps), slot["stream"].cuda_stream))
+            if copy:
+                lib.lidar_host_copy_wake()          # the copy workers spin through the DMA instead of sleeping
             slot["stream"].synchronize()
         self._last_d2h = self.d2h_bytes(n, v, nx, ny)
         self._scan_hint = n > 0 and (2 * ((int(desc.key_space) + 223) // 224) > 3 * n or 2 * v < n)
 
+        # owned results: one recycled host buffer per frame, laid out like the staging block (`ResultPool`)
+        dst = self._pool.take(off[6]) if copy else None
+
+        jobs: list[tuple[int, int]] = []                 # (offset, bytes) of every array copied out of the staging block
+
         def arr(k, dtype, count, shape=None):
-            view = np.frombuffer(raw, dtype=dtype, count=count, offset=off[k])
             if copy:
-                out = np.empty(count, dtype=dtype)
+                view = np.frombuffer(dst, dtype=dtype, count=count, offset=off[k])
                 if count:
-                    check(lib.lidar_host_memcpy(out.ctypes.data, slot["h_out"].ptr + off[k], out.nbytes))
-                view = out
+                    jobs.append((off[k], view.nbytes))
+            else:
+                view = np.frombuffer(raw, dtype=dtype, count=count, offset=off[k])
             return view if shape is None else view.reshape(shape)
 
         out = {
@@ -619,6 +660,13 @@ class HostFramePipeline:
             out["voxel_key"] = arr(0, np.int32, n)
         if self.grid_size > 0:
             out["grid_counts"] = arr(5, np.int32, nx * ny, (nx, ny))
+        if jobs:
+            # ONE job for the copy workers: all arrays of the frame, staging block -> the caller's buffer
+            k = len(jobs)
+            base_d, base_s = dst.ctypes.data, slot["h_out"].ptr
+            check(lib.lidar_host_memcpy_batch(k, (C.c_void_p * k)(*[base_d + o for o, _ in jobs]),
+                                              (C.c_void_p * k)(*[base_s + o for o, _ in jobs]),
+                                              (C.c_size_t * k)(*[b for _, b in jobs])))
         return out
 
     def process(self, points, origin=None, xy_range=None) -> dict:

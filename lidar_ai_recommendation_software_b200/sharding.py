@@ -120,6 +120,7 @@ class ScanDensity:
         self._h_desc = _capi.ScanDesc.from_address(self._h_ptr)
         self._h_arr = np.ctypeslib.as_array((C.c_double * ((self._h_bytes - 256) // 8)).from_address(self._h_ptr + 256))
         self.epoch = 0
+        self._pool = ops.ResultPool()
         self.comm = None          # ScanComm of the fused multi-rank path
         self.nccl = None          # lidar_nccl communicator of the fallback
         self.grid = None
@@ -274,9 +275,14 @@ class ScanDensity:
         _capi.check(cp(base, self.gx.data_ptr(), 8 * nx, 0, st))
         _capi.check(cp(base + 8 * self.max_nx, self.gy.data_ptr(), 8 * ny, 0, st))
         _capi.check(cp(base + 8 * o, self.density.data_ptr(), 8 * nx * ny, 0, st))
+        if 8 * nx * ny >= (1 << 20):
+            _capi.lib.lidar_host_copy_wake()
         stream.synchronize()
         a = self._h_arr
-        return a[:nx].copy(), a[self.max_nx:self.max_nx + ny].copy(), a[o:o + nx * ny].reshape(nx, ny).copy()
+        # owned by the caller: a recycled host buffer (ops.ResultPool: reused only when no array referencing it is alive)
+        dens = np.frombuffer(self._pool.take(8 * nx * ny), dtype=np.float64, count=nx * ny).reshape(nx, ny)
+        _capi.check(_capi.lib.lidar_host_memcpy(dens.ctypes.data, base + 8 * o, dens.nbytes))
+        return a[:nx].copy(), a[self.max_nx:self.max_nx + ny].copy(), dens
 
     def __call__(self, points: torch.Tensor, grid_size: float):
         self.enqueue(points, grid_size)
