@@ -444,19 +444,32 @@ class _PinnedBlock:
 
 
 class ResultPool:
-    """Host memory for results the caller owns, without a page fault per page per call.
+    """Host memory for results the caller owns — page-locked, so the device writes them directly.
 
     The drop-in surfaces return arrays the caller may keep for as long as it likes (SURVEY.md §8b "Ownership"), so a
-    result can never be a view of a staging buffer the library rewrites.  But a FRESH 28 MB numpy allocation per frame
-    costs more than the copy into it: glibc serves it with mmap, and every 4 KB page faults on first touch.  The pool
-    keeps a few ordinary (pageable) byte buffers and hands one out only when NO array referencing it is alive — numpy
-    makes every view, and every view of a view, hold a reference to the buffer object that owns the memory, so
-    `sys.getrefcount` of the buffer tells exactly that.  A caller that keeps its results simply makes the pool allocate
-    new buffers; nothing it holds is ever overwritten."""
+    result can never be a view of a staging buffer the library rewrites.  A FRESH 28 MB numpy allocation per frame
+    plus a copy into it costs more than the DMA itself (mmap, a page fault per page, 2 x 28 MB of memory traffic on a
+    host whose memory bandwidth the DMA needs as well).  The pool keeps a few page-locked buffers (`lidar_host_alloc`)
+    and hands one out only when NO array referencing it is alive — numpy makes every view, and every view of a view,
+    hold a reference to the object that owns the memory, so `sys.getrefcount` of the pooled array tells exactly that.
+    The read-back lands in the buffer itself: no host copy at all.  A caller that keeps its results simply makes the
+    pool allocate new buffers (each frees its page-locked block when the last view dies); nothing a caller holds is
+    ever overwritten.  `pinned=False` gives ordinary pageable buffers (no CUDA needed)."""
 
-    def __init__(self, max_buffers: int = 6):
+    def __init__(self, max_buffers: int = 6, pinned: bool = True):
         self.bufs: list[np.ndarray] = []
         self.max_buffers = int(max_buffers)
+        self.pinned = bool(pinned)
+
+    def _new(self, nbytes: int) -> np.ndarray:
+        nbytes = (nbytes + 4095) & ~4095
+        if not self.pinned:
+            return np.empty(nbytes, dtype=np.uint8)
+        block = _PinnedBlock(nbytes)
+        cbuf = (C.c_uint8 * nbytes).from_address(block.ptr)
+        cbuf._lidar_owner = block               # the ctypes buffer (numpy's base object) keeps the page-locked block alive
+        block.u8 = None
+        return np.ctypeslib.as_array(cbuf)
 
     def take(self, nbytes: int) -> np.ndarray:
         nbytes = max(int(nbytes), 64)
@@ -464,7 +477,7 @@ class ResultPool:
             # references: the list, and the temporary inside getrefcount()
             if self.bufs[k].nbytes >= nbytes and sys.getrefcount(self.bufs[k]) == 2:
                 return self.bufs[k]
-        buf = np.empty((nbytes + 4095) & ~4095, dtype=np.uint8)
+        buf = self._new(nbytes)
         if len(self.bufs) >= self.max_buffers:
             for k in range(len(self.bufs)):                       # drop a buffer nobody uses (too small), else keep none
                 if sys.getrefcount(self.bufs[k]) == 2:
@@ -626,24 +639,26 @@ class HostFramePipeline:
             raise _capi.LidarError(int(desc.status), "frame exceeded its capacities")
         v = int(desc.n_voxels)
         nx, ny = (int(desc.nx), int(desc.ny)) if self.grid_size > 0 else (0, 0)
+        # owned results (`copy=True`): a recycled page-locked buffer laid out like the staging block (`ResultPool`).
+        # Two-stage form: the device writes the arrays straight into it (no host copy); one-copy form: the frame-sized
+        # block already sits in the slot's staging memory and is copied out by the worker pool.
+        dst = self._pool.take(off[6]) if copy else None
+        direct = copy and self.two_stage
         if self.two_stage:
-            check(lib.lidar_frame_host_fetch(n, v, nx, ny, _ptr(slot["d_out"]), slot["h_out"].ptr, self.flags,
+            target = dst.ctypes.data if direct else slot["h_out"].ptr
+            check(lib.lidar_frame_host_fetch(n, v, nx, ny, _ptr(slot["d_out"]), target, self.flags,
                                              C.byref(self.caps), slot["stream"].cuda_stream))
-            if copy:
-                lib.lidar_host_copy_wake()          # the copy workers spin through the DMA instead of sleeping
             slot["stream"].synchronize()
+        elif copy:
+            lib.lidar_host_copy_wake()
         self._last_d2h = self.d2h_bytes(n, v, nx, ny)
         self._scan_hint = n > 0 and (2 * ((int(desc.key_space) + 223) // 224) > 3 * n or 2 * v < n)
-
-        # owned results: one recycled host buffer per frame, laid out like the staging block (`ResultPool`)
-        dst = self._pool.take(off[6]) if copy else None
-
         jobs: list[tuple[int, int]] = []                 # (offset, bytes) of every array copied out of the staging block
 
         def arr(k, dtype, count, shape=None):
             if copy:
                 view = np.frombuffer(dst, dtype=dtype, count=count, offset=off[k])
-                if count:
+                if count and not direct:
                     jobs.append((off[k], view.nbytes))
             else:
                 view = np.frombuffer(raw, dtype=dtype, count=count, offset=off[k])

@@ -112,8 +112,8 @@ class ScanDensity:
         self.gy = torch.empty(self.max_ny, dtype=torch.float64, device=dev)
         self.desc_dev = torch.zeros(C.sizeof(_capi.ScanDesc), dtype=torch.uint8, device=dev)
         self.packed = torch.empty(4, dtype=torch.float64, device=dev)
-        # page-locked + device-mapped: [ScanDesc (256 B) | gx | gy | density]
-        self._h_bytes = 256 + 8 * (self.max_nx + self.max_ny + self.cap_cells)
+        # page-locked + device-mapped: [ScanDesc (256 B) | gx | gy]
+        self._h_bytes = 256 + 8 * (self.max_nx + self.max_ny)
         p = C.c_void_p()
         _capi.check(lib.lidar_host_alloc(self._h_bytes, C.byref(p)))
         self._h_ptr = p.value
@@ -270,18 +270,15 @@ class ScanDensity:
             raise _capi.LidarError(int(d.status), f"scan density grid exceeds the capacities "
                                                   f"(max {self.max_nx} x {self.max_ny}, {self.cap_cells} cells)")
         nx, ny = int(d.nx), int(d.ny)
-        o = self.max_nx + self.max_ny
+        # the density lands directly in a recycled page-locked buffer the caller then owns (ops.ResultPool: reused only
+        # when no array referencing it is alive); the two short coordinate vectors go through the staging block
+        dens = np.frombuffer(self._pool.take(8 * nx * ny), dtype=np.float64, count=nx * ny).reshape(nx, ny)
         base, st, cp = self._h_ptr + 256, stream.cuda_stream, _capi.lib.lidar_copy_async
         _capi.check(cp(base, self.gx.data_ptr(), 8 * nx, 0, st))
         _capi.check(cp(base + 8 * self.max_nx, self.gy.data_ptr(), 8 * ny, 0, st))
-        _capi.check(cp(base + 8 * o, self.density.data_ptr(), 8 * nx * ny, 0, st))
-        if 8 * nx * ny >= (1 << 20):
-            _capi.lib.lidar_host_copy_wake()
+        _capi.check(cp(dens.ctypes.data, self.density.data_ptr(), 8 * nx * ny, 0, st))
         stream.synchronize()
         a = self._h_arr
-        # owned by the caller: a recycled host buffer (ops.ResultPool: reused only when no array referencing it is alive)
-        dens = np.frombuffer(self._pool.take(8 * nx * ny), dtype=np.float64, count=nx * ny).reshape(nx, ny)
-        _capi.check(_capi.lib.lidar_host_memcpy(dens.ctypes.data, base + 8 * o, dens.nbytes))
         return a[:nx].copy(), a[self.max_nx:self.max_nx + ny].copy(), dens
 
     def __call__(self, points: torch.Tensor, grid_size: float):
