@@ -19,7 +19,7 @@ The JSON line carries
   roofline   dominant kernel: algorithmic bytes / measured launch duration vs the measured HBM peak
   cpu_baseline  the CPU oracle (numpy restatement; the reference has no voxel op — "port") timed on
              the host cores of this box, bounded sample
-  extra      the other named configs in the same run: extra.scan50m (configs[4], 50 M points sharded
+  extra      extra.pcie = host <-> device copy rates with all ranks copying at once; the other named configs in the same run: extra.scan50m (configs[4], 50 M points sharded
              by points, fused NVLink all-reduce), extra.seq (configs[3], 300-frame 128-beam
              sequence, frames sharded), extra.sa (configs[2], set abstraction, N = 1 only)
 `--impl reference` times that CPU path as the line's own value (rank 0 only).
@@ -257,6 +257,52 @@ def e2e_leg(ops, torch, dist, world, dev, n, frames, steps, threads, slots, mode
             "d2h_bytes_per_step": int(d2h), "steps": total, "threads": threads}
 
 
+def measure_pcie(torch, dist, dev, rank, world):
+    """Host <-> device copy rates with EVERY rank copying at the same time (page-locked memory from the C ABI, CUDA
+    events): what the end-to-end legs can at best move on this box.  Whole-job GB/s = sum over ranks."""
+    from lidar_ai_recommendation_software_b200 import _capi, ops
+    nb = 128 << 20
+    pin_a, pin_b = ops._PinnedBlock(nb), ops._PinnedBlock(nb)
+    d_a = torch.empty(nb, dtype=torch.uint8, device=dev)
+    d_b = torch.empty(nb, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    cp = _capi.lib.lidar_copy_async
+
+    def timed(h2d, d2h, reps=4):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s1.wait_event(e0)
+        s2.wait_event(e0)
+        for _ in range(reps):
+            if h2d:
+                cp(d_a.data_ptr(), pin_a.ptr, nb, 1, s1.cuda_stream)
+            if d2h:
+                cp(pin_b.ptr, d_b.data_ptr(), nb, 0, s2.cuda_stream)
+        torch.cuda.current_stream().wait_stream(s1)
+        torch.cuda.current_stream().wait_stream(s2)
+        e1.record()
+        torch.cuda.synchronize()
+        return reps * nb / (e0.elapsed_time(e1) * 1e-3) / 1e9      # GB/s per direction
+
+    timed(True, True, 1)
+    rates = torch.tensor([timed(True, False), timed(False, True), timed(True, True)], dtype=torch.float64, device=dev)
+    lo = rates.clone()
+    if world > 1:
+        dist.all_reduce(rates, op=dist.ReduceOp.SUM)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    pin_a.free()
+    pin_b.free()
+    if rank != 0:
+        return None
+    r, m = rates.tolist(), lo.tolist()
+    return {"h2d_GBs_total": r[0], "d2h_GBs_total": r[1], "both_GBs_per_direction_total": r[2],
+            "h2d_GBs_slowest_rank": m[0], "d2h_GBs_slowest_rank": m[1], "both_GBs_per_direction_slowest_rank": m[2],
+            "note": f"{world} rank(s) copying concurrently, 4 x 128 MB per direction per rank, page-locked host memory"}
+
+
 def run_extras(args, torch, dist, dev, rank, world):
     """The other named shapes of BASELINE.json (configs[2], [3], [4]) in the same run, so that the driver's N = 1/2/4/8
     records carry them: extra.sa (N = 1 only), extra.seq (frames sharded), extra.scan50m (points sharded)."""
@@ -277,6 +323,8 @@ def run_extras(args, torch, dist, dev, rank, world):
             out["bench_wall_s"] = time.perf_counter() - t0
             extra[name] = out
 
+    if "pcie" in args.extras:
+        guarded("pcie", lambda: measure_pcie(torch, dist, dev, rank, world))
     if "scan" in args.extras:
         a = types.SimpleNamespace(points=args.scan_points, host_shards=8, reps=10)
         guarded("scan50m", lambda: bc.run_scan(a, torch, dev, rank, world, dist))
@@ -302,7 +350,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=240, help="frames per rank in each end-to-end leg")
     ap.add_argument("--e2e-slots", type=int, default=3, help="frames in flight in the streaming end-to-end legs")
     ap.add_argument("--e2e-threads", type=int, default=3, help="driver threads of the drop-in end-to-end leg")
-    ap.add_argument("--extras", default="scan,seq,sa", help="comma list of the extra configs to measure ('' = none)")
+    ap.add_argument("--extras", default="pcie,scan,seq,sa", help="comma list of the extra configs to measure ('' = none)")
     ap.add_argument("--scan-points", type=int, default=50_000_000)
     ap.add_argument("--seq-frames", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

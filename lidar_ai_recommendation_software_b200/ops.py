@@ -418,6 +418,12 @@ def bind_to_device_numa(device: torch.device | int | None = None) -> tuple[int, 
         node, cpus = C.c_int(-1), C.c_int(0)
         check(lib.lidar_bind_to_device_numa(idx, C.byref(node), C.byref(cpus)))
         _numa_bound[idx] = (int(node.value), int(cpus.value))
+        # one rank per GPU shares the host with its siblings: the copy workers of all ranks together must not
+        # oversubscribe the CPUs (torchrun exports LOCAL_WORLD_SIZE); half the rank's share, at most 8, at least 1
+        import os
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+        share = max(1, int(cpus.value) // local_world)
+        check(lib.lidar_host_copy_threads(max(1, min(8, share // 2))))
     return _numa_bound[idx]
 
 
