@@ -243,6 +243,14 @@ int lidar_flow_box_max(int nx, int ny, const double* d_positions, const double* 
                        double* d_box_max, void* stream);
 int lidar_radius_count(const double* d_centres_xy, int n_centres, const double* d_qx, int nqx, const double* d_qy,
                        int nqy, double radius, int32_t* d_counts, void* stream);
+/* plot_crowd_metrics join (utils/visualization.py:306-326): for every flow lattice node the nearest density cell centre of
+ * the rectilinear grid repeat(grid_x, ny) x tile(grid_y, nx) — cKDTree(centres).query(nodes, k=1) — as the flat index
+ * ix*ny + iy (int64) and the Euclidean distance; with d_density_flat / d_speed also the joined density, the congestion
+ * risk density / (speed + 0.1) and its maximum (the normalisation of :322-323 is risk / max * 10).  Exact fp64 squared
+ * distances; an exact tie between cells goes to the lowest flat index. */
+int lidar_nearest_grid_cell(const double* d_nodes_xy, int n_nodes, const double* d_gx, int nx, const double* d_gy, int ny,
+                            const double* d_density_flat, const double* d_speed, int64_t* d_index, double* d_distance,
+                            double* d_density_at, double* d_risk, double* d_risk_max, void* stream);
 int lidar_frame_flow_match(const float* d_prev_xy, int n_prev, const float* d_cur_xy, int n_cur, float dt, float gate,
                            int32_t* d_match, float* d_velocity, void* stream);
 int lidar_frame_flow_field(const double* d_lattice_xy, int n_lattice, const float* d_cur_xy, const int32_t* d_match,

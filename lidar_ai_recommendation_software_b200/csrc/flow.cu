@@ -264,6 +264,64 @@ frame_flow_field_kernel(const double* __restrict__ lattice, int g, const float* 
     mag[i] = sqrt(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
 }
 
+
+// plot_crowd_metrics join (utils/visualization.py:306-326): cKDTree(density cell centres).query(flow nodes, k=1) and the
+// congestion-risk columns built from it.  The cell centres are the rectilinear grid repeat(grid_x, ny) x tile(grid_y, nx)
+// of CrowdDensityModel.analyze (models/crowd_density_model.py:57-59), so the nearest centre is found per axis: the two
+// grid lines around the node (binary search), then the four candidate cells are compared on the fp64 squared distance
+// dx*dx + dy*dy the KD-tree itself minimises.  An exact tie goes to the lowest flat index (cKDTree breaks ties by
+// traversal order; the DISTANCE is unique either way).
+__device__ __forceinline__ int lower_line(const double* __restrict__ g, int n, double x) {
+    int lo = 0, hi = n;                 // first index with g[idx] > x, minus one, clamped to [0, n-1]
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (g[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    const int k = lo - 1;
+    return k < 0 ? 0 : k;
+}
+
+__global__ void __launch_bounds__(128)
+nearest_cell_kernel(const double* __restrict__ nodes_xy, int n_nodes, const double* __restrict__ gx, int nx,
+                    const double* __restrict__ gy, int ny, const double* __restrict__ density_flat,
+                    const double* __restrict__ speed, long long* __restrict__ index, double* __restrict__ distance,
+                    double* __restrict__ density_at, double* __restrict__ risk, unsigned long long* __restrict__ risk_max_bits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double r = 0.0;
+    if (i < n_nodes) {
+        const double x = nodes_xy[2 * i], y = nodes_xy[2 * i + 1];
+        const int kx = lower_line(gx, nx, x), ky = lower_line(gy, ny, y);
+        double best = INFINITY;
+        long long arg = 0;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int cx = kx + a < nx ? kx + a : nx - 1;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int cy = ky + b < ny ? ky + b : ny - 1;
+                const double dx = __dsub_rn(x, gx[cx]), dy = __dsub_rn(y, gy[cy]);
+                const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                const long long flat = (long long)cx * ny + cy;
+                if (d2 < best || (d2 == best && flat < arg)) { best = d2; arg = flat; }
+            }
+        }
+        index[i] = arg;
+        distance[i] = __dsqrt_rn(best);
+        if (density_flat) {
+            const double d = density_flat[arg];
+            density_at[i] = d;
+            r = __ddiv_rn(d, __dadd_rn(speed[i], 0.1));           // congestion_risk = density / (speed + 0.1)
+            risk[i] = r;
+        }
+    }
+    if (risk_max_bits) {
+        // max over non-negative doubles = max over their bit patterns (NaN aside: density and speed are finite)
+        r = r > 0.0 ? r : 0.0;
+        r = warp_max(r);
+        if (lane_id() == 0 && r > 0.0) atomicMax(risk_max_bits, (unsigned long long)__double_as_longlong(r));
+    }
+}
+
 }  // namespace lidar
 
 using namespace lidar;
@@ -325,6 +383,24 @@ int lidar_radius_count(const double* d_centres_xy, int n_centres, const double* 
     const int n = nqx * nqy;
     radius_count_kernel<<<(n + 127) / 128, 128, 2048 * sizeof(double), as_stream(stream)>>>(
         d_centres_xy, n_centres, d_qx, nqx, d_qy, nqy, radius * radius, d_counts);
+    LIDAR_CHECK_LAUNCH();
+    return LIDAR_OK;
+}
+
+int lidar_nearest_grid_cell(const double* d_nodes_xy, int n_nodes, const double* d_gx, int nx, const double* d_gy, int ny,
+                            const double* d_density_flat, const double* d_speed, int64_t* d_index, double* d_distance,
+                            double* d_density_at, double* d_risk, double* d_risk_max, void* stream) {
+    LIDAR_REQUIRE(n_nodes >= 0 && nx > 0 && ny > 0 && d_gx && d_gy && d_index && d_distance, LIDAR_ERR_INVALID,
+                  "lidar_nearest_grid_cell: bad argument");
+    LIDAR_REQUIRE(!d_density_flat || (d_speed && d_density_at && d_risk && d_risk_max), LIDAR_ERR_INVALID,
+                  "lidar_nearest_grid_cell: the risk columns need speed, density_at, risk and risk_max");
+    if (n_nodes == 0) return LIDAR_OK;
+    LIDAR_REQUIRE(d_nodes_xy != nullptr, LIDAR_ERR_INVALID, "lidar_nearest_grid_cell: NULL nodes");
+    cudaStream_t st = as_stream(stream);
+    if (d_risk_max) LIDAR_CUDA_TRY(cudaMemsetAsync(d_risk_max, 0, sizeof(double), st));
+    nearest_cell_kernel<<<(n_nodes + 127) / 128, 128, 0, st>>>(d_nodes_xy, n_nodes, d_gx, nx, d_gy, ny, d_density_flat, d_speed,
+                                                               reinterpret_cast<long long*>(d_index), d_distance, d_density_at,
+                                                               d_risk, reinterpret_cast<unsigned long long*>(d_risk_max));
     LIDAR_CHECK_LAUNCH();
     return LIDAR_OK;
 }

@@ -83,6 +83,14 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld_16x256b_x4(unsigned taddr, unsigned (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+
 // x = hi + lo with hi = bf16(x), lo = bf16(x - hi), two values per instruction: cvt.rn.bf16x2.f32 (F2FP, a
 // full-rate ALU op; the scalar F2F conversion runs at a quarter of that and was 21 % of the kernel's stall samples)
 __device__ __forceinline__ void split_pair(float a, float b, unsigned& hi, unsigned& lo) {
@@ -178,47 +186,110 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
     float n0, n1, n2;
     load_point(blockIdx.x, load_index(blockIdx.x), n0, n1, n2);
     int next_src = load_index(blockIdx.x + tstep);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += tstep) {
-        const int centre = tile * 4 + warp;           // global centre index b*m + mm
-        const bool live = centre < n_centres;
-        const int row = threadIdx.x;
-        // ---- gather + layer 1 (fp32 CUDA cores) -> A (hi, lo) ------------------------------------
-        const float g0 = n0, g1 = n1, g2 = n2;
-        const int src1 = next_src;
-        next_src = load_index(tile + 2 * tstep);
-        load_point(tile + tstep, src1, n0, n1, n2);
+    const int row = threadIdx.x;
+
+    // layer 1 of a tile on the CUDA cores, result kept in registers (the A buffer may still feed the tensor core)
+    auto layer1 = [&](float g0, float g1, float g2, float (&h)[kC1]) {
+#pragma unroll
+        for (int o = 0; o < kC1; ++o) {
+            float a = sB1[o];
+            a = fmaf(sW1[o * 3], g0, a);
+            a = fmaf(sW1[o * 3 + 1], g1, a);
+            a = fmaf(sW1[o * 3 + 2], g2, a);
+            h[o] = fmaxf(a, 0.f);
+        }
+    };
+    auto write_a = [&](const float (&h)[kC1]) {
 #pragma unroll
         for (int kc = 0; kc < 8; ++kc) {
-            float h[8];
+            float x[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int o = kc * 8 + i;
-                float a = sB1[o];
-                a = fmaf(sW1[o * 3], g0, a);
-                a = fmaf(sW1[o * 3 + 1], g1, a);
-                a = fmaf(sW1[o * 3 + 2], g2, a);
-                h[i] = fmaxf(a, 0.f);
-            }
-            store_chunk(smem, row, kc, h);
+            for (int i = 0; i < 8; ++i) x[i] = h[kc * 8 + i];
+            store_chunk(smem, row, kc, x);
         }
-        // generic-proxy smem writes -> visible to the tensor core (async proxy); TMEM reads of the previous
-        // tile are complete (tcgen05.wait::ld) and ordered before the MMAs that overwrite the accumulators
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        // ---- layer 2: D2[128x64] = A1 * W2^T ----------------------------------------------------
+    };
+    auto issue = [&](int w_hi, int w_lo, unsigned tmem_d, unsigned idesc) {   // 12 MMAs: K = 64 in steps of 16, hi*hi + hi*lo + lo*hi
         if (threadIdx.x == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {   // K = 64 in steps of 16 (two 16-byte chunks = 256 B)
+            for (int j = 0; j < 4; ++j) {
                 const unsigned long long ah = umma_desc(sbase + kOffAh + j * 256), al = umma_desc(sbase + kOffAl + j * 256);
-                const unsigned long long wh = umma_desc(sbase + kOffW2h + j * 256), wl = umma_desc(sbase + kOffW2l + j * 256);
-                umma_f16(tmem_base, ah, wh, idesc2, j > 0);
-                umma_f16(tmem_base, ah, wl, idesc2, 1);
-                umma_f16(tmem_base, al, wh, idesc2, 1);
+                const unsigned long long wh = umma_desc(sbase + w_hi + j * 256), wl = umma_desc(sbase + w_lo + j * 256);
+                umma_f16(tmem_d, ah, wh, idesc, j > 0);
+                umma_f16(tmem_d, ah, wl, idesc, 1);
+                umma_f16(tmem_d, al, wh, idesc, 1);
             }
             umma_commit(bar);
         }
+    };
+    auto publish_a = [&]() {
+        // generic-proxy smem writes -> visible to the tensor core (async proxy); this thread's TMEM reads are complete
+        // (tcgen05.wait::ld) and ordered before the MMAs that overwrite the accumulators
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+    };
+    // epilogue of layer 3 = bias + ReLU + max over the 32 neighbours of a centre, i.e. over the 32 TMEM lanes of this warp.
+    // max_j relu(v_j + b) == relu(max_j v_j + b) bit for bit (rounding is monotone), so the maximum is taken on the raw
+    // accumulators.  tcgen05.ld.16x256b hands every thread FOUR rows of the same two columns per 8-column group (rows
+    // t/4, t/4+8 of each 16-lane half; columns 2(t%4), 2(t%4)+1 -- the mma accumulator fragment layout, checked on the
+    // device with profiles/tools/tmem_map.cu): three in-thread FMNMX per column, then a reduce-scatter butterfly over
+    // the 8 threads that share t%4 (7 shuffles per 32 columns) instead of one REDUX per column and lane.
+    auto epilogue3 = [&](int centre) {
+        const bool live = centre < n_centres;
+        const int b = live ? centre / m : 0, mm = live ? centre % m : 0;
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+        const int colsel = 8 * (2 * (int)b4 + (int)b3) + 2 * (int)(lane & 3) + (int)b2;
+#pragma unroll
+        for (int chunk = 0; chunk < 4; ++chunk) {
+            unsigned a[16], c[16];
+            const unsigned t0 = tmem_base + ((unsigned)(warp * 32) << 16) + kC2 + chunk * 32;
+            tmem_ld_16x256b_x4(t0, a);
+            tmem_ld_16x256b_x4(t0 + (16u << 16), c);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float v[8];
+#pragma unroll
+            for (int rep = 0; rep < 4; ++rep) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    v[2 * rep + e] = fmaxf(fmaxf(__uint_as_float(a[4 * rep + e]), __uint_as_float(a[4 * rep + 2 + e])),
+                                           fmaxf(__uint_as_float(c[4 * rep + e]), __uint_as_float(c[4 * rep + 2 + e])));
+            }
+            float w4[4], w2[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float mine = b4 ? v[4 + i] : v[i], send = b4 ? v[i] : v[4 + i];
+                w4[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 16));
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float mine = b3 ? w4[2 + e] : w4[e], send = b3 ? w4[e] : w4[2 + e];
+                w2[e] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 8));
+            }
+            const float mine = b2 ? w2[1] : w2[0], send = b2 ? w2[0] : w2[1];
+            const float top = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 4));
+            const int col = chunk * 32 + colsel;
+            if (live) out[((size_t)b * kC3 + col) * m + mm] = fmaxf(top + sB3[col], 0.f);
+        }
+    };
+
+    // ---- software pipeline: the tensor core works on one layer while the CUDA cores do the other layers' share ----
+    //   issue L2(t) | epilogue 3(t-1) | wait L2 | epilogue 2(t) -> A | issue L3(t) | layer 1(t+1) in registers | wait L3 |
+    //   A <- layer 1(t+1) | issue L2(t+1) | ...
+    int tile = blockIdx.x;
+    if (tile < n_tiles) {
+        float h[kC1];
+        layer1(n0, n1, n2, h);
+        const int src1 = next_src;
+        next_src = load_index(tile + 2 * tstep);
+        load_point(tile + tstep, src1, n0, n1, n2);
+        write_a(h);
+        publish_a();
+        issue(kOffW2h, kOffW2l, tmem_base, idesc2);
+    }
+    int prev_centre = -1;
+    for (; tile < n_tiles; tile += tstep) {
+        if (prev_centre >= 0) epilogue3(prev_centre);             // under the layer-2 MMAs of this tile
         bar_wait(bar, phase);
         phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -229,47 +300,34 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
             tmem_ld16(tmem_lane + q * 16, v);
 #pragma unroll
             for (int hlf = 0; hlf < 2; ++hlf) {
-                float h[8];
+                float x[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) h[i] = fmaxf(v[hlf * 8 + i] + sB2[q * 16 + hlf * 8 + i], 0.f);
-                store_chunk(smem, row, q * 2 + hlf, h);
+                for (int i = 0; i < 8; ++i) x[i] = fmaxf(v[hlf * 8 + i] + sB2[q * 16 + hlf * 8 + i], 0.f);
+                store_chunk(smem, row, q * 2 + hlf, x);
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        // ---- layer 3: D3[128x128] = A2 * W3^T ---------------------------------------------------
-        if (threadIdx.x == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const unsigned long long ah = umma_desc(sbase + kOffAh + j * 256), al = umma_desc(sbase + kOffAl + j * 256);
-                const unsigned long long wh = umma_desc(sbase + kOffW3h + j * 256), wl = umma_desc(sbase + kOffW3l + j * 256);
-                umma_f16(tmem_base + kC2, ah, wh, idesc3, j > 0);
-                umma_f16(tmem_base + kC2, ah, wl, idesc3, 1);
-                umma_f16(tmem_base + kC2, al, wh, idesc3, 1);
-            }
-            umma_commit(bar);
+        publish_a();
+        issue(kOffW3h, kOffW3l, tmem_base + kC2, idesc3);
+        prev_centre = tile * 4 + warp;
+        // ---- layer 1 of the next tile, under the layer-3 MMAs ---------------------------------------
+        const bool more = tile + tstep < n_tiles;
+        float h[kC1];
+        if (more) {
+            layer1(n0, n1, n2, h);
+            const int src1 = next_src;
+            next_src = load_index(tile + 3 * tstep);
+            load_point(tile + 2 * tstep, src1, n0, n1, n2);
         }
-        bar_wait(bar, phase);
+        bar_wait(bar, phase);                                    // layer 3 done: the A buffer is free, D3 is complete
         phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- epilogue 3: bias + ReLU + max over the 32 neighbours (= the 32 lanes of this warp) ----
-        const int b = live ? centre / m : 0, mm = live ? centre % m : 0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float v[16];
-            tmem_ld16(tmem_lane + kC2 + q * 16, v);
-            float keep = 0.f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float a = fmaxf(v[i] + sB3[q * 16 + i], 0.f);
-                const unsigned mx = __reduce_max_sync(0xffffffffu, __float_as_uint(a));   // a >= 0: uint order = float order
-                if ((int)lane == i) keep = __uint_as_float(mx);
-            }
-            if (live && lane < 16) out[((size_t)b * kC3 + q * 16 + lane) * m + mm] = keep;
+        if (more) {
+            write_a(h);
+            publish_a();
+            issue(kOffW2h, kOffW2l, tmem_base, idesc2);
         }
     }
+    if (prev_centre >= 0) epilogue3(prev_centre);
     // ---- teardown ----------------------------------------------------------------------------------
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

@@ -225,7 +225,7 @@ class CloudFile:
     def _ascii_blocks(self, fh, rows: int, sep, cols, limit: int | None) -> Iterator[np.ndarray]:
         import pandas as pd
         kw = dict(header=None, comment="#", skip_blank_lines=True, chunksize=rows, engine="c", usecols=None,
-                  on_bad_lines="skip", nrows=limit)
+                  on_bad_lines="skip", nrows=limit, float_precision="round_trip")   # correctly rounded, like float()
         kw["sep"] = sep if sep else r"\s+"
         try:
             reader = pd.read_csv(fh, **kw)

@@ -985,3 +985,27 @@ def frame_flow_field(lattice, cur_f32, match, vel, radius: float = 3.0):
     check(lib.lidar_frame_flow_field(_ptr(lat), g, _ptr(cur_f32), _ptr(match), _ptr(vel), cur_f32.shape[0],
                                      float(radius), _ptr(vec), _ptr(mag), _stream_ptr()))
     return vec, mag
+
+
+def nearest_grid_cell(nodes_xy, grid_x, grid_y, density_flat=None, speed=None):
+    """cKDTree(cell centres).query(nodes, k=1) on the rectilinear density grid (utils/visualization.py:306-314): returns
+    device tensors (index int64 (G,), distance (G,)) and, with `density_flat` / `speed`, also (density_at, risk, risk_max)."""
+    dev = require_cuda()
+    nodes = _f64_dev(nodes_xy, dev).reshape(-1, 2)
+    gx, gy = _f64_dev(grid_x, dev), _f64_dev(grid_y, dev)
+    g = nodes.shape[0]
+    index = torch.empty(g, dtype=torch.int64, device=dev)
+    dist = torch.empty(g, dtype=torch.float64, device=dev)
+    if density_flat is None:
+        check(lib.lidar_nearest_grid_cell(_ptr(nodes), g, _ptr(gx), gx.numel(), _ptr(gy), gy.numel(), None, None, _ptr(index),
+                                          _ptr(dist), None, None, None, _stream_ptr()))
+        return index, dist
+    dens, spd = _f64_dev(density_flat, dev).reshape(-1), _f64_dev(speed, dev).reshape(-1)
+    if dens.numel() != gx.numel() * gy.numel() or spd.numel() != g:
+        raise ValueError("density_flat must have nx*ny entries and speed one entry per node")
+    at = torch.empty(g, dtype=torch.float64, device=dev)
+    risk = torch.empty(g, dtype=torch.float64, device=dev)
+    rmax = torch.zeros(1, dtype=torch.float64, device=dev)
+    check(lib.lidar_nearest_grid_cell(_ptr(nodes), g, _ptr(gx), gx.numel(), _ptr(gy), gy.numel(), _ptr(dens), _ptr(spd),
+                                      _ptr(index), _ptr(dist), _ptr(at), _ptr(risk), _ptr(rmax), _stream_ptr()))
+    return index, dist, at, risk, rmax

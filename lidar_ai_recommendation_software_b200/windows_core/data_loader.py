@@ -1,242 +1,211 @@
-"""Mirror of the desktop shell's loader, `windows_implementation/core/data_loader.py:15-447`.
+"""`Dataset` / `DataLoader` of the desktop shell (windows_implementation/core/data_loader.py:15-447)
+on top of the streaming loader (`lidar_ai_recommendation_software_b200.loader`).
 
-Same classes (`Dataset`, `DataLoader`), same dispatch by extension, same accepted inputs, same metadata keys and the
-same exceptions — pinned to the unmodified reference by the fixtures under tests/golden/loader.  The bodies are
-parsed with vectorised readers (pandas / numpy) where that provably gives the reference's rows, and with the
-reference's own per-line rule (first three fields of a line, lines that do not convert are skipped) otherwise.
-`Dataset.points` is what `windows_core.run_analysis` takes.
+Same interface — `DataLoader().load_file(path) -> Dataset(points (n,3) float64, metadata)`, the reference's metadata
+keys, its exceptions for the inputs it rejects — but the bodies are read by `loader.CloudFile`: chunked, vectorised,
+binary PCD / PLY and real LAS included (every record, header scale and offset; the reference's LAS reader keeps the
+first 10 000 records and multiplies the raw integers by a fixed 0.01, core/data_loader.py:405-423).
+
+`DataLoader(reference_compat=True)` reproduces the reference's quirks instead, bit for bit, for the fixtures under
+tests/golden/loader that pin them: binary PCD / PLY are refused, LAS goes through the toy decoding (wrong header
+offsets included), `.xyz` / `.txt` go through `np.loadtxt` with the delimiter sniffed from the first line, and a CSV
+always spends its first row as the header.
 """
 from __future__ import annotations
 
-import io as _io
 import logging
 import os
 import struct
 
 import numpy as np
-import pandas as pd
+
+from .. import loader as _loader
 
 logger = logging.getLogger(__name__)
 
 
 class Dataset:
-    """Represents a dataset with point cloud data (core/data_loader.py:15-27)."""
+    """A point cloud and what is known about its file (core/data_loader.py:15-27)."""
 
     def __init__(self, points, metadata=None):
         self.points = points
         self.metadata = metadata or {}
 
 
-def _rows_skip_invalid(lines) -> list:
-    """core/data_loader.py:201-209 / 332-339: first three fields of every line with >= 3 fields; lines whose
-    fields do not convert to float are skipped."""
-    out = []
-    for line in lines:
-        values = line.strip().split()
-        if len(values) >= 3:
+def _first_three_numeric(lines) -> np.ndarray:
+    """Rows made of the first three whitespace-separated fields of every line that has three and converts to float —
+    the acceptance rule of the reference's ASCII PCD / PLY bodies (core/data_loader.py:201-209, 332-339).  One
+    vectorised parse when every candidate line is numeric; otherwise line by line, dropping the lines that fail."""
+    cand = [ln.split() for ln in lines]
+    cand = [c[:3] for c in cand if len(c) >= 3]
+    if not cand:
+        return np.empty((0, 3))
+    try:
+        return np.array(cand, dtype=np.float64)            # numpy parses the strings with Python's float()
+    except ValueError:
+        good = []
+        for c in cand:
             try:
-                out.append([float(values[0]), float(values[1]), float(values[2])])
+                good.append((float(c[0]), float(c[1]), float(c[2])))
             except ValueError:
-                continue
-    return out
-
-
-def _ascii_block(lines) -> np.ndarray:
-    """Rows of a block of text lines: one vectorised parse when every line is a regular numeric row, the
-    reference's per-line rule otherwise."""
-    text = "".join(lines)
-    if text.strip():
-        try:
-            df = pd.read_csv(_io.StringIO(text), sep=r"\s+", header=None, usecols=[0, 1, 2], dtype=np.float64,
-                             engine="c", skip_blank_lines=True)
-            arr = df.to_numpy(dtype=np.float64)
-            n_candidates = sum(1 for ln in lines if len(ln.split()) >= 3)
-            if not np.isnan(arr).any() and len(arr) == n_candidates:
-                return arr
-        except Exception:
-            pass
-    rows = _rows_skip_invalid(lines)
-    return np.array(rows, dtype=float) if rows else np.empty((0, 3))
+                pass
+        return np.array(good, dtype=np.float64) if good else np.empty((0, 3))
 
 
 class DataLoader:
-    """Loads and parses various LiDAR data formats (core/data_loader.py:30-447)."""
+    """Reads csv / xyz / txt / pcd / ply / las into a `Dataset` (core/data_loader.py:30-447)."""
 
-    def __init__(self):
-        pass
+    _BY_EXTENSION = {".csv": "csv", ".xyz": "xyz", ".txt": "xyz", ".pcd": "pcd", ".ply": "ply", ".las": "las", ".laz": "las"}
 
+    def __init__(self, reference_compat: bool = False):
+        self.reference_compat = bool(reference_compat)
+
+    # ---- entry point ---------------------------------------------------------------------------------
     def load_file(self, file_path):
         if not os.path.exists(file_path):
             raise FileNotFoundError(f"File not found: {file_path}")
         ext = os.path.splitext(file_path)[1].lower()
-        if ext == ".csv":
-            return self._load_csv(file_path)
-        elif ext == ".xyz" or ext == ".txt":
-            return self._load_xyz(file_path)
-        elif ext == ".pcd":
-            return self._load_pcd(file_path)
-        elif ext == ".ply":
-            return self._load_ply(file_path)
-        elif ext == ".las" or ext == ".laz":
-            return self._load_las(file_path)
-        else:
+        kind = self._BY_EXTENSION.get(ext)
+        if kind is None:
             raise ValueError(f"Unsupported file format: {ext}")
-
-    def _load_csv(self, file_path):
+        label = {"csv": "CSV", "xyz": "XYZ/TXT", "pcd": "PCD", "ply": "PLY", "las": "LAS/LAZ"}[kind]
         try:
-            headers = pd.read_csv(file_path, nrows=0).columns.tolist()
-            x_col, y_col, z_col = None, None, None
-            for header in headers:
-                low = header.lower()
-                if low == "x":
-                    x_col = header
-                elif low == "y":
-                    y_col = header
-                elif low == "z":
-                    z_col = header
-            if x_col and y_col and z_col:
-                df = pd.read_csv(file_path, usecols=[x_col, y_col, z_col])
-                points = df[[x_col, y_col, z_col]].values
-            else:
-                df = pd.read_csv(file_path)
-                if len(df.columns) >= 3:
-                    points = df.iloc[:, :3].values
-                else:
-                    raise ValueError("CSV file doesn't have at least 3 columns for X, Y, Z coordinates")
-            metadata = {"file_format": "csv", "file_path": file_path, "point_count": len(points), "columns": headers}
-            return Dataset(points, metadata)
+            points, extra = getattr(self, f"_read_{kind}")(file_path)
         except Exception as e:
-            logger.error(f"Error loading CSV file: {str(e)}")
-            raise
-
-    def _load_xyz(self, file_path):
-        try:
-            with open(file_path, "r") as f:
-                first_line = f.readline().strip()
-            if "," in first_line:
-                delimiter = ","
-            elif ";" in first_line:
-                delimiter = ";"
-            else:
-                delimiter = None
-            points = np.loadtxt(file_path, delimiter=delimiter)
-            if points.shape[1] > 3:
-                points = points[:, :3]
-            metadata = {"file_format": "xyz", "file_path": file_path, "point_count": len(points), "delimiter": delimiter}
-            return Dataset(points, metadata)
-        except Exception as e:
-            logger.error(f"Error loading XYZ/TXT file: {str(e)}")
-            raise
-
-    def _load_pcd(self, file_path):
-        try:
-            with open(file_path, "rb") as f:
-                lines = [ln.decode("utf-8", errors="ignore") for ln in f]
-            header = {}
-            data_start = None
-            for i, line in enumerate(lines):
-                if line.startswith("#"):
-                    continue
-                if line.strip() == "DATA ascii":
-                    data_start = i + 1
-                    break
-                if line.strip() == "DATA binary":
-                    raise ValueError("Binary PCD format not supported by this implementation")
-                parts = line.strip().split()
-                if len(parts) >= 2:
-                    header[parts[0].lower()] = " ".join(parts[1:])
-            points_array = _ascii_block(lines[data_start:]) if data_start is not None else np.empty((0, 3))
-            if len(points_array) == 0:
-                raise ValueError("No valid points found in PCD file")
-            metadata = {"file_format": "pcd", "file_path": file_path, "point_count": len(points_array), "header": header}
-            return Dataset(points_array, metadata)
-        except Exception as e:
-            logger.error(f"Error loading PCD file: {str(e)}")
-            raise
-
-    def _load_ply(self, file_path):
-        try:
-            with open(file_path, "rb") as f:
-                lines = [ln.decode("utf-8", errors="ignore") for ln in f]
-            vertex_count = 0
-            x_prop = y_prop = z_prop = None
-            data_format = "ascii"
-            body_start = len(lines)
-            for i, raw in enumerate(lines):
-                line = raw.strip()
-                if line == "end_header":
-                    body_start = i + 1
-                    break
-                if line.startswith("format"):
-                    parts = line.split()
-                    if len(parts) >= 2:
-                        data_format = parts[1]
-                if line.startswith("element vertex"):
-                    parts = line.split()
-                    if len(parts) >= 3:
-                        vertex_count = int(parts[2])
-                if line.startswith("property float") or line.startswith("property double"):
-                    parts = line.split()
-                    if len(parts) >= 3:
-                        name = parts[2].lower()
-                        if name == "x":
-                            x_prop = True
-                        elif name == "y":
-                            y_prop = True
-                        elif name == "z":
-                            z_prop = True
-            if not (x_prop and y_prop and z_prop):
-                raise ValueError("PLY file doesn't have valid X, Y, Z properties")
-            if data_format != "ascii":
-                raise ValueError(f"PLY format '{data_format}' not supported by this implementation")
-            points_array = _ascii_block(lines[body_start: body_start + vertex_count])
-            if len(points_array) == 0:
-                raise ValueError("No valid points found in PLY file")
-            metadata = {"file_format": "ply", "file_path": file_path, "point_count": len(points_array),
-                        "vertex_count": vertex_count, "data_format": data_format}
-            return Dataset(points_array, metadata)
-        except Exception as e:
-            logger.error(f"Error loading PLY file: {str(e)}")
-            raise
-
-    def _load_las(self, file_path):
-        """The reference's simplified reader (core/data_loader.py:359-447), field offsets and all: format id at byte
-        104, record length at 105, record count read at byte 107, data offset at 96, at most 10 000 records, a fixed
-        0.01 scale.  The records are decoded in one `np.frombuffer` instead of three `struct.unpack` per point."""
-        try:
-            if file_path.lower().endswith(".laz"):
-                raise ValueError("LAZ files require the laspy library with laszip support")
-            with open(file_path, "rb") as f:
-                raw = f.read()
-            if raw[:4].decode() != "LASF":
-                raise ValueError("Invalid LAS file signature")
-            point_data_format_id = struct.unpack("<B", raw[104:105])[0]
-            record_length = struct.unpack("<H", raw[105:107])[0]
-            num_point_records = struct.unpack("<I", raw[107:111])[0]
-            point_data_offset = struct.unpack("<I", raw[96:100])[0]
-            want = min(num_point_records, 10000)
-            body = raw[point_data_offset:]
-            if record_length >= 12:
-                have = min(want, len(body) // record_length)
-                # a trailing partial record still counts if it holds X, Y, Z
-                if have < want and len(body) - have * record_length >= 12:
-                    tail = body[have * record_length: have * record_length + 12]
-                else:
-                    tail = b""
-                rec = np.frombuffer(body, dtype=np.uint8, count=have * record_length).reshape(have, record_length)
-                xyz = np.ascontiguousarray(rec[:, :12]).view("<i4").reshape(have, 3)
-                if tail:
-                    xyz = np.concatenate([xyz, np.frombuffer(tail, dtype="<i4").reshape(1, 3)])
-                points_array = xyz.astype(float) * 0.01
-            else:
-                points_array = np.empty((0, 3))      # f.read(record_length) < 12 bytes: the reference stops at once
-            if len(points_array) == 0:
-                raise ValueError("No valid points found in LAS file")
-            metadata = {"file_format": "las", "file_path": file_path, "point_count": len(points_array),
-                        "point_data_format_id": point_data_format_id, "total_points": num_point_records}
-            return Dataset(points_array, metadata)
-        except Exception as e:
-            logger.error(f"Error loading LAS/LAZ file: {str(e)}")
-            if "LAZ files require the laspy library" in str(e):
+            logger.error(f"Error loading {label} file: {str(e)}")
+            if kind == "las" and "LAZ" in str(e):
                 raise ValueError("LAZ files require additional libraries. Please install with: pip install laspy[laszip]")
             raise
+        meta = {"file_format": kind, "file_path": file_path, "point_count": len(points)}
+        meta.update(extra)
+        return Dataset(points, meta)
+
+    # ---- csv -------------------------------------------------------------------------------------------
+    def _read_csv(self, path):
+        import pandas as pd
+        names = pd.read_csv(path, nrows=0).columns.tolist()
+        by_lower = {str(c).lower(): c for c in names}
+        if all(k in by_lower for k in "xyz"):
+            pick = [by_lower[k] for k in "xyz"]
+            points = pd.read_csv(path, usecols=pick)[pick].values
+        else:
+            table = pd.read_csv(path)
+            if table.shape[1] < 3:
+                raise ValueError("CSV file doesn't have at least 3 columns for X, Y, Z coordinates")
+            points = table.iloc[:, :3].values
+        return points, {"columns": names}
+
+    # ---- xyz / txt -------------------------------------------------------------------------------------
+    def _read_xyz(self, path):
+        with open(path, "r") as fh:
+            head = fh.readline().strip()
+        delimiter = "," if "," in head else ";" if ";" in head else None
+        if self.reference_compat:
+            points = np.loadtxt(path, delimiter=delimiter)      # 1-D for a one-line file, IndexError for an empty one
+            if points.shape[1] > 3:
+                points = points[:, :3]
+        else:
+            points = _loader.CloudFile(path).read_xyz()
+            if len(points) == 0:
+                raise ValueError("No valid points found in XYZ/TXT file")
+        return points, {"delimiter": delimiter}
+
+    # ---- pcd -------------------------------------------------------------------------------------------
+    def _read_pcd(self, path):
+        with open(path, "rb") as fh:
+            raw = fh.read()
+        header, body_at, encoding = {}, None, None
+        pos = 0
+        while pos < len(raw):
+            end = raw.find(b"\n", pos)
+            end = len(raw) if end < 0 else end
+            line = raw[pos:end].decode("utf-8", errors="ignore").strip()
+            pos = end + 1
+            if line.startswith("#"):
+                continue
+            if line in ("DATA ascii", "DATA binary"):
+                encoding, body_at = line.split()[1], pos
+                break
+            parts = line.split()
+            if len(parts) >= 2:
+                header[parts[0].lower()] = " ".join(parts[1:])
+        if encoding == "binary":
+            if self.reference_compat:
+                raise ValueError("Binary PCD format not supported by this implementation")
+            points = _loader.CloudFile(path).read_xyz()
+        elif encoding == "ascii":
+            points = _first_three_numeric(raw[body_at:].decode("utf-8", errors="ignore").splitlines())
+        else:
+            points = np.empty((0, 3))
+        if len(points) == 0:
+            raise ValueError("No valid points found in PCD file")
+        return points, {"header": header}
+
+    # ---- ply -------------------------------------------------------------------------------------------
+    def _read_ply(self, path):
+        with open(path, "rb") as fh:
+            raw = fh.read()
+        text_end = raw.find(b"end_header")
+        head = raw[: text_end if text_end >= 0 else len(raw)].decode("utf-8", errors="ignore").splitlines()
+        vertex_count, data_format, seen = 0, "ascii", set()
+        for line in (ln.strip() for ln in head):
+            parts = line.split()
+            if line.startswith("format") and len(parts) >= 2:
+                data_format = parts[1]
+            elif line.startswith("element vertex") and len(parts) >= 3:
+                vertex_count = int(parts[2])
+            elif line.startswith(("property float", "property double")) and len(parts) >= 3:
+                seen.add(parts[2].lower())
+        if not {"x", "y", "z"} <= seen:
+            raise ValueError("PLY file doesn't have valid X, Y, Z properties")
+        if data_format != "ascii":
+            if self.reference_compat:
+                raise ValueError(f"PLY format '{data_format}' not supported by this implementation")
+            points = _loader.CloudFile(path).read_xyz()
+        else:
+            nl = raw.find(b"\n", text_end) if text_end >= 0 else -1
+            body = raw[nl + 1:].decode("utf-8", errors="ignore").splitlines() if nl >= 0 else []
+            points = _first_three_numeric(body[:vertex_count])
+        if len(points) == 0:
+            raise ValueError("No valid points found in PLY file")
+        return points, {"vertex_count": vertex_count, "data_format": data_format}
+
+    # ---- las -------------------------------------------------------------------------------------------
+    def _read_las(self, path):
+        if path.lower().endswith(".laz"):
+            raise ValueError("LAZ files require the laspy library with laszip support")
+        if not self.reference_compat:
+            f = _loader.CloudFile(path)
+            points = f.read_xyz()
+            if len(points) == 0:
+                raise ValueError("No valid points found in LAS file")
+            x = f.header.extra
+            return points, {"point_data_format_id": x["point_format"], "total_points": f.header.n_points,
+                            "las_version": x["version"], "scale": x["scale"], "offset": x["offset"]}
+        return self._read_las_reference_toy(path)
+
+    @staticmethod
+    def _read_las_reference_toy(path):
+        """core/data_loader.py:359-447 as it is: the format id read at byte 104, the record length at 105, the record
+        COUNT at byte 107 and the data offset at 96 — then at most 10 000 records of int32 X, Y, Z times a fixed 0.01,
+        header scale and offset ignored.  Decoded with one strided view instead of three struct.unpack per point."""
+        with open(path, "rb") as fh:
+            raw = fh.read()
+        if raw[:4].decode() != "LASF":
+            raise ValueError("Invalid LAS file signature")
+        fmt_id = struct.unpack("<B", raw[104:105])[0]
+        rec_len = struct.unpack("<H", raw[105:107])[0]
+        n_records = struct.unpack("<I", raw[107:111])[0]
+        body = raw[struct.unpack("<I", raw[96:100])[0]:]
+        points = np.empty((0, 3))
+        if rec_len >= 12:
+            want = min(n_records, 10000)
+            whole = min(want, len(body) // rec_len)
+            xyz = np.ndarray((whole, 3), dtype="<i4", buffer=body, strides=(rec_len, 4)) if whole else np.empty((0, 3), dtype="<i4")
+            rest = len(body) - whole * rec_len
+            if whole < want and rest >= 12:                          # a cut-off last record still holds X, Y, Z
+                xyz = np.concatenate([xyz, np.frombuffer(body, dtype="<i4", count=3, offset=whole * rec_len).reshape(1, 3)])
+            points = xyz.astype(float) * 0.01
+        if len(points) == 0:
+            raise ValueError("No valid points found in LAS file")
+        return points, {"point_data_format_id": fmt_id, "total_points": n_records}

@@ -454,3 +454,37 @@ def test_errors_are_python_exceptions(pkg):
         pkg.dp.preprocess_lidar_data(np.zeros((0, 3)))
     with pytest.raises(Exception):
         pkg.dp.load_lidar_data("/nonexistent/file.xyz")
+
+
+def test_crowd_metrics_table_matches_ckdtree_join(pkg, processed_b):
+    """plot_crowd_metrics' join (utils/visualization.py:295-323): nearest density cell per flow node, congestion risk and
+    its 0-10 normalisation against scipy's cKDTree + the reference's pandas expressions.  Indices are compared where
+    the nearest cell is unique (jittered nodes); on the reference's own lattice (every node exactly half-way between
+    two centres) the nearest DISTANCE must agree and the chosen cell must be one of the equally near ones."""
+    from scipy.spatial import cKDTree
+    from lidar_ai_recommendation_software_b200.utils import visualization as viz
+    pd_ = processed_b("crowd_20k")
+    dres = pkg.CDM(grid_size=1.0).analyze(pd_)
+    fres = pkg.CFM().analyze(pd_)
+    dpts = np.column_stack(dres["grid_coordinates"])
+    tree = cKDTree(dpts)
+    # (1) unique nearest cells: jitter the lattice nodes off the half-way lines
+    rng = np.random.default_rng(0)
+    jit = {"flow_vectors": dict(fres["flow_vectors"])}
+    jit["flow_vectors"]["positions"] = fres["flow_vectors"]["positions"] + rng.uniform(0.05, 0.45, fres["flow_vectors"]["positions"].shape)
+    got = viz.crowd_metrics_table(dres, jit)
+    dist, idx = tree.query(jit["flow_vectors"]["positions"], k=1)
+    assert np.array_equal(got["nearest_index"], idx)
+    assert np.allclose(got["nearest_distance"], dist, rtol=1e-15, atol=0)
+    dens = dres["density_values"][idx]
+    risk = dens / (jit["flow_vectors"]["magnitudes"] + 0.1)
+    assert np.array_equal(got["density"], dens) and np.array_equal(got["congestion_risk"], risk)
+    assert np.array_equal(got["congestion_risk_normalized"], risk / risk.max() * 10)
+    assert np.array_equal(got["speed"], jit["flow_vectors"]["magnitudes"])
+    # (2) the reference's own lattice: ties everywhere
+    tie = viz.crowd_metrics_table(dres, fres)
+    dist, idx = tree.query(fres["flow_vectors"]["positions"], k=1)
+    assert np.allclose(tie["nearest_distance"], dist, rtol=1e-15, atol=0)
+    chosen = dpts[tie["nearest_index"]]
+    d_chosen = np.sqrt(((chosen - fres["flow_vectors"]["positions"]) ** 2).sum(1))
+    assert np.allclose(d_chosen, dist, rtol=1e-12, atol=1e-12)

@@ -92,7 +92,8 @@ def test_loader_matches_reference_fixtures():
 
 def test_windows_data_loader_matches_reference_fixtures():
     """The desktop shell's DataLoader (windows_implementation/core/data_loader.py:30-447): points, metadata and
-    exceptions of the UNMODIFIED reference for every fixture file (tests/golden/make_golden_loader.py)."""
+    exceptions of the UNMODIFIED reference for every fixture file (tests/golden/make_golden_loader.py), reproduced by
+    `DataLoader(reference_compat=True)`; the default mode reads the same files through the streaming loader."""
     import json
     import logging
     import warnings
@@ -108,17 +109,27 @@ def test_windows_data_loader_matches_reference_fixtures():
             if name + ":error" in exp.files:
                 with pytest.raises(Exception) as ei, warnings.catch_warnings():
                     warnings.simplefilter("ignore")
-                    DataLoader().load_file(str(d / name))
+                    DataLoader(reference_compat=True).load_file(str(d / name))
                 got = type(ei.value).__name__ + ": " + str(ei.value).replace(str(d), "<dir>")
                 assert got == str(exp[name + ":error"]), name
             else:
-                ds = DataLoader().load_file(str(d / name))
+                ds = DataLoader(reference_compat=True).load_file(str(d / name))
                 assert isinstance(ds, Dataset)
                 pts = np.asarray(ds.points, dtype=np.float64)
                 assert pts.shape == exp[name].shape and np.array_equal(pts, exp[name], equal_nan=True), name
                 assert ds.metadata["file_path"] == str(d / name)
                 meta = {k: v for k, v in ds.metadata.items() if k != "file_path"}
                 assert json.loads(json.dumps(meta, sort_keys=True)) == json.loads(str(exp[name + ":meta"])), name
+        # default mode: same rows for everything the reference reads correctly, and the files it cannot read
+        for name in ("cloud.pcd", "cloud.xyz", "cloud.txt", "semi.txt", "named.csv", "plain.csv", "mesh.ply", "dirty.pcd", "dirty.ply"):
+            ds = DataLoader().load_file(str(d / name))
+            assert np.array_equal(np.asarray(ds.points, dtype=np.float64), exp[name], equal_nan=True), name
+        for name in ("bin.pcd", "bin.ply"):
+            ds = DataLoader().load_file(str(d / name))               # refused by the reference, read here
+            assert ds.points.shape[1] == 3 and ds.metadata["point_count"] == len(ds.points) > 0
+        full = DataLoader().load_file(str(d / "scan.las"))            # header scale / offset instead of the fixed 0.01
+        # (the fixture's last record is cut short on purpose: 30 whole records on disk under a header that says 31)
+        assert full.metadata["total_points"] == 30 and len(full.points) == 30 and "scale" in full.metadata
     finally:
         logging.disable(logging.NOTSET)
 
