@@ -437,6 +437,35 @@ int lidar_frame_voxel_density_timed(const void* d_points, int64_t n, double voxe
                                     size_t ws_bytes, void* stream, void** h_events6);
 
 /* ------------------------------------------------------------------------------------------- *
+ * K5, general path: voxel downsample with 64-bit keys by a deterministic radix sort by voxel key + segmented
+ * reduction ("int64; use 32-bit when it fits").  No key-space limit: a far outlier or a
+ * 1 km x 1 km x 30 m venue at 0.05 m (2.4e11 cells) is fine; the occupancy-bitmap frame kernels above stop at 2^31.
+ * Optional ROI crop fused in front (Appendix B.2: keep <=> lo <= p <= hi on x,y,z, fp32 compares against the bounds
+ * cast to fp32): cropped points get voxel_key = inverse = -1 and take no part in the bbox / origin.
+ *   d_voxel_key   int64[n]   (ix*Dy + iy)*Dz + iz per point            d_inverse  int32[n] rank of the point's voxel
+ *   d_centroids4  float[4 n] x,y,z,mean intensity per voxel (capacity n), ascending key
+ *   d_counts      int32[n]   d_unique_keys int64[n]                     d_desc     origin, dims, counts, status
+ * One enqueue, no host round trip: the number of 8-bit sort passes follows the key width found on the device (the
+ * launches of the passes a frame does not need return at once).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct lidar_sorted_desc {
+    double origin[3], bbox_min[3], bbox_max[3];
+    double voxel, fix_scale_xyz, fix_scale_w;
+    int64_t dims[3];
+    int64_t key_space;     /* Dx*Dy*Dz (< 2^63) */
+    int64_t n_points;      /* input points */
+    int64_t n_kept;        /* points inside the ROI box (= n_points without one) */
+    int64_t n_voxels;
+    int32_t passes;        /* radix passes that ran */
+    int32_t status;        /* 0, LIDAR_ERR_INVALID (a point below a caller-given origin), LIDAR_ERR_CAPACITY (key space >= 2^63) */
+} lidar_sorted_desc;
+size_t lidar_voxel_sorted_workspace_bytes(int64_t n);
+int lidar_voxel_downsample_sorted(const void* d_points, int64_t n, double voxel_size, const double* h_origin3,
+                                  const double* h_roi_lo3, const double* h_roi_hi3, int64_t* d_voxel_key, int32_t* d_inverse,
+                                  float* d_centroids4, int32_t* d_counts, int64_t* d_unique_keys, lidar_sorted_desc* d_desc,
+                                  void* d_ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
  * The same frame from HOST buffers, in ONE call (the path a sensor driver or the numpy surface
  * takes): copy-in, the frame kernel(s), the SoA repack and ONE copy-out are enqueued on `stream`.
  *

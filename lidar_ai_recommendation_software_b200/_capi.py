@@ -87,6 +87,17 @@ class FrontDesc(C.Structure):
     ]
 
 
+class SortedDesc(C.Structure):
+    """Mirror of `lidar_sorted_desc` (the 64-bit-key sort path of voxel downsample)."""
+
+    _fields_ = [
+        ("origin", C.c_double * 3), ("bbox_min", C.c_double * 3), ("bbox_max", C.c_double * 3),
+        ("voxel", C.c_double), ("fix_scale_xyz", C.c_double), ("fix_scale_w", C.c_double),
+        ("dims", C.c_int64 * 3), ("key_space", C.c_int64), ("n_points", C.c_int64), ("n_kept", C.c_int64),
+        ("n_voxels", C.c_int64), ("passes", C.c_int32), ("status", C.c_int32),
+    ]
+
+
 class ScanDesc(C.Structure):
     """Mirror of `lidar_scan_desc`: the point-sharded density grid's device-derived descriptor."""
 
@@ -201,6 +212,9 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_host_memcpy_batch": (_i32, [_i32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "lidar_host_copy_wake": (_i32, []),
     "lidar_copy_async": (_i32, [_vp, _vp, _sz, _i32, _vp]),
+    "lidar_voxel_sorted_workspace_bytes": (_sz, [_i64]),
+    "lidar_voxel_downsample_sorted": (_i32, [_vp, _i64, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                             C.POINTER(C.c_double), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "lidar_frame_workspace_init": (_i32, [_vp, _sz, C.POINTER(FrameCaps), _vp]),
     "lidar_frame_voxel_density": (_i32, [_vp, _i64, _dbl, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                          _vp, _vp, _vp, _vp, _vp, C.POINTER(FrameCaps), _vp, _sz, _vp]),

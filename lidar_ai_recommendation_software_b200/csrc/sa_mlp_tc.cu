@@ -1,8 +1,11 @@
 // K13 (tensor-core path) — fused gather + shared MLP 3-64-64-128 + max-pool over k = 32 on the
 // 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).  NEW op, SURVEY.md Appendix B.7.
 //
-// One CTA tile = 128 rows = 4 centres x 32 neighbours, so TMEM lane r / thread r / warp w line up with
-// (neighbour r % 32 of centre w): the max-pool over the neighbours is a warp REDUX, no shared memory.
+// One CTA tile = 128 rows = 4 centres x 32 neighbours, so TMEM lane r / row r / lane quarter w line up with
+// (neighbour r % 32 of centre w): the max-pool over the neighbours stays inside a warp, no shared memory.
+// 256 threads: warps w and w + 4 share lane quarter w (a warp may only touch TMEM lanes 32 (w % 4) ...) and split
+// the CHANNELS of every phase between them -- 16 resident warps per SM instead of 8 (the kernel is bound by issue
+// slots: 2 warps per scheduler issued 31 % of the cycles, profiles/r2_ncu_mlp_v1_raw.csv).
 //   layer 1 (K = 3)        CUDA cores, straight from the gathered (xyz[idx] - centre)
 //   layer 2 (128x64x64)    tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM columns 0..63)
 //   layer 3 (128x128x64)   tcgen05.mma kind::f16 (TMEM columns 64..191)
@@ -19,7 +22,7 @@
 
 namespace lidar {
 
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 256;     // two warps per TMEM lane quarter: each takes half of the channels of its 32 rows
 constexpr int kTcRows = 128;
 constexpr int kTcK = 32;            // neighbours per centre
 constexpr int kC1 = 64, kC2 = 64, kC3 = 128;
@@ -83,6 +86,13 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(unsigned taddr, unsigned (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_16x256b_x4(unsigned taddr, unsigned (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -124,7 +134,7 @@ __device__ __forceinline__ void stage_weights(const float* __restrict__ W, int r
     }
 }
 
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kTcThreads, 2)
 shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx, const float* __restrict__ new_xyz,
                      int n, int m, int n_centres, const float* __restrict__ W1, const float* __restrict__ B1,
                      const float* __restrict__ W2, const float* __restrict__ B2, const float* __restrict__ W3,
@@ -137,6 +147,8 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + kOffBar);
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + kOffBar + 8);
     const int warp = threadIdx.x >> 5;
+    const int qwarp = warp & 3;               // TMEM lane quarter = centre of the tile
+    const int half = threadIdx.x >> 7;        // which half of the channels this thread works on
     const unsigned lane = lane_id();
 
     // ---- one-time setup: weights, barrier, TMEM ------------------------------------------------
@@ -158,7 +170,7 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem_base = *tmem_slot;
-    const unsigned tmem_lane = tmem_base + ((unsigned)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+    const unsigned tmem_lane = tmem_base + ((unsigned)(qwarp * 32) << 16);   // this warp's 32 TMEM lanes
     const unsigned sbase = s_addr(smem);
     const unsigned idesc2 = umma_idesc(kTcRows, kC2), idesc3 = umma_idesc(kTcRows, kC3);
     unsigned phase = 0;
@@ -169,11 +181,11 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
     // tile ago) are in flight, so neither latency is exposed (the source-level profile had 10 % of the stall samples
     // on the address computation that waits for the index).
     auto load_index = [&](int t) -> int {
-        const int c_ = t * 4 + warp;
+        const int c_ = t * 4 + qwarp;
         return (t < n_tiles && c_ < n_centres) ? __ldg(idx + (size_t)c_ * kTcK + lane) : -1;
     };
     auto load_point = [&](int t, int src, float& a0, float& a1, float& a2) {
-        const int c_ = t * 4 + warp;
+        const int c_ = t * 4 + qwarp;
         a0 = a1 = a2 = 0.f;
         if (src >= 0) {
             const int b_ = c_ / m;
@@ -186,26 +198,29 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
     float n0, n1, n2;
     load_point(blockIdx.x, load_index(blockIdx.x), n0, n1, n2);
     int next_src = load_index(blockIdx.x + tstep);
-    const int row = threadIdx.x;
+    const int row = threadIdx.x & 127;
+    constexpr int kHalf1 = kC1 / 2;           // channels of layer 1 per thread
 
-    // layer 1 of a tile on the CUDA cores, result kept in registers (the A buffer may still feed the tensor core)
-    auto layer1 = [&](float g0, float g1, float g2, float (&h)[kC1]) {
+    // layer 1 of a tile on the CUDA cores (this thread's half of the channels), result kept in registers: the A buffer
+    // may still feed the tensor core
+    auto layer1 = [&](float g0, float g1, float g2, float (&h)[kHalf1]) {
 #pragma unroll
-        for (int o = 0; o < kC1; ++o) {
+        for (int i = 0; i < kHalf1; ++i) {
+            const int o = half * kHalf1 + i;
             float a = sB1[o];
             a = fmaf(sW1[o * 3], g0, a);
             a = fmaf(sW1[o * 3 + 1], g1, a);
             a = fmaf(sW1[o * 3 + 2], g2, a);
-            h[o] = fmaxf(a, 0.f);
+            h[i] = fmaxf(a, 0.f);
         }
     };
-    auto write_a = [&](const float (&h)[kC1]) {
+    auto write_a = [&](const float (&h)[kHalf1]) {
 #pragma unroll
-        for (int kc = 0; kc < 8; ++kc) {
+        for (int kc = 0; kc < kHalf1 / 8; ++kc) {
             float x[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) x[i] = h[kc * 8 + i];
-            store_chunk(smem, row, kc, x);
+            store_chunk(smem, row, half * (kHalf1 / 8) + kc, x);
         }
     };
     auto issue = [&](int w_hi, int w_lo, unsigned tmem_d, unsigned idesc) {   // 12 MMAs: K = 64 in steps of 16, hi*hi + hi*lo + lo*hi
@@ -240,13 +255,19 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
         const int b = live ? centre / m : 0, mm = live ? centre % m : 0;
         const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
         const int colsel = 8 * (2 * (int)b4 + (int)b3) + 2 * (int)(lane & 3) + (int)b2;
+        unsigned ra[2][16], rc[2][16];
 #pragma unroll
-        for (int chunk = 0; chunk < 4; ++chunk) {
-            unsigned a[16], c[16];
-            const unsigned t0 = tmem_base + ((unsigned)(warp * 32) << 16) + kC2 + chunk * 32;
-            tmem_ld_16x256b_x4(t0, a);
-            tmem_ld_16x256b_x4(t0 + (16u << 16), c);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int cc = 0; cc < 2; ++cc) {                          // this warp's half of the 128 channels: four loads in flight
+            const unsigned t0 = tmem_base + ((unsigned)(qwarp * 32) << 16) + kC2 + (half * 2 + cc) * 32;
+            tmem_ld_16x256b_x4(t0, ra[cc]);
+            tmem_ld_16x256b_x4(t0 + (16u << 16), rc[cc]);
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            const int chunk = half * 2 + cc;
+            const unsigned (&a)[16] = ra[cc];
+            const unsigned (&c)[16] = rc[cc];
             float v[8];
 #pragma unroll
             for (int rep = 0; rep < 4; ++rep) {
@@ -278,7 +299,7 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
     //   A <- layer 1(t+1) | issue L2(t+1) | ...
     int tile = blockIdx.x;
     if (tile < n_tiles) {
-        float h[kC1];
+        float h[kHalf1];
         layer1(n0, n1, n2, h);
         const int src1 = next_src;
         next_src = load_index(tile + 2 * tstep);
@@ -294,24 +315,30 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
         phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // ---- epilogue 2: bias + ReLU, re-split, becomes the A operand of layer 3 -----------------
+        {
+            unsigned r0[16], r1[16];                              // this thread's 32 of the 64 channels: both loads in flight
+            tmem_ld16_nowait(tmem_lane + (half * 2) * 16, r0);
+            tmem_ld16_nowait(tmem_lane + (half * 2 + 1) * 16, r1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float v[16];
-            tmem_ld16(tmem_lane + q * 16, v);
+            for (int qq = 0; qq < 2; ++qq) {
+                const int q = half * 2 + qq;
 #pragma unroll
-            for (int hlf = 0; hlf < 2; ++hlf) {
-                float x[8];
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    float x[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = fmaxf(v[hlf * 8 + i] + sB2[q * 16 + hlf * 8 + i], 0.f);
-                store_chunk(smem, row, q * 2 + hlf, x);
+                    for (int i = 0; i < 8; ++i)
+                        x[i] = fmaxf(__uint_as_float(qq ? r1[hlf * 8 + i] : r0[hlf * 8 + i]) + sB2[q * 16 + hlf * 8 + i], 0.f);
+                    store_chunk(smem, row, q * 2 + hlf, x);
+                }
             }
         }
         publish_a();
         issue(kOffW3h, kOffW3l, tmem_base + kC2, idesc3);
-        prev_centre = tile * 4 + warp;
+        prev_centre = tile * 4 + qwarp;
         // ---- layer 1 of the next tile, under the layer-3 MMAs ---------------------------------------
         const bool more = tile + tstep < n_tiles;
-        float h[kC1];
+        float h[kHalf1];
         if (more) {
             layer1(n0, n1, n2, h);
             const int src1 = next_src;
@@ -343,7 +370,7 @@ int launch_shared_mlp_tc(const float* xyz, const int* idx, const float* new_xyz,
     LIDAR_CUDA_TRY(cudaFuncSetAttribute(shared_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
     const int n_centres = b * m;
     const int n_tiles = (n_centres + 3) / 4;
-    int grid = sm_count() * 2;   // 2 CTAs per SM: 2 x 256 TMEM columns, 2 x 82 KB of shared memory
+    int grid = sm_count() * 2;   // 2 CTAs per SM: 2 x 256 TMEM columns, 2 x 82 KB of shared memory, 2 x 256 threads
     if (grid > n_tiles) grid = n_tiles;
     shared_mlp_tc_kernel<<<grid, kTcThreads, kTcSmem, st>>>(xyz, idx, new_xyz, n, m, n_centres, W1, B1, W2, B2, W3, B3, out);
     LIDAR_CHECK_LAUNCH();

@@ -19,7 +19,7 @@ from ._capi import FMT_F32X4, FMT_F64X3, HIST_AUTO, FrameCaps, FrameDesc, check,
 
 __all__ = [
     "require_cuda", "point_format", "bbox", "moments", "hist2d_counts", "hist2d_points_counts", "roi_crop", "ball_count", "set_dbscan_dense", "set_frame_streaming", "set_frame_scan_order", "preprocess_front",
-    "FramePipeline", "HostFramePipeline", "voxel_downsample", "arange_edges", "linspace_edges",
+    "FramePipeline", "HostFramePipeline", "voxel_downsample", "voxel_downsample_sorted", "arange_edges", "linspace_edges",
 ]
 
 
@@ -695,19 +695,72 @@ class HostFramePipeline:
         return self.collect()
 
 
+@dataclass
+class SortedVoxelResult:
+    """Result of the 64-bit-key sort path (`voxel_downsample_sorted`); per-point entries of cropped points are -1."""
+    desc: "_capi.SortedDesc"
+    voxel_key: torch.Tensor      # (n,) int64
+    inverse: torch.Tensor        # (n,) int32
+    centroids: torch.Tensor      # (V,4) float32
+    counts: torch.Tensor         # (V,) int32
+    unique_keys: torch.Tensor    # (V,) int64
+    dims: tuple
+    origin: tuple
+
+    @property
+    def n_voxels(self) -> int:
+        return int(self.desc.n_voxels)
+
+    @property
+    def n_kept(self) -> int:
+        return int(self.desc.n_kept)
+
+
+def voxel_downsample_sorted(points: torch.Tensor, voxel_size: float, origin=None, roi=None) -> SortedVoxelResult:
+    """Voxel downsample with int64 keys, any key space — deterministic radix sort by voxel key +
+    segmented reduction (`lidar_voxel_downsample_sorted`), one enqueue and one read-back of the descriptor.
+    `roi=(lo3, hi3)` fuses the ROI crop of Appendix B.2 in front: cropped points take no part in the origin / bbox and get
+    voxel_key = inverse = -1."""
+    if point_format(points) != FMT_F32X4:
+        raise ValueError("voxel_downsample_sorted takes (n,4) float32 frames")
+    dev, n = points.device, points.shape[0]
+    cap = max(n, 1)
+    key = torch.empty(cap, dtype=torch.int64, device=dev)
+    inv = torch.empty(cap, dtype=torch.int32, device=dev)
+    cent = torch.empty((cap, 4), dtype=torch.float32, device=dev)
+    cnt = torch.empty(cap, dtype=torch.int32, device=dev)
+    ukey = torch.empty(cap, dtype=torch.int64, device=dev)
+    d_desc = torch.zeros(C.sizeof(_capi.SortedDesc), dtype=torch.uint8, device=dev)
+    ws = _scratch.get("voxel_sorted", lib.lidar_voxel_sorted_workspace_bytes(n), dev)
+    o3 = (C.c_double * 3)(*[float(v) for v in origin]) if origin is not None else None
+    lo3 = (C.c_double * 3)(*[float(v) for v in roi[0]]) if roi is not None else None
+    hi3 = (C.c_double * 3)(*[float(v) for v in roi[1]]) if roi is not None else None
+    check(lib.lidar_voxel_downsample_sorted(_ptr(points), n, float(voxel_size), o3, lo3, hi3, _ptr(key), _ptr(inv), _ptr(cent),
+                                            _ptr(cnt), _ptr(ukey), _ptr(d_desc), _ptr(ws), ws.numel(), _stream_ptr()))
+    desc = _capi.SortedDesc.from_buffer_copy(fetch("sorted_desc", d_desc)[0].tobytes())
+    if desc.status != 0:
+        raise _capi.LidarError(int(desc.status), "voxel_downsample_sorted: a point lies below the given origin" if desc.status == -1
+                               else "voxel_downsample_sorted: the voxel key space does not fit 63 bits")
+    v = int(desc.n_voxels)
+    return SortedVoxelResult(desc, key[:n], inv[:n], cent[:v], cnt[:v], ukey[:v], tuple(int(d) for d in desc.dims),
+                             tuple(float(o) for o in desc.origin))
+
+
 def voxel_downsample(points: torch.Tensor, voxel_size: float, origin=None, max_key_space: int | None = None):
     """One-shot voxel downsample of an (n,4) float32 CUDA tensor.
 
-    Returns a `FrameResult` whose tensors are owned by the caller.
+    Returns a `FrameResult` (int32 keys, the occupancy-bitmap frame kernel) whose tensors are owned by the caller, or —
+    when the key space of the cloud needs more than 31 bits (one far outlier is enough) — a `SortedVoxelResult` with
+    int64 keys from the sort path: the same fields, the same values.
     """
     n = points.shape[0]
     if max_key_space is None:
         bb = bbox(points).cpu().numpy()
         org = bb[:3] if origin is None else np.asarray(origin, dtype=np.float64)
         dims = np.floor((bb[4:7] - org) / float(voxel_size)) + 1
-        max_key_space = int(max(1, np.prod(np.maximum(dims, 1))))
+        max_key_space = int(max(1, np.prod(np.maximum(dims, 1)))) if np.all(np.isfinite(dims)) else 1
         if max_key_space >= (1 << 31):
-            raise _capi.LidarError(-4, f"voxel key space {max_key_space} needs more than 31 bits")
+            return voxel_downsample_sorted(points, voxel_size, origin=origin)
     pipe = FramePipeline(max(n, 1), voxel_size, 0.0, max_key_space=max_key_space, device=points.device)
     pipe.enqueue(points, origin=origin)
     return pipe.result()
