@@ -95,7 +95,7 @@ def test_property_random_clouds_with_an_outlier(n, seed, voxel, far):
     from lidar_ai_recommendation_software_b200 import ops
     rng = np.random.default_rng(seed)
     pts = np.column_stack([rng.normal(0, 3, n), rng.normal(0, 3, n), rng.uniform(0, 2, n), rng.uniform(0, 1, n)]).astype(np.float32)
-    pts[rng.integers(0, n)] += np.float32(far)
+    pts[rng.integers(0, n), :2] += np.float32(far)                    # x and y: up to 2e7 x 2e7 x 40 cells, still < 2^63
     if n > 4:
         pts[: n // 3] = pts[n // 3: 2 * (n // 3)]                        # exact duplicates
     check(ops, pts, voxel)
