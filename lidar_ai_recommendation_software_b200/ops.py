@@ -14,7 +14,7 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
-from . import _capi
+from . import _capi, _torch_ext
 from ._capi import FMT_F32X4, FMT_F64X3, HIST_AUTO, FrameCaps, FrameDesc, check, lib
 
 __all__ = [
@@ -111,13 +111,9 @@ def point_format(points: torch.Tensor) -> int:
 def bbox(points: torch.Tensor) -> torch.Tensor:
     """(8,) float64 device tensor {min x,y,z,w, max x,y,z,w}; np.min/np.max of
     utils/data_processing.py:143,207-208."""
-    fmt = point_format(points)
-    dev = points.device
-    out = torch.empty(8, dtype=torch.float64, device=dev)
-    nb = lib.lidar_reduce_workspace_bytes()
-    ws = _scratch.get("reduce", nb, dev)
-    check(lib.lidar_bbox(_ptr(points), fmt, points.shape[0], _ptr(out), _ptr(ws), ws.numel(), _stream_ptr()))
-    return out
+    point_format(points)
+    ws = _scratch.get("reduce", lib.lidar_reduce_workspace_bytes(), points.device)
+    return _ext_call(_torch_ext.ops.bbox, points, ws)   # thin torch extension -> lidar_bbox on PyTorch's current stream
 
 
 def moments(points: torch.Tensor, center=(0.0, 0.0, 0.0)) -> torch.Tensor:
@@ -200,8 +196,9 @@ def hist2d_points_counts(points: torch.Tensor, x_edges, y_edges, mode: int = HIS
     nx, ny = ex.numel() - 1, ey.numel() - 1
     if out is None:
         out = torch.zeros((nx, ny), dtype=torch.int32, device=dev)
-    check(lib.lidar_hist2d_points(_ptr(points), fmt, points.shape[0], _ptr(ex), nx, _ptr(ey), ny, _ptr(out),
-                                  mode, _stream_ptr()))
+    if nx < 1 or ny < 1:
+        raise ValueError("need at least two edges per axis")
+    _ext_call(_torch_ext.ops.hist2d_points, points, ex, ey, out, int(mode))
     return out
 
 
@@ -233,6 +230,21 @@ def roi_crop(points: torch.Tensor, lo, hi, return_mask: bool = True):
 # K5 (+K6) frame pipeline
 # ------------------------------------------------------------------------------------------------
 FRAME_AUTO, FRAME_MULTIKERNEL, FRAME_FUSED, FRAME_PARTITIONED = 0, 1, 2, 3
+USE_TORCH_EXTENSION = True            # FramePipeline.enqueue through torch.ops.lidar_b200 (False: the ctypes binding)
+_EMPTY_F64 = torch.empty(0, dtype=torch.float64)
+
+
+def _ext_call(fn, *args):
+    """Call an operator of the thin torch extension; a C-ABI status it reports becomes the package's `LidarError`
+    (same exception type and code as the ctypes path)."""
+    try:
+        return fn(*args)
+    except RuntimeError as e:
+        import re
+        m = re.search(r"status (-?\d+) \((.*?)\)\s*(?:\n|$)", str(e), re.S)
+        if m:
+            raise _capi.LidarError(int(m.group(1)), m.group(2)) from None
+        raise
 
 
 def set_frame_mode(mode: int = FRAME_AUTO, threads: int = 0, ctas_per_sm: int = 0, smem_kb: int = 0) -> None:
@@ -371,7 +383,16 @@ class FramePipeline:
                 _ptr(self.inverse), _ptr(self.voxels), _ptr(self.grid), _ptr(self.desc_dev), C.byref(self.caps),
                 _ptr(self.ws), self.ws.numel(), _stream_ptr())
         try:
-            if events is None:
+            if events is None and USE_TORCH_EXTENSION:
+                # the per-frame hot call goes through the thin torch extension: one dispatcher call, the stream is taken
+                # in C++, no ctypes marshalling of fifteen arguments
+                _ext_call(
+                    _torch_ext.ops.frame_voxel_density, points, self.voxel_size, self.grid_size,
+                    _EMPTY_F64 if origin is None else torch.tensor([float(v) for v in origin], dtype=torch.float64),
+                    _EMPTY_F64 if xy_range is None else torch.tensor([float(v) for v in xy_range], dtype=torch.float64),
+                    self.voxel_key, self.inverse, self.voxels, self.grid, self.desc_dev, self.ws,
+                    self.caps.max_points, self.caps.max_key_space, self.caps.max_nx, self.caps.max_ny)
+            elif events is None:
                 check(lib.lidar_frame_voxel_density(*args))
             else:
                 if len(events) != 6:

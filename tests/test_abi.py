@@ -90,3 +90,16 @@ def test_argument_errors_do_not_need_a_gpu():
     assert rc == -1 and "lidar_hist2d_f64" in _capi.last_error()
     with pytest.raises(_capi.LidarError):
         _capi.check(rc)
+
+
+def test_thin_torch_extension_builds_and_registers_its_operators():
+    """The north star's "thin PyTorch C++ extension with a C-ABI core": lidar_b200_torch.so is built in-tree next to
+    liblidar_b200.so, registers torch.ops.lidar_b200.* and reports the ABI version of the core it links against."""
+    import torch
+    from lidar_ai_recommendation_software_b200 import _capi, _torch_ext
+    assert _torch_ext.EXT_PATH.exists() and _torch_ext.EXT_PATH.parent == _capi.LIB_PATH.parent
+    assert int(torch.ops.lidar_b200.abi_version()) == _capi.abi_version()
+    for name in ("frame_voxel_density", "hist2d_points", "bbox"):
+        assert hasattr(torch.ops.lidar_b200, name)
+    with pytest.raises((RuntimeError, NotImplementedError)):      # CPU tensors: no kernel registered for that backend
+        torch.ops.lidar_b200.bbox(torch.zeros((4, 4)), torch.zeros(16, dtype=torch.uint8))
