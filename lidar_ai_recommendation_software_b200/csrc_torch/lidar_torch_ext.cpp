@@ -3,22 +3,19 @@
 //
 // Nothing is computed here: every operator checks its tensors, takes the CURRENT CUDA stream of the tensor's device
 // from PyTorch (c10::cuda::getCurrentCUDAStream — no `int(stream.cuda_stream)` round trip through Python), calls one
-// extern "C" entry of liblidar_b200.so (include/lidar_b200.h) and turns a negative status into a C++ exception that
-// PyTorch re-raises as RuntimeError with lidar_last_error()'s text.  Registered as torch.ops.lidar_b200.* (TORCH_LIBRARY:
+// extern "C" entry of liblidar_b200.so (include/lidar_b200.h) and RETURNS its status (0 = ok); the Python side turns a
+// negative status into the package's LidarError with lidar_last_error()'s text, exactly as it does for the ctypes
+// binding (no C++ exception crosses the dispatcher for a C-ABI status).  Registered as torch.ops.lidar_b200.* (TORCH_LIBRARY:
 // no Python.h, no pybind).  The ctypes binding (_capi.py) stays the complete one; these are the per-frame hot calls,
 // where the marshalling of 15 ctypes arguments costs more than the launch itself.
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
-#include <ATen/ops/empty.h>
 #include <torch/library.h>
 
 #include "lidar_b200.h"
 
 namespace {
 
-void check(int rc, const char* what) {
-    TORCH_CHECK(rc == LIDAR_OK, what, ": status ", rc, " (", lidar_last_error(), ")");
-}
 void* stream_of(const at::Tensor& t) { return at::cuda::getCurrentCUDAStream(t.get_device()).stream(); }
 
 void need_cuda(const at::Tensor& t, const char* name) {
@@ -33,7 +30,7 @@ int point_format(const at::Tensor& p) {
 
 // One frame: bbox -> voxel downsample (+ density grid) into the caller's preallocated outputs (FramePipeline's buffers).
 // origin / xy_range: empty tensors = derived from the cloud (CPU float64 tensors of 3 / 4 values otherwise).
-void frame_voxel_density(const at::Tensor& points, double voxel_size, double grid_size, const at::Tensor& origin,
+int64_t frame_voxel_density(const at::Tensor& points, double voxel_size, double grid_size, const at::Tensor& origin,
                          const at::Tensor& xy_range, at::Tensor voxel_key, at::Tensor inverse, at::Tensor voxels,
                          const c10::optional<at::Tensor>& grid, at::Tensor desc, at::Tensor ws, int64_t max_points,
                          int64_t max_key_space, int64_t max_nx, int64_t max_ny) {
@@ -48,35 +45,31 @@ void frame_voxel_density(const at::Tensor& points, double voxel_size, double gri
     if (origin.numel() == 3) { auto a = origin.to(at::kCPU, at::kDouble).contiguous(); for (int i = 0; i < 3; ++i) o3[i] = a.data_ptr<double>()[i]; po = o3; }
     if (xy_range.numel() == 4) { auto a = xy_range.to(at::kCPU, at::kDouble).contiguous(); for (int i = 0; i < 4; ++i) r4[i] = a.data_ptr<double>()[i]; pr = r4; }
     int32_t* g = grid.has_value() && grid->defined() && grid->numel() ? grid->data_ptr<int32_t>() : nullptr;
-    check(lidar_frame_voxel_density(points.data_ptr(), points.size(0), voxel_size, grid_size, po, pr, voxel_key.data_ptr<int32_t>(),
-                                    inverse.data_ptr<int32_t>(), reinterpret_cast<lidar_voxel*>(voxels.data_ptr()), g,
-                                    reinterpret_cast<lidar_frame_desc*>(desc.data_ptr()), &caps, ws.data_ptr(), (size_t)ws.numel(),
-                                    stream_of(points)),
-          "lidar_frame_voxel_density");
+    return lidar_frame_voxel_density(points.data_ptr(), points.size(0), voxel_size, grid_size, po, pr, voxel_key.data_ptr<int32_t>(),
+                                     inverse.data_ptr<int32_t>(), reinterpret_cast<lidar_voxel*>(voxels.data_ptr()), g,
+                                     reinterpret_cast<lidar_frame_desc*>(desc.data_ptr()), &caps, ws.data_ptr(), (size_t)ws.numel(),
+                                     stream_of(points));
 }
 
 // np.histogram2d semantics on the x / y of a cloud; counts are ADDED into `counts` (int32 [nx][ny]).
-void hist2d_points(const at::Tensor& points, const at::Tensor& x_edges, const at::Tensor& y_edges, at::Tensor counts, int64_t mode) {
+int64_t hist2d_points(const at::Tensor& points, const at::Tensor& x_edges, const at::Tensor& y_edges, at::Tensor counts, int64_t mode) {
     const int fmt = point_format(points);
     need_cuda(x_edges, "x_edges"); need_cuda(y_edges, "y_edges"); need_cuda(counts, "counts");
     TORCH_CHECK(x_edges.scalar_type() == at::kDouble && y_edges.scalar_type() == at::kDouble && counts.scalar_type() == at::kInt,
                 "edges are float64, counts int32");
     const c10::cuda::CUDAGuard guard(points.device());
-    check(lidar_hist2d_points(points.data_ptr(), fmt, points.size(0), x_edges.data_ptr<double>(), (int)x_edges.numel() - 1,
-                              y_edges.data_ptr<double>(), (int)y_edges.numel() - 1, counts.data_ptr<int32_t>(), (int)mode,
-                              stream_of(points)),
-          "lidar_hist2d_points");
+    return lidar_hist2d_points(points.data_ptr(), fmt, points.size(0), x_edges.data_ptr<double>(), (int)x_edges.numel() - 1,
+                               y_edges.data_ptr<double>(), (int)y_edges.numel() - 1, counts.data_ptr<int32_t>(), (int)mode,
+                               stream_of(points));
 }
 
-// {min x,y,z,w, max x,y,z,w} as float64; `ws` >= lidar_reduce_workspace_bytes().
-at::Tensor bbox(const at::Tensor& points, at::Tensor ws) {
+// out8 <- {min x,y,z,w, max x,y,z,w} as float64; `ws` >= lidar_reduce_workspace_bytes().
+int64_t bbox(const at::Tensor& points, at::Tensor out8, at::Tensor ws) {
     const int fmt = point_format(points);
-    need_cuda(ws, "ws");
+    need_cuda(ws, "ws"); need_cuda(out8, "out8");
+    TORCH_CHECK(out8.scalar_type() == at::kDouble && out8.numel() == 8, "out8 must hold 8 float64 values");
     const c10::cuda::CUDAGuard guard(points.device());
-    at::Tensor out = at::empty({8}, points.options().dtype(at::kDouble));
-    check(lidar_bbox(points.data_ptr(), fmt, points.size(0), out.data_ptr<double>(), ws.data_ptr(), (size_t)ws.numel(), stream_of(points)),
-          "lidar_bbox");
-    return out;
+    return lidar_bbox(points.data_ptr(), fmt, points.size(0), out8.data_ptr<double>(), ws.data_ptr(), (size_t)ws.numel(), stream_of(points));
 }
 
 int64_t abi_version() { return lidar_abi_version(); }
@@ -86,9 +79,9 @@ int64_t abi_version() { return lidar_abi_version(); }
 TORCH_LIBRARY(lidar_b200, m) {
     m.def("frame_voxel_density(Tensor points, float voxel_size, float grid_size, Tensor origin, Tensor xy_range, Tensor(a!) voxel_key, "
           "Tensor(b!) inverse, Tensor(c!) voxels, Tensor(d!)? grid, Tensor(e!) desc, Tensor(f!) ws, int max_points, int max_key_space, "
-          "int max_nx, int max_ny) -> ()");
-    m.def("hist2d_points(Tensor points, Tensor x_edges, Tensor y_edges, Tensor(a!) counts, int mode) -> ()");
-    m.def("bbox(Tensor points, Tensor(a!) ws) -> Tensor");
+          "int max_nx, int max_ny) -> int");
+    m.def("hist2d_points(Tensor points, Tensor x_edges, Tensor y_edges, Tensor(a!) counts, int mode) -> int");
+    m.def("bbox(Tensor points, Tensor(a!) out8, Tensor(b!) ws) -> int");
     m.def("abi_version() -> int");
 }
 TORCH_LIBRARY_IMPL(lidar_b200, CUDA, m) {

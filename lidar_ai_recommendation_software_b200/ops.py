@@ -113,7 +113,9 @@ def bbox(points: torch.Tensor) -> torch.Tensor:
     utils/data_processing.py:143,207-208."""
     point_format(points)
     ws = _scratch.get("reduce", lib.lidar_reduce_workspace_bytes(), points.device)
-    return _ext_call(_torch_ext.ops.bbox, points, ws)   # thin torch extension -> lidar_bbox on PyTorch's current stream
+    out = torch.empty(8, dtype=torch.float64, device=points.device)
+    _ext_call(_torch_ext.ops.bbox, points, out, ws)      # thin torch extension -> lidar_bbox on PyTorch's current stream
+    return out
 
 
 def moments(points: torch.Tensor, center=(0.0, 0.0, 0.0)) -> torch.Tensor:
@@ -235,16 +237,9 @@ _EMPTY_F64 = torch.empty(0, dtype=torch.float64)
 
 
 def _ext_call(fn, *args):
-    """Call an operator of the thin torch extension; a C-ABI status it reports becomes the package's `LidarError`
-    (same exception type and code as the ctypes path)."""
-    try:
-        return fn(*args)
-    except RuntimeError as e:
-        import re
-        m = re.search(r"status (-?\d+) \((.*?)\)\s*(?:\n|$)", str(e), re.S)
-        if m:
-            raise _capi.LidarError(int(m.group(1)), m.group(2)) from None
-        raise
+    """Call an operator of the thin torch extension: it returns the C-ABI status, which becomes the package's
+    `LidarError` exactly as on the ctypes path (`lidar_last_error()` is thread-local and the operator ran on this thread)."""
+    check(int(fn(*args)))
 
 
 def set_frame_mode(mode: int = FRAME_AUTO, threads: int = 0, ctas_per_sm: int = 0, smem_kb: int = 0) -> None:

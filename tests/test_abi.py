@@ -102,4 +102,4 @@ def test_thin_torch_extension_builds_and_registers_its_operators():
     for name in ("frame_voxel_density", "hist2d_points", "bbox"):
         assert hasattr(torch.ops.lidar_b200, name)
     with pytest.raises((RuntimeError, NotImplementedError)):      # CPU tensors: no kernel registered for that backend
-        torch.ops.lidar_b200.bbox(torch.zeros((4, 4)), torch.zeros(16, dtype=torch.uint8))
+        torch.ops.lidar_b200.bbox(torch.zeros((4, 4)), torch.zeros(8, dtype=torch.float64), torch.zeros(16, dtype=torch.uint8))
