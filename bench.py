@@ -329,7 +329,11 @@ def run_extras(args, torch, dist, dev, rank, world):
         a = types.SimpleNamespace(points=args.scan_points, host_shards=8, reps=10)
         guarded("scan50m", lambda: bc.run_scan(a, torch, dev, rank, world, dist))
     if "seq" in args.extras:
-        a = types.SimpleNamespace(frames=args.seq_frames, pool=4, rings=128, azimuth=20480, dropin=False, workers=3)
+        # preprocess worker threads per rank: three when the rank has the CPUs for them (each worker drives a stream and
+        # waits on the device twice per frame), two when eight ranks share a 32-vCPU host
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+        workers = 3 if (os.cpu_count() or 1) // local_world >= 6 else 2
+        a = types.SimpleNamespace(frames=args.seq_frames, pool=4, rings=128, azimuth=20480, dropin=False, workers=workers)
         guarded("seq", lambda: bc.run_seq(a, torch, dev, rank, world, dist))
     if "sa" in args.extras and world == 1:
         a = types.SimpleNamespace(reps=20)

@@ -869,16 +869,19 @@ __device__ __forceinline__ void fused_grid_barrier(unsigned* ctr, unsigned targe
 // phases and (b) a scan / clean that walks a summary bitmap of the occupied groups instead of streaming every group.
 // The default instantiation (kScan = false) contains none of that code: the kernel is instruction-cache bound, and
 // compiling both into one body cost the shuffled benchmark 5 %.
-template <bool kScan>
-__global__ void __launch_bounds__(kFusedMaxThreads, 1)
+// kMaxT = the largest block the instantiation may be launched with: 512 (up to 128 registers per thread: four points in
+// flight without spills) or 1024 (64 registers, ~100 bytes of spills, but 32 resident warps per SM instead of 16 -- the
+// kernel is bound by dependent-instruction latency, profiles/r2_ncu_fused_streaming_raw.csv).
+template <bool kScan, int kMaxT>
+__global__ void __launch_bounds__(kMaxT, 1)
 k_frame_fused(const FusedArgs A) {
     extern __shared__ __align__(128) unsigned char fsm[];
     __shared__ lidar_frame_desc D;
     __shared__ __align__(8) unsigned long long s_bar[kFusedLoadStages];
-    __shared__ double s_red[kFusedMaxThreads / 32][8];
+    __shared__ double s_red[kMaxT / 32][8];
     __shared__ double s_bb[8];
-    __shared__ unsigned s_wsum[kFusedMaxThreads / 32];
-    __shared__ unsigned long long s_wlook[kFusedMaxThreads / 32][2];
+    __shared__ unsigned s_wsum[kMaxT / 32];
+    __shared__ unsigned long long s_wlook[kMaxT / 32][2];
     __shared__ unsigned long long s_base_total[2];
     __shared__ unsigned long long s_trace[16];
     __shared__ int s_stat[8];
@@ -2130,8 +2133,8 @@ int lidar_frame_set_fused(int mode, int threads, int ctas_per_sm, int smem_kb) {
     LIDAR_REQUIRE(mode == LIDAR_FRAME_AUTO || mode == LIDAR_FRAME_MULTIKERNEL || mode == LIDAR_FRAME_FUSED ||
                       mode == LIDAR_FRAME_PARTITIONED,
                   LIDAR_ERR_INVALID, "lidar_frame_set_fused: unknown mode %d", mode);
-    LIDAR_REQUIRE(threads == 0 || (threads >= 128 && threads <= kFusedMaxThreads && threads % 32 == 0),
-                  LIDAR_ERR_INVALID, "lidar_frame_set_fused: threads must be a multiple of 32 in [128, 512]");
+    LIDAR_REQUIRE(threads == 0 || (threads >= 128 && threads <= 1024 && threads % 32 == 0),
+                  LIDAR_ERR_INVALID, "lidar_frame_set_fused: threads must be a multiple of 32 in [128, 1024]");
     LIDAR_REQUIRE(ctas_per_sm >= 0 && ctas_per_sm <= 4, LIDAR_ERR_INVALID, "lidar_frame_set_fused: ctas_per_sm 0..4");
     LIDAR_REQUIRE(smem_kb >= 0 && smem_kb <= 227, LIDAR_ERR_INVALID, "lidar_frame_set_fused: smem_kb 0..227");
     g_fused_mode = mode;
@@ -2281,9 +2284,13 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
         int cur_dev = 0;
         LIDAR_CUDA_TRY(cudaGetDevice(&cur_dev));
         if (cur_dev < 0 || cur_dev >= 64 || !g_fused_attr_set[cur_dev]) {
-            LIDAR_CUDA_TRY(cudaFuncSetAttribute(k_frame_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            LIDAR_CUDA_TRY(cudaFuncSetAttribute(k_frame_fused<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)(smem_optin() - static_bytes)));
-            LIDAR_CUDA_TRY(cudaFuncSetAttribute(k_frame_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            LIDAR_CUDA_TRY(cudaFuncSetAttribute(k_frame_fused<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(smem_optin() - static_bytes)));
+            LIDAR_CUDA_TRY(cudaFuncSetAttribute(k_frame_fused<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(smem_optin() - static_bytes)));
+            LIDAR_CUDA_TRY(cudaFuncSetAttribute(k_frame_fused<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)(smem_optin() - static_bytes)));
             if (cur_dev >= 0 && cur_dev < 64) g_fused_attr_set[cur_dev] = true;
         }
@@ -2320,7 +2327,8 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
             size_t union_bytes = (size_t)per * 4 > owner_bytes ? (size_t)per * 4 : owner_bytes;   // {cell, slot} | owner | inverse
             union_bytes = (union_bytes + 127) & ~(size_t)127;
             dyn_part = (size_t)per * 22 + (size_t)pcap * 8 + ring_part + union_bytes;
-            const bool fits = pcap <= kPartMax && dyn_part + static_bytes <= smem_optin() && per < 65536 && (T & (T - 1)) == 0;
+            const bool fits = pcap <= kPartMax && dyn_part + static_bytes <= smem_optin() && per < 65536 && (T & (T - 1)) == 0 &&
+                              T <= kFusedMaxThreads;
             LIDAR_REQUIRE(fits || g_fused_mode != LIDAR_FRAME_PARTITIONED, LIDAR_ERR_CAPACITY,
                           "lidar_frame_voxel_density: the partitioned back end needs caps.max_key_space <= 2^29 and the frame "
                           "resident in shared memory (%lld points per CTA, %zu B of %zu B)", (long long)per,
@@ -2375,8 +2383,10 @@ static int frame_voxel_density_impl(const void* d_points, int64_t n, double voxe
         cfg.attrs = attr;
         cfg.numAttrs = na;
         cudaError_t le = use_part ? cudaLaunchKernelEx(&cfg, k_frame_part, PA)
-                         : g_fused_scan_order ? cudaLaunchKernelEx(&cfg, k_frame_fused<true>, A)
-                                              : cudaLaunchKernelEx(&cfg, k_frame_fused<false>, A);
+                         : T > 512 ? (g_fused_scan_order ? cudaLaunchKernelEx(&cfg, k_frame_fused<true, 1024>, A)
+                                                         : cudaLaunchKernelEx(&cfg, k_frame_fused<false, 1024>, A))
+                                   : (g_fused_scan_order ? cudaLaunchKernelEx(&cfg, k_frame_fused<true, 512>, A)
+                                                         : cudaLaunchKernelEx(&cfg, k_frame_fused<false, 512>, A));
         if (le == cudaSuccess) {
             for (int i = 1; i <= 5; ++i) LIDAR_CUDA_TRY(mark(i));
             return LIDAR_OK;

@@ -56,6 +56,8 @@ def test_struct_mirrors_match_c_layout():
       printf("%zu %zu %zu %zu %zu %zu\n", sizeof(lidar_scan_desc), offsetof(lidar_scan_desc, n_local),
              offsetof(lidar_scan_desc, status), sizeof(lidar_scan_comm), offsetof(lidar_scan_comm, peer_ptrs),
              offsetof(lidar_scan_comm, multicast_ptr));
+      printf("%zu %zu %zu %zu\n", sizeof(lidar_sorted_desc), offsetof(lidar_sorted_desc, dims),
+             offsetof(lidar_sorted_desc, n_voxels), offsetof(lidar_sorted_desc, status));
       return 0; }'''
     import tempfile
     with tempfile.TemporaryDirectory() as td:
@@ -70,7 +72,9 @@ def test_struct_mirrors_match_c_layout():
             ctypes.sizeof(_capi.FrameCaps),
             ctypes.sizeof(F), F.n_in.offset, F.z_thr.offset, F.plane.offset, F.eps.offset, F.key_ng.offset,
             ctypes.sizeof(_capi.ScanDesc), _capi.ScanDesc.n_local.offset, _capi.ScanDesc.status.offset,
-            ctypes.sizeof(_capi.ScanComm), _capi.ScanComm.peer_ptrs.offset, _capi.ScanComm.multicast_ptr.offset]
+            ctypes.sizeof(_capi.ScanComm), _capi.ScanComm.peer_ptrs.offset, _capi.ScanComm.multicast_ptr.offset,
+            ctypes.sizeof(_capi.SortedDesc), _capi.SortedDesc.dims.offset, _capi.SortedDesc.n_voxels.offset,
+            _capi.SortedDesc.status.offset]
     assert [int(x) for x in out] == want
 
 

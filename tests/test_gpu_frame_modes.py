@@ -16,6 +16,8 @@ FUSED_CONFIGS = [
     (2, 256, 2, 0),       # two CTAs per SM
     (2, 256, 1, 24),      # tiny shared-memory budget: nearly everything spills
     (2, 128, 1, 0),
+    (2, 1024, 1, 0),      # 32 warps per SM: the 64-register instantiation (round 2)
+    (2, 1024, 1, 100),
 ]
 
 
