@@ -256,12 +256,19 @@ class ScanDensity:
         stream.synchronize()
         return _capi.ScanDesc.from_buffer_copy(bytes(C.string_at(self._h_ptr, nb)))
 
-    def result(self):
+    def result(self, fetch: bool = True):
         """(grid_x, grid_y, density) of the enqueued call as owned numpy arrays — the reference's return value
-        (utils/data_processing.py:324-328); (None, None, None) for an empty scan (:297-298)."""
+        (utils/data_processing.py:324-328); (None, None, None) for an empty scan (:297-298).
+        `fetch=False` (a rank that does not need the arrays on its host: every rank's DEVICE copy is complete and
+        identical) only waits for the call and checks its status; returns None."""
         _capi = self._capi
         d = self._wait_desc()
         stream = torch.cuda.current_stream(self.device)
+        if not fetch:
+            stream.synchronize()
+            if d.status not in (0, _capi.SCAN_EMPTY):
+                raise _capi.LidarError(int(d.status), "scan density grid exceeds the capacities")
+            return None
         if d.status == _capi.SCAN_EMPTY:
             stream.synchronize()
             return None, None, None
