@@ -266,79 +266,153 @@ db_union(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* 
 // The common case of a (point, neighbour cell) visit is "that cell has no core point" or "it is already in my
 // set": both are decided from ONE load of the cell's representative (crep, filled by db_core) plus a find, without
 // touching the cell's start offsets, its core flags or its index list.
+// Neighbour cells with at least this many returns are scanned by the whole WARP for one point at a time.
+constexpr int kDbTeamScan = 48;
+
 template <int kAhead>
 __global__ void __launch_bounds__(kDbThreads)
 db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* __restrict__ scell,
                const int* __restrict__ sidx, const double* __restrict__ sx, const double* __restrict__ sy,
                const double* __restrict__ sz, double eps2, double tol, const uint8_t* __restrict__ core_s,
                int* __restrict__ parent, unsigned long long* __restrict__ guard, const int* __restrict__ crep) {
+    // Every lane walks the SAME list of 62 forward cell offsets, so that the warp meets at one point per offset: a lane
+    // that has to search a heavy neighbour cell (hundreds of returns near the sensor of a ring scan) does not scan it
+    // alone while its 31 neighbours idle -- measured on a 128-beam frame: 2 871 heavy cell pairs never merge (two people
+    // 0.31 m apart), the worst holds 770 x 619 returns, a handful of points of A survive the box test and each walked all
+    // of B: 2 000 dependent candidates per thread were the kernel's 0.5 ms tail -- the warp takes the requests one by one
+    // and tests 32 candidates per step, stopping at the first certain pair (lowest index, as the serial scan).
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= m || !core_s[pos]) return;
-    const int oi = sidx[pos];
-    const int c = scell[pos];
+    const unsigned lane = lane_id();
+    const bool active = pos < m && core_s[pos];
+    const int oi = active ? sidx[pos] : 0;
+    const int c = active ? scell[pos] : 0;
     unsigned band = 0;   // decisions of this point that rest on a pair inside the tol band (certificate)
     // (a) the core points of one cell are mutual neighbours: link to the cell's representative
-    {
+    if (active) {
         const int rep = crep[c];
         if (rep != oi) uf_union(parent, oi, rep);
     }
-    int myroot = uf_find(parent, oi);
+    // lanes of the warp that hold core points of the same cell form a group; its first lane answers for the cell
+    const unsigned peers = __match_any_sync(0xffffffffu, active ? c : -1 - (int)lane);
+    const int leader = __ffs(peers) - 1;
+    const bool is_leader = active && (int)lane == leader;
+    int myroot = is_leader ? uf_find(parent, oi) : 0;
     // (b) neighbour cells with a larger id (the pair is examined from the smaller side): one core pair within
     //     eps merges the two cells; cells already in this point's set are skipped without a distance test
-    const double x = sx[pos], y = sy[pos], z = sz[pos];
+    const double x = active ? sx[pos] : 0.0, y = active ? sy[pos] : 0.0, z = active ? sz[pos] : 0.0;
     const int cz = c % G.g[2];
     const int t = c / G.g[2];
     const int cy = t % G.g[1];
     const int cx = t / G.g[1];
-    const int R = G.reach;
-    const int z0 = cz - R > 0 ? cz - R : 0;
-    const int z1 = cz + R < G.g[2] - 1 ? cz + R : G.g[2] - 1;
-    for (int ax = (cx - R > 0 ? cx - R : 0); ax <= (cx + R < G.g[0] - 1 ? cx + R : G.g[0] - 1); ++ax)
-        for (int ay = (cy - R > 0 ? cy - R : 0); ay <= (cy + R < G.g[1] - 1 ? cy + R : G.g[1] - 1); ++ay) {
-            const int col = cell_id(G, ax, ay, 0);
-            if (col + z1 <= c) continue;
-            for (int az = z0; az <= z1; ++az) {
-                if (col + az <= c) continue;
-                const int rep = crep[col + az];
-                if (rep >= kNoRep) continue;
-                if (cell_box_dist2(G, ax, ay, az, x, y, z) > eps2 + tol) continue;
-                myroot = uf_find(parent, myroot);
-                if (uf_find(parent, rep) == myroot) continue;
-                const int jf = (int)cell_start[col + az];
-                const unsigned b1 = cell_start[col + az + 1];
+    const int R = G.reach;                       // 2 on this grid
+    // squared distance from the point to the slab of cells at offset d along one axis (0 inside the own slab), shrunk
+    // like cell_box_dist2: the box distance of a neighbour cell is the sum of three of these -- hoisted out of the
+    // inner loops, the test costs two additions per cell instead of a dozen fp64 operations
+    auto slab = [&](double p, double lo_own, int d) {
+        const double lo = lo_own + d * G.cell;
+        const double gap = fmax(0.0, fmax(lo - p, p - (lo + G.cell)));
+        return gap * gap;
+    };
+    const double lox = G.min[0] + cx * G.cell, loy = G.min[1] + cy * G.cell, loz = G.min[2] + cz * G.cell;
+    const double lim = (eps2 + tol + 1e-300) / (1.0 - 1e-9);        // d2 * (1 - 1e-9) - 1e-300 > eps2 + tol  <=>  d2 > lim
+    for (int dx = 0; dx <= R; ++dx) {                                // forward cells: (dx, dy, dz) > (0, 0, 0) lexicographically
+        const int ax = cx + dx;
+        const bool okx = active && ax < G.g[0];
+        const double ddx = slab(x, lox, dx);
+        for (int dy = (dx == 0 ? 0 : -R); dy <= R; ++dy) {
+            const int ay = cy + dy;
+            const bool okxy = okx && ay >= 0 && ay < G.g[1];
+            const double ddxy = ddx + slab(y, loy, dy);
+            const int col = okxy ? cell_id(G, ax, ay, 0) : 0;
+            for (int dz = ((dx == 0 && dy == 0) ? 1 : -R); dz <= R; ++dz) {
+                const int az = cz + dz;
+                // cell-level part, ONCE per cell of the warp (its first core lane): does the neighbour hold a core point, and
+                // is it in this cell's set already?  Every core point of a cell is in the set of the cell's representative
+                // (step a), so the answer is the same for all of them -- and the find()s it takes are volatile loads that go
+                // to L2: per point they were most of the kernel's memory traffic (62 offsets x 1 M points)
+                int jf = 0, b1 = 0, c_need = 0;
+                if (is_leader && okxy && az >= 0 && az < G.g[2]) {
+                    const int nc = col + az;
+                    const int rep = crep[nc];
+                    if (rep < kNoRep) {
+                        myroot = uf_find(parent, myroot);
+                        if (uf_find(parent, rep) != myroot) {
+                            c_need = 1;
+                            jf = (int)cell_start[nc];
+                            b1 = (int)cell_start[nc + 1];
+                        }
+                    }
+                }
+                c_need = __shfl_sync(0xffffffffu, c_need, leader);
+                jf = __shfl_sync(0xffffffffu, jf, leader);
+                b1 = __shfl_sync(0xffffffffu, b1, leader);
+                // point-level part: the box of that cell must reach into this point's eps ball
+                const bool need = active && c_need && !(ddxy + slab(z, loz, dz) > lim);
                 // merge on a pair that is certainly within eps; pairs inside the band are used only if no certain
                 // pair exists, and then count against the certificate (as do near misses)
                 int hit = -1, maybe = -1;
                 unsigned miss = 0;
-                // kAhead (four) candidates are loaded before the first is judged: the scan is one dependent L2 round trip per
-                // iteration otherwise (measured per thread: ~1000 clocks per candidate, and threads that scan one or
-                // two thousand candidates of heavy cells are the kernel's 0.5 ms tail).  Judged in index order, so
-                // the decisions are the ones of the plain loop.
-                for (int j0 = jf; j0 < (int)b1 && hit < 0; j0 += kAhead) {
-                    uint8_t cf[kAhead];
-                    double qx[kAhead], qy[kAhead], qz[kAhead];
-#pragma unroll
-                    for (int k = 0; k < kAhead; ++k) {
-                        const int j = j0 + k < (int)b1 ? j0 + k : (int)b1 - 1;
-                        cf[k] = core_s[j];
-                        qx[k] = sx[j]; qy[k] = sy[j]; qz[k] = sz[j];
+                const bool heavy = need && (b1 - jf) >= kDbTeamScan;
+                unsigned req = __ballot_sync(0xffffffffu, heavy);
+                while (req) {
+                    const int L = __ffs(req) - 1;
+                    req &= req - 1;
+                    const double qx = __shfl_sync(0xffffffffu, x, L), qy = __shfl_sync(0xffffffffu, y, L), qz = __shfl_sync(0xffffffffu, z, L);
+                    const int f0 = __shfl_sync(0xffffffffu, jf, L), f1 = __shfl_sync(0xffffffffu, b1, L);
+                    int t_hit = -1, t_maybe = -1;
+                    unsigned t_miss = 0;
+                    for (int j0 = f0; j0 < f1 && t_hit < 0; j0 += 32) {
+                        const int j = j0 + (int)lane;
+                        bool certain = false, in_band_in = false, in_band_out = false;
+                        if (j < f1 && core_s[j]) {
+                            const double r = rdist_of(qx, qy, qz, sx[j], sy[j], sz[j]);
+                            if (tol > 0.0 && fabs(r - eps2) <= tol) { in_band_in = r <= eps2; in_band_out = !in_band_in; }
+                            else certain = r <= eps2;
+                        }
+                        const unsigned hm = __ballot_sync(0xffffffffu, certain);
+                        if (tol > 0.0) {
+                            // only candidates BEFORE the first certain pair count, as in the serial scan
+                            const unsigned before = hm ? ((1u << (__ffs(hm) - 1)) - 1u) : 0xffffffffu;
+                            const unsigned mb = __ballot_sync(0xffffffffu, in_band_in) & before;
+                            t_miss += __popc(__ballot_sync(0xffffffffu, in_band_out) & before);
+                            if (mb) t_maybe = j0 + 31 - __clz((int)mb);
+                        }
+                        if (hm) t_hit = j0 + __ffs(hm) - 1;
                     }
-#pragma unroll
-                    for (int k = 0; k < kAhead; ++k) {
-                        if (j0 + k >= (int)b1 || !cf[k] || hit >= 0) continue;
-                        const double r = rdist_of(x, y, z, qx[k], qy[k], qz[k]);
-                        if (tol > 0.0 && fabs(r - eps2) <= tol) {
-                            if (r <= eps2) maybe = j0 + k; else ++miss;
-                        } else if (r <= eps2) hit = j0 + k;
+                    if ((int)lane == L) { hit = t_hit; maybe = t_maybe; miss = t_miss; }
+                }
+                if (need && !heavy) {
+                    // kAhead (four) candidates are loaded before the first is judged: the scan is one dependent L2 round trip per
+                    // iteration otherwise.  Judged in index order, so the decisions are the ones of the plain loop.
+                    for (int j0 = jf; j0 < b1 && hit < 0; j0 += kAhead) {
+                        uint8_t cf[kAhead];
+                        double qx[kAhead], qy[kAhead], qz[kAhead];
+        #pragma unroll
+                        for (int k = 0; k < kAhead; ++k) {
+                            const int j = j0 + k < b1 ? j0 + k : b1 - 1;
+                            cf[k] = core_s[j];
+                            qx[k] = sx[j]; qy[k] = sy[j]; qz[k] = sz[j];
+                        }
+        #pragma unroll
+                        for (int k = 0; k < kAhead; ++k) {
+                            if (j0 + k >= b1 || !cf[k] || hit >= 0) continue;
+                            const double r = rdist_of(x, y, z, qx[k], qy[k], qz[k]);
+                            if (tol > 0.0 && fabs(r - eps2) <= tol) {
+                                if (r <= eps2) maybe = j0 + k; else ++miss;
+                            } else if (r <= eps2) hit = j0 + k;
+                        }
                     }
                 }
-                if (hit >= 0) uf_union(parent, oi, sidx[hit]);
-                else {
-                    if (maybe >= 0) { uf_union(parent, oi, sidx[maybe]); ++band; }
-                    band += miss;
+                if (need) {
+                    if (hit >= 0) uf_union(parent, oi, sidx[hit]);
+                    else {
+                        if (maybe >= 0) { uf_union(parent, oi, sidx[maybe]); ++band; }
+                        band += miss;
+                    }
                 }
             }
         }
+    }
     if (band) atomicAdd(guard, (unsigned long long)band);
 }
 
