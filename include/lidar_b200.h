@@ -591,6 +591,8 @@ int lidar_nccl_allreduce(void* comm, void* d_buf, int64_t count, int op, void* s
  *       the calling thread's affinity mask / 2)).
  *   lidar_host_memcpy           memcpy split over the worker pool: pageable numpy <-> page-locked staging at
  *       the memory system's rate instead of one core's.
+ *   lidar_host_copy_nontemporal 1: slices of 256 KB and more are written with non-temporal stores (no
+ *       read-for-ownership of staging memory the CPU never reads back); 0: plain memcpy.
  *   lidar_copy_async            the DMA leg between page-locked staging and the device.
  * ------------------------------------------------------------------------------------------- */
 int lidar_bind_to_device_numa(int device, int* node_out, int* ncpus_out);
@@ -598,6 +600,7 @@ int lidar_host_alloc(size_t bytes, void** h_ptr_out);
 int lidar_host_free(void* h_ptr);
 int lidar_host_copy_threads(int threads);
 int lidar_host_memcpy(void* dst, const void* src, size_t bytes);
+int lidar_host_copy_nontemporal(int on);
 /* several copies as ONE job for the pool (the arrays of a frame's result): the segments are treated as one byte range
  * and cut into equal slices, so the workers are woken once.  count <= 64. */
 int lidar_host_memcpy_batch(int count, void* const* dst, const void* const* src, const size_t* bytes);

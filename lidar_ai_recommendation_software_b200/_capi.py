@@ -208,6 +208,7 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_host_alloc": (_i32, [_sz, C.POINTER(C.c_void_p)]),
     "lidar_host_free": (_i32, [_vp]),
     "lidar_host_copy_threads": (_i32, [_i32]),
+    "lidar_host_copy_nontemporal": (_i32, [_i32]),
     "lidar_host_memcpy": (_i32, [_vp, _vp, _sz]),
     "lidar_host_memcpy_batch": (_i32, [_i32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "lidar_host_copy_wake": (_i32, []),

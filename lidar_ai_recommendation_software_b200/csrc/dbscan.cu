@@ -228,6 +228,23 @@ __device__ __forceinline__ int uf_find(int* parent, int x) {
     }
     return x;
 }
+// find() for a set-membership QUESTION (not for linking): the walk runs on ordinary cached loads.  A stale L1 copy of a
+// parent pointer is still an ancestor of the node -- links are only ever replaced by links closer to the root, roots are
+// only ever hung under other roots -- so a stale walk ends at an ancestor, and the coherent find() that finishes the job
+// starts from there.
+__device__ __forceinline__ int ld_cached(const int* p) {
+    int v;
+    asm volatile("ld.global.ca.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int uf_find_cached(int* parent, int x) {
+    int p = ld_cached(parent + x);
+    while (p != x) {
+        x = p;
+        p = ld_cached(parent + x);
+    }
+    return uf_find(parent, x);
+}
 __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
     while (true) {
         a = uf_find(parent, a);
@@ -275,8 +292,8 @@ db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const
                const int* __restrict__ sidx, const double* __restrict__ sx, const double* __restrict__ sy,
                const double* __restrict__ sz, double eps2, double tol, const uint8_t* __restrict__ core_s,
                int* __restrict__ parent, unsigned long long* __restrict__ guard, const int* __restrict__ crep) {
-    // Every lane walks the SAME list of 62 forward cell offsets, so that the warp meets at one point per offset: a lane
-    // that has to search a heavy neighbour cell (hundreds of returns near the sensor of a ring scan) does not scan it
+    // Every lane walks the SAME list of forward cell offsets (the union of the occupied forward cells of the warp's
+    // cells), so that the warp meets at one point per offset: a lane that has to search a heavy neighbour cell (hundreds of returns near the sensor of a ring scan) does not scan it
     // alone while its 31 neighbours idle -- measured on a 128-beam frame: 2 871 heavy cell pairs never merge (two people
     // 0.31 m apart), the worst holds 770 x 619 returns, a handful of points of A survive the box test and each walked all
     // of B: 2 000 dependent candidates per thread were the kernel's 0.5 ms tail -- the warp takes the requests one by one
@@ -304,10 +321,10 @@ db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const
     const int t = c / G.g[2];
     const int cy = t % G.g[1];
     const int cx = t / G.g[1];
-    const int R = G.reach;                       // 2 on this grid
+    constexpr int R = 2, W = 2 * R + 1;           // the dense grid's reach (make_grid); the host checks G.reach == R
+    constexpr int kFwd = (W * W * W) / 2;         // 62 forward cells: (dx, dy, dz) > (0, 0, 0) lexicographically
     // squared distance from the point to the slab of cells at offset d along one axis (0 inside the own slab), shrunk
-    // like cell_box_dist2: the box distance of a neighbour cell is the sum of three of these -- hoisted out of the
-    // inner loops, the test costs two additions per cell instead of a dozen fp64 operations
+    // like cell_box_dist2: the box distance of a neighbour cell is the sum of three of these
     auto slab = [&](double p, double lo_own, int d) {
         const double lo = lo_own + d * G.cell;
         const double gap = fmax(0.0, fmax(lo - p, p - (lo + G.cell)));
@@ -315,101 +332,123 @@ db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const
     };
     const double lox = G.min[0] + cx * G.cell, loy = G.min[1] + cy * G.cell, loz = G.min[2] + cz * G.cell;
     const double lim = (eps2 + tol + 1e-300) / (1.0 - 1e-9);        // d2 * (1 - 1e-9) - 1e-300 > eps2 + tol  <=>  d2 > lim
-    for (int dx = 0; dx <= R; ++dx) {                                // forward cells: (dx, dy, dz) > (0, 0, 0) lexicographically
-        const int ax = cx + dx;
-        const bool okx = active && ax < G.g[0];
-        const double ddx = slab(x, lox, dx);
-        for (int dy = (dx == 0 ? 0 : -R); dy <= R; ++dy) {
-            const int ay = cy + dy;
-            const bool okxy = okx && ay >= 0 && ay < G.g[1];
-            const double ddxy = ddx + slab(y, loy, dy);
-            const int col = okxy ? cell_id(G, ax, ay, 0) : 0;
-            for (int dz = ((dx == 0 && dy == 0) ? 1 : -R); dz <= R; ++dz) {
-                const int az = cz + dz;
-                // cell-level part, ONCE per cell of the warp (its first core lane): does the neighbour hold a core point, and
-                // is it in this cell's set already?  Every core point of a cell is in the set of the cell's representative
-                // (step a), so the answer is the same for all of them -- and the find()s it takes are volatile loads that go
-                // to L2: per point they were most of the kernel's memory traffic (62 offsets x 1 M points)
-                int jf = 0, b1 = 0, c_need = 0;
-                if (is_leader && okxy && az >= 0 && az < G.g[2]) {
-                    const int nc = col + az;
-                    const int rep = crep[nc];
-                    if (rep < kNoRep) {
-                        myroot = uf_find(parent, myroot);
-                        if (uf_find(parent, rep) != myroot) {
-                            c_need = 1;
-                            jf = (int)cell_start[nc];
-                            b1 = (int)cell_start[nc + 1];
-                        }
-                    }
+    // (b0) which of the 62 forward cells hold a core point at all: the first core lane of every cell of the warp looks
+    //      ONCE (returns lie on surfaces: most of the 5 x 5 x 5 half-neighbourhood is empty), and the warp then walks the
+    //      union of these masks instead of all 62 offsets -- every step of that walk costs the whole warp a round of
+    //      shuffles and votes whether or not any lane has work in it
+    unsigned long long occ = 0;
+    if (is_leader) {
+        int k = 0;
+        for (int dx = 0; dx <= R; ++dx)
+            for (int dy = (dx == 0 ? 0 : -R); dy <= R; ++dy) {
+                const int ax = cx + dx, ay = cy + dy;
+                const bool okxy = ax < G.g[0] && ay >= 0 && ay < G.g[1];
+                const int col = okxy ? cell_id(G, ax, ay, 0) : 0;
+                for (int dz = ((dx == 0 && dy == 0) ? 1 : -R); dz <= R; ++dz, ++k) {
+                    const int az = cz + dz;
+                    if (okxy && az >= 0 && az < G.g[2] && crep[col + az] < kNoRep) occ |= 1ull << k;
                 }
-                c_need = __shfl_sync(0xffffffffu, c_need, leader);
-                jf = __shfl_sync(0xffffffffu, jf, leader);
-                b1 = __shfl_sync(0xffffffffu, b1, leader);
-                // point-level part: the box of that cell must reach into this point's eps ball
-                const bool need = active && c_need && !(ddxy + slab(z, loz, dz) > lim);
-                // merge on a pair that is certainly within eps; pairs inside the band are used only if no certain
-                // pair exists, and then count against the certificate (as do near misses)
-                int hit = -1, maybe = -1;
-                unsigned miss = 0;
-                const bool heavy = need && (b1 - jf) >= kDbTeamScan;
-                unsigned req = __ballot_sync(0xffffffffu, heavy);
-                while (req) {
-                    const int L = __ffs(req) - 1;
-                    req &= req - 1;
-                    const double qx = __shfl_sync(0xffffffffu, x, L), qy = __shfl_sync(0xffffffffu, y, L), qz = __shfl_sync(0xffffffffu, z, L);
-                    const int f0 = __shfl_sync(0xffffffffu, jf, L), f1 = __shfl_sync(0xffffffffu, b1, L);
-                    int t_hit = -1, t_maybe = -1;
-                    unsigned t_miss = 0;
-                    for (int j0 = f0; j0 < f1 && t_hit < 0; j0 += 32) {
-                        const int j = j0 + (int)lane;
-                        bool certain = false, in_band_in = false, in_band_out = false;
-                        if (j < f1 && core_s[j]) {
-                            const double r = rdist_of(qx, qy, qz, sx[j], sy[j], sz[j]);
-                            if (tol > 0.0 && fabs(r - eps2) <= tol) { in_band_in = r <= eps2; in_band_out = !in_band_in; }
-                            else certain = r <= eps2;
-                        }
-                        const unsigned hm = __ballot_sync(0xffffffffu, certain);
-                        if (tol > 0.0) {
-                            // only candidates BEFORE the first certain pair count, as in the serial scan
-                            const unsigned before = hm ? ((1u << (__ffs(hm) - 1)) - 1u) : 0xffffffffu;
-                            const unsigned mb = __ballot_sync(0xffffffffu, in_band_in) & before;
-                            t_miss += __popc(__ballot_sync(0xffffffffu, in_band_out) & before);
-                            if (mb) t_maybe = j0 + 31 - __clz((int)mb);
-                        }
-                        if (hm) t_hit = j0 + __ffs(hm) - 1;
-                    }
-                    if ((int)lane == L) { hit = t_hit; maybe = t_maybe; miss = t_miss; }
+            }
+    }
+    unsigned long long todo = ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned)(occ >> 32)) << 32) |
+                              __reduce_or_sync(0xffffffffu, (unsigned)occ);
+    while (todo) {
+        const int k = __ffsll((long long)todo) - 1;                  // ascending k = the lexicographic order of the plain loops
+        todo &= todo - 1;
+        const int Lc = kFwd + 1 + k;                                 // linear index inside the 5 x 5 x 5 cube (centre = 62)
+        const int dx = Lc / (W * W) - R, dy = (Lc / W) % W - R, dz = Lc % W - R;
+        // cell-level part, ONCE per cell of the warp (its first core lane): is the neighbour in this cell's set already?
+        // Every core point of a cell is in the set of the cell's representative (step a), so the answer is the same for
+        // all of them -- and the find()s it takes are volatile loads that go to L2
+        int jf = 0, b1 = 0, c_need = 0;
+        if (is_leader && ((occ >> k) & 1ull)) {
+            const int nc = cell_id(G, cx + dx, cy + dy, cz + dz);
+            // a root that equals the remembered root of this cell's set answers "same set" even if the remembered value
+            // is old (sets only grow); a mismatch may just mean it IS old: refresh and compare again
+            const int nroot = uf_find_cached(parent, crep[nc]);
+            if (nroot != myroot) myroot = uf_find(parent, myroot);
+            if (nroot != myroot) {
+                c_need = 1;
+                jf = (int)cell_start[nc];
+                b1 = (int)cell_start[nc + 1];
+            }
+        }
+        c_need = __shfl_sync(0xffffffffu, c_need, leader);
+        if (!__any_sync(0xffffffffu, c_need)) continue;
+        jf = __shfl_sync(0xffffffffu, jf, leader);
+        b1 = __shfl_sync(0xffffffffu, b1, leader);
+        // point-level part: the box of that cell must reach into this point's eps ball
+        const bool need = active && c_need && !(slab(x, lox, dx) + slab(y, loy, dy) + slab(z, loz, dz) > lim);
+        // ONE pair that is certainly within eps merges the two cells, whichever lane of the cell's group finds it: the
+        // group stops at the first.  Pairs inside the band are used only if the group found no certain pair, and then
+        // count against the certificate (as do near misses)
+        int hit = -1, maybe = -1;
+        unsigned miss = 0;
+        const bool heavy = need && (b1 - jf) >= kDbTeamScan;         // the same for every lane of a group
+        unsigned req = __ballot_sync(0xffffffffu, heavy);
+        while (req) {
+            const int L = __ffs(req) - 1;
+            req &= req - 1;
+            const double qx = __shfl_sync(0xffffffffu, x, L), qy = __shfl_sync(0xffffffffu, y, L), qz = __shfl_sync(0xffffffffu, z, L);
+            const int f0 = __shfl_sync(0xffffffffu, jf, L), f1 = __shfl_sync(0xffffffffu, b1, L);
+            const unsigned group = __shfl_sync(0xffffffffu, peers, L);
+            int t_hit = -1, t_maybe = -1;
+            unsigned t_miss = 0;
+            for (int j0 = f0; j0 < f1 && t_hit < 0; j0 += 32) {
+                const int j = j0 + (int)lane;
+                bool certain = false, in_band_in = false, in_band_out = false;
+                if (j < f1 && core_s[j]) {
+                    const double r = rdist_of(qx, qy, qz, sx[j], sy[j], sz[j]);
+                    if (tol > 0.0 && fabs(r - eps2) <= tol) { in_band_in = r <= eps2; in_band_out = !in_band_in; }
+                    else certain = r <= eps2;
                 }
-                if (need && !heavy) {
-                    // kAhead (four) candidates are loaded before the first is judged: the scan is one dependent L2 round trip per
-                    // iteration otherwise.  Judged in index order, so the decisions are the ones of the plain loop.
-                    for (int j0 = jf; j0 < b1 && hit < 0; j0 += kAhead) {
-                        uint8_t cf[kAhead];
-                        double qx[kAhead], qy[kAhead], qz[kAhead];
-        #pragma unroll
-                        for (int k = 0; k < kAhead; ++k) {
-                            const int j = j0 + k < b1 ? j0 + k : b1 - 1;
-                            cf[k] = core_s[j];
-                            qx[k] = sx[j]; qy[k] = sy[j]; qz[k] = sz[j];
-                        }
-        #pragma unroll
-                        for (int k = 0; k < kAhead; ++k) {
-                            if (j0 + k >= b1 || !cf[k] || hit >= 0) continue;
-                            const double r = rdist_of(x, y, z, qx[k], qy[k], qz[k]);
-                            if (tol > 0.0 && fabs(r - eps2) <= tol) {
-                                if (r <= eps2) maybe = j0 + k; else ++miss;
-                            } else if (r <= eps2) hit = j0 + k;
-                        }
-                    }
+                const unsigned hm = __ballot_sync(0xffffffffu, certain);
+                if (tol > 0.0) {
+                    // only candidates BEFORE the first certain pair count, as in the serial scan
+                    const unsigned before = hm ? ((1u << (__ffs(hm) - 1)) - 1u) : 0xffffffffu;
+                    const unsigned mb = __ballot_sync(0xffffffffu, in_band_in) & before;
+                    t_miss += __popc(__ballot_sync(0xffffffffu, in_band_out) & before);
+                    if (mb) t_maybe = j0 + 31 - __clz((int)mb);
                 }
-                if (need) {
-                    if (hit >= 0) uf_union(parent, oi, sidx[hit]);
-                    else {
-                        if (maybe >= 0) { uf_union(parent, oi, sidx[maybe]); ++band; }
-                        band += miss;
-                    }
+                if (hm) t_hit = j0 + __ffs(hm) - 1;
+            }
+            if ((int)lane == L) { hit = t_hit; maybe = t_maybe; miss = t_miss; }
+            if (t_hit >= 0) req &= ~group;                           // the cell pair is merged: its other requests are moot
+        }
+        // light cells: every lane scans for its own point, kAhead (four) candidates loaded before the first is judged (the
+        // scan is one dependent L2 round trip per iteration otherwise), judged in index order; the lanes of a group vote
+        // after every round
+        bool scanning = need && !heavy;
+        int j0 = jf;
+        while (__any_sync(0xffffffffu, scanning)) {
+            if (scanning) {
+                uint8_t cf[kAhead];
+                double qx[kAhead], qy[kAhead], qz[kAhead];
+#pragma unroll
+                for (int q = 0; q < kAhead; ++q) {
+                    const int j = j0 + q < b1 ? j0 + q : b1 - 1;
+                    cf[q] = core_s[j];
+                    qx[q] = sx[j]; qy[q] = sy[j]; qz[q] = sz[j];
                 }
+#pragma unroll
+                for (int q = 0; q < kAhead; ++q) {
+                    if (j0 + q >= b1 || !cf[q] || hit >= 0) continue;
+                    const double r = rdist_of(x, y, z, qx[q], qy[q], qz[q]);
+                    if (tol > 0.0 && fabs(r - eps2) <= tol) {
+                        if (r <= eps2) maybe = j0 + q; else ++miss;
+                    } else if (r <= eps2) hit = j0 + q;
+                }
+                j0 += kAhead;
+            }
+            const unsigned hm = __ballot_sync(0xffffffffu, hit >= 0);
+            if (scanning && ((hm & peers) || j0 >= b1)) scanning = false;
+        }
+        const bool group_hit = (__ballot_sync(0xffffffffu, hit >= 0) & peers) != 0;
+        if (need) {
+            if (hit >= 0) uf_union(parent, oi, sidx[hit]);
+            else if (!group_hit) {
+                if (maybe >= 0) { uf_union(parent, oi, sidx[maybe]); ++band; }
+                band += miss;
             }
         }
     }
@@ -814,6 +853,7 @@ int lidar_dbscan(const double* d_points, int64_t m, double eps, int min_samples,
                                          core_o, guard, crep);
     LIDAR_CHECK_LAUNCH();
     // look-ahead of 4 candidates (56 registers): whole DBSCAN of a 128-beam frame 0.95 -> 0.79 ms; 2: 0.80 ms, 8: 1.02 ms (92 registers)
+    LIDAR_REQUIRE(!G.dense || G.reach == 2, LIDAR_ERR_INVALID, "lidar_dbscan: the dense grid kernels assume reach 2");
     if (G.dense) db_union_dense<4><<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard, crep);
     else db_union<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard);
     LIDAR_CHECK_LAUNCH();
