@@ -237,13 +237,13 @@ __device__ __forceinline__ int ld_cached(const int* p) {
     asm volatile("ld.global.ca.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-__device__ __forceinline__ int uf_find_cached(int* parent, int x) {
+__device__ __forceinline__ int uf_walk_cached(const int* parent, int x) {
     int p = ld_cached(parent + x);
     while (p != x) {
         x = p;
         p = ld_cached(parent + x);
     }
-    return uf_find(parent, x);
+    return x;   // an ancestor of the start node: the root as far as this SM's L1 knows
 }
 __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
     while (true) {
@@ -306,8 +306,13 @@ db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const
     unsigned band = 0;   // decisions of this point that rest on a pair inside the tol band (certificate)
     // (a) the core points of one cell are mutual neighbours: link to the cell's representative
     if (active) {
+        // rep <= oi, and oi is usually still its own root: ONE atomic hangs it under the representative; if somebody linked
+        // oi elsewhere first, that other parent and the representative are united the long way
         const int rep = crep[c];
-        if (rep != oi) uf_union(parent, oi, rep);
+        if (rep != oi) {
+            const int old = atomicMin(&parent[oi], rep);
+            if (old != oi && old != rep) uf_union(parent, old, rep);
+        }
     }
     // lanes of the warp that hold core points of the same cell form a group; its first lane answers for the cell
     const unsigned peers = __match_any_sync(0xffffffffu, active ? c : -1 - (int)lane);
@@ -365,8 +370,16 @@ db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const
             const int nc = cell_id(G, cx + dx, cy + dy, cz + dz);
             // a root that equals the remembered root of this cell's set answers "same set" even if the remembered value
             // is old (sets only grow); a mismatch may just mean it IS old: refresh and compare again
-            const int nroot = uf_find_cached(parent, crep[nc]);
-            if (nroot != myroot) myroot = uf_find(parent, myroot);
+            // -- and the walk may run on stale L1 copies: its end point is an ancestor of the neighbour's representative, so
+            // meeting the remembered root proves "same set" without one coherent load.  Anything else is settled in L2, and
+            // the true root is written into the walked node (path compression; the store also drops the stale L1 line)
+            const int nrep = crep[nc];
+            int nroot = uf_walk_cached(parent, nrep);
+            if (nroot != myroot) {
+                nroot = uf_find(parent, nroot);
+                if (nroot != nrep && ((volatile int*)parent)[nrep] != nrep) parent[nrep] = nroot;
+                myroot = uf_find(parent, myroot);
+            }
             if (nroot != myroot) {
                 c_need = 1;
                 jf = (int)cell_start[nc];
