@@ -101,11 +101,38 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(unsigned taddr, unsigned (&r)
         : "r"(taddr) : "memory");
 }
 
+// Packed fp32 arithmetic of sm_100 (add / sub / fma .f32x2 on a 64-bit register pair, SASS FADD2 / FFMA2): two IEEE
+// operations per issue slot, each rounded exactly like the scalar instruction -- this kernel is bound by issue slots.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // x = hi + lo with hi = bf16(x), lo = bf16(x - hi), two values per instruction: cvt.rn.bf16x2.f32 (F2FP, a
 // full-rate ALU op; the scalar F2F conversion runs at a quarter of that and was 21 % of the kernel's stall samples)
 __device__ __forceinline__ void split_pair(float a, float b, unsigned& hi, unsigned& lo) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));           // low half <- a, high half <- b
-    const float ra = __fsub_rn(a, __uint_as_float(hi << 16)), rb = __fsub_rn(b, __uint_as_float(hi & 0xffff0000u));
+    float ra, rb;
+    unpack2(sub2(pack2(a, b), pack2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u))), ra, rb);
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 // split 8 fp32 values into bf16 hi / lo and store them as one 16-byte K chunk each
@@ -141,7 +168,6 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
                      const float* __restrict__ B3, float* __restrict__ out) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float* sW1 = reinterpret_cast<float*>(smem + kOffW1);
-    float* sB1 = reinterpret_cast<float*>(smem + kOffB1);
     float* sB2 = reinterpret_cast<float*>(smem + kOffB2);
     float* sB3 = reinterpret_cast<float*>(smem + kOffB3);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + kOffBar);
@@ -154,8 +180,12 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
     // ---- one-time setup: weights, barrier, TMEM ------------------------------------------------
     stage_weights(W2, kC2, smem + kOffW2h, smem + kOffW2l);
     stage_weights(W3, kC3, smem + kOffW3h, smem + kOffW3l);
-    for (int i = threadIdx.x; i < kC1 * 3; i += kTcThreads) sW1[i] = W1[i];
-    for (int i = threadIdx.x; i < kC1; i += kTcThreads) sB1[i] = B1[i];
+    // layer 1 as channel PAIRS for the packed FMA: {w0(o), w0(o+1), w1(o), w1(o+1), w2(o), w2(o+1), b(o), b(o+1)}, o = 2p
+    // (two 16-byte shared loads per pair instead of eight scalar ones; kOffW1 .. kOffB2 is one 1 KB block)
+    for (int i = threadIdx.x; i < kC1 * 4; i += kTcThreads) {
+        const int pr = i >> 3, e = i & 7, o = 2 * pr + (e & 1), w = e >> 1;
+        sW1[i] = w < 3 ? W1[o * 3 + w] : B1[o];
+    }
     for (int i = threadIdx.x; i < kC2; i += kTcThreads) sB2[i] = B2[i];
     for (int i = threadIdx.x; i < kC3; i += kTcThreads) sB3[i] = B3[i];
     if (threadIdx.x == 0) {
@@ -184,19 +214,33 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
         const int c_ = t * 4 + qwarp;
         return (t < n_tiles && c_ < n_centres) ? __ldg(idx + (size_t)c_ * kTcK + lane) : -1;
     };
-    auto load_point = [&](int t, int src, float& a0, float& a1, float& a2) {
-        const int c_ = t * 4 + qwarp;
+    // centre -> (batch, centre inside the batch) without a division per tile: the centres a warp visits advance by a fixed
+    // step (the emulated 32-bit divisions were 6 % of the kernel's instructions)
+    const int cstep = 4 * (int)gridDim.x;
+    auto advance = [&](int& b_, int& mm_) {
+        mm_ += cstep;
+        if (cstep < 8 * m) {
+            while (mm_ >= m) { mm_ -= m; ++b_; }
+        } else {
+            b_ += mm_ / m;
+            mm_ %= m;
+        }
+    };
+    const int c_first = (int)blockIdx.x * 4 + qwarp;
+    int lp_b = c_first / m, lp_mm = c_first % m;                 // of the next tile load_point is asked for
+    int ep_b = lp_b, ep_mm = lp_mm;                              // of the next tile epilogue3 is asked for
+    auto load_point = [&](int src, float& a0, float& a1, float& a2) {   // tiles in visiting order, one call per tile
         a0 = a1 = a2 = 0.f;
         if (src >= 0) {
-            const int b_ = c_ / m;
-            const float* p = xyz + ((size_t)b_ * n + src) * 3;
-            const float* c = new_xyz + (size_t)c_ * 3;
+            const float* p = xyz + ((size_t)lp_b * n + src) * 3;
+            const float* c = new_xyz + ((size_t)lp_b * m + lp_mm) * 3;
             a0 = __fsub_rn(__ldg(p), __ldg(c)); a1 = __fsub_rn(__ldg(p + 1), __ldg(c + 1)); a2 = __fsub_rn(__ldg(p + 2), __ldg(c + 2));
         }
+        advance(lp_b, lp_mm);
     };
     const int tstep = gridDim.x;
     float n0, n1, n2;
-    load_point(blockIdx.x, load_index(blockIdx.x), n0, n1, n2);
+    load_point(load_index(blockIdx.x), n0, n1, n2);
     int next_src = load_index(blockIdx.x + tstep);
     const int row = threadIdx.x & 127;
     constexpr int kHalf1 = kC1 / 2;           // channels of layer 1 per thread
@@ -204,14 +248,19 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
     // layer 1 of a tile on the CUDA cores (this thread's half of the channels), result kept in registers: the A buffer
     // may still feed the tensor core
     auto layer1 = [&](float g0, float g1, float g2, float (&h)[kHalf1]) {
+        const unsigned long long G0 = pack2(g0, g0), G1 = pack2(g1, g1), G2 = pack2(g2, g2);
+        const float4* wp = reinterpret_cast<const float4*>(sW1) + half * kHalf1;     // two float4 per channel pair
 #pragma unroll
-        for (int i = 0; i < kHalf1; ++i) {
-            const int o = half * kHalf1 + i;
-            float a = sB1[o];
-            a = fmaf(sW1[o * 3], g0, a);
-            a = fmaf(sW1[o * 3 + 1], g1, a);
-            a = fmaf(sW1[o * 3 + 2], g2, a);
-            h[i] = fmaxf(a, 0.f);
+        for (int i = 0; i < kHalf1 / 2; ++i) {
+            const float4 wa = wp[2 * i], wb = wp[2 * i + 1];
+            unsigned long long acc = pack2(wb.z, wb.w);                               // same order as the scalar chain:
+            acc = fma2(pack2(wa.x, wa.y), G0, acc);                                   // b + w0 g0, + w1 g1, + w2 g2
+            acc = fma2(pack2(wa.z, wa.w), G1, acc);
+            acc = fma2(pack2(wb.x, wb.y), G2, acc);
+            float a0, a1;
+            unpack2(acc, a0, a1);
+            h[2 * i] = fmaxf(a0, 0.f);
+            h[2 * i + 1] = fmaxf(a1, 0.f);
         }
     };
     auto write_a = [&](const float (&h)[kHalf1]) {
@@ -250,11 +299,12 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
     // t/4, t/4+8 of each 16-lane half; columns 2(t%4), 2(t%4)+1 -- the mma accumulator fragment layout, checked on the
     // device with profiles/tools/tmem_map.cu): three in-thread FMNMX per column, then a reduce-scatter butterfly over
     // the 8 threads that share t%4 (7 shuffles per 32 columns) instead of one REDUX per column and lane.
-    auto epilogue3 = [&](int centre) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    const int colsel = 8 * (2 * (int)b4 + (int)b3) + 2 * (int)(lane & 3) + (int)b2;
+    auto epilogue3 = [&](int centre) {                           // tiles in visiting order, one call per tile
         const bool live = centre < n_centres;
-        const int b = live ? centre / m : 0, mm = live ? centre % m : 0;
-        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-        const int colsel = 8 * (2 * (int)b4 + (int)b3) + 2 * (int)(lane & 3) + (int)b2;
+        float* const obase = out + (size_t)ep_b * kC3 * m + ep_mm;
+        advance(ep_b, ep_mm);
         unsigned ra[2][16], rc[2][16];
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {                          // this warp's half of the 128 channels: four loads in flight
@@ -290,7 +340,7 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
             const float mine = b2 ? w2[1] : w2[0], send = b2 ? w2[0] : w2[1];
             const float top = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 4));
             const int col = chunk * 32 + colsel;
-            if (live) out[((size_t)b * kC3 + col) * m + mm] = fmaxf(top + sB3[col], 0.f);
+            if (live) obase[(size_t)col * m] = fmaxf(top + sB3[col], 0.f);
         }
     };
 
@@ -303,7 +353,7 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
         layer1(n0, n1, n2, h);
         const int src1 = next_src;
         next_src = load_index(tile + 2 * tstep);
-        load_point(tile + tstep, src1, n0, n1, n2);
+        load_point(src1, n0, n1, n2);
         write_a(h);
         publish_a();
         issue(kOffW2h, kOffW2l, tmem_base, idesc2);
@@ -326,9 +376,17 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
 #pragma unroll
                 for (int hlf = 0; hlf < 2; ++hlf) {
                     float x[8];
+                    const float4* bp = reinterpret_cast<const float4*>(sB2 + q * 16 + hlf * 8);
+                    const float4 ba = bp[0], bb = bp[1];
+                    const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        x[i] = fmaxf(__uint_as_float(qq ? r1[hlf * 8 + i] : r0[hlf * 8 + i]) + sB2[q * 16 + hlf * 8 + i], 0.f);
+                    for (int i = 0; i < 8; i += 2) {
+                        const unsigned u0 = qq ? r1[hlf * 8 + i] : r0[hlf * 8 + i], u1 = qq ? r1[hlf * 8 + i + 1] : r0[hlf * 8 + i + 1];
+                        float s0, s1;
+                        unpack2(add2(pack2(__uint_as_float(u0), __uint_as_float(u1)), pack2(bias[i], bias[i + 1])), s0, s1);
+                        x[i] = fmaxf(s0, 0.f);
+                        x[i + 1] = fmaxf(s1, 0.f);
+                    }
                     store_chunk(smem, row, q * 2 + hlf, x);
                 }
             }
@@ -343,7 +401,7 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
             layer1(n0, n1, n2, h);
             const int src1 = next_src;
             next_src = load_index(tile + 3 * tstep);
-            load_point(tile + 2 * tstep, src1, n0, n1, n2);
+            load_point(src1, n0, n1, n2);
         }
         bar_wait(bar, phase);                                    // layer 3 done: the A buffer is free, D3 is complete
         phase ^= 1;

@@ -2,7 +2,7 @@ import sys, time, numpy as np
 sys.path.insert(0, '.')
 from lidar_ai_recommendation_software_b200 import synth
 from scipy.spatial import cKDTree
-f = synth.ring_sequence_frame(1)
+f = synth.ring_sequence_frame(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 p = f[:, :3].astype(np.float64)
 m0 = (np.abs(p - p.mean(0)) < 3 * p.std(0)).all(1); p = p[m0]
 thr = np.percentile(p[:, 2], 30); ng = p[p[:, 2] > thr]
