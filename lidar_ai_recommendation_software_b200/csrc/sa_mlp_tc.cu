@@ -172,6 +172,7 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
     float* sB3 = reinterpret_cast<float*>(smem + kOffB3);
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + kOffBar);
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + kOffBar + 8);
+    unsigned* arrive_cnt = reinterpret_cast<unsigned*>(smem + kOffBar + 12);
     const int warp = threadIdx.x >> 5;
     const int qwarp = warp & 3;               // TMEM lane quarter = centre of the tile
     const int half = threadIdx.x >> 7;        // which half of the channels this thread works on
@@ -189,6 +190,7 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
     for (int i = threadIdx.x; i < kC2; i += kTcThreads) sB2[i] = B2[i];
     for (int i = threadIdx.x; i < kC3; i += kTcThreads) sB3[i] = B3[i];
     if (threadIdx.x == 0) {
+        *arrive_cnt = 0u;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_addr(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -229,18 +231,22 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
     const int c_first = (int)blockIdx.x * 4 + qwarp;
     int lp_b = c_first / m, lp_mm = c_first % m;                 // of the next tile load_point is asked for
     int ep_b = lp_b, ep_mm = lp_mm;                              // of the next tile epilogue3 is asked for
-    auto load_point = [&](int src, float& a0, float& a1, float& a2) {   // tiles in visiting order, one call per tile
-        a0 = a1 = a2 = 0.f;
+    // (the subtraction neighbour - centre is left to the consumer one phase later: done here, the FADD would sit on the
+    // loads' scoreboard and hold up everything behind it -- 7.6 % of the stall samples of the previous version)
+    auto load_point = [&](int src, float (&g)[6]) {              // tiles in visiting order, one call per tile
+#pragma unroll
+        for (int i = 0; i < 6; ++i) g[i] = 0.f;
         if (src >= 0) {
             const float* p = xyz + ((size_t)lp_b * n + src) * 3;
             const float* c = new_xyz + ((size_t)lp_b * m + lp_mm) * 3;
-            a0 = __fsub_rn(__ldg(p), __ldg(c)); a1 = __fsub_rn(__ldg(p + 1), __ldg(c + 1)); a2 = __fsub_rn(__ldg(p + 2), __ldg(c + 2));
+            g[0] = __ldg(p); g[1] = __ldg(p + 1); g[2] = __ldg(p + 2);
+            g[3] = __ldg(c); g[4] = __ldg(c + 1); g[5] = __ldg(c + 2);
         }
         advance(lp_b, lp_mm);
     };
     const int tstep = gridDim.x;
-    float n0, n1, n2;
-    load_point(load_index(blockIdx.x), n0, n1, n2);
+    float ng[6];
+    load_point(load_index(blockIdx.x), ng);
     int next_src = load_index(blockIdx.x + tstep);
     const int row = threadIdx.x & 127;
     constexpr int kHalf1 = kC1 / 2;           // channels of layer 1 per thread
@@ -272,26 +278,36 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
             store_chunk(smem, row, half * (kHalf1 / 8) + kc, x);
         }
     };
-    auto issue = [&](int w_hi, int w_lo, unsigned tmem_d, unsigned idesc) {   // 12 MMAs: K = 64 in steps of 16, hi*hi + hi*lo + lo*hi
-        if (threadIdx.x == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const unsigned long long ah = umma_desc(sbase + kOffAh + j * 256), al = umma_desc(sbase + kOffAl + j * 256);
-                const unsigned long long wh = umma_desc(sbase + w_hi + j * 256), wl = umma_desc(sbase + w_lo + j * 256);
-                umma_f16(tmem_d, ah, wh, idesc, j > 0);
-                umma_f16(tmem_d, ah, wl, idesc, 1);
-                umma_f16(tmem_d, al, wh, idesc, 1);
-            }
-            umma_commit(bar);
-        }
-    };
-    auto publish_a = [&]() {
+    // Hand-over of a finished A operand to the tensor core WITHOUT a CTA barrier: every warp counts itself in on a shared
+    // counter once its lanes' stores are fenced, and the warp that completes the round issues the MMAs.  Nobody waits for
+    // anybody here -- the data hazards (A still being read, accumulators still being drained) are all covered by the
+    // MMA-completion mbarrier every warp waits on before it touches A or TMEM again -- so the warps drift apart and the
+    // CUDA-core phases of some overlap the tensor-core phases of others (BAR.SYNC and the instruction behind it held
+    // 12 % of the stall samples of the version with __syncthreads + thread 0).
+    unsigned arrive_target = 0;
+    auto publish_and_issue = [&](int w_hi, int w_lo, unsigned tmem_d, unsigned idesc) {
         // generic-proxy smem writes -> visible to the tensor core (async proxy); this thread's TMEM reads are complete
         // (tcgen05.wait::ld) and ordered before the MMAs that overwrite the accumulators
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        __syncwarp();
+        arrive_target += kTcThreads / 32;
+        if (lane == 0) {
+            unsigned before;
+            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(before) : "r"(s_addr(arrive_cnt)) : "memory");
+            if (before + 1 == arrive_target) {                    // 12 MMAs: K = 64 in steps of 16, hi*hi + hi*lo + lo*hi
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned long long ah = umma_desc(sbase + kOffAh + j * 256), al = umma_desc(sbase + kOffAl + j * 256);
+                    const unsigned long long wh = umma_desc(sbase + w_hi + j * 256), wl = umma_desc(sbase + w_lo + j * 256);
+                    umma_f16(tmem_d, ah, wh, idesc, j > 0);
+                    umma_f16(tmem_d, ah, wl, idesc, 1);
+                    umma_f16(tmem_d, al, wh, idesc, 1);
+                }
+                umma_commit(bar);
+            }
+        }
     };
     // epilogue of layer 3 = bias + ReLU + max over the 32 neighbours of a centre, i.e. over the 32 TMEM lanes of this warp.
     // max_j relu(v_j + b) == relu(max_j v_j + b) bit for bit (rounding is monotone), so the maximum is taken on the raw
@@ -350,13 +366,12 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
     int tile = blockIdx.x;
     if (tile < n_tiles) {
         float h[kHalf1];
-        layer1(n0, n1, n2, h);
+        layer1(__fsub_rn(ng[0], ng[3]), __fsub_rn(ng[1], ng[4]), __fsub_rn(ng[2], ng[5]), h);
         const int src1 = next_src;
         next_src = load_index(tile + 2 * tstep);
-        load_point(src1, n0, n1, n2);
+        load_point(src1, ng);
         write_a(h);
-        publish_a();
-        issue(kOffW2h, kOffW2l, tmem_base, idesc2);
+        publish_and_issue(kOffW2h, kOffW2l, tmem_base, idesc2);
     }
     int prev_centre = -1;
     for (; tile < n_tiles; tile += tstep) {
@@ -391,25 +406,23 @@ shared_mlp_tc_kernel(const float* __restrict__ xyz, const int* __restrict__ idx,
                 }
             }
         }
-        publish_a();
-        issue(kOffW3h, kOffW3l, tmem_base + kC2, idesc3);
+        publish_and_issue(kOffW3h, kOffW3l, tmem_base + kC2, idesc3);
         prev_centre = tile * 4 + qwarp;
         // ---- layer 1 of the next tile, under the layer-3 MMAs ---------------------------------------
         const bool more = tile + tstep < n_tiles;
         float h[kHalf1];
         if (more) {
-            layer1(n0, n1, n2, h);
+            layer1(__fsub_rn(ng[0], ng[3]), __fsub_rn(ng[1], ng[4]), __fsub_rn(ng[2], ng[5]), h);
             const int src1 = next_src;
             next_src = load_index(tile + 3 * tstep);
-            load_point(src1, n0, n1, n2);
+            load_point(src1, ng);
         }
         bar_wait(bar, phase);                                    // layer 3 done: the A buffer is free, D3 is complete
         phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (more) {
             write_a(h);
-            publish_a();
-            issue(kOffW2h, kOffW2l, tmem_base, idesc2);
+            publish_and_issue(kOffW2h, kOffW2l, tmem_base, idesc2);
         }
     }
     if (prev_centre >= 0) epilogue3(prev_centre);
