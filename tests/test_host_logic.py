@@ -147,3 +147,27 @@ def test_hotspot_selection_is_upstreams_stable_sort():
         ref = sorted([{"i": int(i), "d": v[i]} for i in cand], key=lambda h: h["d"], reverse=True)[:5]
         top = cand[np.argsort(-v[cand], kind="stable")[:5]]
         assert [h["i"] for h in ref] == [int(i) for i in top]
+
+
+def test_parallel_host_memcpy_both_store_kinds():
+    """lidar_host_memcpy (the staging copy of the host-buffer entries) with plain and with non-temporal stores: every
+    byte arrives, nothing outside the destination range is touched, whatever the alignment of either side.  Host code
+    only -- no device is needed."""
+    from lidar_ai_recommendation_software_b200 import _capi
+    lib = _capi.lib
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, 256, (6 << 20) + 333, dtype=np.uint8)
+    dst = np.zeros(src.size + 256, dtype=np.uint8)
+    try:
+        for nt in (0, 1):
+            assert lib.lidar_host_copy_nontemporal(nt) == 0
+            for threads in (1, 4):
+                assert lib.lidar_host_copy_threads(threads) == 0
+                for d_off, s_off, n in ((0, 0, src.size), (1, 3, src.size - 64), (63, 17, (1 << 20) + 5), (7, 0, 1000), (5, 5, 0)):
+                    dst[:] = 0xEE
+                    assert lib.lidar_host_memcpy(dst.ctypes.data + d_off, src.ctypes.data + s_off, n) == 0
+                    assert np.array_equal(dst[d_off:d_off + n], src[s_off:s_off + n])
+                    assert (dst[:d_off] == 0xEE).all() and (dst[d_off + n:] == 0xEE).all()
+    finally:
+        lib.lidar_host_copy_nontemporal(1)
+        lib.lidar_host_copy_threads(2)
