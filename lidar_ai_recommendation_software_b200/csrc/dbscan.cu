@@ -280,18 +280,57 @@ db_union(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* 
 }
 
 // ---- dense grid ------------------------------------------------------------------------------------
+// Neighbour cells with at least this many returns are scanned by the whole WARP for one point at a time.
+constexpr int kDbTeamScan = 48;
+// Tight bounding box of the points of every such HEAVY cell (fp32, rounded outwards, as order-preserving unsigned keys
+// so that atomicMin / atomicMax build it): slot = (start of the cell's sorted run) / kDbTeamScan -- unique, because a
+// heavy cell's run is at least that long.  A cell of a ring scan near the sensor holds a slice of a person's surface:
+// its points fill a fraction of the cell's box, and two people 0.31 m apart put hundreds of returns into neighbouring
+// cells that never merge.  Against the CELL box most of A survives the distance test and each survivor walks all of B;
+// against B's tight box 70 % of them do not (measured on two ring frames: 285 k -> 82 k warp scans of 32 candidates).
+constexpr int kDbBoxWords = 3;
+__device__ __forceinline__ unsigned f32_okey(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ double f32_okey_inv(unsigned k) {
+    return (double)__uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__global__ void __launch_bounds__(256)
+db_heavy_boxes(int m, const unsigned* __restrict__ cell_start, const int* __restrict__ scell,
+               const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ sz,
+               unsigned* __restrict__ hmin, unsigned* __restrict__ hmax) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = lane_id();
+    const bool in = pos < m;
+    const int c = in ? scell[pos] : 0;
+    const unsigned s0 = in ? cell_start[c] : 0u, s1 = in ? cell_start[c + 1] : 0u;
+    const bool heavy = in && (int)(s1 - s0) >= kDbTeamScan;
+    const unsigned peers = __match_any_sync(0xffffffffu, heavy ? c : -1 - (int)lane);   // sorted by cell: mostly one group
+    if (!heavy) return;
+    const double p[3] = {sx[pos], sy[pos], sz[pos]};
+    const size_t slot = (size_t)(s0 / kDbTeamScan) * kDbBoxWords;
+    const bool first = (int)lane == __ffs(peers) - 1;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const unsigned lo = __reduce_min_sync(peers, f32_okey(__double2float_rd(p[a])));
+        const unsigned hi = __reduce_max_sync(peers, f32_okey(__double2float_ru(p[a])));
+        if (first) {
+            atomicMin(hmin + slot + a, lo);
+            atomicMax(hmax + slot + a, hi);
+        }
+    }
+}
 // The common case of a (point, neighbour cell) visit is "that cell has no core point" or "it is already in my
 // set": both are decided from ONE load of the cell's representative (crep, filled by db_core) plus a find, without
 // touching the cell's start offsets, its core flags or its index list.
-// Neighbour cells with at least this many returns are scanned by the whole WARP for one point at a time.
-constexpr int kDbTeamScan = 48;
-
 template <int kAhead>
 __global__ void __launch_bounds__(kDbThreads)
 db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int* __restrict__ scell,
                const int* __restrict__ sidx, const double* __restrict__ sx, const double* __restrict__ sy,
                const double* __restrict__ sz, double eps2, double tol, const uint8_t* __restrict__ core_s,
-               int* __restrict__ parent, unsigned long long* __restrict__ guard, const int* __restrict__ crep) {
+               int* __restrict__ parent, unsigned long long* __restrict__ guard, const int* __restrict__ crep,
+               const unsigned* __restrict__ hmin, const unsigned* __restrict__ hmax) {
     // Every lane walks the SAME list of forward cell offsets (the union of the occupied forward cells of the warp's
     // cells), so that the warp meets at one point per offset: a lane that has to search a heavy neighbour cell (hundreds of returns near the sensor of a ring scan) does not scan it
     // alone while its 31 neighbours idle -- measured on a 128-beam frame: 2 871 heavy cell pairs never merge (two people
@@ -391,7 +430,18 @@ db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const
         jf = __shfl_sync(0xffffffffu, jf, leader);
         b1 = __shfl_sync(0xffffffffu, b1, leader);
         // point-level part: the box of that cell must reach into this point's eps ball
-        const bool need = active && c_need && !(slab(x, lox, dx) + slab(y, loy, dy) + slab(z, loz, dz) > lim);
+        bool need = active && c_need && !(slab(x, lox, dx) + slab(y, loy, dy) + slab(z, loz, dz) > lim);
+        if (need && (b1 - jf) >= kDbTeamScan) {                      // heavy neighbour: its points' own box (db_heavy_boxes)
+            const size_t slot = (size_t)(jf / kDbTeamScan) * kDbBoxWords;
+            const double p[3] = {x, y, z};
+            double d2 = 0.0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double gap = fmax(0.0, fmax(f32_okey_inv(__ldg(hmin + slot + a)) - p[a], p[a] - f32_okey_inv(__ldg(hmax + slot + a))));
+                d2 += gap * gap;
+            }
+            need = !(d2 > lim);
+        }
         // ONE pair that is certainly within eps merges the two cells, whichever lane of the cell's group finds it: the
         // group stops at the first.  Pairs inside the band are used only if the group found no certain pair, and then
         // count against the certificate (as do near misses)
@@ -407,23 +457,29 @@ db_union_dense(int m, CellGrid G, const unsigned* __restrict__ cell_start, const
             const unsigned group = __shfl_sync(0xffffffffu, peers, L);
             int t_hit = -1, t_maybe = -1;
             unsigned t_miss = 0;
-            for (int j0 = f0; j0 < f1 && t_hit < 0; j0 += 32) {
-                const int j = j0 + (int)lane;
+            // one block of 32 candidates: the first certain pair in index order ends the scan; band pairs before it count
+            auto judge = [&](int jbase, bool has, double cx_, double cy_, double cz_) {
                 bool certain = false, in_band_in = false, in_band_out = false;
-                if (j < f1 && core_s[j]) {
-                    const double r = rdist_of(qx, qy, qz, sx[j], sy[j], sz[j]);
+                if (has) {
+                    const double r = rdist_of(qx, qy, qz, cx_, cy_, cz_);
                     if (tol > 0.0 && fabs(r - eps2) <= tol) { in_band_in = r <= eps2; in_band_out = !in_band_in; }
                     else certain = r <= eps2;
                 }
                 const unsigned hm = __ballot_sync(0xffffffffu, certain);
                 if (tol > 0.0) {
-                    // only candidates BEFORE the first certain pair count, as in the serial scan
                     const unsigned before = hm ? ((1u << (__ffs(hm) - 1)) - 1u) : 0xffffffffu;
                     const unsigned mb = __ballot_sync(0xffffffffu, in_band_in) & before;
                     t_miss += __popc(__ballot_sync(0xffffffffu, in_band_out) & before);
-                    if (mb) t_maybe = j0 + 31 - __clz((int)mb);
+                    if (mb) t_maybe = jbase + 31 - __clz((int)mb);
                 }
-                if (hm) t_hit = j0 + __ffs(hm) - 1;
+                if (hm) t_hit = jbase + __ffs(hm) - 1;
+            };
+            for (int j0 = f0; j0 < f1 && t_hit < 0; j0 += 32) {
+                const int ja = j0 + (int)lane;
+                const bool ha = ja < f1 && core_s[ja];
+                double ax_ = 0, ay_ = 0, az_ = 0;
+                if (ha) { ax_ = sx[ja]; ay_ = sy[ja]; az_ = sz[ja]; }
+                judge(j0, ha, ax_, ay_, az_);
             }
             if ((int)lane == L) { hit = t_hit; maybe = t_maybe; miss = t_miss; }
             if (t_hit >= 0) req &= ~group;                           // the cell pair is merged: its other requests are moot
@@ -623,7 +679,7 @@ db_border(int m, CellGrid G, const unsigned* __restrict__ cell_start, const int*
 
 struct DbLayout {
     size_t off_cell, off_slot, off_count, off_start, off_sidx, off_scell, off_sx, off_sy, off_sz, off_parent,
-        off_core_s, off_core_o, off_isroot, off_rank, off_label_s, off_scan, total;
+        off_core_s, off_core_o, off_isroot, off_rank, off_label_s, off_hbox, off_scan, total;
 };
 static DbLayout db_layout(int64_t m, int64_t ncell) {
     DbLayout L;
@@ -635,6 +691,7 @@ static DbLayout db_layout(int64_t m, int64_t ncell) {
     L.off_sx = take(8 * m); L.off_sy = take(8 * m); L.off_sz = take(8 * m);
     L.off_parent = take(4 * m); L.off_core_s = take(m); L.off_core_o = take(m);
     L.off_isroot = take(4 * (m + 1)); L.off_rank = take(4 * (m + 2)); L.off_label_s = take(4 * m);
+    L.off_hbox = take(2 * kDbBoxWords * sizeof(unsigned) * (size_t)(m / kDbTeamScan + 2));   // tight boxes of the heavy cells
     const int64_t big = m > ncell ? m : ncell;
     L.off_scan = take(scan_workspace_bytes(big + 1));
     L.total = ws_align(o);
@@ -862,12 +919,21 @@ int lidar_dbscan(const double* d_points, int64_t m, double eps, int min_samples,
     // the per-cell counters are dead after the scan: the same array now holds the cells' representatives
     int* crep = reinterpret_cast<int*>(cell_count);
     if (G.dense) LIDAR_CUDA_TRY(cudaMemsetAsync(crep, 0x7f, sizeof(int) * G.ncell, st));
+    const size_t hbox_words = (size_t)kDbBoxWords * (size_t)(m / kDbTeamScan + 2);
+    unsigned* hmin = reinterpret_cast<unsigned*>(ws + L.off_hbox);
+    unsigned* hmax = hmin + hbox_words;
+    if (G.dense) {
+        LIDAR_CUDA_TRY(cudaMemsetAsync(hmin, 0xff, sizeof(unsigned) * hbox_words, st));
+        LIDAR_CUDA_TRY(cudaMemsetAsync(hmax, 0x00, sizeof(unsigned) * hbox_words, st));
+        db_heavy_boxes<<<g256, 256, 0, st>>>(mi, cell_start, scell, sx, sy, sz, hmin, hmax);
+        LIDAR_CHECK_LAUNCH();
+    }
     db_core<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, min_samples, core_s,
                                          core_o, guard, crep);
     LIDAR_CHECK_LAUNCH();
     // look-ahead of 4 candidates (56 registers): whole DBSCAN of a 128-beam frame 0.95 -> 0.79 ms; 2: 0.80 ms, 8: 1.02 ms (92 registers)
     LIDAR_REQUIRE(!G.dense || G.reach == 2, LIDAR_ERR_INVALID, "lidar_dbscan: the dense grid kernels assume reach 2");
-    if (G.dense) db_union_dense<4><<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard, crep);
+    if (G.dense) db_union_dense<4><<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard, crep, hmin, hmax);
     else db_union<<<gdb, kDbThreads, 0, st>>>(mi, G, cell_start, scell, sidx, sx, sy, sz, eps2, tol, core_s, parent, guard);
     LIDAR_CHECK_LAUNCH();
     db_roots<<<g256, 256, 0, st>>>(mi, core_o, parent, is_root);
