@@ -787,7 +787,12 @@ static bool make_grid_radius(const double* mn, const double* mx, double r, CellG
 __global__ void __launch_bounds__(256)
 centroid_accumulate(const double* __restrict__ pts, const long long* __restrict__ labels64,
                     const int* __restrict__ labels32, int64_t n, int n_clusters,
-                    long long* __restrict__ acc /*[C][6]*/, unsigned* __restrict__ cnt) {
+                    long long* __restrict__ acc /*[reps][C][6]*/, unsigned* __restrict__ cnt /*[reps][C]*/, int reps) {
+    // CTA b adds into replica b % reps: a person next to the sensor holds tens of thousands of returns, and every warp
+    // that meets her sends seven atomics to the same two sectors -- with one copy of the accumulators those serialise
+    // in L2 and the kernel waits for them (76 us for 1 M points; the sums are integers, so the fold order is free).
+    acc += (size_t)(blockIdx.x % reps) * (size_t)n_clusters * 6;
+    cnt += (size_t)(blockIdx.x % reps) * (size_t)n_clusters;
     const int64_t n_round = ((n + 31) / 32) * 32;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += step) {
@@ -835,16 +840,24 @@ centroid_accumulate(const double* __restrict__ pts, const long long* __restrict_
 }
 
 __global__ void centroid_finalize(int n_clusters, const long long* __restrict__ acc, const unsigned* __restrict__ cnt,
-                                  double* __restrict__ out /*[C][3]*/, long long* __restrict__ counts) {
+                                  int reps, double* __restrict__ out /*[C][3]*/, long long* __restrict__ counts) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_clusters) return;
-    const double k = (double)cnt[c];
-    for (int a = 0; a < 3; ++a) {
-        const double hi = __dmul_rn((double)acc[(size_t)c * 6 + 2 * a], 1.0 / 1048576.0);
-        const double lo = __dmul_rn((double)acc[(size_t)c * 6 + 2 * a + 1], 1.0 / 1152921504606846976.0);
-        out[(size_t)c * 3 + a] = cnt[c] ? __ddiv_rn(__dadd_rn(hi, lo), k) : 0.0;
+    long long sum[6] = {0, 0, 0, 0, 0, 0};
+    unsigned members = 0;
+    for (int r = 0; r < reps; ++r) {                      // two's-complement integer sums: exact in any order
+        const long long* A = acc + ((size_t)r * n_clusters + c) * 6;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) sum[i] = (long long)((unsigned long long)sum[i] + (unsigned long long)A[i]);
+        members += cnt[(size_t)r * n_clusters + c];
     }
-    if (counts) counts[c] = (long long)cnt[c];
+    const double k = (double)members;
+    for (int a = 0; a < 3; ++a) {
+        const double hi = __dmul_rn((double)sum[2 * a], 1.0 / 1048576.0);
+        const double lo = __dmul_rn((double)sum[2 * a + 1], 1.0 / 1152921504606846976.0);
+        out[(size_t)c * 3 + a] = members ? __ddiv_rn(__dadd_rn(hi, lo), k) : 0.0;
+    }
+    if (counts) counts[c] = (long long)members;
 }
 
 }  // namespace lidar
@@ -995,9 +1008,13 @@ int lidar_ball_count(const double* d_points, int64_t m, double radius, const dou
     return LIDAR_OK;
 }
 
+// replicas of the accumulators (centroid_accumulate): eight while that stays under a few MB, fewer for many clusters
+static int centroid_reps(int n_clusters) { return n_clusters <= 8192 ? 8 : n_clusters <= 65536 ? 2 : 1; }
+
 size_t lidar_centroid_workspace_bytes(int n_clusters) {
     if (n_clusters < 0) return 0;
-    return ws_align(sizeof(long long) * 6 * (size_t)n_clusters) + ws_align(sizeof(unsigned) * (size_t)n_clusters);
+    const size_t r = (size_t)centroid_reps(n_clusters);
+    return ws_align(sizeof(long long) * 6 * r * (size_t)n_clusters) + ws_align(sizeof(unsigned) * r * (size_t)n_clusters);
 }
 
 int lidar_cluster_centroids(const double* d_points, const void* d_labels, int labels_are_i64, int64_t n,
@@ -1012,17 +1029,18 @@ int lidar_cluster_centroids(const double* d_points, const void* d_labels, int la
     cudaStream_t st = as_stream(stream);
     LIDAR_CUDA_TRY(cudaMemsetAsync(d_ws, 0, need, st));
     long long* acc = static_cast<long long*>(d_ws);
-    unsigned* cnt = reinterpret_cast<unsigned*>(static_cast<char*>(d_ws) + ws_align(sizeof(long long) * 6 * (size_t)n_clusters));
+    const int reps = centroid_reps(n_clusters);
+    unsigned* cnt = reinterpret_cast<unsigned*>(static_cast<char*>(d_ws) + ws_align(sizeof(long long) * 6 * (size_t)reps * (size_t)n_clusters));
     if (n > 0) {
         int64_t want = (n + 255) / 256;
         const int64_t cap = (int64_t)sm_count() * 8;
         const int grid = (int)(want < cap ? want : cap);
         centroid_accumulate<<<grid, 256, 0, st>>>(d_points, labels_are_i64 ? static_cast<const long long*>(d_labels) : nullptr,
                                                   labels_are_i64 ? nullptr : static_cast<const int*>(d_labels), n,
-                                                  n_clusters, acc, cnt);
+                                                  n_clusters, acc, cnt, reps);
         LIDAR_CHECK_LAUNCH();
     }
-    centroid_finalize<<<(n_clusters + 127) / 128, 128, 0, st>>>(n_clusters, acc, cnt, d_centroids3,
+    centroid_finalize<<<(n_clusters + 127) / 128, 128, 0, st>>>(n_clusters, acc, cnt, reps, d_centroids3,
                                                                 reinterpret_cast<long long*>(d_counts));
     LIDAR_CHECK_LAUNCH();
     return LIDAR_OK;
