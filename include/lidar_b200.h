@@ -609,6 +609,8 @@ int lidar_host_memcpy_batch(int count, void* const* dst, const void* const* src,
 int lidar_host_copy_wake(void);
 /* cudaMemcpyAsync between page-locked host memory and the device on `stream` (to_device: host -> device) */
 int lidar_copy_async(void* dst, const void* src, size_t bytes, int to_device, void* stream);
+/* cudaStreamSynchronize(stream): the wait of the small read-backs, callable from the binding without a stream object. */
+int lidar_stream_synchronize(void* stream);
 
 #ifdef __cplusplus
 }

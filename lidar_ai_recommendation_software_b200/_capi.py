@@ -213,6 +213,7 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_host_memcpy_batch": (_i32, [_i32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "lidar_host_copy_wake": (_i32, []),
     "lidar_copy_async": (_i32, [_vp, _vp, _sz, _i32, _vp]),
+    "lidar_stream_synchronize": (_i32, [_vp]),
     "lidar_voxel_sorted_workspace_bytes": (_sz, [_i64]),
     "lidar_voxel_downsample_sorted": (_i32, [_vp, _i64, _dbl, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                              C.POINTER(C.c_double), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

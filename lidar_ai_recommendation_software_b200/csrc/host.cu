@@ -314,6 +314,11 @@ int lidar_copy_async(void* dst, const void* src, size_t bytes, int to_device, vo
     return LIDAR_OK;
 }
 
+int lidar_stream_synchronize(void* stream) {
+    LIDAR_CUDA_TRY(cudaStreamSynchronize(as_stream(stream)));
+    return LIDAR_OK;
+}
+
 int lidar_host_copy_threads(int threads) {
     LIDAR_REQUIRE(threads >= 1 && threads <= 64, LIDAR_ERR_INVALID, "lidar_host_copy_threads: 1..64");
     pool().resize(threads - 1);

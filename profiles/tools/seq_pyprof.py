@@ -21,4 +21,4 @@ pr = cProfile.Profile(); pr.enable()
 for i in range(60): frame(i)
 torch.cuda.synchronize()
 pr.disable()
-st = pstats.Stats(pr); st.sort_stats('tottime').print_stats(28)
+st = pstats.Stats(pr); st.strip_dirs(); st.sort_stats('cumulative').print_stats(45); st.sort_stats('tottime').print_stats(25)
