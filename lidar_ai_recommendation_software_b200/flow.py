@@ -78,9 +78,10 @@ def bottlenecks_b(flow, handles):
     return sorted(out, key=lambda b: b["severity"], reverse=True)[:5]
 
 
-def frame_flow(prev_positions, positions, dt, x_range, y_range, gate=1.5, radius=3.0):
+def frame_flow(prev_positions, positions, dt, x_range, y_range, gate=1.5, radius=3.0, _centroids=None):
     """NEW op: real frame-to-frame displacement binned onto the same lattice
-    as the simulated field.  Returns the reference's flow_vectors dict plus the match indices."""
+    as the simulated field.  Returns the reference's flow_vectors dict plus the match indices.
+    (`positions` may be a (C,2) CUDA tensor; `_centroids` = device tensors to bring back in the same read-back.)"""
     x_grid, y_grid = lattice_axes(x_range, y_range)
     # the lattice np.vstack([X.ravel(), Y.ravel()]).T of np.meshgrid(x_grid, y_grid) is built on the device from the two
     # axes (copies, no arithmetic) and comes back with the results: meshgrid + vstack + the upload of 58 k nodes cost
@@ -91,5 +92,22 @@ def frame_flow(prev_positions, positions, dt, x_range, y_range, gate=1.5, radius
     match, vel, cur32 = ops.frame_flow_match(prev_positions, positions, dt, gate)
     vec, mag = ops.frame_flow_field(d_lattice, cur32, match, vel, radius)
     # one read-back (one wait) for everything; the arrays handed out are the caller's own copies
-    lattice, h_vec, h_mag, h_match, h_vel = (a.copy() for a in ops.fetch("frame_flow", d_lattice, vec, mag, match, vel))
-    return {"positions": lattice, "vectors": h_vec, "magnitudes": h_mag}, h_match, h_vel
+    extra = tuple(_centroids) if _centroids is not None else ()
+    got = [a.copy() for a in ops.fetch("frame_flow", d_lattice, vec, mag, match, vel, *extra)]
+    lattice, h_vec, h_mag, h_match, h_vel = got[:5]
+    out = ({"positions": lattice, "vectors": h_vec, "magnitudes": h_mag}, h_match, h_vel)
+    return out + (tuple(got[5:]),) if extra else out
+
+
+def frame_flow_from_clusters(prev_positions, points, clusters, n_clusters, dt, x_range, y_range, gate=1.5, radius=3.0):
+    """`frame_flow` for a frame whose clusters are still on the device (sequence mode): the centroids go from the
+    accumulation kernel straight into the match, and they come back together with the flow field -- ONE wait per frame
+    for the ordered stage instead of two.  Returns (flow, match, velocity, people_positions (C,2) float64), or None when a
+    cluster id has no member (caller-built labels): the general path handles that."""
+    cent, counts = ops.cluster_centroids(points, clusters, n_clusters)
+    cur = cent[:, :2].contiguous()
+    flow, match, vel, (h_cent, h_counts) = frame_flow(prev_positions, cur, dt, x_range, y_range, gate, radius,
+                                                      _centroids=(cent, counts))
+    if not (h_counts > 0).all():
+        return None
+    return flow, match, vel, np.ascontiguousarray(h_cent[:, :2])

@@ -10,6 +10,7 @@ from __future__ import annotations
 import numpy as np
 
 from .. import flow as _flow
+from .. import preprocess as _pre
 from ..utils.data_processing import extract_people_positions
 
 
@@ -47,16 +48,26 @@ class CrowdFlowModel:
     def analyze_sequence_frame(self, processed_data, dt=0.1, gate=1.5):
         """Frame of a sequence: the first call behaves like `analyze`; later calls replace the simulated
         field by the measured displacement field of the people matched against the previous frame."""
-        people_positions = extract_people_positions(processed_data)
-        if len(people_positions) == 0:
-            self.prev_positions = None
-            return self._empty()
-        if self.prev_positions is None or len(self.prev_positions) == 0:
-            self.prev_positions = people_positions
-            return self.analyze(processed_data)
         dims = processed_data["dimensions"]
-        flow, match, _ = _flow.frame_flow(self.prev_positions, people_positions, dt, dims["x_range"],
-                                          dims["y_range"], gate=gate)
+        fast = None
+        cache = processed_data.get(_pre.DEVICE_KEY)
+        if (self.prev_positions is not None and len(self.prev_positions) > 0 and isinstance(cache, _pre.DeviceCache)
+                and cache.matches(processed_data) and cache.n_clusters):
+            # clusters still on the device: centroids -> match -> field without a trip to the host in between
+            fast = _flow.frame_flow_from_clusters(self.prev_positions, cache.points, cache.clusters, cache.n_clusters,
+                                                  dt, dims["x_range"], dims["y_range"], gate=gate)
+        if fast is not None:
+            flow, match, _, people_positions = fast
+        else:
+            people_positions = extract_people_positions(processed_data)
+            if len(people_positions) == 0:
+                self.prev_positions = None
+                return self._empty()
+            if self.prev_positions is None or len(self.prev_positions) == 0:
+                self.prev_positions = people_positions
+                return self.analyze(processed_data)
+            flow, match, _ = _flow.frame_flow(self.prev_positions, people_positions, dt, dims["x_range"],
+                                              dims["y_range"], gate=gate)
         self.prev_positions = people_positions
         self.flow_vectors = flow
         vectors, magnitudes = flow["vectors"], flow["magnitudes"]
