@@ -182,6 +182,8 @@ def run_seq(args, torch, dev, rank, world, dist):
     pool64 = [torch.from_numpy(np.ascontiguousarray(p[:, :3], dtype=np.float64)).pin_memory() for p in pool]
     dpool = [torch.from_numpy(p).to(dev) for p in pool]
     nmax = max(p.shape[0] for p in pool)
+    if getattr(args, "seq_frame_mode", "fused") == "multikernel":
+        ops.set_frame_mode(ops.FRAME_MULTIKERNEL)
     pipe = ops.FramePipeline(max_points=nmax, voxel_size=0.05, grid_size=0.5, max_key_space=(1 << 31) - 1,
                              max_nx=1024, max_ny=1024, device=dev)
     model = CrowdFlowModel()
@@ -410,6 +412,8 @@ def main():
     ap.add_argument("--rings", type=int, default=128)
     ap.add_argument("--azimuth", type=int, default=20480)
     ap.add_argument("--dropin", action="store_true", help="seq: time the numpy-in / numpy-out drop-in surface instead")
+    ap.add_argument("--seq-frame-mode", default="fused", choices=["fused", "multikernel"],
+                    help="seq: back end of the voxel / density pipeline that shares the device with the preprocess workers")
     ap.add_argument("--workers", type=int, default=2,
                     help="seq: preprocess worker threads (one CUDA stream each); 1 = the serial loop")
     ap.add_argument("--points", type=int, default=50_000_000)
