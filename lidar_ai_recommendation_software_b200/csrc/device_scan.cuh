@@ -6,7 +6,7 @@
 namespace lidar {
 
 constexpr int kDsThreads = 256;
-constexpr int kDsItems = 8;
+constexpr int kDsItems = 16;
 constexpr int kDsTile = kDsThreads * kDsItems;
 
 struct ScanCtrl {
@@ -39,10 +39,27 @@ exclusive_scan_kernel(const T* __restrict__ in, unsigned* __restrict__ out, int6
         const int64_t base = (int64_t)tile * kDsTile + (int64_t)threadIdx.x * kDsItems;
         unsigned v[kDsItems];
         unsigned sum = 0;
+        // whole tiles of 4-byte items move as 16-byte vectors (four loads in flight per thread; the scalar form with
+        // its per-item bound checks ran at a fifth of the memory rate: 24 us for the 3.6 M-cell directory of a ring frame)
+        const bool vec = sizeof(T) == 4 && (int64_t)tile * kDsTile + kDsTile <= n &&
+                         ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+        if (vec) {
+            const uint4* src = reinterpret_cast<const uint4*>(in + base);
+            uint4 q[kDsItems / 4];
 #pragma unroll
-        for (int k = 0; k < kDsItems; ++k) {
-            v[k] = (base + k < n) ? (unsigned)in[base + k] : 0u;
-            sum += v[k];
+            for (int k = 0; k < kDsItems / 4; ++k) q[k] = __ldg(src + k);
+#pragma unroll
+            for (int k = 0; k < kDsItems / 4; ++k) {
+                v[4 * k] = q[k].x; v[4 * k + 1] = q[k].y; v[4 * k + 2] = q[k].z; v[4 * k + 3] = q[k].w;
+            }
+#pragma unroll
+            for (int k = 0; k < kDsItems; ++k) sum += v[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < kDsItems; ++k) {
+                v[k] = (base + k < n) ? (unsigned)in[base + k] : 0u;
+                sum += v[k];
+            }
         }
         unsigned inc = sum;
 #pragma unroll
@@ -71,10 +88,23 @@ exclusive_scan_kernel(const T* __restrict__ in, unsigned* __restrict__ out, int6
         }
         __syncthreads();
         unsigned run = (unsigned)s_excl + warp_off + (inc - sum);
+        if (vec) {
+            uint4* dst = reinterpret_cast<uint4*>(out + base);
 #pragma unroll
-        for (int k = 0; k < kDsItems; ++k) {
-            if (base + k < n) out[base + k] = run;
-            run += v[k];
+            for (int k = 0; k < kDsItems / 4; ++k) {
+                uint4 o;
+                o.x = run; run += v[4 * k];
+                o.y = run; run += v[4 * k + 1];
+                o.z = run; run += v[4 * k + 2];
+                o.w = run; run += v[4 * k + 3];
+                dst[k] = o;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kDsItems; ++k) {
+                if (base + k < n) out[base + k] = run;
+                run += v[k];
+            }
         }
         __syncthreads();
     }
