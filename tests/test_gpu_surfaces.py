@@ -449,6 +449,40 @@ def test_sequence_runner_equals_serial_loop(pkg):
             assert np.array_equal(r_g["matches"], r_w["matches"])
 
 
+@pytest.mark.gpu
+def test_sequence_runner_state_and_empty_frames(pkg):
+    """The concurrent flow step (a frame needs its predecessor's POSITIONS only) against the serial, stateful
+    `analyze_sequence_frame`: every key of every result, across a frame without any cluster (the next frame falls back to
+    the simulated field, as the first one does), across two `run` calls (the model's `prev_positions` carries over), and
+    the state the model is left in."""
+    from lidar_ai_recommendation_software_b200.sequence import SequenceRunner
+    ring = [np.ascontiguousarray(pkg.synth.ring_sequence_frame(i, rings=48, azimuth_steps=4096)[:, :3], dtype=np.float64)
+            for i in range(4)]
+    noise = np.random.default_rng(3).uniform(-50.0, 50.0, (3000, 3))           # nothing within eps = 0.3 of anything
+    frames = [ring[0], ring[1], noise, ring[2], ring[3], ring[0]]
+    serial = pkg.CFM()
+    want = [serial.analyze_sequence_frame(pkg.pre.run(f, variant="B", host_arrays=False), dt=0.1) for f in frames]
+    assert want[2]["dominant_direction"] == "N/A" and "matches" not in want[3] and "matches" in want[4]
+    for workers in (2, 4):
+        runner = SequenceRunner(variant="B", workers=workers, dt=0.1)
+        got = [res for _, res in runner.run(iter(frames[:3]))] + [res for _, res in runner.run(iter(frames[3:]))]
+        runner.close()
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert sorted(g) == sorted(w)
+            assert g["dominant_direction"] == w["dominant_direction"] and g["bottlenecks"] == w["bottlenecks"]
+            if "matches" in w:        # measured field: np.mean on the host; the simulated one sums with device atomics
+                assert np.array_equal(np.asarray(g["avg_speed"]), np.asarray(w["avg_speed"]))
+            else:
+                assert np.isclose(g["avg_speed"], w["avg_speed"], rtol=1e-12, atol=0.0)
+            for k in ("positions", "vectors", "magnitudes"):
+                assert np.array_equal(g["flow_vectors"][k], w["flow_vectors"][k]), k
+            if "matches" in w:
+                assert np.array_equal(g["matches"], w["matches"])
+        assert np.array_equal(runner.model.prev_positions, serial.prev_positions)
+        assert np.array_equal(runner.model.flow_vectors["vectors"], serial.flow_vectors["vectors"])
+
+
 def test_errors_are_python_exceptions(pkg):
     with pytest.raises(Exception):
         pkg.dp.preprocess_lidar_data(np.zeros((0, 3)))
