@@ -256,6 +256,13 @@ int lidar_frame_flow_match(const float* d_prev_xy, int n_prev, const float* d_cu
 int lidar_frame_flow_field(const double* d_lattice_xy, int n_lattice, const float* d_cur_xy, const int32_t* d_match,
                            const float* d_velocity, int n_cur, double radius, double* d_vectors, double* d_magnitudes,
                            void* stream);
+/* The two above behind ONE call, with the lattice built on the device: node iy*nx + ix = (x_grid[ix], y_grid[iy]), i.e.
+ * np.vstack([X.ravel(), Y.ravel()]).T of np.meshgrid(x_grid, y_grid) (models/crowd_flow_model.py:107-111).  d_velocity is
+ * zeroed first (unmatched people keep 0).  The per-frame flow step of a sequence is then one staging copy in, this call,
+ * one copy out. */
+int lidar_frame_flow(const float* d_prev_xy, int n_prev, const float* d_cur_xy, int n_cur, float dt, float gate,
+                     const double* d_x_grid, int nx, const double* d_y_grid, int ny, double radius, int32_t* d_match,
+                     float* d_velocity, double* d_lattice_xy, double* d_vectors, double* d_magnitudes, void* stream);
 
 /* ------------------------------------------------------------------------------------------- *
  * K11-K13  PointNet++-style set abstraction (NEW ops; the reference only

@@ -166,6 +166,7 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_nearest_grid_cell": (_i32, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lidar_frame_flow_match": (_i32, [_vp, _i32, _vp, _i32, C.c_float, C.c_float, _vp, _vp, _vp]),
     "lidar_frame_flow_field": (_i32, [_vp, _i32, _vp, _vp, _vp, _i32, _dbl, _vp, _vp, _vp]),
+    "lidar_frame_flow": (_i32, [_vp, _i32, _vp, _i32, C.c_float, C.c_float, _vp, _i32, _vp, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lidar_fps_workspace_bytes": (_sz, [_i32, _i32]),
     "lidar_fps": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "lidar_ball_query": (_i32, [_vp, _vp, _i32, _i32, _i32, C.c_float, _i32, _vp, _vp]),

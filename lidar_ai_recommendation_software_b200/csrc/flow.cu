@@ -265,6 +265,15 @@ frame_flow_field_kernel(const double* __restrict__ lattice, int g, const float* 
 }
 
 
+// np.vstack([X.ravel(), Y.ravel()]).T of X, Y = np.meshgrid(x_grid, y_grid) (models/crowd_flow_model.py:110-111): node
+// i = iy * nx + ix is (x_grid[ix], y_grid[iy]).  Copies, no arithmetic.
+__global__ void lattice_kernel(const double* __restrict__ xg, int nx, const double* __restrict__ yg, int ny,
+                               double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nx * ny) return;
+    reinterpret_cast<double2*>(out)[i] = make_double2(xg[i % nx], yg[i / nx]);
+}
+
 // plot_crowd_metrics join (utils/visualization.py:306-326): cKDTree(density cell centres).query(flow nodes, k=1) and the
 // congestion-risk columns built from it.  The cell centres are the rectilinear grid repeat(grid_x, ny) x tile(grid_y, nx)
 // of CrowdDensityModel.analyze (models/crowd_density_model.py:57-59), so the nearest centre is found per axis: the two
@@ -428,6 +437,23 @@ int lidar_frame_flow_field(const double* d_lattice_xy, int n_lattice, const floa
         d_lattice_xy, n_lattice, d_cur_xy, d_match, d_velocity, n_cur, radius * radius, d_vectors, d_magnitudes);
     LIDAR_CHECK_LAUNCH();
     return LIDAR_OK;
+}
+
+int lidar_frame_flow(const float* d_prev_xy, int n_prev, const float* d_cur_xy, int n_cur, float dt, float gate,
+                     const double* d_x_grid, int nx, const double* d_y_grid, int ny, double radius, int32_t* d_match,
+                     float* d_velocity, double* d_lattice_xy, double* d_vectors, double* d_magnitudes, void* stream) {
+    LIDAR_REQUIRE(nx >= 0 && ny >= 0 && (int64_t)nx * ny < (1ll << 31), LIDAR_ERR_INVALID, "lidar_frame_flow: bad lattice");
+    const int g = nx * ny;
+    cudaStream_t st = as_stream(stream);
+    if (g > 0) {
+        LIDAR_REQUIRE(d_x_grid && d_y_grid && d_lattice_xy, LIDAR_ERR_INVALID, "lidar_frame_flow: NULL lattice argument");
+        lattice_kernel<<<(g + 255) / 256, 256, 0, st>>>(d_x_grid, nx, d_y_grid, ny, d_lattice_xy);
+        LIDAR_CHECK_LAUNCH();
+    }
+    if (n_cur > 0 && d_velocity) LIDAR_CUDA_TRY(cudaMemsetAsync(d_velocity, 0, sizeof(float) * 2 * (size_t)n_cur, st));
+    int rc = lidar_frame_flow_match(d_prev_xy, n_prev, d_cur_xy, n_cur, dt, gate, d_match, d_velocity, stream);
+    if (rc != LIDAR_OK) return rc;
+    return lidar_frame_flow_field(d_lattice_xy, g, d_cur_xy, d_match, d_velocity, n_cur, radius, d_vectors, d_magnitudes, stream);
 }
 
 }  // extern "C"

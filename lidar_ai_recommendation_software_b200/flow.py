@@ -83,17 +83,10 @@ def frame_flow(prev_positions, positions, dt, x_range, y_range, gate=1.5, radius
     as the simulated field.  Returns the reference's flow_vectors dict plus the match indices.
     (`positions` may be a (C,2) CUDA tensor; `_centroids` = device tensors to bring back in the same read-back.)"""
     x_grid, y_grid = lattice_axes(x_range, y_range)
-    # the lattice np.vstack([X.ravel(), Y.ravel()]).T of np.meshgrid(x_grid, y_grid) is built on the device from the two
-    # axes (copies, no arithmetic) and comes back with the results: meshgrid + vstack + the upload of 58 k nodes cost
-    # 0.2 ms of host time per frame
-    dev = ops.require_cuda()
-    xg, yg = torch.from_numpy(x_grid).to(dev), torch.from_numpy(y_grid).to(dev)
-    d_lattice = torch.stack([xg.repeat(yg.numel()), yg.repeat_interleave(xg.numel())], dim=1)
-    match, vel, cur32 = ops.frame_flow_match(prev_positions, positions, dt, gate)
-    vec, mag = ops.frame_flow_field(d_lattice, cur32, match, vel, radius)
-    # one read-back (one wait) for everything; the arrays handed out are the caller's own copies
+    # lattice (np.vstack([X.ravel(), Y.ravel()]).T of np.meshgrid: built on the device from the two axes), match and field
+    # behind one call, one copy in, one copy out
     extra = tuple(_centroids) if _centroids is not None else ()
-    got = [a.copy() for a in ops.fetch("frame_flow", d_lattice, vec, mag, match, vel, *extra)]
+    got = ops.frame_flow_step(prev_positions, positions, x_grid, y_grid, dt, gate, radius, extra=extra)
     lattice, h_vec, h_mag, h_match, h_vel = got[:5]
     out = ({"positions": lattice, "vectors": h_vec, "magnitudes": h_mag}, h_match, h_vel)
     return out + (tuple(got[5:]),) if extra else out

@@ -1073,6 +1073,56 @@ def frame_flow_field(lattice, cur_f32, match, vel, radius: float = 3.0):
     return vec, mag
 
 
+def frame_flow_step(prev_xy, cur_xy, x_grid, y_grid, dt: float, gate: float = 1.5, radius: float = 3.0, extra=()):
+    """The flow step of one sequence frame as ONE staging copy in, ONE C call (`lidar_frame_flow`: lattice, match, field)
+    and ONE copy out: (lattice (G,2) f64, vectors (G,2) f64, magnitudes (G,) f64, match (C,) i32, velocity (C,2) f32) as
+    numpy arrays cut from one buffer the caller owns, followed by host copies of the device tensors in `extra`.
+    `cur_xy`: (C,2) numpy or CUDA tensor (any float dtype; the match runs in float32 as B.3 says).  A dozen torch calls
+    per frame (uploads, zeros, views, read-backs) were a third of the interpreter time of a sequence frame."""
+    dev = require_cuda()
+    xg = np.ascontiguousarray(x_grid, dtype=np.float64)
+    yg = np.ascontiguousarray(y_grid, dtype=np.float64)
+    prev = np.ascontiguousarray(prev_xy, dtype=np.float32).reshape(-1, 2)
+    cur_dev = cur_xy.to(device=dev, dtype=torch.float32).contiguous().reshape(-1, 2) if isinstance(cur_xy, torch.Tensor) else None
+    cur = None if cur_dev is not None else np.ascontiguousarray(cur_xy, dtype=np.float32).reshape(-1, 2)
+    nx, ny, n_prev = xg.size, yg.size, prev.shape[0]
+    n_cur = cur_dev.shape[0] if cur_dev is not None else cur.shape[0]
+    g = nx * ny
+    # ---- in: [x_grid | y_grid | prev | cur] through this thread's pinned staging, one async copy -------------------
+    parts = [xg, yg, prev] + ([cur] if cur is not None else [])
+    offs, o = [], 0
+    for a in parts:
+        offs.append(o)
+        o += (a.nbytes + 15) & ~15
+    h_in = _pinned.get("flow_in", o)
+    hv = h_in.numpy()
+    for a, off in zip(parts, offs):
+        hv[off:off + a.nbytes] = a.reshape(-1).view(np.uint8)
+    d_in = _scratch.get("flow_in", o, dev)
+    d_in[:o].copy_(h_in[:o], non_blocking=True)
+    base = d_in.data_ptr()
+    p_cur = cur_dev.data_ptr() if cur_dev is not None else base + offs[3]
+    # ---- out: [lattice | vectors | magnitudes | match | velocity] in one device block -------------------------------
+    sizes = [g * 16, g * 16, g * 8, n_cur * 4, n_cur * 8]
+    ooffs, total = [], 0
+    for b in sizes:
+        ooffs.append(total)
+        total += (b + 15) & ~15
+    d_out = _scratch.get("flow_out", total, dev)
+    ob = d_out.data_ptr()
+    check(lib.lidar_frame_flow(base + offs[2], n_prev, p_cur, n_cur, float(dt), float(gate), base + offs[0], nx,
+                               base + offs[1], ny, float(radius), ob + ooffs[3], ob + ooffs[4], ob + ooffs[0],
+                               ob + ooffs[1], ob + ooffs[2], _stream_ptr()))
+    got = fetch("flow_out", d_out[:total], *extra)
+    own = got[0].copy()                                   # one memcpy: the results live in a buffer the caller owns
+    lattice = own[ooffs[0]:ooffs[0] + sizes[0]].view(np.float64).reshape(g, 2)
+    vec = own[ooffs[1]:ooffs[1] + sizes[1]].view(np.float64).reshape(g, 2)
+    mag = own[ooffs[2]:ooffs[2] + sizes[2]].view(np.float64)
+    match = own[ooffs[3]:ooffs[3] + sizes[3]].view(np.int32)
+    vel = own[ooffs[4]:ooffs[4] + sizes[4]].view(np.float32).reshape(n_cur, 2)
+    return (lattice, vec, mag, match, vel) + tuple(a.copy() for a in got[1:])
+
+
 def nearest_grid_cell(nodes_xy, grid_x, grid_y, density_flat=None, speed=None):
     """cKDTree(cell centres).query(nodes, k=1) on the rectilinear density grid (utils/visualization.py:306-314): returns
     device tensors (index int64 (G,), distance (G,)) and, with `density_flat` / `speed`, also (density_at, risk, risk_max)."""
