@@ -332,7 +332,8 @@ def run_extras(args, torch, dist, dev, rank, world):
         # preprocess worker threads per rank: three when the rank has the CPUs for them (each worker drives a stream and
         # waits on the device twice per frame), two when eight ranks share a 32-vCPU host
         local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
-        workers = 3 if (os.cpu_count() or 1) // local_world >= 6 else 2
+        per_rank = (os.cpu_count() or 1) // local_world      # the per-frame path is bound by its host side: a worker per ~3 vCPUs
+        workers = 5 if per_rank >= 12 else 4 if per_rank >= 8 else 3 if per_rank >= 6 else 2
         a = types.SimpleNamespace(frames=args.seq_frames, pool=4, rings=128, azimuth=20480, dropin=False, workers=workers)
         guarded("seq", lambda: bc.run_seq(a, torch, dev, rank, world, dist))
     if "sa" in args.extras and world == 1:

@@ -510,6 +510,12 @@ class ResultPool:
         block.u8 = None
         return np.ctypeslib.as_array(cbuf)
 
+    def reserve(self, count: int, nbytes: int) -> None:
+        """Allocate `count` buffers of `nbytes` now: a page-locked allocation costs ~10 ms and stalls every CUDA call of
+        the process while it runs -- not something to meet on the first frames of a stream."""
+        while len(self.bufs) < min(int(count), self.max_buffers):
+            self.bufs.append(self._new(max(int(nbytes), 64)))
+
     def take(self, nbytes: int) -> np.ndarray:
         nbytes = max(int(nbytes), 64)
         for k in range(len(self.bufs)):
@@ -594,6 +600,9 @@ class HostFramePipeline:
         self._pending: list[dict] = []
         self._last_d2h = 0
         self._pool = ResultPool()
+        if self.two_stage:
+            # the results in flight plus the one the caller is still looking at while it collects the next
+            self._pool.reserve(slots + 1, block)
         torch.cuda.synchronize(self.device)   # workspace zeroing ran on the constructing stream
 
     def close(self):
