@@ -483,6 +483,30 @@ def test_sequence_runner_state_and_empty_frames(pkg):
         assert np.array_equal(runner.model.flow_vectors["vectors"], serial.flow_vectors["vectors"])
 
 
+def test_frame_flow_step_equals_separate_entries(pkg):
+    """`ops.frame_flow_step` (one copy in, `lidar_frame_flow`, one copy out) against the separate match / field entries fed
+    with the numpy lattice of models/crowd_flow_model.py:107-111 -- host and device positions, bit for bit."""
+    import torch
+    rng = np.random.default_rng(11)
+    prev = rng.uniform(-20.0, 20.0, (300, 2))
+    cur = prev[rng.permutation(300)[:260]] + rng.normal(0.0, 0.05, (260, 2))
+    x_grid, y_grid = np.arange(-21.5, 22.0, 1.0), np.arange(-20.25, 21.0, 1.0)
+    X, Y = np.meshgrid(x_grid, y_grid)
+    lattice = np.vstack([X.ravel(), Y.ravel()]).T
+    match, vel, cur32 = pkg.ops.frame_flow_match(prev, cur, 0.1, 1.5)
+    vec, mag = pkg.ops.frame_flow_field(lattice, cur32, match, vel, 3.0)
+    want = (lattice, vec.cpu().numpy(), mag.cpu().numpy(), match.cpu().numpy(), vel.cpu().numpy())
+    assert (want[3] >= 0).sum() > 200 and np.count_nonzero(want[2]) > 100
+    for positions in (cur, torch.from_numpy(cur).cuda()):
+        got = pkg.ops.frame_flow_step(prev, positions, x_grid, y_grid, 0.1, 1.5, 3.0)
+        assert len(got) == 5
+        for g, w in zip(got, want):
+            assert g.dtype == w.dtype and np.array_equal(g, w)
+    extra = torch.arange(7, dtype=torch.int64, device="cuda")
+    got = pkg.ops.frame_flow_step(prev, cur, x_grid, y_grid, 0.1, 1.5, 3.0, extra=(extra,))
+    assert np.array_equal(got[5], np.arange(7)) and np.array_equal(got[1], want[1])
+
+
 def test_errors_are_python_exceptions(pkg):
     with pytest.raises(Exception):
         pkg.dp.preprocess_lidar_data(np.zeros((0, 3)))

@@ -171,3 +171,29 @@ def test_parallel_host_memcpy_both_store_kinds():
     finally:
         lib.lidar_host_copy_nontemporal(1)
         lib.lidar_host_copy_threads(2)
+
+
+def test_result_pool_reserve_and_reuse():
+    """ResultPool (ops.py): reserved buffers are handed out without a new allocation, a buffer is reused only when no array
+    references it any more, and nothing a caller still holds is ever handed out again.  Pageable buffers: no device needed."""
+    from lidar_ai_recommendation_software_b200 import ops
+    pool = ops.ResultPool(max_buffers=3, pinned=False)
+    pool.reserve(2, 1 << 16)
+    assert len(pool.bufs) == 2
+    ids = {id(b) for b in pool.bufs}
+    a = pool.take(1000)
+    view = np.frombuffer(a, dtype=np.int32, count=10)         # what collect() hands to the caller: a view of the buffer
+    view[:] = 7
+    del a
+    b = pool.take(1000)
+    assert id(b) in ids and not np.shares_memory(b, view)     # the second reserved buffer, not the one still in use
+    c = pool.take(1000)                                       # both in use: a third one is allocated (and kept)
+    assert id(c) not in ids and len(pool.bufs) == 3
+    d = pool.take(1000)                                       # pool full and all in use: a buffer outside the pool
+    assert not any(np.shares_memory(d, x) for x in (view, b, c)) and len(pool.bufs) == 3
+    assert (view == 7).all()
+    del view, d
+    e = pool.take(1000)                                       # the first buffer is free again
+    assert id(e) in ids
+    big = pool.take(1 << 20)                                  # larger than anything pooled: a new buffer
+    assert big.nbytes >= (1 << 20)
