@@ -8,7 +8,6 @@ list handling.  Everything per lattice node runs in csrc/flow.cu.
 from __future__ import annotations
 
 import numpy as np
-import torch
 
 from . import ops
 
