@@ -587,6 +587,34 @@ int lidar_nccl_comm_destroy(void* comm);
 int lidar_nccl_allreduce(void* comm, void* d_buf, int64_t count, int op, void* stream);
 
 /* ------------------------------------------------------------------------------------------- *
+ * One frame of a sequence (BASELINE configs[3]) behind one call: lidar_preprocess_front (no colours, no scaler) -> wait for
+ * its descriptor -> lidar_dbscan(eps, min_samples, tol 0) on the non-ground points inside the descriptor's bounding box
+ * (m <= 10: one cluster, app_simplified.py:108-110) -> lidar_scatter_labels over the inliers -> wait for the cluster count
+ * -> lidar_cluster_centroids of the inliers (utils/data_processing.py:251-280) -> wait.  Same entries, same results as
+ * calling them one by one; the host steps between them run in C, so a worker thread of a Python process spends the frame
+ * outside the interpreter lock.  Capacities: every per-point buffer holds n rows; d_centroids3 / d_counts hold
+ * centroid_cap clusters; h_pinned = page-locked staging of at least sizeof(lidar_front_desc) + 64 + 32 * centroid_cap
+ * bytes: [descriptor | n_clusters, guard | centroids (centroid_cap x 3 fp64) | counts (centroid_cap int64)].
+ * Returns LIDAR_ERR_WORKSPACE with out->need_dbscan_ws set when the DBSCAN workspace is too small for this frame's bounding
+ * box (grow it and call again).  out->centroids_done = 0 when the frame has more clusters than centroid_cap or the centroid
+ * workspace is too small (out->need_centroid_ws): everything else is complete, compute the centroids separately.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct lidar_sequence_frame_out {
+    lidar_front_desc front;
+    int32_t n_clusters;
+    int32_t centroids_done;
+    uint64_t guard_dbscan;
+    uint64_t need_dbscan_ws;
+    uint64_t need_centroid_ws;
+} lidar_sequence_frame_out;
+int lidar_sequence_frame_b(const double* d_points, int64_t n, double eps, int min_samples, double* d_inliers,
+                           double* d_nonground, int32_t* d_ng_index, int32_t* d_labels, int64_t* d_full_labels,
+                           double* d_centroids3, int64_t* d_counts, int centroid_cap, lidar_front_desc* d_front,
+                           uint64_t* d_info2, void* h_pinned, size_t pinned_bytes, void* d_ws_front, size_t ws_front,
+                           void* d_ws_dbscan, size_t ws_dbscan, void* d_ws_centroid, size_t ws_centroid,
+                           lidar_sequence_frame_out* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
  * Host side of the copies (the drop-in surface takes and returns numpy arrays, SURVEY.md 8b "Ownership").
  *   lidar_bind_to_device_numa   pin the calling thread (and the threads it creates) to the CPUs of the NUMA
  *       node `device` hangs off and prefer that node's memory (sched_setaffinity + set_mempolicy from

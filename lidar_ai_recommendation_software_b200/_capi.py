@@ -87,6 +87,13 @@ class FrontDesc(C.Structure):
     ]
 
 
+class SequenceFrameOut(C.Structure):
+    """Mirror of `lidar_sequence_frame_out`."""
+
+    _fields_ = [("front", FrontDesc), ("n_clusters", C.c_int32), ("centroids_done", C.c_int32), ("guard_dbscan", C.c_uint64),
+                ("need_dbscan_ws", C.c_uint64), ("need_centroid_ws", C.c_uint64)]
+
+
 class SortedDesc(C.Structure):
     """Mirror of `lidar_sorted_desc` (the 64-bit-key sort path of voxel downsample)."""
 
@@ -166,6 +173,8 @@ PROTOTYPES: dict[str, tuple] = {
     "lidar_nearest_grid_cell": (_i32, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lidar_frame_flow_match": (_i32, [_vp, _i32, _vp, _i32, C.c_float, C.c_float, _vp, _vp, _vp]),
     "lidar_frame_flow_field": (_i32, [_vp, _i32, _vp, _vp, _vp, _i32, _dbl, _vp, _vp, _vp]),
+    "lidar_sequence_frame_b": (_i32, [_vp, _i64, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _sz,
+                               _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
     "lidar_frame_flow": (_i32, [_vp, _i32, _vp, _i32, C.c_float, C.c_float, _vp, _i32, _vp, _i32, _dbl, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lidar_fps_workspace_bytes": (_sz, [_i32, _i32]),
     "lidar_fps": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _sz, _vp]),

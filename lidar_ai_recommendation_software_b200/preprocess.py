@@ -20,7 +20,7 @@ from dataclasses import dataclass, field
 import numpy as np
 import torch
 
-from . import ops
+from . import _capi, ops
 
 DEVICE_KEY = "_lidar_b200"   # extra dict entry carrying the device-resident copy of the outputs
 
@@ -34,6 +34,7 @@ class DeviceCache:
     ids: tuple
     n_clusters: int
     guards: dict = field(default_factory=dict)
+    positions: np.ndarray | None = None      # people positions, when the producer has computed them already (sequence mode)
 
     def matches(self, processed: dict) -> bool:
         if self.ids is None:      # device-only dict (run(..., host_arrays=False)): nothing to go stale
@@ -202,6 +203,76 @@ def run(points, variant: str = "A", host_arrays: bool = True) -> dict:
     return out
 
 
+def run_sequence_frame(points: torch.Tensor, centroid_cap: int = 8192) -> dict:
+    """`run(points, variant="B", host_arrays=False)` followed by `people_positions`, behind ONE call of the C ABI
+    (`lidar_sequence_frame_b`): the same entries in the same order, the host steps between them (wait for the front's
+    descriptor, size the cell grid, wait for the cluster count, size the accumulators) in C.  `points`: (n,3) float64 CUDA
+    tensor.  Returns the same dict; the people positions ride in the DeviceCache, so `extract_people_positions` and the
+    flow step find them without another kernel.  The whole call runs outside the interpreter lock."""
+    dev = ops.require_cuda()
+    if not (isinstance(points, torch.Tensor) and points.is_cuda and points.dim() == 2 and points.shape[1] == 3
+            and points.dtype == torch.float64):
+        raise ValueError("run_sequence_frame takes an (n,3) float64 CUDA tensor")
+    d_pts = points.contiguous()
+    n = d_pts.shape[0]
+    if n == 0:
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")
+    lib, C = _capi.lib, _capi.C
+    inl = torch.empty_like(d_pts)
+    ng = torch.empty_like(d_pts)
+    idx = torch.empty(n, dtype=torch.int32, device=dev)
+    labels = torch.empty(n, dtype=torch.int32, device=dev)
+    full = torch.empty(n, dtype=torch.int64, device=dev)
+    S = ops._scratch
+    cap = int(centroid_cap)
+    small = S.get("seq_small", C.sizeof(_capi.FrontDesc) + 128 + cap * 32, dev)        # descriptor | info | centroids | counts
+    o_info = (C.sizeof(_capi.FrontDesc) + 15) & ~15
+    o_cent, o_cnt = o_info + 64, o_info + 64 + cap * 24
+    ws_front = S.get("front", lib.lidar_preprocess_front_workspace_bytes(n), dev)
+    ws_cent = S.get("centroid", lib.lidar_centroid_workspace_bytes(cap), dev)
+    h_pin = ops._pinned.get("seq_frame", C.sizeof(_capi.FrontDesc) + 64 + cap * 32)
+    out = _capi.SequenceFrameOut()
+    ws_db = S.bufs.get(("dbscan", dev.index))
+    base = small.data_ptr()
+    for attempt in range(2):
+        rc = lib.lidar_sequence_frame_b(d_pts.data_ptr(), n, 0.3, 5, inl.data_ptr(), ng.data_ptr(), idx.data_ptr(),
+                                        labels.data_ptr(), full.data_ptr(), base + o_cent, base + o_cnt, cap, base,
+                                        base + o_info, h_pin.data_ptr(), h_pin.numel(), ws_front.data_ptr(), ws_front.numel(),
+                                        ws_db.data_ptr() if ws_db is not None else None, ws_db.numel() if ws_db is not None else 0,
+                                        ws_cent.data_ptr(), ws_cent.numel(), C.byref(out), ops._stream_ptr())
+        if rc == -3 and attempt == 0 and out.need_dbscan_ws:      # LIDAR_ERR_WORKSPACE: the cell grid of this bbox needs more
+            ws_db = S.get("dbscan", int(out.need_dbscan_ws) + (int(out.need_dbscan_ws) >> 2), dev)   # 25 % head room: the bbox moves
+            continue
+        _capi.check(rc)
+        break
+    desc = out.front
+    n_in, m = int(desc.n_in), int(desc.n_nonground)
+    if n_in == 0:
+        raise IndexError("index -1 is out of bounds for axis 0 with size 0")   # np.percentile of an empty array
+    lo3, hi3 = np.array(desc.bbox_in[:3]), np.array(desc.bbox_in[3:])
+    dims = {
+        "x_range": (lo3[0], hi3[0]), "y_range": (lo3[1], hi3[1]), "z_range": (lo3[2], hi3[2]),
+        "width": hi3[0] - lo3[0], "length": hi3[1] - lo3[1], "height": hi3[2] - lo3[2],
+    }
+    guards = {"sigma": int(desc.guard_sigma), "dbscan": int(out.guard_dbscan)}
+    nc = int(out.n_clusters)
+    positions = None
+    if nc == 0:
+        positions = np.array([])
+    elif out.centroids_done:
+        hv = h_pin.numpy()
+        o = C.sizeof(_capi.FrontDesc) + 64
+        cent = np.frombuffer(hv, dtype=np.float64, count=3 * nc, offset=o).reshape(nc, 3)
+        counts = np.frombuffer(hv, dtype=np.int64, count=nc, offset=o + cap * 24)
+        positions = np.ascontiguousarray(cent[counts > 0][:, :2])
+    result = {"dimensions": dims}
+    result[DEVICE_KEY] = DeviceCache(inl[:n_in], full[:n_in], None, nc, guards, positions)
+    if guards["sigma"] or guards["dbscan"]:
+        warnings.warn(f"lidar_b200 preprocess: {guards['sigma']} point(s) within 1e-9 sigma of the 3-sigma threshold and "
+                      f"{guards['dbscan']} neighbour pair(s) within 1e-12 of eps^2", RuntimeWarning, stacklevel=2)
+    return result
+
+
 def device_view(processed: dict):
     """(points (n,3) f64 CUDA, clusters (n,) int64 CUDA) of a processed_data dict — from the cache
     when it still mirrors the host arrays, else uploaded."""
@@ -219,10 +290,12 @@ def people_positions(processed: dict) -> np.ndarray:
     ascending id.  Labels of our own DBSCAN are 0..C-1 and go straight to the device accumulators; a
     caller-built dict may carry ANY int64 ids (the reference's np.unique accepts them): sparse or huge ids are ranked
     with np.unique on the host first, so the accumulators are sized by the number of clusters, never by the largest id."""
+    cache = processed.get(DEVICE_KEY)
+    if isinstance(cache, DeviceCache) and cache.positions is not None and cache.matches(processed):
+        return cache.positions.copy()
     pts, lab = device_view(processed)
     if lab.numel() == 0:
         return np.array([])
-    cache = processed.get(DEVICE_KEY)
     if isinstance(cache, DeviceCache) and cache.matches(processed) and cache.n_clusters is not None:
         n_ids = cache.n_clusters             # labels of our own DBSCAN: 0..n_clusters-1, known without a read-back
     else:

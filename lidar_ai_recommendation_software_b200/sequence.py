@@ -37,8 +37,11 @@ class SequenceRunner:
         with torch.cuda.device(self._dev), torch.cuda.stream(self._streams[slot]):
             if isinstance(frame, torch.Tensor) and not frame.is_cuda:
                 frame = frame.to(self._dev, non_blocking=True)      # pinned host tensor -> device
-            out = _pre.run(frame, variant=self.variant, host_arrays=False)
-            self._streams[slot].synchronize()
+            if self.variant == "B" and isinstance(frame, torch.Tensor) and frame.dtype == torch.float64:
+                out = _pre.run_sequence_frame(frame)        # the whole frame behind one C call, outside the interpreter lock
+            else:
+                out = _pre.run(frame, variant=self.variant, host_arrays=False)
+                self._streams[slot].synchronize()
         return out
 
     def _frame(self, frame, slot: int, mine: Future, before: Future | None, first_prev):

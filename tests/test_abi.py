@@ -58,6 +58,8 @@ def test_struct_mirrors_match_c_layout():
              offsetof(lidar_scan_comm, multicast_ptr));
       printf("%zu %zu %zu %zu\n", sizeof(lidar_sorted_desc), offsetof(lidar_sorted_desc, dims),
              offsetof(lidar_sorted_desc, n_voxels), offsetof(lidar_sorted_desc, status));
+      printf("%zu %zu %zu %zu\n", sizeof(lidar_sequence_frame_out), offsetof(lidar_sequence_frame_out, n_clusters),
+             offsetof(lidar_sequence_frame_out, guard_dbscan), offsetof(lidar_sequence_frame_out, need_centroid_ws));
       return 0; }'''
     import tempfile
     with tempfile.TemporaryDirectory() as td:
@@ -74,7 +76,9 @@ def test_struct_mirrors_match_c_layout():
             ctypes.sizeof(_capi.ScanDesc), _capi.ScanDesc.n_local.offset, _capi.ScanDesc.status.offset,
             ctypes.sizeof(_capi.ScanComm), _capi.ScanComm.peer_ptrs.offset, _capi.ScanComm.multicast_ptr.offset,
             ctypes.sizeof(_capi.SortedDesc), _capi.SortedDesc.dims.offset, _capi.SortedDesc.n_voxels.offset,
-            _capi.SortedDesc.status.offset]
+            _capi.SortedDesc.status.offset,
+            ctypes.sizeof(_capi.SequenceFrameOut), _capi.SequenceFrameOut.n_clusters.offset,
+            _capi.SequenceFrameOut.guard_dbscan.offset, _capi.SequenceFrameOut.need_centroid_ws.offset]
     assert [int(x) for x in out] == want
 
 

@@ -483,6 +483,32 @@ def test_sequence_runner_state_and_empty_frames(pkg):
         assert np.array_equal(runner.model.flow_vectors["vectors"], serial.flow_vectors["vectors"])
 
 
+def test_run_sequence_frame_equals_the_separate_calls(pkg):
+    """`preprocess.run_sequence_frame` (one C call: front, DBSCAN, labels, centroids, the waits between them in C) against
+    `run(variant="B", host_arrays=False)` + `people_positions`: inliers, labels, cluster count, dimensions, guards and
+    people positions, on ring frames, on a frame without clusters, on a frame with fewer than 11 non-ground points and
+    with a centroid capacity that is too small (the positions then come from the ordinary path)."""
+    import torch
+    frames = [np.ascontiguousarray(pkg.synth.ring_sequence_frame(i, rings=48, azimuth_steps=4096)[:, :3], dtype=np.float64)
+              for i in range(2)]
+    frames.append(np.random.default_rng(3).uniform(-50.0, 50.0, (3000, 3)))
+    tiny = np.random.default_rng(4).uniform(-1.0, 1.0, (30, 3))
+    tiny[:21, 2] -= 10.0                                   # 30th percentile leaves 9 non-ground points: one cluster
+    frames.append(tiny)
+    for f in frames:
+        want = pkg.pre.run(f, variant="B", host_arrays=False)
+        want_pos = pkg.pre.people_positions(want)
+        for cap in (8192, 3):
+            got = pkg.pre.run_sequence_frame(torch.from_numpy(f).cuda(), centroid_cap=cap)
+            cw, cg = want[pkg.pre.DEVICE_KEY], got[pkg.pre.DEVICE_KEY]
+            assert got["dimensions"] == want["dimensions"] and sorted(got) == sorted(want)
+            assert cg.n_clusters == cw.n_clusters and cg.guards == cw.guards
+            assert torch.equal(cg.points, cw.points) and torch.equal(cg.clusters, cw.clusters)
+            assert (cg.positions is not None) == (cg.n_clusters <= cap)
+            got_pos = pkg.pre.people_positions(got)
+            assert got_pos.shape == want_pos.shape and np.array_equal(got_pos, want_pos)
+
+
 def test_frame_flow_step_equals_separate_entries(pkg):
     """`ops.frame_flow_step` (one copy in, `lidar_frame_flow`, one copy out) against the separate match / field entries fed
     with the numpy lattice of models/crowd_flow_model.py:107-111 -- host and device positions, bit for bit."""
